@@ -1,0 +1,164 @@
+/*
+ * taco_b200.h -- C ABI of the B200-native Tacotron synthesis forward path.
+ *
+ * The reference (Jim-Song/tacotron_multispeaker) is pure Python on TensorFlow
+ * 1.x and has no FFI of its own; the boundary it offers for this path is the
+ * Python contract
+ *     Tacotron.initialize(inputs, input_lengths, mel_targets, linear_targets,
+ *                         identities, id_num)          models/tacotron.py:18
+ *     Synthesizer.load / Synthesizer.synthesize       synthesizer.py:14,37
+ * whose body is one tf.Session.run (synthesizer.py:47).  This header is what a
+ * binding for that body links against: each entry point below names the
+ * reference lines it replaces.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *  - plain C, no torch / CUDA types in signatures; `stream` is a cudaStream_t
+ *    passed as void* (NULL = legacy default stream).
+ *  - every data pointer is a DEVICE pointer unless the name ends in `_host`.
+ *  - all work is enqueued on the caller's stream; the only host syncs are the
+ *    ones documented (`steps_out_host` read-back, workspace growth).
+ *  - return value: 0 = TACO_OK, negative = error; taco_last_error() gives text.
+ *  - one handle per GPU; a handle is not thread-safe.
+ *  - tensors are dense row-major float32 / int32 with the reference's layouts:
+ *      inputs [N,T_in] i32, input_lengths [N] i32, identities [N] i32,
+ *      mel_targets [N,T_tgt,num_mels], mel_outputs [N,max_steps*r,num_mels],
+ *      linear_outputs [N,max_steps*r,num_freq], alignments [N,T_in,max_steps]
+ *    where max_steps = taco_max_steps(...).  Only the first `steps` decoder
+ *    steps (steps*r frames) of each utterance are written.
+ */
+#ifndef TACO_B200_H_
+#define TACO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct taco_handle taco_handle;
+
+/* Subset of reference hparams.py:5-53 that the forward path reads. */
+typedef struct taco_hparams {
+  int32_t num_mels;                /* hparams.py:11  (80)   */
+  int32_t num_freq;                /* hparams.py:12  (1025) */
+  int32_t outputs_per_step;        /* hparams.py:22  r      */
+  int32_t max_iters;               /* hparams.py:34         */
+  int32_t embedding_text_channels; /* hparams.py:39  (256)  */
+  int32_t embedding_id_channels;   /* hparams.py:40  (64)   */
+  int32_t num_symbols;             /* len(symbols2), models/tacotron.py:40 (7352) */
+  int32_t id_num;                  /* rows of embedding_id; <=1 = single speaker (tacotron.py:48) */
+} taco_hparams;
+
+enum {
+  TACO_OK = 0,
+  TACO_ERR_INVALID = -1,        /* bad argument / shape                         */
+  TACO_ERR_CUDA = -2,           /* a CUDA runtime call failed                   */
+  TACO_ERR_MISSING_WEIGHT = -3, /* finalize: a variable was never set           */
+  TACO_ERR_STATE = -4,          /* call order (e.g. forward before finalize)    */
+  TACO_ERR_OOB_ID = -5,         /* symbol / speaker id outside its table        */
+  TACO_ERR_UNSUPPORTED = -6     /* device is not sm_100 / shape beyond limits   */
+};
+
+enum { TACO_BN_MOVING = 0, TACO_BN_BATCH = 1 };   /* tf.layers.batch_normalization(training=) */
+enum { TACO_ACT_NONE = 0, TACO_ACT_RELU = 1, TACO_ACT_SIGMOID = 2, TACO_ACT_TANH = 3 };
+enum { TACO_CBHG_ENCODER = 0, TACO_CBHG_POST = 1 };
+
+/* ---- lifetime ----------------------------------------------------------- */
+/* Replaces create_model()+Tacotron.__init__ (models/__init__.py:4-8,
+ * models/tacotron.py:14-15).  Fails with TACO_ERR_UNSUPPORTED when `device`
+ * is not a compute-capability-10.x GPU: there is no CPU fallback. */
+int taco_create(const taco_hparams* hp, int device, taco_handle** out);
+int taco_destroy(taco_handle* h);
+const char* taco_last_error(const taco_handle* h);
+const char* taco_version(void);
+
+/* ---- weights ------------------------------------------------------------ */
+/* Replaces Saver.restore (synthesizer.py:33-34): one call per variable, named
+ * as in the TF checkpoint with or without the "model/inference/" prefix
+ * (SURVEY.md Appendix A).  `data_host` is HOST float32, copied immediately. */
+int taco_set_weight(taco_handle* h, const char* tf_name, const float* data_host,
+                    const int64_t* shape, int ndim);
+/* Packs the variables into kernel layouts (BN folded to scale/shift, GRU
+ * kernels split into input/recurrent parts, decoder matrices sliced per CTA of
+ * the decode cluster) and uploads them.  Must be called once after all
+ * taco_set_weight calls and again after any later taco_set_weight. */
+int taco_finalize_weights(taco_handle* h);
+/* Number of variables the path expects / name of the i-th one. */
+int taco_num_weights(const taco_handle* h);
+const char* taco_weight_name(const taco_handle* h, int i);
+
+/* ---- shapes ------------------------------------------------------------- */
+/* Decoder steps the loop can take: min(max_iters, T_tgt / r) when teacher
+ * forcing (helpers.py:48-55,73), else max_iters (tacotron.py:94). */
+int taco_max_steps(const taco_handle* h, int teacher_force, int T_tgt);
+
+/* ---- the whole path: body of Tacotron.initialize (tacotron.py:35-104) ---- */
+/* spk may be NULL (single-speaker branch, tacotron.py:56-58); mel_targets may
+ * be NULL unless teacher_force.  bn_mode / teacher_force are separate because
+ * the reference ties both to `linear_targets is not None` (tacotron.py:36) and
+ * the host layer decides.  linear_out / align_out may be NULL to skip the
+ * post-net / the alignment stack.  Writes the step count to *steps_out_host
+ * (one stream sync). */
+int taco_forward(taco_handle* h, const int32_t* ids, const int32_t* lengths, const int32_t* spk,
+                 const float* mel_targets, int N, int T_in, int T_tgt, int bn_mode,
+                 int teacher_force, float* mel_out, float* linear_out, float* align_out,
+                 int32_t* steps_out_host, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): copies inputs to the
+ * device, runs taco_forward, copies the outputs back and synchronises.  This
+ * is the shape of session.run(feed_dict) at synthesizer.py:42-47. */
+int taco_forward_host(taco_handle* h, const int32_t* ids_host, const int32_t* lengths_host,
+                      const int32_t* spk_host, const float* mel_targets_host, int N, int T_in,
+                      int T_tgt, int bn_mode, int teacher_force, float* mel_out_host,
+                      float* linear_out_host, float* align_out_host, int32_t* steps_out_host,
+                      void* stream);
+
+/* ---- stage-level entry points (unit parity against the oracle) ----------- */
+/* tacotron.py:46-55: out [N,T_in,E(+E_id)].  OOB ids write a zero row and make
+ * the call return TACO_ERR_OOB_ID at the next taco_check_ids(). */
+int taco_embed(taco_handle* h, const int32_t* ids, const int32_t* spk, int N, int T_in,
+               float* out, void* stream);
+int taco_check_ids(taco_handle* h, void* stream); /* syncs; 0 or TACO_ERR_OOB_ID */
+/* tacotron.py:46-63: embeddings -> prenet -> encoder CBHG.  memory_out [N,T_in,256]. */
+int taco_encoder(taco_handle* h, const int32_t* ids, const int32_t* lengths, const int32_t* spk,
+                 int N, int T_in, int bn_mode, float* memory_out, void* stream);
+/* tacotron.py:66-97,104: attention decoder loop.  dec_out [N,max_steps,num_mels*r]
+ * (== mel_outputs [N,max_steps*r,num_mels]), align_out [N,T_in,max_steps] or NULL. */
+int taco_decode(taco_handle* h, const float* memory, int N, int T_in, const float* mel_targets,
+                int T_tgt, int teacher_force, float* dec_out, float* align_out,
+                int32_t* steps_out_host, void* stream);
+/* modules.py:35-74 on arbitrary input: which = TACO_CBHG_ENCODER ([N,T,128] in)
+ * or TACO_CBHG_POST ([N,T,num_mels] in); lengths may be NULL; out [N,T,256].
+ * x_batch_stride / out_batch_stride are in floats (0 = dense). */
+int taco_cbhg(taco_handle* h, int which, const float* x, const int32_t* lengths, int N, int T,
+              int bn_mode, int64_t x_batch_stride, float* out, void* stream);
+/* tacotron.py:100-101: post CBHG + dense(num_freq).  mel [N,T,num_mels] with
+ * batch stride mel_batch_stride floats, linear_out likewise. */
+int taco_postnet(taco_handle* h, const float* mel, int N, int T, int bn_mode,
+                 int64_t mel_batch_stride, float* linear_out, int64_t linear_batch_stride,
+                 void* stream);
+/* modules.py:68-74 alone: x [N,T,128] -> out [N,T,256]. */
+int taco_bigru(taco_handle* h, int which, const float* x, const int32_t* lengths, int N, int T,
+               float* out, void* stream);
+/* tf.layers.conv1d(padding='same') + bias + activation on caller-supplied
+ * device weights (modules.py:95-100; k=1 is tf.layers.dense).  x [N,T,Cin],
+ * kernel [k,Cin,Cout], bias [Cout] or NULL, out [N,T,Cout]. */
+int taco_conv1d(taco_handle* h, const float* x, int N, int T, int Cin, const float* kernel,
+                const float* bias, int k, int Cout, int act, float* out, void* stream);
+
+/* ---- introspection for bench / tests ------------------------------------- */
+/* Kernel launches issued by this handle since creation. */
+int64_t taco_launch_count(const taco_handle* h);
+/* Decoder launch geometry chosen at finalize: CTAs per cluster, samples per
+ * cluster used for batch N. */
+int taco_decoder_geometry(const taco_handle* h, int N, int* cluster_size, int* samples_per_cluster,
+                          int* num_clusters);
+/* Device time (ms, CUDA events on `stream`) of the stages of the last
+ * taco_forward when profiling is on: [0]=encoder [1]=decoder [2]=postnet. */
+int taco_set_profiling(taco_handle* h, int on);
+int taco_last_stage_ms(const taco_handle* h, float* ms3_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TACO_B200_H_ */

@@ -1,0 +1,558 @@
+// K7: the attention decoder loop as one persistent, cluster-resident kernel.
+//
+// Replaces tf.contrib.seq2seq.dynamic_decode(BasicDecoder(output_cell, helper,
+// zero_state), maximum_iterations=max_iters) at reference
+// models/tacotron.py:66-94 -- a tf.while_loop of ~60 small ops per step --
+// including DecoderPrenetWrapper / ConcatOutputAndAttentionWrapper
+// (models/rnn_wrappers.py:22-24,50-52), BahdanauAttention + AttentionWrapper
+// (SURVEY.md Appendix B.2), the two ResidualWrapper(GRUCell(256)), the
+// OutputProjectionWrapper(80*r) and TacoTestHelper / TacoTrainingHelper
+// (models/helpers.py:26-38,68-77).  The whole loop runs on the device.
+//
+// Decomposition.  A thread-block CLUSTER of CS CTAs (16, or 8 where 16 cannot
+// be scheduled) owns S utterances for all steps; clusters never talk to each
+// other, so there is no grid-wide barrier.  Inside a cluster every weight
+// matrix is cut by output columns: CTA q computes columns [q*Mc,(q+1)*Mc) of
+// each of the 13 dependent mat-vec phases of a step for the S samples, then
+// PUSHES its slice of the result into the shared memory of all CS CTAs
+// (st.shared::cluster) and the cluster meets at a hardware cluster barrier
+// (release/acquire).  Activations therefore never leave shared memory; the
+// only per-step global traffic is the weight stream (L2-resident, prefetched
+// into registers across the barrier), the keys/memory rows of the attention,
+// and the outputs.
+//
+// Per-CTA mat-vec: the slice W_q[K][Mc] is streamed with one 128-bit load per
+// (k, 4 columns); a thread keeps 4 x S accumulators, reduces over the threads
+// that share its column group with shuffles, then across warps through shared
+// memory.  Activations are stored [k][S] so the S samples of one k are one
+// vector load.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace taco {
+
+namespace {
+constexpr int NT = 512;       // threads per CTA
+constexpr int NW = NT / 32;   // warps per CTA
+constexpr int DH = 256;       // decoder width (GRUCell(256), attention depth 256)
+constexpr int DP = 128;       // prenet output
+
+__host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- streamed mat-vec pieces ------------------------------------------------
+// MAXI = max rows per thread = ceil(Kmax * (MC/4) / NT).
+template <int MC, int KMAX>
+struct GemmCfg {
+  static constexpr int CG = MC / 4;            // column groups of 4 (power of two <= 32)
+  static constexpr int KR = NT / CG;           // rows in flight per pass
+  static constexpr int MAXI = ceil_div(KMAX, KR);
+};
+
+template <int MC, int KMAX>
+__device__ __forceinline__ void gemm_load(const float* __restrict__ W, int K,
+                                          float4 (&w)[GemmCfg<MC, KMAX>::MAXI]) {
+  using C = GemmCfg<MC, KMAX>;
+  const int tid = threadIdx.x;
+  const int cg = tid & (C::CG - 1), kr = tid / C::CG;
+#pragma unroll
+  for (int i = 0; i < C::MAXI; ++i) {
+    const int k = kr + i * C::KR;
+    w[i] = (k < K) ? ldg_f4(W + (size_t)k * MC + cg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// xs: shared activations [K][S]; red: [NW][S][MC] warp partial sums.
+template <int S, int MC, int KMAX>
+__device__ __forceinline__ void gemm_fma(const float4 (&w)[GemmCfg<MC, KMAX>::MAXI], int K,
+                                         const float* __restrict__ xs, float* __restrict__ red) {
+  using C = GemmCfg<MC, KMAX>;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cg = tid & (C::CG - 1), kr = tid / C::CG;
+  float acc[S][4];
+#pragma unroll
+  for (int s = 0; s < S; ++s) acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.f;
+#pragma unroll
+  for (int i = 0; i < C::MAXI; ++i) {
+    const int k = kr + i * C::KR;
+    if (k < K) {
+      float x[S];
+      if constexpr (S % 4 == 0) {
+#pragma unroll
+        for (int s4 = 0; s4 < S / 4; ++s4) {
+          const float4 v = *reinterpret_cast<const float4*>(xs + (size_t)k * S + s4 * 4);
+          x[s4 * 4 + 0] = v.x; x[s4 * 4 + 1] = v.y; x[s4 * 4 + 2] = v.z; x[s4 * 4 + 3] = v.w;
+        }
+      } else if constexpr (S == 2) {
+        const float2 v = *reinterpret_cast<const float2*>(xs + (size_t)k * 2);
+        x[0] = v.x; x[1] = v.y;
+      } else {
+#pragma unroll
+        for (int s = 0; s < S; ++s) x[s] = xs[(size_t)k * S + s];
+      }
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        acc[s][0] = fmaf(x[s], w[i].x, acc[s][0]);
+        acc[s][1] = fmaf(x[s], w[i].y, acc[s][1]);
+        acc[s][2] = fmaf(x[s], w[i].z, acc[s][2]);
+        acc[s][3] = fmaf(x[s], w[i].w, acc[s][3]);
+      }
+    }
+  }
+  // lanes l and l^off share a column group whenever off is a multiple of CG
+#pragma unroll
+  for (int off = 16; off >= C::CG; off >>= 1) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[s][j] += __shfl_xor_sync(0xffffffffu, acc[s][j], off);
+    }
+  }
+  if (lane < C::CG) {
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+      *reinterpret_cast<float4*>(red + ((size_t)(warp * S + s) * MC + cg * 4)) =
+          make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
+  }
+}
+
+template <int S, int MC>
+__device__ __forceinline__ float red_sum(const float* __restrict__ red, int s, int c) {
+  float v = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) v += red[(size_t)(w * S + s) * MC + c];
+  return v;
+}
+
+// Copy `n` floats from local `src` into every CTA of the cluster at the address
+// that corresponds to local `dst` (same shared-memory offset in each CTA).
+__device__ __forceinline__ void push_block(float* dst, const float* src, int n, int CS) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t d0 = smem_u32(dst);
+  const bool vec = ((n & 3) == 0) && ((d0 & 15u) == 0) && ((smem_u32(src) & 15u) == 0);
+  for (int p = warp; p < CS; p += NW) {
+    const uint32_t rbase = mapa_u32(d0, (uint32_t)p);
+    if (vec) {
+      for (int i = lane; i < (n >> 2); i += 32)
+        st_cluster_f4(rbase + i * 16, *reinterpret_cast<const float4*>(src + i * 4));
+    } else {
+      for (int i = lane; i < n; i += 32) st_cluster_f32(rbase + i * 4, src[i]);
+    }
+  }
+}
+
+// Shared-memory carve-up (floats).  Everything that peers push into sits at the
+// same offset in every CTA of the cluster.
+struct Layout {
+  int xin, p1, in3, rhA, pq, sc, in9, rh1, in11, rh2, y2, red, stage, stage2, locu, loccx, locy0h, total;
+};
+__host__ __device__ inline Layout make_layout(int S, int T_in, int M, int CS) {
+  const int Hc = DH / CS;
+  Layout L;
+  int o = 0;
+  auto take = [&](int nfloats) { int r = o; o += (nfloats + 3) & ~3; return r; };
+  L.xin = take((M + DH) * S);       // [frame(M) | context(256)]      rows x S
+  L.p1 = take(DH * S);              // prenet layer 1
+  L.in3 = take((DP + DH) * S);      // [prenet out(128) | h_att(256)]
+  L.rhA = take(DH * S);             // r * h_att
+  L.pq = take(DH * S);              // processed query, layout [S][256]
+  L.sc = take(T_in * S);            // scores / alignments [T_in][S]
+  L.in9 = take(2 * DH * S);         // [y0 | h1]
+  L.rh1 = take(DH * S);
+  L.in11 = take(2 * DH * S);        // [y1 | h2]
+  L.rh2 = take(DH * S);
+  L.y2 = take(DH * S);
+  L.red = take(NW * S * 3 * Hc);    // warp partials: gates (2Hc) + candidate-x (Hc)
+  L.stage = take(S * 64 > S * 2 * Hc ? S * 64 : S * 2 * Hc);
+  L.stage2 = take(S * 64);
+  L.locu = take(S * Hc);
+  L.loccx = take(S * Hc);
+  L.locy0h = take(S * Hc);
+  L.total = o;
+  return L;
+}
+
+template <int S, int CS>
+__global__ void __launch_bounds__(NT, 1)
+decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
+  constexpr int Hc = DH / CS;     // columns of a 256-wide layer per CTA
+  constexpr int Pc = DP / CS;     // columns of the 128-wide prenet layer per CTA
+  constexpr int McO = (CS == 16) ? 32 : 64;   // padded slice of the 80*r output projection
+  constexpr int K1MAX = 128 + DH; // num_mels <= 128
+
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = (int)cluster_ctarank();
+  const int n0 = (int)cluster_id_x() * S;
+  const int M = w.M, K1 = M + DH, Dout = w.Dout;
+  const int T_in = a.T_in;
+  const Layout L = make_layout(S, T_in, M, CS);
+  float* xin = smem + L.xin;   float* p1 = smem + L.p1;     float* in3 = smem + L.in3;
+  float* rhA = smem + L.rhA;   float* pqT = smem + L.pq;    float* sc = smem + L.sc;
+  float* in9 = smem + L.in9;   float* rh1 = smem + L.rh1;   float* in11 = smem + L.in11;
+  float* rh2 = smem + L.rh2;   float* y2 = smem + L.y2;     float* red = smem + L.red;
+  float* stage = smem + L.stage; float* stage2 = smem + L.stage2;
+  float* locu = smem + L.locu; float* loccx = smem + L.loccx; float* locy0h = smem + L.locy0h;
+  float* redB = red + NW * S * 2 * Hc;   // second partial-sum region (candidate x-part)
+
+  for (int i = tid; i < L.total; i += NT) smem[i] = 0.f;   // zero_state + <GO> frame
+
+  // per-CTA weight slices
+  const float* W1 = w.p1_s + (size_t)q * K1 * Hc;
+  const float* W2 = w.p2_s + (size_t)q * DH * Pc;
+  const float* WgA = w.ga_s + (size_t)q * (DP + DH) * 2 * Hc;
+  const float* WcxA = w.cxa_s + (size_t)q * DP * Hc;
+  const float* WchA = w.cha_s + (size_t)q * DH * Hc;
+  const float* Wqp = w.qp_s + (size_t)q * DH * 2 * Hc;
+  const float* Wpc = w.pc_s + (size_t)q * DH * Hc;
+  const float* Wg1 = w.g1_s + (size_t)q * 2 * DH * 2 * Hc;
+  const float* Wcx1 = w.cx1_s + (size_t)q * DH * Hc;
+  const float* Wch1 = w.ch1_s + (size_t)q * DH * Hc;
+  const float* Wg2 = w.g2_s + (size_t)q * 2 * DH * 2 * Hc;
+  const float* Wcx2 = w.cx2_s + (size_t)q * DH * Hc;
+  const float* Wch2 = w.ch2_s + (size_t)q * DH * Hc;
+  const float* Wo = w.o_s + (size_t)q * DH * McO;
+
+  // attention slice of this CTA: encoder positions [j0, j1)
+  const int Tj = ceil_div(T_in, CS);
+  const int j0 = min(q * Tj, T_in), j1 = min(j0 + Tj, T_in);
+  float vreg[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) vreg[i] = __ldg(w.att_v + lane + 32 * i);
+
+  // epilogue role: thread o -> (sample es, column ec) with the column fastest
+  const int es = tid / Hc, ec = tid % Hc;        // valid when tid < S*Hc
+  const bool e_on = tid < S * Hc;
+
+  // register double-buffer for the streamed weights of the NEXT phase
+  float4 wa[GemmCfg<2 * Hc, 2 * DH>::MAXI];      // widest: GRU gates, K=512
+  float4 wb[GemmCfg<Hc, K1MAX>::MAXI];           // Hc-wide matrices (K <= 384)
+  float4 wo[GemmCfg<McO, DH>::MAXI];
+  float4 w2[GemmCfg<Pc, DH>::MAXI];
+
+  __syncthreads();
+  gemm_load<Hc, K1MAX>(W1, K1, wb);
+  cluster_sync_all();   // every CTA has zeroed its buffers before anyone pushes
+
+  for (int t = 0; t < a.steps; ++t) {
+    // ---- teacher forcing: next input = mel_targets[:, (t-1)*r + r-1, :] (helpers.py:48,75) ----
+    if (a.targets != nullptr && t > 0) {
+      for (int i = tid; i < M * S; i += NT) {
+        const int f = i / S, s = i - f * S, n = n0 + s;
+        xin[i] = (n < a.N) ? __ldg(a.targets + ((size_t)n * a.T_tgt + (size_t)(t - 1) * a.r + a.r - 1) * M + f) : 0.f;
+      }
+      __syncthreads();
+    }
+    // ================= P1: decoder prenet dense_1 + ReLU  [frame|ctx] -> 256 =================
+    gemm_fma<S, Hc, K1MAX>(wb, K1, xin, red);
+    __syncthreads();
+    if (e_on) stage[ec * S + es] = fmaxf(red_sum<S, Hc>(red, es, ec) + __ldg(w.p1_b + q * Hc + ec), 0.f);
+    __syncthreads();
+    push_block(p1 + q * Hc * S, stage, Hc * S, CS);
+    cluster_arrive();
+    gemm_load<Pc, DH>(W2, DH, w2);
+    cluster_wait();
+    // ================= P2: prenet dense_2 + ReLU  256 -> 128 =================
+    gemm_fma<S, Pc, DH>(w2, DH, p1, red);
+    __syncthreads();
+    if (tid < S * Pc) {
+      const int s = tid / Pc, c = tid % Pc;
+      stage[c * S + s] = fmaxf(red_sum<S, Pc>(red, s, c) + __ldg(w.p2_b + q * Pc + c), 0.f);
+    }
+    __syncthreads();
+    push_block(in3 + q * Pc * S, stage, Pc * S, CS);
+    cluster_arrive();
+    gemm_load<2 * Hc, 2 * DH>(WgA, DP + DH, wa);
+    gemm_load<Hc, K1MAX>(WcxA, DP, wb);
+    cluster_wait();
+    // ================= P3: attention GRU gates + candidate x-part =================
+    gemm_fma<S, 2 * Hc, 2 * DH>(wa, DP + DH, in3, red);
+    gemm_fma<S, Hc, K1MAX>(wb, DP, in3, redB);
+    __syncthreads();
+    if (e_on) {
+      const float r = sigmoid_f(red_sum<S, 2 * Hc>(red, es, ec) + __ldg(w.ga_b + q * 2 * Hc + ec));
+      const float u = sigmoid_f(red_sum<S, 2 * Hc>(red, es, Hc + ec) + __ldg(w.ga_b + q * 2 * Hc + Hc + ec));
+      const float hold = in3[(DP + q * Hc + ec) * S + es];
+      stage[ec * S + es] = r * hold;
+      locu[tid] = u;
+      loccx[tid] = red_sum<S, Hc>(redB, es, ec);
+    }
+    __syncthreads();
+    push_block(rhA + q * Hc * S, stage, Hc * S, CS);
+    cluster_arrive();
+    gemm_load<Hc, K1MAX>(WchA, DH, wb);
+    cluster_wait();
+    // ================= P4: attention GRU candidate h-part -> h_att' =================
+    gemm_fma<S, Hc, K1MAX>(wb, DH, rhA, red);
+    __syncthreads();
+    if (e_on) {
+      const float c = tanh_f(red_sum<S, Hc>(red, es, ec) + loccx[tid] + __ldg(w.ca_b + q * Hc + ec));
+      const float u = locu[tid];
+      const float hold = in3[(DP + q * Hc + ec) * S + es];
+      stage[ec * S + es] = u * hold + (1.0f - u) * c;
+    }
+    __syncthreads();
+    push_block(in3 + (DP + q * Hc) * S, stage, Hc * S, CS);
+    cluster_arrive();
+    gemm_load<2 * Hc, 2 * DH>(Wqp, DH, wa);
+    cluster_wait();
+    // ================= P5: query layer + h_att' part of the 512->256 projection =================
+    gemm_fma<S, 2 * Hc, 2 * DH>(wa, DH, in3 + DP * S, red);
+    __syncthreads();
+    if (e_on) {
+      stage[es * Hc + ec] = red_sum<S, 2 * Hc>(red, es, ec);          // layout [S][Hc] for pqT
+      locy0h[tid] = red_sum<S, 2 * Hc>(red, es, Hc + ec);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < S; ++s) push_block(pqT + s * DH + q * Hc, stage + s * Hc, Hc, CS);
+    cluster_arrive();
+    gemm_load<Hc, K1MAX>(Wpc, DH, wb);
+    cluster_wait();
+    // ================= P6: Bahdanau scores for positions [j0,j1) =================
+    {
+      const int npairs = S * (j1 - j0);
+      for (int pi = warp; pi < npairs; pi += NW) {
+        const int jj = pi / S, s = pi - jj * S, n = n0 + s;
+        float e = 0.f;
+        if (n < a.N) {
+          const float* krow = a.keys + ((size_t)n * T_in + (j0 + jj)) * DH;
+          const float* prow = pqT + s * DH;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            e = fmaf(vreg[i], tanh_f(__ldg(krow + lane + 32 * i) + prow[lane + 32 * i]), e);
+        }
+        e = warp_sum(e);
+        if (lane == 0) stage[jj * S + s] = e;
+      }
+    }
+    __syncthreads();
+    if (j1 > j0) push_block(sc + j0 * S, stage, (j1 - j0) * S, CS);
+    cluster_sync_all();
+    // ================= P7: softmax over all T_in (no mask) + context slice =================
+    if (warp < S) {
+      const int s = warp;
+      float m = -INFINITY;
+      for (int j = lane; j < T_in; j += 32) m = fmaxf(m, sc[j * S + s]);
+      m = warp_max(m);
+      float l = 0.f;
+      for (int j = lane; j < T_in; j += 32) {
+        const float e = __expf(sc[j * S + s] - m);
+        sc[j * S + s] = e;
+        l += e;
+      }
+      l = warp_sum(l);
+      const float inv = 1.0f / l;
+      for (int j = lane; j < T_in; j += 32) sc[j * S + s] *= inv;
+    }
+    __syncthreads();
+    if (a.align_out != nullptr) {
+      for (int i = tid; i < S * (j1 - j0); i += NT) {
+        const int jj = i / S, s = i - jj * S, n = n0 + s;
+        if (n < a.N) a.align_out[((size_t)n * T_in + (j0 + jj)) * a.max_steps + t] = sc[(j0 + jj) * S + s];
+      }
+    }
+    {
+      constexpr int JC = NT / (S * Hc);              // j-chunks per (sample, dim)
+      const int d = tid % Hc, jc = (tid / Hc) % JC, s = tid / (Hc * JC), n = n0 + s;
+      float acc = 0.f;
+      if (n < a.N) {
+        const float* mp = a.memory + (size_t)n * T_in * DH + q * Hc + d;
+        for (int j = jc; j < T_in; j += JC) acc = fmaf(sc[j * S + s], __ldg(mp + (size_t)j * DH), acc);
+      }
+      red[(s * JC + jc) * Hc + d] = acc;
+      __syncthreads();
+      if (e_on) {
+        float v = 0.f;
+#pragma unroll
+        for (int c = 0; c < JC; ++c) v += red[(es * JC + c) * Hc + ec];
+        stage[ec * S + es] = v;
+      }
+    }
+    __syncthreads();
+    push_block(xin + (M + q * Hc) * S, stage, Hc * S, CS);
+    cluster_sync_all();
+    // ================= P8: y0 = [h_att'|ctx] W_p + b  (ctx part; h part from P5) =================
+    gemm_fma<S, Hc, K1MAX>(wb, DH, xin + M * S, red);
+    __syncthreads();
+    if (e_on) stage[ec * S + es] = red_sum<S, Hc>(red, es, ec) + locy0h[tid] + __ldg(w.pc_b + q * Hc + ec);
+    __syncthreads();
+    push_block(in9 + q * Hc * S, stage, Hc * S, CS);
+    cluster_arrive();
+    gemm_load<2 * Hc, 2 * DH>(Wg1, 2 * DH, wa);
+    gemm_load<Hc, K1MAX>(Wcx1, DH, wb);
+    cluster_wait();
+    // ================= P9/P10: residual GRU 1 =================
+    gemm_fma<S, 2 * Hc, 2 * DH>(wa, 2 * DH, in9, red);
+    gemm_fma<S, Hc, K1MAX>(wb, DH, in9, redB);
+    __syncthreads();
+    if (e_on) {
+      const float r = sigmoid_f(red_sum<S, 2 * Hc>(red, es, ec) + __ldg(w.g1_b + q * 2 * Hc + ec));
+      const float u = sigmoid_f(red_sum<S, 2 * Hc>(red, es, Hc + ec) + __ldg(w.g1_b + q * 2 * Hc + Hc + ec));
+      stage[ec * S + es] = r * in9[(DH + q * Hc + ec) * S + es];
+      locu[tid] = u;
+      loccx[tid] = red_sum<S, Hc>(redB, es, ec);
+    }
+    __syncthreads();
+    push_block(rh1 + q * Hc * S, stage, Hc * S, CS);
+    cluster_arrive();
+    gemm_load<Hc, K1MAX>(Wch1, DH, wb);
+    cluster_wait();
+    gemm_fma<S, Hc, K1MAX>(wb, DH, rh1, red);
+    __syncthreads();
+    if (e_on) {
+      const float c = tanh_f(red_sum<S, Hc>(red, es, ec) + loccx[tid] + __ldg(w.c1_b + q * Hc + ec));
+      const float u = locu[tid];
+      const float hold = in9[(DH + q * Hc + ec) * S + es];
+      const float hn = u * hold + (1.0f - u) * c;
+      stage[ec * S + es] = hn;
+      stage2[ec * S + es] = in9[(q * Hc + ec) * S + es] + hn;     // y1 = y0 + GRU1(y0)  (ResidualWrapper)
+    }
+    __syncthreads();
+    push_block(in9 + (DH + q * Hc) * S, stage, Hc * S, CS);
+    push_block(in11 + q * Hc * S, stage2, Hc * S, CS);
+    cluster_arrive();
+    gemm_load<2 * Hc, 2 * DH>(Wg2, 2 * DH, wa);
+    gemm_load<Hc, K1MAX>(Wcx2, DH, wb);
+    cluster_wait();
+    // ================= P11/P12: residual GRU 2 =================
+    gemm_fma<S, 2 * Hc, 2 * DH>(wa, 2 * DH, in11, red);
+    gemm_fma<S, Hc, K1MAX>(wb, DH, in11, redB);
+    __syncthreads();
+    if (e_on) {
+      const float r = sigmoid_f(red_sum<S, 2 * Hc>(red, es, ec) + __ldg(w.g2_b + q * 2 * Hc + ec));
+      const float u = sigmoid_f(red_sum<S, 2 * Hc>(red, es, Hc + ec) + __ldg(w.g2_b + q * 2 * Hc + Hc + ec));
+      stage[ec * S + es] = r * in11[(DH + q * Hc + ec) * S + es];
+      locu[tid] = u;
+      loccx[tid] = red_sum<S, Hc>(redB, es, ec);
+    }
+    __syncthreads();
+    push_block(rh2 + q * Hc * S, stage, Hc * S, CS);
+    cluster_arrive();
+    gemm_load<Hc, K1MAX>(Wch2, DH, wb);
+    cluster_wait();
+    gemm_fma<S, Hc, K1MAX>(wb, DH, rh2, red);
+    __syncthreads();
+    if (e_on) {
+      const float c = tanh_f(red_sum<S, Hc>(red, es, ec) + loccx[tid] + __ldg(w.c2_b + q * Hc + ec));
+      const float u = locu[tid];
+      const float hold = in11[(DH + q * Hc + ec) * S + es];
+      const float hn = u * hold + (1.0f - u) * c;
+      stage[ec * S + es] = hn;
+      stage2[ec * S + es] = in11[(q * Hc + ec) * S + es] + hn;    // y2 = y1 + GRU2(y1)
+    }
+    __syncthreads();
+    push_block(in11 + (DH + q * Hc) * S, stage, Hc * S, CS);
+    push_block(y2 + q * Hc * S, stage2, Hc * S, CS);
+    cluster_arrive();
+    gemm_load<McO, DH>(Wo, DH, wo);
+    cluster_wait();
+    // ================= P13: output projection 256 -> 80*r, write frames, feed back =================
+    gemm_fma<S, McO, DH>(wo, DH, y2, red);
+    __syncthreads();
+    const int fb0 = Dout - M;                                  // first fed-back column (helpers.py:37)
+    const int c_lo = max(q * McO, fb0), c_hi = min((q + 1) * McO, Dout);
+    if (tid < S * McO) {
+      const int s = tid / McO, c = tid % McO, col = q * McO + c, n = n0 + s;
+      if (col < Dout) {
+        const float v = red_sum<S, McO>(red, s, c) + __ldg(w.o_b + col);
+        if (n < a.N) a.dec_out[((size_t)n * a.max_steps + t) * Dout + col] = v;
+        if (col >= fb0) stage[(col - c_lo) * S + s] = v;
+      }
+    }
+    __syncthreads();
+    if (a.targets == nullptr && c_hi > c_lo) push_block(xin + (c_lo - fb0) * S, stage, (c_hi - c_lo) * S, CS);
+    cluster_arrive();
+    gemm_load<Hc, K1MAX>(W1, K1, wb);
+    cluster_wait();
+  }
+}
+
+template <int S, int CS>
+cudaError_t launch_decoder_t(const DecoderWeights& w, const DecoderArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)make_layout(S, a.T_in, w.M, CS).total * sizeof(float);
+  auto kern = decoder_kernel<S, CS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (CS > 8) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+  }
+  const int nclusters = ceil_div(a.N, S);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nclusters * CS);
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, w, a);
+}
+
+template <int CS>
+cudaError_t launch_decoder_cs(const DecoderWeights& w, const DecoderArgs& a, int S, cudaStream_t st) {
+  switch (S) {
+    case 1: return launch_decoder_t<1, CS>(w, a, st);
+    case 2: return launch_decoder_t<2, CS>(w, a, st);
+    case 4: return launch_decoder_t<4, CS>(w, a, st);
+    case 8: return launch_decoder_t<8, CS>(w, a, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <int CS>
+int max_active_clusters() {
+  auto kern = decoder_kernel<1, CS>;
+  const size_t smem = (size_t)make_layout(1, 128, 80, CS).total * sizeof(float);
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  if (CS > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(CS);
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+}  // namespace
+
+size_t decoder_smem_bytes(int S, int T_in, int CS) {
+  return (size_t)make_layout(S, T_in, 80, CS).total * sizeof(float);
+}
+
+int decoder_pick_cluster_size() {
+  if (max_active_clusters<16>() >= 1) return 16;
+  return 8;
+}
+
+int decoder_max_clusters(int CS) { return CS == 16 ? max_active_clusters<16>() : max_active_clusters<8>(); }
+
+cudaError_t launch_decoder(const DecoderWeights& w, const DecoderArgs& a, int S, cudaStream_t st) {
+  if (a.N <= 0 || a.steps <= 0) return cudaSuccess;
+  if (w.CS == 16) return launch_decoder_cs<16>(w, a, S, st);
+  if (w.CS == 8) return launch_decoder_cs<8>(w, a, S, st);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace taco

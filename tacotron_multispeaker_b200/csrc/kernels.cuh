@@ -1,0 +1,87 @@
+// Launcher interfaces of the CUDA kernels (one .cu per kernel family).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace taco {
+
+// ---- K1: embedding gather + speaker concat (gather.cu) --------------------
+// out[n,t,:] = [ table[ids[n,t]] (E) | spk_table[spk[n]] (Es) ]; Es = 0 when spk == nullptr.
+// Out-of-range ids write zeros and set *oob_flag (bit0 symbol, bit1 speaker).
+void launch_gather_concat(const int32_t* ids, const int32_t* spk, const float* table, int V, int E,
+                          const float* spk_table, int S, int Es, int N, int T, float* out,
+                          int* oob_flag, cudaStream_t st);
+
+// ---- conv1d-as-GEMM (conv_gemm.cu) -----------------------------------------
+// out[n,t,col_off+o] = epi( sum_{j<k, c<Cin} x[n, t+j-pl, c] * w[(j*Cin+c)*ldw + o] ),  pl=(k-1)/2,
+// rows outside [0,T) read as zero (tf 'same' padding).  k=1 is a dense layer.
+enum { EPI_PLAIN = 0, EPI_HIGHWAY = 1 };
+struct ConvGemm {
+  const float* x; int64_t x_bs; int ldx;   // x[n*x_bs + t*ldx + c]
+  int N, T, Cin, k;
+  const float* w; int ldw;                  // ldw % 4 == 0
+  const float* bias;                        // [Cout] or null
+  const float* scale; const float* shift;   // per-channel affine after the activation, or null
+  const float* res; int64_t res_bs; int ldres;  // residual (PLAIN) / carry input (HIGHWAY), or null
+  float* out; int64_t out_bs; int ldo; int col_off;
+  int Cout;                                 // GEMM columns (HIGHWAY: 2*channels, interleaved H,T)
+  int act; int epi;
+};
+void launch_conv_gemm(const ConvGemm& p, cudaStream_t st);
+
+// ---- elementwise / statistics (elementwise.cu) -----------------------------
+// Per-channel batch statistics over all (n,t) rows -> scale/shift of
+// tf.layers.batch_normalization(training=True): biased variance, eps.
+// acc: [2*C] doubles of scratch (zeroed inside).
+void launch_bn_batch_stats(const float* x, int64_t x_bs, int ldx, int col_off, int N, int T, int C,
+                           const float* gamma, const float* beta, float eps, double* acc,
+                           float* scale_out, float* shift_out, cudaStream_t st);
+// y[n,t,c] = max(a(x[n,t,c]), a(x[n,t+1,c])) with a = per-channel affine (or identity when
+// scale == nullptr); last row passes through (max_pooling1d(2,1,'same')).
+void launch_affine_maxpool(const float* x, float* y, int N, int T, int C, const float* scale,
+                           const float* shift, cudaStream_t st);
+// x[n,t,c] = x*scale[c] + shift[c] (+ res[n,t,c]) in place.
+void launch_affine_inplace(float* x, int64_t x_bs, int ldx, int N, int T, int C, const float* scale,
+                           const float* shift, const float* res, int64_t res_bs, int ldres,
+                           cudaStream_t st);
+// Decoder epilogue: number of steps taken by dynamic_decode given dec_out [N,max_steps,D].
+void launch_find_steps(const float* dec_out, int N, int max_steps, int D, int* first_fin /*[N]*/,
+                       int* steps_out /*[1]*/, cudaStream_t st);
+
+// ---- K6b: bidirectional GRU recurrence (bigru.cu) ---------------------------
+// xproj [N,T,768] = x*[Wg_fw|Wc_fw|Wg_bw|Wc_bw] + biases (hoisted input projection);
+// ug [2][128][256], uc [2][128][128] recurrent kernels; lengths nullable; out [N,T,256] (+bs).
+void launch_bigru(const float* xproj, const float* ug, const float* uc, const int32_t* lengths,
+                  int N, int T, float* out, int64_t out_bs, cudaStream_t st);
+
+// ---- K7: attention decoder (decoder.cu) --------------------------------------
+struct DecoderWeights {   // all device pointers; *_s are per-CTA column slices [CS][K][Mc]
+  int CS;                 // CTAs per cluster the slices were cut for
+  int M;                  // num_mels
+  int Dout, McO;          // num_mels*r and its per-CTA padded slice width
+  const float *p1_s, *p1_b;     // prenet dense_1 [M+256 -> 256]
+  const float *p2_s, *p2_b;     // prenet dense_2 [256 -> 128]
+  const float *ga_s, *ga_b;     // attention GRU gates [384 -> (r|u) slice], bias permuted likewise
+  const float *cxa_s, *cha_s, *ca_b;  // candidate: x-part [128->256], h-part [256->256], bias
+  const float *qp_s;            // [256 -> (Wq | Wproj[:256])] slices
+  const float *att_v;           // [256]
+  const float *pc_s, *pc_b;     // Wproj[256:] [256 -> 256], bias
+  const float *g1_s, *g1_b, *cx1_s, *ch1_s, *c1_b;   // decoder GRU 1
+  const float *g2_s, *g2_b, *cx2_s, *ch2_s, *c2_b;   // decoder GRU 2
+  const float *o_s, *o_b;       // output projection [256 -> McO*CS], bias padded
+};
+struct DecoderArgs {
+  const float* memory;   // [N,T_in,256]
+  const float* keys;     // [N,T_in,256] = memory * W_mem
+  const float* targets;  // [N,T_tgt,M] or null (free running)
+  int N, T_in, T_tgt, r, steps, max_steps;
+  float* dec_out;        // [N,max_steps,Dout]
+  float* align_out;      // [N,T_in,max_steps] or null
+};
+// S = samples per cluster (1,2,4,8).  Returns cudaError of the launch.
+cudaError_t launch_decoder(const DecoderWeights& w, const DecoderArgs& a, int S, cudaStream_t st);
+// Largest cluster size (16 or 8) the device can co-schedule for the decoder kernel.
+int decoder_pick_cluster_size();
+size_t decoder_smem_bytes(int S, int T_in, int CS);
+
+}  // namespace taco

@@ -1,0 +1,993 @@
+// C ABI of the B200 Tacotron forward path (include/taco_b200.h): handle,
+// variable store keyed by TF checkpoint names, packing into kernel layouts,
+// and the launch sequence that replaces Tacotron.initialize's graph
+// (reference models/tacotron.py:35-104) + Session.run (synthesizer.py:47).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/taco_b200.h"
+#include "kernels.cuh"
+
+namespace taco {
+int decoder_max_clusters(int CS);
+}
+using namespace taco;
+
+namespace {
+
+constexpr float kBnEps = 1e-3f;   // tf.layers.batch_normalization default
+constexpr int DH = 256, DP = 128;
+
+const char* kATT =
+    "decoder/output_projection_wrapper/multi_rnn_cell/cell_0/output_projection_wrapper/"
+    "concat_output_and_attention_wrapper/attention_wrapper/";
+const char* kMRC = "decoder/output_projection_wrapper/multi_rnn_cell/";
+const char* kPrefix = "model/inference/";
+
+struct HostVar {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  bool set = false;
+};
+
+struct CbhgDev {   // offsets (floats) into the device weight arena
+  int K = 0, Cin = 0, P1 = 0, P2 = 0;
+  std::vector<size_t> bank_w, bank_b;
+  size_t bank_scale = 0, bank_shift = 0, bank_gamma = 0, bank_beta = 0;
+  size_t p1_w = 0, p1_b = 0, p1_scale = 0, p1_shift = 0, p1_gamma = 0, p1_beta = 0;
+  size_t p2_w = 0, p2_b = 0, p2_scale = 0, p2_shift = 0, p2_gamma = 0, p2_beta = 0;
+  size_t dense_w = 0, dense_b = 0;
+  size_t hw_w[4] = {0, 0, 0, 0}, hw_b[4] = {0, 0, 0, 0};
+  size_t gru_wx = 0, gru_bx = 0, gru_ug = 0, gru_uc = 0;
+};
+
+struct Arena {   // host staging of the packed weights
+  std::vector<float> buf;
+  size_t alloc(size_t n) {
+    size_t off = (buf.size() + 63) & ~size_t(63);
+    buf.resize(off + n, 0.0f);
+    return off;
+  }
+};
+
+}  // namespace
+
+struct taco_handle {
+  taco_hparams hp;
+  int device = 0;
+  std::string err;
+  std::vector<std::string> names;             // expected variables (short names)
+  std::map<std::string, HostVar> vars;
+  bool finalized = false;
+  // packed weights
+  float* dW = nullptr;
+  size_t emb = 0, emb_id = 0, pre1_w = 0, pre1_b = 0, pre2_w = 0, pre2_b = 0, mem_w = 0, lin_w = 0, lin_b = 0;
+  int lin_ld = 0, emb_dim = 0;
+  CbhgDev enc, post;
+  DecoderWeights dec;
+  int CS = 16, max_clusters = 8;
+  // workspace
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+  int* d_ints = nullptr;      // [0]=oob flag, [1]=steps, [2..]=first_fin[N]
+  int d_ints_n = 0;
+  int* h_pinned = nullptr;    // [0]=oob, [1]=steps
+  int64_t launches = 0;
+  bool profiling = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float stage_ms[3] = {0, 0, 0};
+};
+
+namespace {
+
+int fail(taco_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+#define CUDA_OK(h, expr)                                                                   \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return fail(h, TACO_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));   \
+  } while (0)
+
+void add_conv_names(std::vector<std::string>& n, const std::string& s) {
+  n.push_back(s + "/conv1d/kernel");
+  n.push_back(s + "/conv1d/bias");
+  n.push_back(s + "/batch_normalization/gamma");
+  n.push_back(s + "/batch_normalization/beta");
+  n.push_back(s + "/batch_normalization/moving_mean");
+  n.push_back(s + "/batch_normalization/moving_variance");
+}
+void add_cbhg_names(std::vector<std::string>& n, const std::string& s, int K, bool has_dense) {
+  for (int k = 1; k <= K; ++k) add_conv_names(n, s + "/conv_bank/conv1d_" + std::to_string(k));
+  add_conv_names(n, s + "/proj_1");
+  add_conv_names(n, s + "/proj_2");
+  if (has_dense) { n.push_back(s + "/dense/kernel"); n.push_back(s + "/dense/bias"); }
+  for (int i = 1; i <= 4; ++i)
+    for (const char* g : {"H", "T"}) {
+      n.push_back(s + "/highway_" + std::to_string(i) + "/" + g + "/kernel");
+      n.push_back(s + "/highway_" + std::to_string(i) + "/" + g + "/bias");
+    }
+  for (const char* d : {"fw", "bw"})
+    for (const char* g : {"gates", "candidate"}) {
+      n.push_back(s + "/bidirectional_rnn/" + d + "/gru_cell/" + g + "/kernel");
+      n.push_back(s + "/bidirectional_rnn/" + d + "/gru_cell/" + g + "/bias");
+    }
+}
+
+// Same inventory as tacotron_multispeaker_b200/weights.py:weight_specs.
+std::vector<std::string> expected_names(const taco_hparams& hp) {
+  std::vector<std::string> n;
+  const std::string att = kATT, dpw = att + "decoder_prenet_wrapper/", mrc = kMRC;
+  n.push_back("embedding");
+  if (hp.id_num > 1) n.push_back("embedding_id");
+  for (const char* d : {"dense_1", "dense_2"}) {
+    n.push_back(std::string("prenet/") + d + "/kernel");
+    n.push_back(std::string("prenet/") + d + "/bias");
+  }
+  add_cbhg_names(n, "encoder_cbhg", 16, false);
+  n.push_back("memory_layer/kernel");
+  n.push_back("decoder/output_projection_wrapper/kernel");
+  n.push_back("decoder/output_projection_wrapper/bias");
+  n.push_back(mrc + "cell_0/output_projection_wrapper/kernel");
+  n.push_back(mrc + "cell_0/output_projection_wrapper/bias");
+  for (const char* d : {"dense_1", "dense_2"}) {
+    n.push_back(dpw + "decoder_prenet/" + d + "/kernel");
+    n.push_back(dpw + "decoder_prenet/" + d + "/bias");
+  }
+  for (const char* g : {"gates", "candidate"}) {
+    n.push_back(dpw + "gru_cell/" + g + "/kernel");
+    n.push_back(dpw + "gru_cell/" + g + "/bias");
+  }
+  n.push_back(att + "bahdanau_attention/query_layer/kernel");
+  n.push_back(att + "bahdanau_attention/attention_v");
+  for (int c = 1; c <= 2; ++c)
+    for (const char* g : {"gates", "candidate"}) {
+      n.push_back(mrc + "cell_" + std::to_string(c) + "/gru_cell/" + g + "/kernel");
+      n.push_back(mrc + "cell_" + std::to_string(c) + "/gru_cell/" + g + "/bias");
+    }
+  add_cbhg_names(n, "post_cbhg", 8, hp.num_mels != 128);
+  n.push_back("dense/kernel");
+  n.push_back("dense/bias");
+  return n;
+}
+
+const HostVar* getv(taco_handle* h, const std::string& name, std::initializer_list<int64_t> shape,
+                    std::string* err) {
+  auto it = h->vars.find(name);
+  if (it == h->vars.end() || !it->second.set) {
+    *err = std::string("missing variable ") + kPrefix + name;
+    return nullptr;
+  }
+  const HostVar& v = it->second;
+  if (v.shape.size() != shape.size() || !std::equal(shape.begin(), shape.end(), v.shape.begin())) {
+    std::string s = "[";
+    for (auto d : v.shape) s += std::to_string(d) + ",";
+    std::string e = "[";
+    for (auto d : shape) e += std::to_string(d) + ",";
+    *err = std::string("variable ") + kPrefix + name + " has shape " + s + "] expected " + e + "]";
+    return nullptr;
+  }
+  return &v;
+}
+
+#define GETV(var, name, ...)                                            \
+  const HostVar* var = getv(h, name, {__VA_ARGS__}, &err);              \
+  if (!var) return false;
+
+// Copy a [rows, cols] matrix into the arena with leading dimension ld (zero padded).
+size_t put_matrix(Arena& A, const float* src, int rows, int cols, int ld) {
+  size_t off = A.alloc((size_t)rows * ld);
+  for (int r = 0; r < rows; ++r) memcpy(&A.buf[off + (size_t)r * ld], src + (size_t)r * cols, sizeof(float) * cols);
+  return off;
+}
+size_t put_vec(Arena& A, const float* src, int n) {
+  size_t off = A.alloc(n);
+  memcpy(&A.buf[off], src, sizeof(float) * n);
+  return off;
+}
+
+// conv1d() of the reference: kernel/bias + BN.  Emits weights, bias and the four
+// BN-derived vectors at given column offset of pre-allocated vectors.
+bool pack_bn(taco_handle* h, const std::string& scope, int C, float* scale, float* shift, float* gamma,
+             float* beta, std::string& err) {
+  const std::string bn = scope + "/batch_normalization/";
+  GETV(g, bn + "gamma", C);
+  GETV(b, bn + "beta", C);
+  GETV(mm, bn + "moving_mean", C);
+  GETV(mv, bn + "moving_variance", C);
+  for (int c = 0; c < C; ++c) {
+    const float sc = g->data[c] / sqrtf(mv->data[c] + kBnEps);
+    scale[c] = sc;
+    shift[c] = b->data[c] - mm->data[c] * sc;
+    gamma[c] = g->data[c];
+    beta[c] = b->data[c];
+  }
+  return true;
+}
+
+bool pack_cbhg(taco_handle* h, Arena& A, const std::string& s, int K, int Cin, int P1, int P2, CbhgDev& D,
+               std::string& err) {
+  D.K = K; D.Cin = Cin; D.P1 = P1; D.P2 = P2;
+  const int BC = K * 128;
+  D.bank_scale = A.alloc(BC); D.bank_shift = A.alloc(BC); D.bank_gamma = A.alloc(BC); D.bank_beta = A.alloc(BC);
+  D.bank_w.resize(K); D.bank_b.resize(K);
+  for (int k = 1; k <= K; ++k) {
+    const std::string sc = s + "/conv_bank/conv1d_" + std::to_string(k);
+    GETV(w, sc + "/conv1d/kernel", k, Cin, 128);
+    GETV(b, sc + "/conv1d/bias", 128);
+    D.bank_w[k - 1] = put_matrix(A, w->data.data(), k * Cin, 128, 128);
+    D.bank_b[k - 1] = put_vec(A, b->data.data(), 128);
+    const int o = (k - 1) * 128;
+    if (!pack_bn(h, sc, 128, &A.buf[D.bank_scale + o], &A.buf[D.bank_shift + o], &A.buf[D.bank_gamma + o],
+                 &A.buf[D.bank_beta + o], err))
+      return false;
+  }
+  {
+    GETV(w, s + "/proj_1/conv1d/kernel", 3, BC, P1);
+    GETV(b, s + "/proj_1/conv1d/bias", P1);
+    D.p1_w = put_matrix(A, w->data.data(), 3 * BC, P1, P1);
+    D.p1_b = put_vec(A, b->data.data(), P1);
+    D.p1_scale = A.alloc(P1); D.p1_shift = A.alloc(P1); D.p1_gamma = A.alloc(P1); D.p1_beta = A.alloc(P1);
+    if (!pack_bn(h, s + "/proj_1", P1, &A.buf[D.p1_scale], &A.buf[D.p1_shift], &A.buf[D.p1_gamma],
+                 &A.buf[D.p1_beta], err))
+      return false;
+  }
+  {
+    GETV(w, s + "/proj_2/conv1d/kernel", 3, P1, P2);
+    GETV(b, s + "/proj_2/conv1d/bias", P2);
+    D.p2_w = put_matrix(A, w->data.data(), 3 * P1, P2, P2);
+    D.p2_b = put_vec(A, b->data.data(), P2);
+    D.p2_scale = A.alloc(P2); D.p2_shift = A.alloc(P2); D.p2_gamma = A.alloc(P2); D.p2_beta = A.alloc(P2);
+    if (!pack_bn(h, s + "/proj_2", P2, &A.buf[D.p2_scale], &A.buf[D.p2_shift], &A.buf[D.p2_gamma],
+                 &A.buf[D.p2_beta], err))
+      return false;
+  }
+  if (P2 != 128) {   // reference modules.py:59-60
+    GETV(w, s + "/dense/kernel", P2, 128);
+    GETV(b, s + "/dense/bias", 128);
+    D.dense_w = put_matrix(A, w->data.data(), P2, 128, 128);
+    D.dense_b = put_vec(A, b->data.data(), 128);
+  }
+  for (int i = 0; i < 4; ++i) {   // highway: interleave columns (H_c, T_c)
+    const std::string hs = s + "/highway_" + std::to_string(i + 1);
+    GETV(wh, hs + "/H/kernel", 128, 128);
+    GETV(bh, hs + "/H/bias", 128);
+    GETV(wt, hs + "/T/kernel", 128, 128);
+    GETV(bt, hs + "/T/bias", 128);
+    D.hw_w[i] = A.alloc(128 * 256);
+    D.hw_b[i] = A.alloc(256);
+    for (int r = 0; r < 128; ++r)
+      for (int c = 0; c < 128; ++c) {
+        A.buf[D.hw_w[i] + (size_t)r * 256 + 2 * c] = wh->data[(size_t)r * 128 + c];
+        A.buf[D.hw_w[i] + (size_t)r * 256 + 2 * c + 1] = wt->data[(size_t)r * 128 + c];
+      }
+    for (int c = 0; c < 128; ++c) {
+      A.buf[D.hw_b[i] + 2 * c] = bh->data[c];
+      A.buf[D.hw_b[i] + 2 * c + 1] = bt->data[c];
+    }
+  }
+  // BiGRU: gates/kernel [256,256] rows = [x(128); h(128)], candidate/kernel [256,128] likewise.
+  D.gru_wx = A.alloc(128 * 768); D.gru_bx = A.alloc(768);
+  D.gru_ug = A.alloc(2 * 128 * 256); D.gru_uc = A.alloc(2 * 128 * 128);
+  int d = 0;
+  for (const char* dn : {"fw", "bw"}) {
+    const std::string gs = s + "/bidirectional_rnn/" + dn + "/gru_cell";
+    GETV(wg, gs + "/gates/kernel", 256, 256);
+    GETV(bg, gs + "/gates/bias", 256);
+    GETV(wc, gs + "/candidate/kernel", 256, 128);
+    GETV(bc, gs + "/candidate/bias", 128);
+    for (int r = 0; r < 128; ++r) {
+      memcpy(&A.buf[D.gru_wx + (size_t)r * 768 + d * 384], &wg->data[(size_t)r * 256], sizeof(float) * 256);
+      memcpy(&A.buf[D.gru_wx + (size_t)r * 768 + d * 384 + 256], &wc->data[(size_t)r * 128], sizeof(float) * 128);
+      memcpy(&A.buf[D.gru_ug + ((size_t)d * 128 + r) * 256], &wg->data[(size_t)(128 + r) * 256], sizeof(float) * 256);
+      memcpy(&A.buf[D.gru_uc + ((size_t)d * 128 + r) * 128], &wc->data[(size_t)(128 + r) * 128], sizeof(float) * 128);
+    }
+    memcpy(&A.buf[D.gru_bx + d * 384], bg->data.data(), sizeof(float) * 256);
+    memcpy(&A.buf[D.gru_bx + d * 384 + 256], bc->data.data(), sizeof(float) * 128);
+    ++d;
+  }
+  return true;
+}
+
+// Cut src[rows r0..r0+K) x given column lists] into CS per-CTA slices [CS][K][Mc].
+// colmap(q, c) -> source column (or -1 for zero padding).
+template <class F>
+size_t put_slices(Arena& A, const float* src, int ld, int r0, int K, int CS, int Mc, F colmap) {
+  size_t off = A.alloc((size_t)CS * K * Mc);
+  for (int q = 0; q < CS; ++q)
+    for (int k = 0; k < K; ++k)
+      for (int c = 0; c < Mc; ++c) {
+        const int sc = colmap(q, c);
+        A.buf[off + ((size_t)q * K + k) * Mc + c] = sc < 0 ? 0.0f : src[(size_t)(r0 + k) * ld + sc];
+      }
+  return off;
+}
+
+struct DecOff {   // arena offsets of the decoder slices
+  size_t p1_s, p1_b, p2_s, p2_b, ga_s, ga_b, cxa_s, cha_s, ca_b, qp_s, att_v, pc_s, pc_b;
+  size_t g1_s, g1_b, cx1_s, ch1_s, c1_b, g2_s, g2_b, cx2_s, ch2_s, c2_b, o_s, o_b;
+};
+
+bool pack_decoder(taco_handle* h, Arena& A, int CS, DecOff& O, int& McO, std::string& err) {
+  const int M = h->hp.num_mels, r = h->hp.outputs_per_step, Dout = M * r;
+  const int Hc = DH / CS, Pc = DP / CS;
+  McO = (CS == 16) ? 32 : 64;
+  const std::string att = kATT, dpw = att + "decoder_prenet_wrapper/", mrc = kMRC;
+  auto plain = [](int Mc) { return [Mc](int q, int c) { return q * Mc + c; }; };
+  // gate columns: slice q = [r-cols q*Hc.. | u-cols 256+q*Hc..]  (TF GRUCell: r first, u second)
+  auto gatecols = [Hc](int q, int c) { return c < Hc ? q * Hc + c : DH + q * Hc + (c - Hc); };
+  {
+    GETV(w1, dpw + "decoder_prenet/dense_1/kernel", M + DH, 256);
+    GETV(b1, dpw + "decoder_prenet/dense_1/bias", 256);
+    GETV(w2, dpw + "decoder_prenet/dense_2/kernel", 256, 128);
+    GETV(b2, dpw + "decoder_prenet/dense_2/bias", 128);
+    O.p1_s = put_slices(A, w1->data.data(), 256, 0, M + DH, CS, Hc, plain(Hc));
+    O.p1_b = put_vec(A, b1->data.data(), 256);
+    O.p2_s = put_slices(A, w2->data.data(), 128, 0, 256, CS, Pc, plain(Pc));
+    O.p2_b = put_vec(A, b2->data.data(), 128);
+  }
+  auto pack_gru = [&](const std::string& scope, int Kx, size_t& g_s, size_t& g_b, size_t& cx_s, size_t& ch_s,
+                      size_t& c_b) -> bool {
+    GETV(wg, scope + "/gates/kernel", Kx + DH, 2 * DH);
+    GETV(bg, scope + "/gates/bias", 2 * DH);
+    GETV(wc, scope + "/candidate/kernel", Kx + DH, DH);
+    GETV(bc, scope + "/candidate/bias", DH);
+    g_s = put_slices(A, wg->data.data(), 2 * DH, 0, Kx + DH, CS, 2 * Hc, gatecols);
+    g_b = A.alloc(2 * DH);
+    for (int q = 0; q < CS; ++q)
+      for (int c = 0; c < 2 * Hc; ++c) A.buf[g_b + q * 2 * Hc + c] = bg->data[gatecols(q, c)];
+    cx_s = put_slices(A, wc->data.data(), DH, 0, Kx, CS, Hc, plain(Hc));
+    ch_s = put_slices(A, wc->data.data(), DH, Kx, DH, CS, Hc, plain(Hc));
+    c_b = put_vec(A, bc->data.data(), DH);
+    return true;
+  };
+  if (!pack_gru(dpw + "gru_cell", DP, O.ga_s, O.ga_b, O.cxa_s, O.cha_s, O.ca_b)) return false;
+  if (!pack_gru(mrc + "cell_1/gru_cell", DH, O.g1_s, O.g1_b, O.cx1_s, O.ch1_s, O.c1_b)) return false;
+  if (!pack_gru(mrc + "cell_2/gru_cell", DH, O.g2_s, O.g2_b, O.cx2_s, O.ch2_s, O.c2_b)) return false;
+  {
+    GETV(wq, att + "bahdanau_attention/query_layer/kernel", 256, 256);
+    GETV(v, att + "bahdanau_attention/attention_v", 256);
+    GETV(wp, mrc + "cell_0/output_projection_wrapper/kernel", 512, 256);
+    GETV(bp, mrc + "cell_0/output_projection_wrapper/bias", 256);
+    // [Wq slice | Wproj[:256] slice] side by side: [CS][256][2*Hc]
+    O.qp_s = A.alloc((size_t)CS * DH * 2 * Hc);
+    for (int q = 0; q < CS; ++q)
+      for (int k = 0; k < DH; ++k)
+        for (int c = 0; c < Hc; ++c) {
+          A.buf[O.qp_s + ((size_t)q * DH + k) * 2 * Hc + c] = wq->data[(size_t)k * 256 + q * Hc + c];
+          A.buf[O.qp_s + ((size_t)q * DH + k) * 2 * Hc + Hc + c] = wp->data[(size_t)k * 256 + q * Hc + c];
+        }
+    O.att_v = put_vec(A, v->data.data(), 256);
+    O.pc_s = put_slices(A, wp->data.data(), 256, 256, DH, CS, Hc, plain(Hc));
+    O.pc_b = put_vec(A, bp->data.data(), 256);
+  }
+  {
+    GETV(wo, "decoder/output_projection_wrapper/kernel", 256, Dout);
+    GETV(bo, "decoder/output_projection_wrapper/bias", Dout);
+    O.o_s = put_slices(A, wo->data.data(), Dout, 0, DH, CS, McO,
+                       [McO, Dout](int q, int c) { int col = q * McO + c; return col < Dout ? col : -1; });
+    O.o_b = A.alloc(CS * McO);
+    memcpy(&A.buf[O.o_b], bo->data.data(), sizeof(float) * Dout);
+  }
+  return true;
+}
+
+// ---- workspace ---------------------------------------------------------------
+struct Bump {
+  char* base; size_t cap, off = 0; bool overflow = false;
+  Bump(char* b, size_t c) : base(b), cap(c) {}
+  template <class T> T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    size_t bytes = n * sizeof(T);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    if (off > cap) overflow = true;
+    return p;
+  }
+};
+
+size_t cbhg_ws_floats(int K, int P1, int P2, int64_t rows) {
+  // bank + pooled + p1 + p2 + dense + 2 highway + xproj, plus slack for alignment
+  return (size_t)rows * ((size_t)2 * K * 128 + P1 + P2 + 128 + 256 + 768) + 32768;
+}
+
+int ensure_ws(taco_handle* h, size_t bytes) {
+  if (bytes <= h->ws_bytes) return TACO_OK;
+  if (h->ws) { cudaDeviceSynchronize(); cudaFree(h->ws); h->ws = nullptr; h->ws_bytes = 0; }
+  bytes += bytes / 8;
+  CUDA_OK(h, cudaMalloc(&h->ws, bytes));
+  h->ws_bytes = bytes;
+  return TACO_OK;
+}
+int ensure_ints(taco_handle* h, int n) {
+  if (n <= h->d_ints_n) return TACO_OK;
+  if (h->d_ints) { cudaDeviceSynchronize(); cudaFree(h->d_ints); h->d_ints = nullptr; }
+  CUDA_OK(h, cudaMalloc(&h->d_ints, sizeof(int) * n));
+  CUDA_OK(h, cudaMemset(h->d_ints, 0, sizeof(int) * n));
+  h->d_ints_n = n;
+  return TACO_OK;
+}
+
+struct Ctx {
+  taco_handle* h;
+  cudaStream_t st;
+  const float* W(size_t off) const { return h->dW + off; }
+};
+
+void conv(Ctx& c, const float* x, int64_t x_bs, int ldx, int N, int T, int Cin, int k, const float* w, int ldw,
+          const float* bias, const float* scale, const float* shift, const float* res, int64_t res_bs, int ldres,
+          float* out, int64_t out_bs, int ldo, int col_off, int Cout, int act, int epi = EPI_PLAIN) {
+  ConvGemm p;
+  p.x = x; p.x_bs = x_bs; p.ldx = ldx; p.N = N; p.T = T; p.Cin = Cin; p.k = k; p.w = w; p.ldw = ldw;
+  p.bias = bias; p.scale = scale; p.shift = shift; p.res = res; p.res_bs = res_bs; p.ldres = ldres;
+  p.out = out; p.out_bs = out_bs; p.ldo = ldo; p.col_off = col_off; p.Cout = Cout; p.act = act; p.epi = epi;
+  launch_conv_gemm(p, c.st);
+  c.h->launches += 1;
+}
+
+// reference cbhg() (models/modules.py:35-74).  x: [N,T,Cin] with batch stride x_bs; out [N,T,256] dense.
+void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, const int32_t* lengths, int N,
+              int T, int bn_mode, float* out) {
+  const int K = D.K, BC = K * 128, Cin = D.Cin;
+  const int64_t rows = (int64_t)N * T;
+  float* bank = ws.take<float>(rows * BC);
+  float* pooled = ws.take<float>(rows * BC);
+  float* p1 = ws.take<float>(rows * D.P1);
+  float* p2 = ws.take<float>(rows * D.P2);
+  float* hwa = ws.take<float>(rows * 128);
+  float* hwb = ws.take<float>(rows * 128);
+  float* xproj = ws.take<float>(rows * 768);
+  float* bnv = ws.take<float>(2 * 2048);          // batch-mode scale | shift
+  double* bnacc = ws.take<double>(2 * 2048);
+  if (ws.overflow) return;
+  const bool batch = bn_mode == TACO_BN_BATCH;
+  // conv bank: K convolutions written side by side (tf.concat, modules.py:39-42)
+  for (int k = 1; k <= K; ++k) {
+    const int o = (k - 1) * 128;
+    conv(c, x, x_bs, Cin, N, T, Cin, k, c.W(D.bank_w[k - 1]), 128, c.W(D.bank_b[k - 1]),
+         batch ? nullptr : c.W(D.bank_scale + o), batch ? nullptr : c.W(D.bank_shift + o), nullptr, 0, 0, bank,
+         (int64_t)T * BC, BC, o, 128, TACO_ACT_RELU);
+  }
+  if (batch) {
+    launch_bn_batch_stats(bank, (int64_t)T * BC, BC, 0, N, T, BC, c.W(D.bank_gamma), c.W(D.bank_beta), kBnEps,
+                          bnacc, bnv, bnv + 2048, c.st);
+    launch_affine_maxpool(bank, pooled, N, T, BC, bnv, bnv + 2048, c.st);
+    c.h->launches += 3;
+  } else {
+    launch_affine_maxpool(bank, pooled, N, T, BC, nullptr, nullptr, c.st);
+    c.h->launches += 1;
+  }
+  // proj_1: conv k=3 + ReLU + BN
+  conv(c, pooled, (int64_t)T * BC, BC, N, T, BC, 3, c.W(D.p1_w), D.P1, c.W(D.p1_b),
+       batch ? nullptr : c.W(D.p1_scale), batch ? nullptr : c.W(D.p1_shift), nullptr, 0, 0, p1,
+       (int64_t)T * D.P1, D.P1, 0, D.P1, TACO_ACT_RELU);
+  if (batch) {
+    launch_bn_batch_stats(p1, (int64_t)T * D.P1, D.P1, 0, N, T, D.P1, c.W(D.p1_gamma), c.W(D.p1_beta), kBnEps,
+                          bnacc, bnv, bnv + 2048, c.st);
+    launch_affine_inplace(p1, (int64_t)T * D.P1, D.P1, N, T, D.P1, bnv, bnv + 2048, nullptr, 0, 0, c.st);
+    c.h->launches += 3;
+  }
+  // proj_2: conv k=3 + BN (no activation) + residual (modules.py:53,56)
+  conv(c, p1, (int64_t)T * D.P1, D.P1, N, T, D.P1, 3, c.W(D.p2_w), D.P2, c.W(D.p2_b),
+       batch ? nullptr : c.W(D.p2_scale), batch ? nullptr : c.W(D.p2_shift), batch ? nullptr : x, x_bs, Cin, p2,
+       (int64_t)T * D.P2, D.P2, 0, D.P2, TACO_ACT_NONE);
+  if (batch) {
+    launch_bn_batch_stats(p2, (int64_t)T * D.P2, D.P2, 0, N, T, D.P2, c.W(D.p2_gamma), c.W(D.p2_beta), kBnEps,
+                          bnacc, bnv, bnv + 2048, c.st);
+    launch_affine_inplace(p2, (int64_t)T * D.P2, D.P2, N, T, D.P2, bnv, bnv + 2048, x, x_bs, Cin, c.st);
+    c.h->launches += 3;
+  }
+  const float* hin = p2;
+  if (D.P2 != 128) {   // modules.py:59-60
+    conv(c, p2, (int64_t)T * D.P2, D.P2, N, T, D.P2, 1, c.W(D.dense_w), 128, c.W(D.dense_b), nullptr, nullptr,
+         nullptr, 0, 0, hwb, (int64_t)T * 128, 128, 0, 128, TACO_ACT_NONE);
+    hin = hwb;
+  }
+  // 4 highway layers (modules.py:63-64)
+  float* bufs[2] = {hwa, hwb};
+  int cur = 0;   // first output goes to hwa (hin is p2 or hwb)
+  for (int i = 0; i < 4; ++i) {
+    float* o = bufs[cur];
+    conv(c, hin, (int64_t)T * 128, 128, N, T, 128, 1, c.W(D.hw_w[i]), 256, c.W(D.hw_b[i]), nullptr, nullptr, hin,
+         (int64_t)T * 128, 128, o, (int64_t)T * 128, 128, 0, 256, TACO_ACT_NONE, EPI_HIGHWAY);
+    hin = o;
+    cur ^= 1;
+  }
+  // hoisted GRU input projection for both directions, then the recurrence
+  conv(c, hin, (int64_t)T * 128, 128, N, T, 128, 1, c.W(D.gru_wx), 768, c.W(D.gru_bx), nullptr, nullptr, nullptr,
+       0, 0, xproj, (int64_t)T * 768, 768, 0, 768, TACO_ACT_NONE);
+  launch_bigru(xproj, c.W(D.gru_ug), c.W(D.gru_uc), lengths, N, T, out, (int64_t)T * 256, c.st);
+  c.h->launches += 1;
+}
+
+int pick_S(const taco_handle* h, int N) {
+  const char* env = getenv("TACO_DEC_S");
+  if (env) {
+    int s = atoi(env);
+    if (s == 1 || s == 2 || s == 4 || s == 8) return s;
+  }
+  for (int s : {1, 2, 4, 8})
+    if ((N + s - 1) / s <= h->max_clusters) return s;
+  return 8;
+}
+
+int check_launch(taco_handle* h, const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(h, TACO_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  }
+  return TACO_OK;
+}
+
+int do_encoder(taco_handle* h, Bump& ws, const int32_t* ids, const int32_t* lengths, const int32_t* spk, int N,
+               int T_in, int bn_mode, float* memory_out, cudaStream_t st) {
+  Ctx c{h, st};
+  const taco_hparams& hp = h->hp;
+  const bool multi = spk != nullptr && hp.id_num > 1;
+  const int E = hp.embedding_text_channels, Es = multi ? hp.embedding_id_channels : 0;
+  const int64_t rows = (int64_t)N * T_in;
+  float* emb = ws.take<float>(rows * (E + Es));
+  float* a1 = ws.take<float>(rows * 256);
+  float* a2 = ws.take<float>(rows * 128);
+  if (ws.overflow) return fail(h, TACO_ERR_INVALID, "workspace overflow (encoder)");
+  launch_gather_concat(ids, multi ? spk : nullptr, c.W(h->emb), hp.num_symbols, E, multi ? c.W(h->emb_id) : nullptr,
+                       hp.id_num, Es, N, T_in, emb, h->d_ints, st);
+  h->launches += 1;
+  // encoder prenet (modules.py:5-12; dropout is the identity)
+  conv(c, emb, (int64_t)T_in * (E + Es), E + Es, N, T_in, E + Es, 1, c.W(h->pre1_w), 256, c.W(h->pre1_b), nullptr,
+       nullptr, nullptr, 0, 0, a1, (int64_t)T_in * 256, 256, 0, 256, TACO_ACT_RELU);
+  conv(c, a1, (int64_t)T_in * 256, 256, N, T_in, 256, 1, c.W(h->pre2_w), 128, c.W(h->pre2_b), nullptr, nullptr,
+       nullptr, 0, 0, a2, (int64_t)T_in * 128, 128, 0, 128, TACO_ACT_RELU);
+  run_cbhg(c, h->enc, ws, a2, (int64_t)T_in * 128, lengths, N, T_in, bn_mode, memory_out);
+  if (ws.overflow) return fail(h, TACO_ERR_INVALID, "workspace overflow (encoder cbhg)");
+  return check_launch(h, "encoder");
+}
+
+size_t encoder_ws_bytes(const taco_handle* h, int N, int T_in) {
+  const int64_t rows = (int64_t)N * T_in;
+  return sizeof(float) * ((size_t)rows * (h->emb_dim + 256 + 128) + cbhg_ws_floats(16, 128, 128, rows)) + 65536;
+}
+size_t postnet_ws_bytes(const taco_handle* h, int N, int T) {
+  const int64_t rows = (int64_t)N * T;
+  return sizeof(float) * ((size_t)rows * 256 + cbhg_ws_floats(8, 256, h->hp.num_mels, rows)) + 65536;
+}
+
+int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, const float* mel_targets, int T_tgt,
+              int teacher_force, float* dec_out, float* align_out, int32_t* steps_out_host, cudaStream_t st) {
+  Ctx c{h, st};
+  const taco_hparams& hp = h->hp;
+  if (T_in > 512) return fail(h, TACO_ERR_UNSUPPORTED, "T_in > 512 not supported by the decoder kernel");
+  if (teacher_force && mel_targets == nullptr) return fail(h, TACO_ERR_INVALID, "teacher_force needs mel_targets");
+  const int max_steps = taco_max_steps(h, teacher_force, T_tgt);
+  if (max_steps <= 0) return fail(h, TACO_ERR_INVALID, "no decoder steps (T_tgt < r?)");
+  float* keys = ws.take<float>((size_t)N * T_in * 256);
+  if (ws.overflow) return fail(h, TACO_ERR_INVALID, "workspace overflow (decoder)");
+  // BahdanauAttention memory_layer (no bias), once per utterance (tacotron.py:68)
+  conv(c, memory, (int64_t)T_in * 256, 256, N, T_in, 256, 1, c.W(h->mem_w), 256, nullptr, nullptr, nullptr, nullptr,
+       0, 0, keys, (int64_t)T_in * 256, 256, 0, 256, TACO_ACT_NONE);
+  DecoderArgs a;
+  a.memory = memory; a.keys = keys; a.targets = teacher_force ? mel_targets : nullptr;
+  a.N = N; a.T_in = T_in; a.T_tgt = T_tgt; a.r = hp.outputs_per_step; a.steps = max_steps; a.max_steps = max_steps;
+  a.dec_out = dec_out; a.align_out = align_out;
+  const int S = pick_S(h, N);
+  cudaError_t e = launch_decoder(h->dec, a, S, st);
+  if (e != cudaSuccess) return fail(h, TACO_ERR_CUDA, std::string("decoder launch: ") + cudaGetErrorString(e));
+  h->launches += 1;
+  int steps = max_steps;
+  if (!teacher_force) {
+    int rc = ensure_ints(h, 2 + N);
+    if (rc) return rc;
+    launch_find_steps(dec_out, N, max_steps, hp.num_mels * hp.outputs_per_step, h->d_ints + 2, h->d_ints + 1, st);
+    h->launches += 3;
+    CUDA_OK(h, cudaMemcpyAsync(h->h_pinned + 1, h->d_ints + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(h, cudaStreamSynchronize(st));
+    steps = h->h_pinned[1];
+  }
+  if (steps_out_host) *steps_out_host = steps;
+  return check_launch(h, "decoder");
+}
+
+int do_postnet(taco_handle* h, Bump& ws, const float* mel, int N, int T, int bn_mode, int64_t mel_bs,
+               float* linear_out, int64_t lin_bs, cudaStream_t st) {
+  Ctx c{h, st};
+  const taco_hparams& hp = h->hp;
+  float* post = ws.take<float>((size_t)N * T * 256);
+  if (ws.overflow) return fail(h, TACO_ERR_INVALID, "workspace overflow (postnet)");
+  run_cbhg(c, h->post, ws, mel, mel_bs, nullptr, N, T, bn_mode, post);
+  if (ws.overflow) return fail(h, TACO_ERR_INVALID, "workspace overflow (postnet cbhg)");
+  // linear_outputs = tf.layers.dense(post_outputs, num_freq)  (tacotron.py:101)
+  conv(c, post, (int64_t)T * 256, 256, N, T, 256, 1, c.W(h->lin_w), h->lin_ld, c.W(h->lin_b), nullptr, nullptr,
+       nullptr, 0, 0, linear_out, lin_bs, hp.num_freq, 0, hp.num_freq, TACO_ACT_NONE);
+  return check_launch(h, "postnet");
+}
+
+}  // namespace
+
+// =============================== C ABI ========================================
+extern "C" {
+
+const char* taco_version(void) { return "taco_b200 0.1 (sm_100a)"; }
+
+int taco_create(const taco_hparams* hp, int device, taco_handle** out) {
+  if (!hp || !out) return TACO_ERR_INVALID;
+  *out = nullptr;
+  if (hp->num_mels <= 0 || hp->num_mels > 128 || hp->num_mels % 4 || hp->outputs_per_step <= 0 ||
+      hp->num_mels * hp->outputs_per_step > 512 || hp->max_iters <= 0 || hp->num_freq <= 0 ||
+      hp->embedding_text_channels <= 0 || hp->embedding_text_channels % 4 || hp->embedding_id_channels % 4 ||
+      hp->num_symbols <= 0)
+    return TACO_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return TACO_ERR_UNSUPPORTED;   // no GPU: this library has no CPU path
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return TACO_ERR_CUDA;
+  if (prop.major != 10) return TACO_ERR_UNSUPPORTED;   // kernels are built for sm_100a only
+  if (cudaSetDevice(device) != cudaSuccess) return TACO_ERR_CUDA;
+  taco_handle* h = new taco_handle();
+  h->hp = *hp;
+  h->device = device;
+  h->names = expected_names(*hp);
+  h->emb_dim = hp->embedding_text_channels + (hp->id_num > 1 ? hp->embedding_id_channels : 0);
+  if (cudaMallocHost(&h->h_pinned, sizeof(int) * 4) != cudaSuccess) { delete h; return TACO_ERR_CUDA; }
+  for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+  if (ensure_ints(h, 2 + 1024) != TACO_OK) { taco_destroy(h); return TACO_ERR_CUDA; }
+  *out = h;
+  return TACO_OK;
+}
+
+int taco_destroy(taco_handle* h) {
+  if (!h) return TACO_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (h->dW) cudaFree(h->dW);
+  if (h->ws) cudaFree(h->ws);
+  if (h->d_ints) cudaFree(h->d_ints);
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  delete h;
+  return TACO_OK;
+}
+
+const char* taco_last_error(const taco_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int taco_num_weights(const taco_handle* h) { return h ? (int)h->names.size() : 0; }
+const char* taco_weight_name(const taco_handle* h, int i) {
+  if (!h || i < 0 || i >= (int)h->names.size()) return nullptr;
+  return h->names[i].c_str();
+}
+
+int taco_set_weight(taco_handle* h, const char* tf_name, const float* data_host, const int64_t* shape, int ndim) {
+  if (!h || !tf_name || !data_host || !shape || ndim < 1 || ndim > 4) return fail(h, TACO_ERR_INVALID, "bad argument");
+  std::string name = tf_name;
+  const size_t pl = strlen(kPrefix);
+  if (name.compare(0, pl, kPrefix) == 0) name = name.substr(pl);
+  bool known = false;
+  for (const auto& n : h->names) if (n == name) { known = true; break; }
+  if (!known) return fail(h, TACO_ERR_INVALID, "unknown variable: " + std::string(tf_name));
+  HostVar& v = h->vars[name];
+  v.shape.assign(shape, shape + ndim);
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { if (shape[i] <= 0) return fail(h, TACO_ERR_INVALID, "bad shape"); n *= (size_t)shape[i]; }
+  v.data.assign(data_host, data_host + n);
+  v.set = true;
+  h->finalized = false;
+  return TACO_OK;
+}
+
+int taco_finalize_weights(taco_handle* h) {
+  if (!h) return TACO_ERR_INVALID;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  const taco_hparams& hp = h->hp;
+  std::string err;
+  Arena A;
+  auto bad = [&](int code) { return fail(h, code, err); };
+  auto build = [&]() -> bool {
+    GETV(emb, "embedding", hp.num_symbols, hp.embedding_text_channels);
+    h->emb = put_vec(A, emb->data.data(), (int)emb->data.size());
+    if (hp.id_num > 1) {
+      GETV(eid, "embedding_id", hp.id_num, hp.embedding_id_channels);
+      h->emb_id = put_vec(A, eid->data.data(), (int)eid->data.size());
+    }
+    GETV(w1, "prenet/dense_1/kernel", h->emb_dim, 256);
+    GETV(b1, "prenet/dense_1/bias", 256);
+    GETV(w2, "prenet/dense_2/kernel", 256, 128);
+    GETV(b2, "prenet/dense_2/bias", 128);
+    h->pre1_w = put_matrix(A, w1->data.data(), h->emb_dim, 256, 256);
+    h->pre1_b = put_vec(A, b1->data.data(), 256);
+    h->pre2_w = put_matrix(A, w2->data.data(), 256, 128, 128);
+    h->pre2_b = put_vec(A, b2->data.data(), 128);
+    if (!pack_cbhg(h, A, "encoder_cbhg", 16, 128, 128, 128, h->enc, err)) return false;
+    GETV(mw, "memory_layer/kernel", 256, 256);
+    h->mem_w = put_matrix(A, mw->data.data(), 256, 256, 256);
+    if (!pack_cbhg(h, A, "post_cbhg", 8, hp.num_mels, 256, hp.num_mels, h->post, err)) return false;
+    GETV(lw, "dense/kernel", 256, hp.num_freq);
+    GETV(lb, "dense/bias", hp.num_freq);
+    h->lin_ld = (hp.num_freq + 3) & ~3;
+    h->lin_w = put_matrix(A, lw->data.data(), 256, hp.num_freq, h->lin_ld);
+    h->lin_b = put_vec(A, lb->data.data(), hp.num_freq);
+    return true;
+  };
+  if (!build()) return bad(err.rfind("missing", 0) == 0 ? TACO_ERR_MISSING_WEIGHT : TACO_ERR_INVALID);
+  // decoder geometry: largest cluster the device schedules; slices are cut for it
+  const char* env = getenv("TACO_DEC_CS");
+  int cs = env ? atoi(env) : 0;
+  if (cs != 8 && cs != 16) cs = decoder_pick_cluster_size();
+  h->CS = cs;
+  h->max_clusters = decoder_max_clusters(cs);
+  if (h->max_clusters < 1) return fail(h, TACO_ERR_UNSUPPORTED, "decoder cluster cannot be scheduled on this device");
+  DecOff O;
+  int McO = 0;
+  if (!pack_decoder(h, A, cs, O, McO, err)) return bad(err.rfind("missing", 0) == 0 ? TACO_ERR_MISSING_WEIGHT : TACO_ERR_INVALID);
+  if (h->dW) { cudaDeviceSynchronize(); cudaFree(h->dW); h->dW = nullptr; }
+  CUDA_OK(h, cudaMalloc(&h->dW, sizeof(float) * A.buf.size()));
+  CUDA_OK(h, cudaMemcpy(h->dW, A.buf.data(), sizeof(float) * A.buf.size(), cudaMemcpyHostToDevice));
+  DecoderWeights& d = h->dec;
+  const float* B = h->dW;
+  d.CS = cs; d.M = hp.num_mels; d.Dout = hp.num_mels * hp.outputs_per_step; d.McO = McO;
+  d.p1_s = B + O.p1_s; d.p1_b = B + O.p1_b; d.p2_s = B + O.p2_s; d.p2_b = B + O.p2_b;
+  d.ga_s = B + O.ga_s; d.ga_b = B + O.ga_b; d.cxa_s = B + O.cxa_s; d.cha_s = B + O.cha_s; d.ca_b = B + O.ca_b;
+  d.qp_s = B + O.qp_s; d.att_v = B + O.att_v; d.pc_s = B + O.pc_s; d.pc_b = B + O.pc_b;
+  d.g1_s = B + O.g1_s; d.g1_b = B + O.g1_b; d.cx1_s = B + O.cx1_s; d.ch1_s = B + O.ch1_s; d.c1_b = B + O.c1_b;
+  d.g2_s = B + O.g2_s; d.g2_b = B + O.g2_b; d.cx2_s = B + O.cx2_s; d.ch2_s = B + O.ch2_s; d.c2_b = B + O.c2_b;
+  d.o_s = B + O.o_s; d.o_b = B + O.o_b;
+  h->finalized = true;
+  return TACO_OK;
+}
+
+int taco_max_steps(const taco_handle* h, int teacher_force, int T_tgt) {
+  if (!h) return 0;
+  if (!teacher_force) return h->hp.max_iters;
+  const int r = h->hp.outputs_per_step;
+  // TacoTrainingHelper feeds targets[:, r-1::r], i.e. floor(T_tgt / r) frames (helpers.py:48-55)
+  const int n = T_tgt / r;
+  return n < h->hp.max_iters ? n : h->hp.max_iters;
+}
+
+#define REQUIRE_READY(h)                                                          \
+  if (!h) return TACO_ERR_INVALID;                                                \
+  if (!h->finalized) return fail(h, TACO_ERR_STATE, "weights not finalized");     \
+  CUDA_OK(h, cudaSetDevice(h->device));
+
+int taco_embed(taco_handle* h, const int32_t* ids, const int32_t* spk, int N, int T_in, float* out, void* stream) {
+  REQUIRE_READY(h);
+  if (!ids || !out || N <= 0 || T_in <= 0) return fail(h, TACO_ERR_INVALID, "bad argument");
+  const taco_hparams& hp = h->hp;
+  const bool multi = spk != nullptr && hp.id_num > 1;
+  launch_gather_concat(ids, multi ? spk : nullptr, h->dW + h->emb, hp.num_symbols, hp.embedding_text_channels,
+                       multi ? h->dW + h->emb_id : nullptr, hp.id_num, multi ? hp.embedding_id_channels : 0, N, T_in,
+                       out, h->d_ints, (cudaStream_t)stream);
+  h->launches += 1;
+  return check_launch(h, "embed");
+}
+
+int taco_check_ids(taco_handle* h, void* stream) {
+  REQUIRE_READY(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_OK(h, cudaMemcpyAsync(h->h_pinned, h->d_ints, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(h, cudaMemsetAsync(h->d_ints, 0, sizeof(int), st));
+  CUDA_OK(h, cudaStreamSynchronize(st));
+  if (h->h_pinned[0] & 1) return fail(h, TACO_ERR_OOB_ID, "symbol id outside the embedding table");
+  if (h->h_pinned[0] & 2) return fail(h, TACO_ERR_OOB_ID, "speaker id outside the embedding_id table");
+  return TACO_OK;
+}
+
+int taco_encoder(taco_handle* h, const int32_t* ids, const int32_t* lengths, const int32_t* spk, int N, int T_in,
+                 int bn_mode, float* memory_out, void* stream) {
+  REQUIRE_READY(h);
+  if (!ids || !memory_out || N <= 0 || T_in <= 0) return fail(h, TACO_ERR_INVALID, "bad argument");
+  int rc = ensure_ws(h, encoder_ws_bytes(h, N, T_in));
+  if (rc) return rc;
+  Bump ws(h->ws, h->ws_bytes);
+  return do_encoder(h, ws, ids, lengths, spk, N, T_in, bn_mode, memory_out, (cudaStream_t)stream);
+}
+
+int taco_decode(taco_handle* h, const float* memory, int N, int T_in, const float* mel_targets, int T_tgt,
+                int teacher_force, float* dec_out, float* align_out, int32_t* steps_out_host, void* stream) {
+  REQUIRE_READY(h);
+  if (!memory || !dec_out || N <= 0 || T_in <= 0) return fail(h, TACO_ERR_INVALID, "bad argument");
+  int rc = ensure_ws(h, sizeof(float) * (size_t)N * T_in * 256 + 65536);
+  if (rc) return rc;
+  Bump ws(h->ws, h->ws_bytes);
+  return do_decode(h, ws, memory, N, T_in, mel_targets, T_tgt, teacher_force, dec_out, align_out, steps_out_host,
+                   (cudaStream_t)stream);
+}
+
+int taco_cbhg(taco_handle* h, int which, const float* x, const int32_t* lengths, int N, int T, int bn_mode,
+              int64_t x_batch_stride, float* out, void* stream) {
+  REQUIRE_READY(h);
+  if (!x || !out || N <= 0 || T <= 0) return fail(h, TACO_ERR_INVALID, "bad argument");
+  const CbhgDev& D = which == TACO_CBHG_ENCODER ? h->enc : h->post;
+  if (x_batch_stride == 0) x_batch_stride = (int64_t)T * D.Cin;
+  int rc = ensure_ws(h, sizeof(float) * cbhg_ws_floats(D.K, D.P1, D.P2, (int64_t)N * T) + 65536);
+  if (rc) return rc;
+  Bump ws(h->ws, h->ws_bytes);
+  Ctx c{h, (cudaStream_t)stream};
+  run_cbhg(c, D, ws, x, x_batch_stride, lengths, N, T, bn_mode, out);
+  if (ws.overflow) return fail(h, TACO_ERR_INVALID, "workspace overflow (cbhg)");
+  return check_launch(h, "cbhg");
+}
+
+int taco_postnet(taco_handle* h, const float* mel, int N, int T, int bn_mode, int64_t mel_batch_stride,
+                 float* linear_out, int64_t linear_batch_stride, void* stream) {
+  REQUIRE_READY(h);
+  if (!mel || !linear_out || N <= 0 || T <= 0) return fail(h, TACO_ERR_INVALID, "bad argument");
+  if (mel_batch_stride == 0) mel_batch_stride = (int64_t)T * h->hp.num_mels;
+  if (linear_batch_stride == 0) linear_batch_stride = (int64_t)T * h->hp.num_freq;
+  int rc = ensure_ws(h, postnet_ws_bytes(h, N, T));
+  if (rc) return rc;
+  Bump ws(h->ws, h->ws_bytes);
+  return do_postnet(h, ws, mel, N, T, bn_mode, mel_batch_stride, linear_out, linear_batch_stride,
+                    (cudaStream_t)stream);
+}
+
+int taco_bigru(taco_handle* h, int which, const float* x, const int32_t* lengths, int N, int T, float* out,
+               void* stream) {
+  REQUIRE_READY(h);
+  if (!x || !out || N <= 0 || T <= 0) return fail(h, TACO_ERR_INVALID, "bad argument");
+  const CbhgDev& D = which == TACO_CBHG_ENCODER ? h->enc : h->post;
+  int rc = ensure_ws(h, sizeof(float) * (size_t)N * T * 768 + 65536);
+  if (rc) return rc;
+  Bump ws(h->ws, h->ws_bytes);
+  Ctx c{h, (cudaStream_t)stream};
+  float* xproj = ws.take<float>((size_t)N * T * 768);
+  conv(c, x, (int64_t)T * 128, 128, N, T, 128, 1, c.W(D.gru_wx), 768, c.W(D.gru_bx), nullptr, nullptr, nullptr, 0, 0,
+       xproj, (int64_t)T * 768, 768, 0, 768, TACO_ACT_NONE);
+  launch_bigru(xproj, c.W(D.gru_ug), c.W(D.gru_uc), lengths, N, T, out, (int64_t)T * 256, c.st);
+  h->launches += 1;
+  return check_launch(h, "bigru");
+}
+
+int taco_conv1d(taco_handle* h, const float* x, int N, int T, int Cin, const float* kernel, const float* bias, int k,
+                int Cout, int act, float* out, void* stream) {
+  if (!h) return TACO_ERR_INVALID;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  if (!x || !kernel || !out || N <= 0 || T <= 0 || Cin <= 0 || Cin % 4 || k <= 0 || Cout <= 0)
+    return fail(h, TACO_ERR_INVALID, "bad argument (Cin must be a multiple of 4)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ldw = (Cout + 3) & ~3;
+  const float* w = kernel;
+  if (ldw != Cout) {   // pad the leading dimension for 128-bit weight loads
+    int rc = ensure_ws(h, sizeof(float) * (size_t)k * Cin * ldw + 65536);
+    if (rc) return rc;
+    CUDA_OK(h, cudaMemsetAsync(h->ws, 0, sizeof(float) * (size_t)k * Cin * ldw, st));
+    CUDA_OK(h, cudaMemcpy2DAsync(h->ws, sizeof(float) * ldw, kernel, sizeof(float) * Cout, sizeof(float) * Cout,
+                                 (size_t)k * Cin, cudaMemcpyDeviceToDevice, st));
+    w = reinterpret_cast<const float*>(h->ws);
+  }
+  Ctx c{h, st};
+  conv(c, x, (int64_t)T * Cin, Cin, N, T, Cin, k, w, ldw, bias, nullptr, nullptr, nullptr, 0, 0, out, (int64_t)T * Cout,
+       Cout, 0, Cout, act);
+  return check_launch(h, "conv1d");
+}
+
+int taco_forward(taco_handle* h, const int32_t* ids, const int32_t* lengths, const int32_t* spk,
+                 const float* mel_targets, int N, int T_in, int T_tgt, int bn_mode, int teacher_force, float* mel_out,
+                 float* linear_out, float* align_out, int32_t* steps_out_host, void* stream) {
+  REQUIRE_READY(h);
+  if (!ids || !mel_out || N <= 0 || T_in <= 0) return fail(h, TACO_ERR_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const taco_hparams& hp = h->hp;
+  const int r = hp.outputs_per_step, M = hp.num_mels;
+  const int max_steps = taco_max_steps(h, teacher_force, T_tgt);
+  if (max_steps <= 0) return fail(h, TACO_ERR_INVALID, "no decoder steps");
+  const int maxT = max_steps * r;
+  size_t need = encoder_ws_bytes(h, N, T_in) + sizeof(float) * (size_t)N * T_in * 512 + 65536;
+  const size_t need_post = postnet_ws_bytes(h, N, maxT) + sizeof(float) * (size_t)N * T_in * 512 + 65536;
+  if (linear_out && need_post > need) need = need_post;
+  int rc = ensure_ws(h, need);
+  if (rc) return rc;
+  rc = ensure_ints(h, 2 + N);
+  if (rc) return rc;
+  Bump ws(h->ws, h->ws_bytes);
+  float* memory = ws.take<float>((size_t)N * T_in * 256);
+  const size_t mark = ws.off;
+  if (h->profiling) cudaEventRecord(h->ev[0], st);
+  rc = do_encoder(h, ws, ids, lengths, spk, N, T_in, bn_mode, memory, st);
+  if (rc) return rc;
+  if (h->profiling) cudaEventRecord(h->ev[1], st);
+  ws.off = mark;   // encoder scratch is dead; stream order keeps reuse safe
+  int steps = 0;
+  rc = do_decode(h, ws, memory, N, T_in, mel_targets, T_tgt, teacher_force, mel_out, align_out, &steps, st);
+  if (rc) return rc;
+  if (h->profiling) cudaEventRecord(h->ev[2], st);
+  if (steps_out_host) *steps_out_host = steps;
+  if (linear_out) {
+    ws.off = mark;
+    rc = do_postnet(h, ws, mel_out, N, steps * r, bn_mode, (int64_t)maxT * M, linear_out,
+                    (int64_t)maxT * hp.num_freq, st);
+    if (rc) return rc;
+  }
+  if (h->profiling) {
+    cudaEventRecord(h->ev[3], st);
+    cudaEventSynchronize(h->ev[3]);
+    for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&h->stage_ms[i], h->ev[i], h->ev[i + 1]);
+  }
+  return TACO_OK;
+}
+
+int taco_forward_host(taco_handle* h, const int32_t* ids_host, const int32_t* lengths_host, const int32_t* spk_host,
+                      const float* mel_targets_host, int N, int T_in, int T_tgt, int bn_mode, int teacher_force,
+                      float* mel_out_host, float* linear_out_host, float* align_out_host, int32_t* steps_out_host,
+                      void* stream) {
+  REQUIRE_READY(h);
+  if (!ids_host || !mel_out_host || N <= 0 || T_in <= 0) return fail(h, TACO_ERR_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const taco_hparams& hp = h->hp;
+  const int max_steps = taco_max_steps(h, teacher_force, T_tgt);
+  if (max_steps <= 0) return fail(h, TACO_ERR_INVALID, "no decoder steps");
+  const int maxT = max_steps * hp.outputs_per_step;
+  // device staging lives in a private allocation so that taco_forward may regrow its workspace
+  const size_t n_ids = (size_t)N * T_in, n_tgt = teacher_force ? (size_t)N * T_tgt * hp.num_mels : 0;
+  const size_t n_mel = (size_t)N * maxT * hp.num_mels, n_lin = linear_out_host ? (size_t)N * maxT * hp.num_freq : 0;
+  const size_t n_al = align_out_host ? (size_t)N * T_in * max_steps : 0;
+  size_t bytes = 256 * 8 + sizeof(int32_t) * (n_ids + 2 * (size_t)N) + sizeof(float) * (n_tgt + n_mel + n_lin + n_al);
+  char* stg = nullptr;
+  CUDA_OK(h, cudaMalloc(&stg, bytes));
+  Bump b(stg, bytes);
+  int32_t* d_ids = b.take<int32_t>(n_ids);
+  int32_t* d_len = b.take<int32_t>(N);
+  int32_t* d_spk = b.take<int32_t>(N);
+  float* d_tgt = n_tgt ? b.take<float>(n_tgt) : nullptr;
+  float* d_mel = b.take<float>(n_mel);
+  float* d_lin = n_lin ? b.take<float>(n_lin) : nullptr;
+  float* d_al = n_al ? b.take<float>(n_al) : nullptr;
+  int rc = TACO_OK;
+  auto cp = [&](void* d, const void* s, size_t n, cudaMemcpyKind k) {
+    if (rc == TACO_OK && cudaMemcpyAsync(d, s, n, k, st) != cudaSuccess) rc = fail(h, TACO_ERR_CUDA, "memcpy failed");
+  };
+  cp(d_ids, ids_host, sizeof(int32_t) * n_ids, cudaMemcpyHostToDevice);
+  if (lengths_host) cp(d_len, lengths_host, sizeof(int32_t) * N, cudaMemcpyHostToDevice);
+  if (spk_host) cp(d_spk, spk_host, sizeof(int32_t) * N, cudaMemcpyHostToDevice);
+  if (n_tgt) cp(d_tgt, mel_targets_host, sizeof(float) * n_tgt, cudaMemcpyHostToDevice);
+  int steps = 0;
+  if (rc == TACO_OK)
+    rc = taco_forward(h, d_ids, lengths_host ? d_len : nullptr, spk_host ? d_spk : nullptr, d_tgt, N, T_in, T_tgt,
+                      bn_mode, teacher_force, d_mel, d_lin, d_al, &steps, stream);
+  if (rc == TACO_OK) {
+    cp(mel_out_host, d_mel, sizeof(float) * n_mel, cudaMemcpyDeviceToHost);
+    if (n_lin) cp(linear_out_host, d_lin, sizeof(float) * n_lin, cudaMemcpyDeviceToHost);
+    if (n_al) cp(align_out_host, d_al, sizeof(float) * n_al, cudaMemcpyDeviceToHost);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(stg);
+  if (rc == TACO_OK && e != cudaSuccess) rc = fail(h, TACO_ERR_CUDA, std::string("sync: ") + cudaGetErrorString(e));
+  if (rc == TACO_OK) rc = taco_check_ids(h, stream);
+  if (steps_out_host) *steps_out_host = steps;
+  return rc;
+}
+
+int64_t taco_launch_count(const taco_handle* h) { return h ? h->launches : 0; }
+
+int taco_decoder_geometry(const taco_handle* h, int N, int* cluster_size, int* samples_per_cluster, int* num_clusters) {
+  if (!h || !h->finalized) return TACO_ERR_STATE;
+  const int S = pick_S(h, N);
+  if (cluster_size) *cluster_size = h->CS;
+  if (samples_per_cluster) *samples_per_cluster = S;
+  if (num_clusters) *num_clusters = (N + S - 1) / S;
+  return TACO_OK;
+}
+
+int taco_set_profiling(taco_handle* h, int on) {
+  if (!h) return TACO_ERR_INVALID;
+  h->profiling = on != 0;
+  return TACO_OK;
+}
+int taco_last_stage_ms(const taco_handle* h, float* ms3_host) {
+  if (!h || !ms3_host) return TACO_ERR_INVALID;
+  for (int i = 0; i < 3; ++i) ms3_host[i] = h->stage_ms[i];
+  return TACO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,299 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerances (fp32 mode): stage outputs 2e-4 max-abs, whole teacher-forced
+forward 1e-3 max-abs on mel / linear (north_star), alignments 1e-4.
+Free-running decodes feed rounding differences back through the loop, so they
+get a looser bound and the exact properties instead (step count, shapes).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_inputs
+
+pytestmark = pytest.mark.gpu
+
+from oracle import taco_oracle as O  # noqa: E402  (tests may use the oracle)
+
+
+@pytest.fixture(scope="module")
+def eng(small_hp, small_weights):
+    from tacotron_multispeaker_b200.engine import Engine
+    e = Engine(small_hp, id_num=6)
+    e.load_weights(small_weights)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def ow(small_weights):
+    return O.W(small_weights, torch.float32)
+
+
+def maxabs(a, b):
+    a = a.detach().cpu().double() if isinstance(a, torch.Tensor) else torch.as_tensor(a).double()
+    b = b.detach().cpu().double() if isinstance(b, torch.Tensor) else torch.as_tensor(b).double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((a - b).abs().max())
+
+
+def test_library_loaded_is_in_tree():
+    from tacotron_multispeaker_b200 import _abi
+    lib = _abi.load()
+    assert os.path.dirname(_abi.LIB_PATH).endswith("tacotron_multispeaker_b200")
+    assert b"sm_100a" in lib.taco_version()
+
+
+def test_weight_inventory_matches_python(eng, small_hp):
+    from tacotron_multispeaker_b200.weights import weight_specs
+    assert sorted(eng.weight_names()) == sorted(weight_specs(small_hp, 6).keys())
+
+
+def test_embed(eng, ow):
+    ids, lengths, spk = make_inputs(5, 13, 6, 0)
+    got = eng.embed(ids, spk)
+    ref = O.embed(ids, spk, ow)
+    assert maxabs(got, ref) == 0.0          # pure gather: bit exact
+    eng.check_ids()
+
+
+def test_embed_oob_id_flags_error(eng):
+    from tacotron_multispeaker_b200._abi import TacoError, TACO_ERR_OOB_ID
+    ids, lengths, spk = make_inputs(2, 5, 6, 1)
+    ids[1, 2] = 7352 + 5
+    out = eng.embed(ids, spk)
+    with pytest.raises(TacoError) as ei:
+        eng.check_ids()
+    assert ei.value.code == TACO_ERR_OOB_ID
+    assert float(out[1, 2, :256].abs().max()) == 0.0   # zero row, like TF GPU gather
+    eng.check_ids()                                    # flag is cleared
+
+
+@pytest.mark.parametrize("k,cin,cout,act", [(1, 128, 128, 1), (2, 80, 128, 1), (3, 256, 80, 0),
+                                            (4, 128, 128, 1), (7, 80, 128, 3), (16, 128, 128, 1),
+                                            (1, 256, 1025, 0), (3, 2048, 128, 2), (1, 320, 256, 1)])
+def test_conv1d_same(eng, k, cin, cout, act):
+    rng = np.random.default_rng(k * 1000 + cin + cout)
+    N, T = 3, 37
+    x = rng.standard_normal((N, T, cin)).astype(np.float32)
+    w = (rng.standard_normal((k, cin, cout)) / np.sqrt(k * cin)).astype(np.float32)
+    b = rng.standard_normal((cout,)).astype(np.float32)
+    got = eng.conv1d(x, w, b, act)
+    ref = O.conv1d_same(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b))
+    ref = [lambda v: v, torch.relu, torch.sigmoid, torch.tanh][act](ref)
+    assert maxabs(got, ref) < 2e-5
+
+
+def test_conv1d_even_kernel_padding_kat(eng):
+    # unit impulse, distinct taps: 'same' pads (k-1)//2 on the left (SURVEY 8c KAT 4)
+    k, T = 4, 9
+    x = np.zeros((1, T, 4), np.float32)
+    x[0, 4, 0] = 1.0
+    w = np.zeros((k, 4, 4), np.float32)
+    for j in range(k):
+        w[j, 0, 0] = j + 1
+    got = eng.conv1d(x, w, None, 0)[0, :, 0].cpu().numpy()
+    exp = np.zeros(T, np.float32)
+    for j in range(k):           # y[t] = sum_j x[t + j - 1] w[j]  -> impulse at t = 4 - j + 1
+        exp[4 - j + 1] = j + 1
+    assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("which,N,T,masked", [(0, 5, 23, True), (0, 3, 11, False), (1, 2, 60, False),
+                                              (0, 80, 9, True)])
+def test_bigru(eng, ow, which, N, T, masked):
+    rng = np.random.default_rng(N * 100 + T)
+    x = rng.standard_normal((N, T, 128)).astype(np.float32)
+    lengths = None
+    if masked:
+        lengths = rng.integers(1, T + 1, (N,)).astype(np.int32)
+        lengths[0] = T
+    got = eng.bigru(which, x, lengths)
+    ref = O.bigru(torch.from_numpy(x), lengths, ow, "encoder_cbhg" if which == 0 else "post_cbhg")
+    assert maxabs(got, ref) < 1e-4
+    if masked:   # outputs exactly zero beyond each length (KAT 7)
+        g = got.cpu().numpy()
+        for i in range(N):
+            assert np.all(g[i, lengths[i]:] == 0.0)
+
+
+@pytest.mark.parametrize("which,bn", [(0, "moving"), (0, "batch"), (1, "moving"), (1, "batch")])
+def test_cbhg(eng, ow, which, bn):
+    rng = np.random.default_rng(which * 10 + len(bn))
+    N, T = 3, 29
+    cin = 128 if which == 0 else 80
+    x = rng.standard_normal((N, T, cin)).astype(np.float32)
+    lengths = np.array([29, 17, 5], np.int32) if which == 0 else None
+    got = eng.cbhg(which, x, lengths, 1 if bn == "batch" else 0)
+    ref = O.cbhg(torch.from_numpy(x), lengths, ow, "encoder_cbhg" if which == 0 else "post_cbhg",
+                 16 if which == 0 else 8, bn)
+    assert maxabs(got, ref) < 2e-4
+
+
+def test_encoder(eng, ow):
+    ids, lengths, spk = make_inputs(4, 21, 6, 3)
+    got = eng.encoder(ids, lengths, spk, 0)
+    ref = O.encoder(ids, lengths, spk, ow, "moving")
+    assert maxabs(got, ref) < 2e-4
+
+
+def _decode_case(eng, ow, hp, N, T_in, teacher, seed, S=None):
+    rng = np.random.default_rng(seed)
+    memory = (rng.standard_normal((N, T_in, 256)) * 0.5).astype(np.float32)
+    targets = rng.uniform(0, 1, (N, hp.max_iters * hp.outputs_per_step, hp.num_mels)).astype(np.float32)
+    if S is not None:
+        os.environ["TACO_DEC_S"] = str(S)
+    try:
+        dec, al, steps = eng.decode(memory, targets if teacher else None, teacher)
+    finally:
+        os.environ.pop("TACO_DEC_S", None)
+    rdec, ral, rsteps = O.decode(torch.from_numpy(memory), ow, hp.num_mels, hp.outputs_per_step, hp.max_iters,
+                                 torch.from_numpy(targets) if teacher else None, teacher)
+    assert steps == rsteps
+    return maxabs(dec, rdec), maxabs(al, ral), al, ral
+
+
+@pytest.mark.parametrize("N,T_in,S", [(1, 7, None), (3, 19, None), (5, 33, 2), (8, 16, 4), (9, 50, 8),
+                                      (17, 100, None), (2, 130, 1)])
+def test_decode_teacher_forced(eng, ow, small_hp, N, T_in, S):
+    e_dec, e_al, al, ral = _decode_case(eng, ow, small_hp, N, T_in, True, N * 7 + T_in, S)
+    assert e_dec < 2e-4 and e_al < 1e-5
+    # identical per-step attention argmax (north_star)
+    assert torch.equal(al.cpu().argmax(dim=1), ral.argmax(dim=1))
+
+
+@pytest.mark.parametrize("N,T_in,S", [(1, 11, None), (4, 25, None), (6, 40, 4)])
+def test_decode_free_running(eng, ow, small_hp, N, T_in, S):
+    e_dec, e_al, _, _ = _decode_case(eng, ow, small_hp, N, T_in, False, N * 11 + T_in, S)
+    assert e_dec < 1e-3 and e_al < 1e-4
+
+
+def test_postnet(eng, ow, small_hp):
+    rng = np.random.default_rng(5)
+    mel = rng.uniform(-0.5, 1.0, (2, 35, 80)).astype(np.float32)
+    got = eng.postnet(mel, 0)
+    post = O.cbhg(torch.from_numpy(mel), None, ow, "post_cbhg", 8, "moving")
+    ref = O.dense(post, ow("dense/kernel"), ow("dense/bias"))
+    assert maxabs(got, ref) < 2e-4
+
+
+@pytest.mark.parametrize("mode", ["free", "teacher_moving", "teacher_batch"])
+def test_forward_whole_path(eng, small_hp, small_weights, mode):
+    hp = small_hp
+    N, T_in = 4, 24
+    ids, lengths, spk = make_inputs(N, T_in, 6, 11)
+    rng = np.random.default_rng(2)
+    T_out = hp.max_iters * hp.outputs_per_step
+    mel_t = rng.uniform(0, 1, (N, T_out, hp.num_mels)).astype(np.float32)
+    lin_t = np.zeros((N, T_out, hp.num_freq), np.float32)
+    if mode == "free":
+        ref = O.tacotron_forward(small_weights, hp, ids, lengths, identities=spk, id_num=6)
+        mel, lin, al, steps = eng.forward(ids, lengths, spk)
+        tol = 1e-3
+    elif mode == "teacher_moving":
+        ref = O.tacotron_forward(small_weights, hp, ids, lengths, mel_targets=mel_t, identities=spk, id_num=6,
+                                 teacher_force=True, bn_mode="moving")
+        mel, lin, al, steps = eng.forward(ids, lengths, spk, mel_t, True, 0)
+        tol = 1e-3
+    else:   # reference-faithful training forward: teacher forcing + batch-statistics BN
+        ref = O.tacotron_forward(small_weights, hp, ids, lengths, mel_targets=mel_t, linear_targets=lin_t,
+                                 identities=spk, id_num=6)
+        mel, lin, al, steps = eng.forward(ids, lengths, spk, mel_t, True, 1)
+        tol = 1e-3
+    assert steps == ref["steps"]
+    assert maxabs(mel, ref["mel_outputs"]) < tol
+    assert maxabs(lin, ref["linear_outputs"]) < tol
+    assert maxabs(al, ref["alignments"]) < 1e-4
+    if mode != "free":
+        assert torch.equal(al.cpu().argmax(dim=1), ref["alignments"].argmax(dim=1))
+
+
+def test_tacotron_initialize_contract(small_hp, small_weights):
+    """reference attribute contract (models/tacotron.py:106-113) through the host class."""
+    from tacotron_multispeaker_b200.tacotron import create_model
+    m = create_model("tacotron", small_hp, verbose=False)
+    m.load_weights(small_weights)
+    ids, lengths, spk = make_inputs(2, 15, 6, 4)
+    m.initialize(ids, lengths, identities=spk, id_num=6)
+    r, steps = small_hp.outputs_per_step, small_hp.max_iters
+    assert tuple(m.mel_outputs.shape) == (2, steps * r, 80)
+    assert tuple(m.linear_outputs.shape) == (2, steps * r, 1025)
+    assert tuple(m.alignments.shape) == (2, 15, steps)
+    assert m.inputs is ids and m.input_lengths is lengths and m.identities is spk
+    assert m.mel_targets is None and m.linear_targets is None
+    ref = O.tacotron_forward(small_weights, small_hp, ids, lengths, identities=spk, id_num=6)
+    assert maxabs(m.mel_outputs, ref["mel_outputs"]) < 1e-3
+    with pytest.raises(Exception):
+        create_model("wavenet", small_hp)
+
+
+def test_single_speaker_branch(small_hp):
+    """identities None or id_num<=1 -> 256-d embedding, no speaker table (tacotron.py:48-58)."""
+    from tacotron_multispeaker_b200.tacotron import Tacotron
+    from tacotron_multispeaker_b200.weights import random_init
+    w = random_init(small_hp, 0, seed=3, randomize_bn=True)
+    m = Tacotron(small_hp, verbose=False)
+    m.load_weights(w)
+    ids, lengths, _ = make_inputs(2, 12, 1, 5)
+    m.initialize(ids, lengths)
+    ref = O.tacotron_forward(w, small_hp, ids, lengths)
+    assert maxabs(m.mel_outputs, ref["mel_outputs"]) < 1e-3
+    assert maxabs(m.linear_outputs, ref["linear_outputs"]) < 1e-3
+
+
+def test_stop_token_kat(small_hp):
+    """Zero output projection -> every sample finishes at step 0 (all outputs == 0.0):
+    steps == 1 and mel_outputs is [N, r, 80] of zeros (helpers.py:35, SURVEY 8c KAT 10)."""
+    from tacotron_multispeaker_b200.engine import Engine
+    from tacotron_multispeaker_b200.weights import random_init
+    w = random_init(small_hp, 0, seed=9)
+    w["model/inference/decoder/output_projection_wrapper/kernel"][:] = 0.0
+    w["model/inference/decoder/output_projection_wrapper/bias"][:] = 0.0
+    e = Engine(small_hp, 0)
+    e.load_weights(w)
+    ids, lengths, _ = make_inputs(3, 9, 1, 6)
+    mel, lin, al, steps = e.forward(ids, lengths)
+    assert steps == 1
+    assert tuple(mel.shape) == (3, small_hp.outputs_per_step, 80) and float(mel.abs().max()) == 0.0
+    assert tuple(lin.shape) == (3, small_hp.outputs_per_step, 1025)
+    assert tuple(al.shape) == (3, 9, 1)
+    ref = O.tacotron_forward(w, small_hp, ids, lengths)
+    assert ref["steps"] == 1
+    assert maxabs(lin, ref["linear_outputs"]) < 1e-3
+    e.close()
+
+
+def test_forward_host_matches_device(eng, small_hp):
+    hp = small_hp
+    N, T_in = 3, 14
+    ids, lengths, spk = make_inputs(N, T_in, 6, 21)
+    mel_d, lin_d, al_d, steps = eng.forward(ids, lengths, spk)
+    ms = eng.max_steps(False)
+    mel = np.zeros((N, ms * hp.outputs_per_step, 80), np.float32)
+    lin = np.zeros((N, ms * hp.outputs_per_step, 1025), np.float32)
+    al = np.zeros((N, T_in, ms), np.float32)
+    s2 = eng.forward_host(ids, lengths, spk, None, False, 0, mel, lin, al)
+    assert s2 == steps
+    assert np.array_equal(mel, mel_d.cpu().numpy())
+    assert np.array_equal(lin, lin_d.cpu().numpy())
+    assert np.array_equal(al, al_d.cpu().numpy())
+
+
+def test_r1_fork_defaults():
+    """The fork's own hparams (outputs_per_step=1) go through the same kernels."""
+    from tacotron_multispeaker_b200.engine import Engine
+    from tacotron_multispeaker_b200.hparams import HParams
+    from tacotron_multispeaker_b200.weights import random_init
+    hp = HParams(outputs_per_step=1, max_iters=12)
+    w = random_init(hp, 4, seed=5, randomize_bn=True)
+    e = Engine(hp, 4)
+    e.load_weights(w)
+    ids, lengths, spk = make_inputs(3, 10, 4, 8)
+    mel, lin, al, steps = e.forward(ids, lengths, spk)
+    ref = O.tacotron_forward(w, hp, ids, lengths, identities=spk, id_num=4)
+    assert steps == ref["steps"] == 12
+    assert maxabs(mel, ref["mel_outputs"]) < 1e-3
+    assert maxabs(lin, ref["linear_outputs"]) < 1e-3
+    e.close()
