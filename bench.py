@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Benchmark of the Tacotron synthesis forward path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path -- embeddings -> encoder CBHG ->
+attention decoder loop -> post-net CBHG -> linear dense -- over one synthetic
+batch: BASELINE.json config 3, multispeaker free-running synthesis, batch 32
+per GPU, ~100 pinyin symbols, max_iters=200 at r=5 (1000 mel frames per
+utterance), mel + post-net linear output.  Metric: mel frames/s (whole job).
+
+ * value : inputs already resident in HBM, K back-to-back steps between CUDA
+           events, barrier + synchronize on both sides, max over ranks.
+ * e2e   : the same step through the C-ABI host call (taco_forward_host) with
+           HOST buffers: H2D of ids/lengths/speakers and D2H of mel, linear and
+           alignments inside the timed region.
+ * roofline : the decoder loop kernel (the dominant kernel): algorithmic bytes
+           per launch (12.90 MB/step fp32 at N=32,T_in=100) over
+           its CUDA-event duration, against the measured HBM copy peak.
+ * cpu_baseline : the CPU oracle (restatement of the reference's TF graph; TF
+           itself cannot run here) on the host cores, one full batch.
+
+`--impl reference` times that CPU restatement alone (rank 0 only).
+N > 1: launched under torchrun, one rank per GPU, each rank runs its own batch
+of 32 utterances (weak scaling, no collective on the data path).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "mel_frames_per_s"
+UNIT = "frames/s"
+BATCH, T_IN, MAX_ITERS, R, ID_NUM = 32, 100, 200, 5, 60
+
+
+def make_batch(seed: int):
+    """BASELINE.md config 3 inputs: lengths ~U{60..100}, ids in the pinyin-phone block, pad id 0."""
+    rng = np.random.default_rng(seed)
+    lengths = rng.integers(60, T_IN + 1, (BATCH,)).astype(np.int32)
+    ids = rng.integers(7108, 7325, (BATCH, T_IN)).astype(np.int32)
+    for i in range(BATCH):
+        ids[i, lengths[i]:] = 0
+    spk = rng.integers(0, ID_NUM, (BATCH,)).astype(np.int32)
+    return ids, lengths, spk
+
+
+def workload_config(n_gpus: int):
+    return {
+        "workload": "BASELINE config 3: multispeaker free-running synthesis, batch %d per GPU, T_in<=%d "
+                    "(lengths U{60..100}), max_iters=%d, r=%d (%d mel frames/utterance), mel + post-net linear"
+                    % (BATCH, T_IN, MAX_ITERS, R, MAX_ITERS * R),
+        "global_batch": BATCH * n_gpus,
+        "frames_per_step": BATCH * n_gpus * MAX_ITERS * R,
+        "parallelism": "utterance-sharded replicas x%d (no data-path collective)" % n_gpus,
+        "weights": "random init with the reference's initializers (seed 1234); 8.80 M params",
+        "l2": "per-step working set ~0.5 GB (post-net activations) exceeds the 126 MB L2; weights (35 MB) stay resident",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        self.lines = []
+        exe = shutil.which("nvidia-smi")
+        if exe is None:
+            return
+        try:
+            self.proc = subprocess.Popen([exe, "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_restatement_seconds(n_threads: int, batch: int = BATCH):
+    """One full batch through the oracle (the reference graph restated op by op on torch CPU)."""
+    import torch
+    from oracle import taco_oracle as O
+    from tacotron_multispeaker_b200.hparams import HParams
+    from tacotron_multispeaker_b200.weights import random_init
+    torch.set_num_threads(n_threads)
+    hp = HParams(outputs_per_step=R, max_iters=MAX_ITERS)
+    w = O.W(random_init(hp, ID_NUM, seed=1234))
+    ids, lengths, spk = make_batch(1)
+    ids, lengths, spk = ids[:batch], lengths[:batch], spk[:batch]
+    t0 = time.perf_counter()
+    out = O.tacotron_forward(w, hp, ids, lengths, identities=spk, id_num=ID_NUM)
+    dt = time.perf_counter() - t0
+    frames = out["mel_outputs"].shape[0] * out["mel_outputs"].shape[1]
+    return dt, frames
+
+
+def run_reference(args):
+    """`--impl reference`: the CPU restatement of the reference graph, host cores only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    times, frames = [], 0
+    for i in range(args.warmup + args.steps):
+        dt, frames = cpu_restatement_seconds(cores)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = frames / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "one full batch (32 utterances x 1000 frames) per step; CPU restatement of the "
+                                   "reference TF graph in torch-CPU fp32 (TensorFlow 1.x is not installable here)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    from tacotron_multispeaker_b200 import _abi
+    from tacotron_multispeaker_b200.engine import Engine
+    from tacotron_multispeaker_b200.hparams import HParams
+    from tacotron_multispeaker_b200.weights import random_init
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    hp = HParams(outputs_per_step=R, max_iters=MAX_ITERS)
+    eng = Engine(hp, ID_NUM, local)
+    eng.load_weights(random_init(hp, ID_NUM, seed=1234))
+    ids_h, len_h, spk_h = make_batch(1 + rank)
+    dev = torch.device("cuda", local)
+    ids = torch.from_numpy(ids_h).to(dev)
+    lengths = torch.from_numpy(len_h).to(dev)
+    spk = torch.from_numpy(spk_h).to(dev)
+    T_out = MAX_ITERS * R
+    outs = (torch.zeros(BATCH, T_out, hp.num_mels, device=dev),
+            torch.zeros(BATCH, T_out, hp.num_freq, device=dev),
+            torch.zeros(BATCH, T_IN, MAX_ITERS, device=dev))
+
+    def step():
+        return eng.forward(ids, lengths, spk, out=outs)
+
+    # ---- device-resident throughput ----
+    for _ in range(max(args.warmup, 3)):
+        step()
+    eng.check_ids()
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    launches0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    steps_taken = 0
+    for _ in range(args.steps):
+        _, _, _, steps_taken = step()
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = eng.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    ms_per_step = ms_total / args.steps
+    frames_per_step = BATCH * steps_taken * R * world
+    value = frames_per_step / (ms_per_step / 1e3)
+
+    # ---- decoder-kernel roofline (measured live, CUDA events on the launch stream) ----
+    eng.set_profiling(True)
+    dk = []
+    for _ in range(3):
+        step()
+        dk.append(eng.last_stage_ms())
+    eng.set_profiling(False)
+    stage = {k: float(np.mean([d[k] for d in dk])) for k in dk[0]}
+    geo = eng.decoder_geometry(BATCH)
+    w_dec = 1399936 + 20560 * R
+    bytes_step = w_dec * 4 + 2 * BATCH * T_IN * 256 * 4 + BATCH * (2 * 4 * 256 + 80 + 80 * R + T_IN) * 4
+    alg_bytes = bytes_step * steps_taken
+    achieved = alg_bytes / (stage["decoder_kernel"] / 1e3) / 1e9
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    roofline = {"bound": "hbm", "kernel": "decoder_kernel<S=%d,CS=%d>" % (geo["samples_per_cluster"], geo["cluster_size"]),
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": stage["decoder_kernel"],
+                "us_per_decoder_step": 1e3 * stage["decoder_kernel"] / steps_taken,
+                "stage_ms": stage}
+
+    # ---- end to end through the C-ABI host entry point (pinned host buffers) ----
+    def pinned(shape, dtype):
+        return torch.empty(shape, dtype=dtype).pin_memory().numpy()
+    ids_p, len_p, spk_p = pinned((BATCH, T_IN), torch.int32), pinned((BATCH,), torch.int32), pinned((BATCH,), torch.int32)
+    ids_p[:], len_p[:], spk_p[:] = ids_h, len_h, spk_h
+    mel_p, lin_p = pinned((BATCH, T_out, hp.num_mels), torch.float32), pinned((BATCH, T_out, hp.num_freq), torch.float32)
+    al_p = pinned((BATCH, T_IN, MAX_ITERS), torch.float32)
+    for _ in range(2):
+        eng.forward_host(ids_p, len_p, spk_p, None, False, _abi.BN_MOVING, mel_p, lin_p, al_p)
+    barrier()
+    k_e2e = max(2, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        eng.forward_host(ids_p, len_p, spk_p, None, False, _abi.BN_MOVING, mel_p, lin_p, al_p)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / k_e2e
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": frames_per_step / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s,
+           "h2d_bytes_per_step": int(ids_p.nbytes + len_p.nbytes + spk_p.nbytes),
+           "d2h_bytes_per_step": int(mel_p.nbytes + lin_p.nbytes + al_p.nbytes),
+           "api": "taco_forward_host (C ABI, pinned host buffers)"}
+
+    # ---- CPU restatement on the host cores (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        dt, frames = cpu_restatement_seconds(cores)
+        cpu = {"value": frames / dt, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
+               "sample": "one full batch (32 utterances x 1000 frames), torch-CPU fp32 restatement of the reference "
+                         "TF graph (TensorFlow 1.x cannot be installed here)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world), "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "decoder_geometry": geo,
+        }
+        print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU restatement leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -154,9 +154,10 @@ int64_t taco_launch_count(const taco_handle* h);
 int taco_decoder_geometry(const taco_handle* h, int N, int* cluster_size, int* samples_per_cluster,
                           int* num_clusters);
 /* Device time (ms, CUDA events on `stream`) of the stages of the last
- * taco_forward when profiling is on: [0]=encoder [1]=decoder [2]=postnet. */
+ * taco_forward when profiling is on: [0]=encoder [1]=decoder stage (memory
+ * layer + loop + step count) [2]=postnet [3]=the decoder loop kernel alone. */
 int taco_set_profiling(taco_handle* h, int on);
-int taco_last_stage_ms(const taco_handle* h, float* ms3_host);
+int taco_last_stage_ms(const taco_handle* h, float* ms4_host);
 
 #ifdef __cplusplus
 }

@@ -18,9 +18,12 @@
 namespace taco {
 
 namespace {
-constexpr int BM = 128, BN = 128, BK = 16, NT = 256, APAD = 4;
+constexpr int BK = 16, NT = 256, APAD = 4;
 
+// BM = 64*HM rows x BN = 64*HN columns per CTA; a thread owns (4*HM) x (4*HN) outputs.
+template <int HM, int HN>
 __global__ void __launch_bounds__(NT, 2) conv_gemm_kernel(const ConvGemm p) {
+  constexpr int BM = 64 * HM, BN = 64 * HN, RM = 4 * HM, RN = 4 * HN;
   __shared__ __align__(16) float As[2][BK][BM + APAD];
   __shared__ __align__(16) float Bs[2][BK][BN];
 
@@ -32,11 +35,11 @@ __global__ void __launch_bounds__(NT, 2) conv_gemm_kernel(const ConvGemm p) {
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
 
   // A-load role: two (row, k-quad) slots per thread.
-  int a_row[2], a_kq[2], a_t[2];
-  const float* a_base[2];
-  bool a_valid[2];
+  int a_row[HM], a_kq[HM], a_t[HM];
+  const float* a_base[HM];
+  bool a_valid[HM];
 #pragma unroll
-  for (int l = 0; l < 2; ++l) {
+  for (int l = 0; l < HM; ++l) {
     const int idx = tid + l * NT;
     a_row[l] = idx >> 2;
     a_kq[l] = idx & 3;
@@ -47,18 +50,18 @@ __global__ void __launch_bounds__(NT, 2) conv_gemm_kernel(const ConvGemm p) {
     a_base[l] = p.x + (int64_t)n * p.x_bs;
   }
   // B-load role.
-  int b_kk[2], b_col[2];
+  int b_kk[HN], b_col[HN];
 #pragma unroll
-  for (int l = 0; l < 2; ++l) {
+  for (int l = 0; l < HN; ++l) {
     const int idx = tid + l * NT;
-    b_kk[l] = idx >> 5;
-    b_col[l] = (idx & 31) << 2;
+    b_kk[l] = idx / (BN / 4);
+    b_col[l] = (idx % (BN / 4)) << 2;
   }
 
-  float4 ra[2], rb[2];
+  float4 ra[HM], rb[HN];
   auto load_tiles = [&](int k0) {
 #pragma unroll
-    for (int l = 0; l < 2; ++l) {
+    for (int l = 0; l < HM; ++l) {
       const int kk = k0 + a_kq[l] * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (a_valid[l] && kk < Ktot) {
@@ -68,6 +71,9 @@ __global__ void __launch_bounds__(NT, 2) conv_gemm_kernel(const ConvGemm p) {
         if (tt >= 0 && tt < p.T) v = ldg_f4(a_base[l] + (int64_t)tt * p.ldx + c);
       }
       ra[l] = v;
+    }
+#pragma unroll
+    for (int l = 0; l < HN; ++l) {
       const int kb = k0 + b_kk[l];
       const int col = n0 + b_col[l];
       float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -77,21 +83,22 @@ __global__ void __launch_bounds__(NT, 2) conv_gemm_kernel(const ConvGemm p) {
   };
   auto store_tiles = [&](int buf) {
 #pragma unroll
-    for (int l = 0; l < 2; ++l) {
+    for (int l = 0; l < HM; ++l) {
       const int kq = a_kq[l] * 4, r = a_row[l];
       As[buf][kq + 0][r] = ra[l].x;
       As[buf][kq + 1][r] = ra[l].y;
       As[buf][kq + 2][r] = ra[l].z;
       As[buf][kq + 3][r] = ra[l].w;
-      *reinterpret_cast<float4*>(&Bs[buf][b_kk[l]][b_col[l]]) = rb[l];
     }
+#pragma unroll
+    for (int l = 0; l < HN; ++l) *reinterpret_cast<float4*>(&Bs[buf][b_kk[l]][b_col[l]]) = rb[l];
   };
 
-  float acc[8][8];
+  float acc[RM][RN];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < RM; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < RN; ++j) acc[i][j] = 0.f;
 
   const int nk = (Ktot + BK - 1) / BK;
   load_tiles(0);
@@ -102,16 +109,21 @@ __global__ void __launch_bounds__(NT, 2) conv_gemm_kernel(const ConvGemm p) {
     if (it + 1 < nk) load_tiles((it + 1) * BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float a[RM], b[RN];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int hh = 0; hh < HM; ++hh) {
+        const float4 t4 = *reinterpret_cast<const float4*>(&As[buf][kk][hh * 64 + ty * 4]);
+        a[hh * 4 + 0] = t4.x; a[hh * 4 + 1] = t4.y; a[hh * 4 + 2] = t4.z; a[hh * 4 + 3] = t4.w;
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int hh = 0; hh < HN; ++hh) {
+        const float4 t4 = *reinterpret_cast<const float4*>(&Bs[buf][kk][hh * 64 + tx * 4]);
+        b[hh * 4 + 0] = t4.x; b[hh * 4 + 1] = t4.y; b[hh * 4 + 2] = t4.z; b[hh * 4 + 3] = t4.w;
+      }
+#pragma unroll
+      for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     if (it + 1 < nk) {
       store_tiles(buf ^ 1);   // other buffer: last read two iterations ago, fenced by the sync below
@@ -121,14 +133,14 @@ __global__ void __launch_bounds__(NT, 2) conv_gemm_kernel(const ConvGemm p) {
 
   // ---- epilogue ----
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+  for (int i = 0; i < RM; ++i) {
+    const int m = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
     if (m >= M) continue;
     const int n = m / p.T, t = m - n * p.T;
     float* orow = p.out + (int64_t)n * p.out_bs + (int64_t)t * p.ldo + p.col_off;
     const float* rrow = p.res ? p.res + (int64_t)n * p.res_bs + (int64_t)t * p.ldres : nullptr;
 #pragma unroll
-    for (int jh = 0; jh < 2; ++jh) {
+    for (int jh = 0; jh < HN; ++jh) {
       const int cbase = n0 + jh * 64 + tx * 4;
       if (p.epi == EPI_PLAIN) {
         float v[4];
@@ -172,8 +184,15 @@ __global__ void __launch_bounds__(NT, 2) conv_gemm_kernel(const ConvGemm p) {
 void launch_conv_gemm(const ConvGemm& p, cudaStream_t st) {
   const int M = p.N * p.T;
   if (M <= 0 || p.Cout <= 0) return;
-  dim3 grid((M + BM - 1) / BM, (p.Cout + BN - 1) / BN);
-  conv_gemm_kernel<<<grid, NT, 0, st>>>(p);
+  // Big tiles when they already fill the 148 SMs, else 64x64 tiles for more CTAs in flight.
+  const int big = ((M + 127) / 128) * ((p.Cout + 127) / 128);
+  if (big >= 148) {
+    dim3 grid((M + 127) / 128, (p.Cout + 127) / 128);
+    conv_gemm_kernel<2, 2><<<grid, NT, 0, st>>>(p);
+  } else {
+    dim3 grid((M + 63) / 64, (p.Cout + 63) / 64);
+    conv_gemm_kernel<1, 1><<<grid, NT, 0, st>>>(p);
+  }
 }
 
 }  // namespace taco

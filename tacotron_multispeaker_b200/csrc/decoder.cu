@@ -26,6 +26,8 @@
 // that share its column group with shuffles, then across warps through shared
 // memory.  Activations are stored [k][S] so the S samples of one k are one
 // vector load.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -39,12 +41,44 @@ constexpr int DP = 128;       // prenet output
 
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- mbarrier / st.async primitives (PTX, sm_90+) -----------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* mb, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mb)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mb, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mb)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* mb, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(mb)), "r"(parity)
+      : "memory");
+}
+// Remote store into a peer CTA's shared memory that also credits `bytes` on the
+// peer's mbarrier: the consumer needs no fence and no cluster-wide barrier.
+__device__ __forceinline__ void st_async_f4(uint32_t raddr, float4 v, uint32_t rmbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1,%2,%3,%4}, [%5];"
+               ::"r"(raddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rmbar) : "memory");
+}
+__device__ __forceinline__ void st_async_f1(uint32_t raddr, float v, uint32_t rmbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];"
+               ::"r"(raddr), "f"(v), "r"(rmbar) : "memory");
+}
+
 // ---- streamed mat-vec pieces ------------------------------------------------
-// MAXI = max rows per thread = ceil(Kmax * (MC/4) / NT).
+// Slice W_q[K][MC] of a weight matrix; thread (kr, cg) owns rows kr, kr+KR, ... and
+// the 4 columns of column group cg.  MAXI = rows per thread.
 template <int MC, int KMAX>
 struct GemmCfg {
-  static constexpr int CG = MC / 4;            // column groups of 4 (power of two <= 32)
-  static constexpr int KR = NT / CG;           // rows in flight per pass
+  static constexpr int CG = MC / 4;            // column groups (power of two, <= 16)
+  static constexpr int KR = NT / CG;           // rows covered per pass
   static constexpr int MAXI = ceil_div(KMAX, KR);
 };
 
@@ -61,16 +95,47 @@ __device__ __forceinline__ void gemm_load(const float* __restrict__ W, int K,
   }
 }
 
-// xs: shared activations [K][S]; red: [NW][S][MC] warp partial sums.
+// Reduce V values per lane over the 32/CG lanes that share a column group by
+// recursive halving: each round a lane keeps one half of its values and receives
+// the partner's sums for that half, so V values cost ~V shuffles instead of
+// V*log2(32/CG).  On return the lane holds NF = max(1, V*CG/32) finished values
+// v[0..NF) for flat indices base..base+NF; `writer` is false on duplicate lanes.
+template <int N, int OFF, int CG>
+struct Halve {
+  template <int V>
+  static __device__ __forceinline__ void run(float (&v)[V], int lane, int& base, bool& writer) {
+    if constexpr (OFF >= CG) {
+      const bool up = (lane & OFF) != 0;
+      if constexpr (N > 1) {
+        constexpr int h = N / 2;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+          const float send = up ? v[i] : v[i + h];
+          const float keep = up ? v[i + h] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+        }
+        if (up) base += h;
+        Halve<h, OFF / 2, CG>::run(v, lane, base, writer);
+      } else {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], OFF);
+        if (up) writer = false;
+        Halve<1, OFF / 2, CG>::run(v, lane, base, writer);
+      }
+    }
+  }
+};
+
+// xs: shared activations [K][S]; red: [NW][S][MC] per-warp partial sums.
 template <int S, int MC, int KMAX>
 __device__ __forceinline__ void gemm_fma(const float4 (&w)[GemmCfg<MC, KMAX>::MAXI], int K,
                                          const float* __restrict__ xs, float* __restrict__ red) {
   using C = GemmCfg<MC, KMAX>;
+  constexpr int V = 4 * S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cg = tid & (C::CG - 1), kr = tid / C::CG;
-  float acc[S][4];
+  float acc[V];
 #pragma unroll
-  for (int s = 0; s < S; ++s) acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.f;
+  for (int i = 0; i < V; ++i) acc[i] = 0.f;
 #pragma unroll
   for (int i = 0; i < C::MAXI; ++i) {
     const int k = kr + i * C::KR;
@@ -79,39 +144,45 @@ __device__ __forceinline__ void gemm_fma(const float4 (&w)[GemmCfg<MC, KMAX>::MA
       if constexpr (S % 4 == 0) {
 #pragma unroll
         for (int s4 = 0; s4 < S / 4; ++s4) {
-          const float4 v = *reinterpret_cast<const float4*>(xs + (size_t)k * S + s4 * 4);
-          x[s4 * 4 + 0] = v.x; x[s4 * 4 + 1] = v.y; x[s4 * 4 + 2] = v.z; x[s4 * 4 + 3] = v.w;
+          const float4 t4 = *reinterpret_cast<const float4*>(xs + (size_t)k * S + s4 * 4);
+          x[s4 * 4 + 0] = t4.x; x[s4 * 4 + 1] = t4.y; x[s4 * 4 + 2] = t4.z; x[s4 * 4 + 3] = t4.w;
         }
       } else if constexpr (S == 2) {
-        const float2 v = *reinterpret_cast<const float2*>(xs + (size_t)k * 2);
-        x[0] = v.x; x[1] = v.y;
+        const float2 t2 = *reinterpret_cast<const float2*>(xs + (size_t)k * 2);
+        x[0] = t2.x; x[1] = t2.y;
       } else {
 #pragma unroll
         for (int s = 0; s < S; ++s) x[s] = xs[(size_t)k * S + s];
       }
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        acc[s][0] = fmaf(x[s], w[i].x, acc[s][0]);
-        acc[s][1] = fmaf(x[s], w[i].y, acc[s][1]);
-        acc[s][2] = fmaf(x[s], w[i].z, acc[s][2]);
-        acc[s][3] = fmaf(x[s], w[i].w, acc[s][3]);
+        acc[s * 4 + 0] = fmaf(x[s], w[i].x, acc[s * 4 + 0]);
+        acc[s * 4 + 1] = fmaf(x[s], w[i].y, acc[s * 4 + 1]);
+        acc[s * 4 + 2] = fmaf(x[s], w[i].z, acc[s * 4 + 2]);
+        acc[s * 4 + 3] = fmaf(x[s], w[i].w, acc[s * 4 + 3]);
       }
     }
   }
-  // lanes l and l^off share a column group whenever off is a multiple of CG
+  int base = 0;
+  bool writer = true;
+  Halve<V, 16, C::CG>::run(acc, lane, base, writer);
+  constexpr int NF = (V * C::CG / 32) > 1 ? (V * C::CG / 32) : 1;   // finished values per lane
+  if (writer) {
+    float* rw = red + (size_t)warp * S * MC + cg * 4;
+    if constexpr (NF >= 4) {
 #pragma unroll
-  for (int off = 16; off >= C::CG; off >>= 1) {
+      for (int i = 0; i < NF; i += 4) {
+        const int idx = base + i;   // = s*4 + 0
+        *reinterpret_cast<float4*>(rw + (size_t)(idx >> 2) * MC) =
+            make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+      }
+    } else {
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[s][j] += __shfl_xor_sync(0xffffffffu, acc[s][j], off);
+      for (int i = 0; i < NF; ++i) {
+        const int idx = base + i;
+        rw[(size_t)(idx >> 2) * MC + (idx & 3)] = acc[i];
+      }
     }
-  }
-  if (lane < C::CG) {
-#pragma unroll
-    for (int s = 0; s < S; ++s)
-      *reinterpret_cast<float4*>(red + ((size_t)(warp * S + s) * MC + cg * 4)) =
-          make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
   }
 }
 
@@ -123,32 +194,34 @@ __device__ __forceinline__ float red_sum(const float* __restrict__ red, int s, i
   return v;
 }
 
-// Copy `n` floats from local `src` into every CTA of the cluster at the address
-// that corresponds to local `dst` (same shared-memory offset in each CTA).
-__device__ __forceinline__ void push_block(float* dst, const float* src, int n, int CS) {
+// Copy `n` floats from local `src` into every CTA of the cluster at the address that
+// corresponds to local `dst`, crediting the bytes on each receiver's mbarrier `mb`.
+__device__ __forceinline__ void push_block(float* dst, const float* src, int n, int CS, uint64_t* mb) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t d0 = smem_u32(dst);
+  const uint32_t d0 = smem_u32(dst), m0 = smem_u32(mb);
   const bool vec = ((n & 3) == 0) && ((d0 & 15u) == 0) && ((smem_u32(src) & 15u) == 0);
   for (int p = warp; p < CS; p += NW) {
-    const uint32_t rbase = mapa_u32(d0, (uint32_t)p);
+    const uint32_t rbase = mapa_u32(d0, (uint32_t)p), rmb = mapa_u32(m0, (uint32_t)p);
     if (vec) {
       for (int i = lane; i < (n >> 2); i += 32)
-        st_cluster_f4(rbase + i * 16, *reinterpret_cast<const float4*>(src + i * 4));
+        st_async_f4(rbase + i * 16, *reinterpret_cast<const float4*>(src + i * 4), rmb);
     } else {
-      for (int i = lane; i < n; i += 32) st_cluster_f32(rbase + i * 4, src[i]);
+      for (int i = lane; i < n; i += 32) st_async_f1(rbase + i * 4, src[i], rmb);
     }
   }
 }
 
 // Shared-memory carve-up (floats).  Everything that peers push into sits at the
 // same offset in every CTA of the cluster.
+enum { NBAR = 16 };
 struct Layout {
-  int xin, p1, in3, rhA, pq, sc, in9, rh1, in11, rh2, y2, red, stage, stage2, locu, loccx, locy0h, total;
+  int xin, p1, in3, rhA, pq, sc, in9, rh1, in11, rh2, y2, red, stage, stage2, locu, loccx, locy0h, bias,
+      ksl, msl, total;
 };
-__host__ __device__ inline Layout make_layout(int S, int T_in, int M, int CS) {
+__host__ __device__ inline Layout make_layout(int S, int T_in, int M, int CS, bool att_res) {
   const int Hc = DH / CS;
   Layout L;
-  int o = 0;
+  int o = 2 * NBAR;                 // mbarriers (8 bytes each) live at the front
   auto take = [&](int nfloats) { int r = o; o += (nfloats + 3) & ~3; return r; };
   L.xin = take((M + DH) * S);       // [frame(M) | context(256)]      rows x S
   L.p1 = take(DH * S);              // prenet layer 1
@@ -167,9 +240,16 @@ __host__ __device__ inline Layout make_layout(int S, int T_in, int M, int CS) {
   L.locu = take(S * Hc);
   L.loccx = take(S * Hc);
   L.locy0h = take(S * Hc);
+  L.bias = take(16 * Hc + 64);
+  const int Tj = ceil_div(T_in, CS);
+  L.ksl = take(att_res ? S * Tj * DH : 0);      // keys rows [j0,j1) of the S samples
+  L.msl = take(att_res ? S * T_in * Hc : 0);    // memory columns [q*Hc,(q+1)*Hc) of the S samples
   L.total = o;
   return L;
 }
+
+// barrier slots: mb[p] completes when the outputs of phase p have landed in this CTA
+enum { B_P1 = 0, B_P2, B_P3, B_P4, B_P5, B_P6, B_P7, B_P8, B_P9, B_P10, B_P11, B_P12, B_P13 };
 
 template <int S, int CS>
 __global__ void __launch_bounds__(NT, 1)
@@ -178,6 +258,7 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
   constexpr int Pc = DP / CS;     // columns of the 128-wide prenet layer per CTA
   constexpr int McO = (CS == 16) ? 32 : 64;   // padded slice of the 80*r output projection
   constexpr int K1MAX = 128 + DH; // num_mels <= 128
+  constexpr uint32_t BLK = CS * Hc * S * 4;   // bytes a CTA receives for one Hc-wide phase
 
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -185,16 +266,37 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
   const int n0 = (int)cluster_id_x() * S;
   const int M = w.M, K1 = M + DH, Dout = w.Dout;
   const int T_in = a.T_in;
-  const Layout L = make_layout(S, T_in, M, CS);
+  const bool att_res = a.att_res != 0;
+  const Layout L = make_layout(S, T_in, M, CS, att_res);
+  uint64_t* mb = reinterpret_cast<uint64_t*>(smem);
   float* xin = smem + L.xin;   float* p1 = smem + L.p1;     float* in3 = smem + L.in3;
   float* rhA = smem + L.rhA;   float* pqT = smem + L.pq;    float* sc = smem + L.sc;
   float* in9 = smem + L.in9;   float* rh1 = smem + L.rh1;   float* in11 = smem + L.in11;
   float* rh2 = smem + L.rh2;   float* y2 = smem + L.y2;     float* red = smem + L.red;
   float* stage = smem + L.stage; float* stage2 = smem + L.stage2;
   float* locu = smem + L.locu; float* loccx = smem + L.loccx; float* locy0h = smem + L.locy0h;
+  float* bs = smem + L.bias;
+  float* ksl = smem + L.ksl;   float* msl = smem + L.msl;
   float* redB = red + NW * S * 2 * Hc;   // second partial-sum region (candidate x-part)
 
-  for (int i = tid; i < L.total; i += NT) smem[i] = 0.f;   // zero_state + <GO> frame
+  for (int i = tid + 2 * NBAR; i < L.total; i += NT) smem[i] = 0.f;   // zero_state + <GO> frame
+  if (tid < NBAR) mbar_init(mb + tid, 1);
+
+  // biases of this CTA's columns -> shared memory (they sit on every phase's critical path)
+  float* b_p1 = bs;            float* b_ga = b_p1 + Hc;     float* b_ca = b_ga + 2 * Hc;
+  float* b_pc = b_ca + Hc;     float* b_g1 = b_pc + Hc;     float* b_c1 = b_g1 + 2 * Hc;
+  float* b_g2 = b_c1 + Hc;     float* b_c2 = b_g2 + 2 * Hc; float* b_p2 = b_c2 + Hc;   // [Pc]
+  float* b_o = b_p2 + Hc;      // [McO] (<= 64)
+  __syncthreads();
+  if (tid < Hc) {
+    b_p1[tid] = w.p1_b[q * Hc + tid]; b_ca[tid] = w.ca_b[q * Hc + tid]; b_pc[tid] = w.pc_b[q * Hc + tid];
+    b_c1[tid] = w.c1_b[q * Hc + tid]; b_c2[tid] = w.c2_b[q * Hc + tid];
+  }
+  if (tid < 2 * Hc) {
+    b_ga[tid] = w.ga_b[q * 2 * Hc + tid]; b_g1[tid] = w.g1_b[q * 2 * Hc + tid]; b_g2[tid] = w.g2_b[q * 2 * Hc + tid];
+  }
+  if (tid < Pc) b_p2[tid] = w.p2_b[q * Pc + tid];
+  if (tid < McO) b_o[tid] = w.o_b[q * McO + tid];
 
   // per-CTA weight slices
   const float* W1 = w.p1_s + (size_t)q * K1 * Hc;
@@ -218,85 +320,115 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
   float vreg[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) vreg[i] = __ldg(w.att_v + lane + 32 * i);
+  if (att_res) {   // keys rows / memory columns this CTA touches every step -> shared memory, once
+    for (int i = tid; i < S * (j1 - j0) * (DH / 4); i += NT) {
+      const int c4 = i % (DH / 4), r = i / (DH / 4), s = r / (j1 - j0), jj = r - s * (j1 - j0), n = n0 + s;
+      const float4 v4 = (n < a.N) ? ldg_f4(a.keys + ((size_t)n * T_in + j0 + jj) * DH + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(ksl + ((size_t)s * Tj + jj) * DH + c4 * 4) = v4;
+    }
+    for (int i = tid; i < S * T_in * (Hc / 4); i += NT) {
+      const int c4 = i % (Hc / 4), r = i / (Hc / 4), s = r / T_in, j = r - s * T_in, n = n0 + s;
+      const float4 v4 = (n < a.N) ? ldg_f4(a.memory + ((size_t)n * T_in + j) * DH + q * Hc + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(msl + ((size_t)s * T_in + j) * Hc + c4 * 4) = v4;
+    }
+  }
 
   // epilogue role: thread o -> (sample es, column ec) with the column fastest
   const int es = tid / Hc, ec = tid % Hc;        // valid when tid < S*Hc
   const bool e_on = tid < S * Hc;
 
-  // register double-buffer for the streamed weights of the NEXT phase
+  // streamed weights of the NEXT phase (loaded right after the current phase's FMA loop)
   float4 wa[GemmCfg<2 * Hc, 2 * DH>::MAXI];      // widest: GRU gates, K=512
   float4 wb[GemmCfg<Hc, K1MAX>::MAXI];           // Hc-wide matrices (K <= 384)
   float4 wo[GemmCfg<McO, DH>::MAXI];
   float4 w2[GemmCfg<Pc, DH>::MAXI];
 
-  __syncthreads();
   gemm_load<Hc, K1MAX>(W1, K1, wb);
-  cluster_sync_all();   // every CTA has zeroed its buffers before anyone pushes
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();   // buffers zeroed and mbarriers initialised everywhere before anyone pushes
 
+  const bool free_run = a.targets == nullptr;
   for (int t = 0; t < a.steps; ++t) {
+    const uint32_t par = (uint32_t)t & 1u;
+    if (free_run && t > 0) mbar_wait(mb + B_P13, par ^ 1u);   // fed-back frame of step t-1 has landed
+    if (tid == 0) {   // post this step's expected byte counts (remote credits may already have arrived)
+      mbar_expect_tx(mb + B_P1, BLK);
+      mbar_expect_tx(mb + B_P2, CS * Pc * S * 4);
+      mbar_expect_tx(mb + B_P3, BLK);
+      mbar_expect_tx(mb + B_P4, BLK);
+      mbar_expect_tx(mb + B_P5, BLK);
+      mbar_expect_tx(mb + B_P6, (uint32_t)T_in * S * 4);
+      mbar_expect_tx(mb + B_P7, BLK);
+      mbar_expect_tx(mb + B_P8, BLK);
+      mbar_expect_tx(mb + B_P9, BLK);
+      mbar_expect_tx(mb + B_P10, 2 * BLK);
+      mbar_expect_tx(mb + B_P11, BLK);
+      mbar_expect_tx(mb + B_P12, 2 * BLK);
+      if (free_run) mbar_expect_tx(mb + B_P13, (uint32_t)M * S * 4);
+    }
     // ---- teacher forcing: next input = mel_targets[:, (t-1)*r + r-1, :] (helpers.py:48,75) ----
-    if (a.targets != nullptr && t > 0) {
-      for (int i = tid; i < M * S; i += NT) {
-        const int f = i / S, s = i - f * S, n = n0 + s;
-        xin[i] = (n < a.N) ? __ldg(a.targets + ((size_t)n * a.T_tgt + (size_t)(t - 1) * a.r + a.r - 1) * M + f) : 0.f;
+    if (!free_run) {
+      if (t > 0) {
+        for (int i = tid; i < M * S; i += NT) {
+          const int f = i / S, s = i - f * S, n = n0 + s;
+          xin[i] = (n < a.N) ? __ldg(a.targets + ((size_t)n * a.T_tgt + (size_t)(t - 1) * a.r + a.r - 1) * M + f) : 0.f;
+        }
       }
       __syncthreads();
     }
     // ================= P1: decoder prenet dense_1 + ReLU  [frame|ctx] -> 256 =================
     gemm_fma<S, Hc, K1MAX>(wb, K1, xin, red);
-    __syncthreads();
-    if (e_on) stage[ec * S + es] = fmaxf(red_sum<S, Hc>(red, es, ec) + __ldg(w.p1_b + q * Hc + ec), 0.f);
-    __syncthreads();
-    push_block(p1 + q * Hc * S, stage, Hc * S, CS);
-    cluster_arrive();
     gemm_load<Pc, DH>(W2, DH, w2);
-    cluster_wait();
+    __syncthreads();
+    if (e_on) stage[ec * S + es] = fmaxf(red_sum<S, Hc>(red, es, ec) + b_p1[ec], 0.f);
+    __syncthreads();
+    push_block(p1 + q * Hc * S, stage, Hc * S, CS, mb + B_P1);
+    mbar_wait(mb + B_P1, par);
     // ================= P2: prenet dense_2 + ReLU  256 -> 128 =================
     gemm_fma<S, Pc, DH>(w2, DH, p1, red);
+    gemm_load<2 * Hc, 2 * DH>(WgA, DP + DH, wa);
+    gemm_load<Hc, K1MAX>(WcxA, DP, wb);
     __syncthreads();
     if (tid < S * Pc) {
       const int s = tid / Pc, c = tid % Pc;
-      stage[c * S + s] = fmaxf(red_sum<S, Pc>(red, s, c) + __ldg(w.p2_b + q * Pc + c), 0.f);
+      stage[c * S + s] = fmaxf(red_sum<S, Pc>(red, s, c) + b_p2[c], 0.f);
     }
     __syncthreads();
-    push_block(in3 + q * Pc * S, stage, Pc * S, CS);
-    cluster_arrive();
-    gemm_load<2 * Hc, 2 * DH>(WgA, DP + DH, wa);
-    gemm_load<Hc, K1MAX>(WcxA, DP, wb);
-    cluster_wait();
+    push_block(in3 + q * Pc * S, stage, Pc * S, CS, mb + B_P2);
+    mbar_wait(mb + B_P2, par);
     // ================= P3: attention GRU gates + candidate x-part =================
     gemm_fma<S, 2 * Hc, 2 * DH>(wa, DP + DH, in3, red);
     gemm_fma<S, Hc, K1MAX>(wb, DP, in3, redB);
+    gemm_load<Hc, K1MAX>(WchA, DH, wb);
     __syncthreads();
     if (e_on) {
-      const float r = sigmoid_f(red_sum<S, 2 * Hc>(red, es, ec) + __ldg(w.ga_b + q * 2 * Hc + ec));
-      const float u = sigmoid_f(red_sum<S, 2 * Hc>(red, es, Hc + ec) + __ldg(w.ga_b + q * 2 * Hc + Hc + ec));
+      const float r = sigmoid_f(red_sum<S, 2 * Hc>(red, es, ec) + b_ga[ec]);
+      const float u = sigmoid_f(red_sum<S, 2 * Hc>(red, es, Hc + ec) + b_ga[Hc + ec]);
       const float hold = in3[(DP + q * Hc + ec) * S + es];
       stage[ec * S + es] = r * hold;
       locu[tid] = u;
       loccx[tid] = red_sum<S, Hc>(redB, es, ec);
     }
     __syncthreads();
-    push_block(rhA + q * Hc * S, stage, Hc * S, CS);
-    cluster_arrive();
-    gemm_load<Hc, K1MAX>(WchA, DH, wb);
-    cluster_wait();
+    push_block(rhA + q * Hc * S, stage, Hc * S, CS, mb + B_P3);
+    mbar_wait(mb + B_P3, par);
     // ================= P4: attention GRU candidate h-part -> h_att' =================
     gemm_fma<S, Hc, K1MAX>(wb, DH, rhA, red);
+    gemm_load<2 * Hc, 2 * DH>(Wqp, DH, wa);
     __syncthreads();
     if (e_on) {
-      const float c = tanh_f(red_sum<S, Hc>(red, es, ec) + loccx[tid] + __ldg(w.ca_b + q * Hc + ec));
+      const float c = tanh_f(red_sum<S, Hc>(red, es, ec) + loccx[tid] + b_ca[ec]);
       const float u = locu[tid];
       const float hold = in3[(DP + q * Hc + ec) * S + es];
       stage[ec * S + es] = u * hold + (1.0f - u) * c;
     }
     __syncthreads();
-    push_block(in3 + (DP + q * Hc) * S, stage, Hc * S, CS);
-    cluster_arrive();
-    gemm_load<2 * Hc, 2 * DH>(Wqp, DH, wa);
-    cluster_wait();
+    push_block(in3 + (DP + q * Hc) * S, stage, Hc * S, CS, mb + B_P4);
+    mbar_wait(mb + B_P4, par);
     // ================= P5: query layer + h_att' part of the 512->256 projection =================
     gemm_fma<S, 2 * Hc, 2 * DH>(wa, DH, in3 + DP * S, red);
+    gemm_load<Hc, K1MAX>(Wpc, DH, wb);
     __syncthreads();
     if (e_on) {
       stage[es * Hc + ec] = red_sum<S, 2 * Hc>(red, es, ec);          // layout [S][Hc] for pqT
@@ -304,30 +436,34 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
     }
     __syncthreads();
 #pragma unroll
-    for (int s = 0; s < S; ++s) push_block(pqT + s * DH + q * Hc, stage + s * Hc, Hc, CS);
-    cluster_arrive();
-    gemm_load<Hc, K1MAX>(Wpc, DH, wb);
-    cluster_wait();
+    for (int s = 0; s < S; ++s) push_block(pqT + s * DH + q * Hc, stage + s * Hc, Hc, CS, mb + B_P5);
+    mbar_wait(mb + B_P5, par);
     // ================= P6: Bahdanau scores for positions [j0,j1) =================
     {
       const int npairs = S * (j1 - j0);
       for (int pi = warp; pi < npairs; pi += NW) {
         const int jj = pi / S, s = pi - jj * S, n = n0 + s;
         float e = 0.f;
-        if (n < a.N) {
-          const float* krow = a.keys + ((size_t)n * T_in + (j0 + jj)) * DH;
-          const float* prow = pqT + s * DH;
+        const float* prow = pqT + s * DH;
+        if (att_res) {
+          const float* krow = ksl + ((size_t)s * Tj + jj) * DH;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            e = fmaf(vreg[i], tanh_f(__ldg(krow + lane + 32 * i) + prow[lane + 32 * i]), e);
+          for (int i = 0; i < 8; ++i) e = fmaf(vreg[i], tanh_f(krow[lane + 32 * i] + prow[lane + 32 * i]), e);
+        } else if (n < a.N) {
+          const float* krow = a.keys + ((size_t)n * T_in + (j0 + jj)) * DH;
+          float kv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) kv[i] = __ldg(krow + lane + 32 * i);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e = fmaf(vreg[i], tanh_f(kv[i] + prow[lane + 32 * i]), e);
         }
         e = warp_sum(e);
         if (lane == 0) stage[jj * S + s] = e;
       }
     }
     __syncthreads();
-    if (j1 > j0) push_block(sc + j0 * S, stage, (j1 - j0) * S, CS);
-    cluster_sync_all();
+    if (j1 > j0) push_block(sc + j0 * S, stage, (j1 - j0) * S, CS, mb + B_P6);
+    mbar_wait(mb + B_P6, par);
     // ================= P7: softmax over all T_in (no mask) + context slice =================
     if (warp < S) {
       const int s = warp;
@@ -354,12 +490,29 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
     {
       constexpr int JC = NT / (S * Hc);              // j-chunks per (sample, dim)
       const int d = tid % Hc, jc = (tid / Hc) % JC, s = tid / (Hc * JC), n = n0 + s;
-      float acc = 0.f;
-      if (n < a.N) {
+      float acc0 = 0.f, acc1 = 0.f;
+      if (att_res) {
+        const float* mp = msl + (size_t)s * T_in * Hc + d;
+        int j = jc;
+        for (; j + JC < T_in; j += 2 * JC) {
+          acc0 = fmaf(sc[j * S + s], mp[(size_t)j * Hc], acc0);
+          acc1 = fmaf(sc[(j + JC) * S + s], mp[(size_t)(j + JC) * Hc], acc1);
+        }
+        if (j < T_in) acc0 = fmaf(sc[j * S + s], mp[(size_t)j * Hc], acc0);
+      } else if (n < a.N) {
         const float* mp = a.memory + (size_t)n * T_in * DH + q * Hc + d;
-        for (int j = jc; j < T_in; j += JC) acc = fmaf(sc[j * S + s], __ldg(mp + (size_t)j * DH), acc);
+        int j = jc;
+        for (; j + 3 * JC < T_in; j += 4 * JC) {
+          const float m0 = __ldg(mp + (size_t)j * DH), m1 = __ldg(mp + (size_t)(j + JC) * DH);
+          const float m2 = __ldg(mp + (size_t)(j + 2 * JC) * DH), m3 = __ldg(mp + (size_t)(j + 3 * JC) * DH);
+          acc0 = fmaf(sc[j * S + s], m0, acc0);
+          acc1 = fmaf(sc[(j + JC) * S + s], m1, acc1);
+          acc0 = fmaf(sc[(j + 2 * JC) * S + s], m2, acc0);
+          acc1 = fmaf(sc[(j + 3 * JC) * S + s], m3, acc1);
+        }
+        for (; j < T_in; j += JC) acc0 = fmaf(sc[j * S + s], __ldg(mp + (size_t)j * DH), acc0);
       }
-      red[(s * JC + jc) * Hc + d] = acc;
+      red[(s * JC + jc) * Hc + d] = acc0 + acc1;
       __syncthreads();
       if (e_on) {
         float v = 0.f;
@@ -369,38 +522,38 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
       }
     }
     __syncthreads();
-    push_block(xin + (M + q * Hc) * S, stage, Hc * S, CS);
-    cluster_sync_all();
+    push_block(xin + (M + q * Hc) * S, stage, Hc * S, CS, mb + B_P7);
+    mbar_wait(mb + B_P7, par);
     // ================= P8: y0 = [h_att'|ctx] W_p + b  (ctx part; h part from P5) =================
     gemm_fma<S, Hc, K1MAX>(wb, DH, xin + M * S, red);
-    __syncthreads();
-    if (e_on) stage[ec * S + es] = red_sum<S, Hc>(red, es, ec) + locy0h[tid] + __ldg(w.pc_b + q * Hc + ec);
-    __syncthreads();
-    push_block(in9 + q * Hc * S, stage, Hc * S, CS);
-    cluster_arrive();
     gemm_load<2 * Hc, 2 * DH>(Wg1, 2 * DH, wa);
     gemm_load<Hc, K1MAX>(Wcx1, DH, wb);
-    cluster_wait();
+    __syncthreads();
+    if (e_on) stage[ec * S + es] = red_sum<S, Hc>(red, es, ec) + locy0h[tid] + b_pc[ec];
+    __syncthreads();
+    push_block(in9 + q * Hc * S, stage, Hc * S, CS, mb + B_P8);
+    mbar_wait(mb + B_P8, par);
     // ================= P9/P10: residual GRU 1 =================
     gemm_fma<S, 2 * Hc, 2 * DH>(wa, 2 * DH, in9, red);
     gemm_fma<S, Hc, K1MAX>(wb, DH, in9, redB);
+    gemm_load<Hc, K1MAX>(Wch1, DH, wb);
     __syncthreads();
     if (e_on) {
-      const float r = sigmoid_f(red_sum<S, 2 * Hc>(red, es, ec) + __ldg(w.g1_b + q * 2 * Hc + ec));
-      const float u = sigmoid_f(red_sum<S, 2 * Hc>(red, es, Hc + ec) + __ldg(w.g1_b + q * 2 * Hc + Hc + ec));
+      const float r = sigmoid_f(red_sum<S, 2 * Hc>(red, es, ec) + b_g1[ec]);
+      const float u = sigmoid_f(red_sum<S, 2 * Hc>(red, es, Hc + ec) + b_g1[Hc + ec]);
       stage[ec * S + es] = r * in9[(DH + q * Hc + ec) * S + es];
       locu[tid] = u;
       loccx[tid] = red_sum<S, Hc>(redB, es, ec);
     }
     __syncthreads();
-    push_block(rh1 + q * Hc * S, stage, Hc * S, CS);
-    cluster_arrive();
-    gemm_load<Hc, K1MAX>(Wch1, DH, wb);
-    cluster_wait();
+    push_block(rh1 + q * Hc * S, stage, Hc * S, CS, mb + B_P9);
+    mbar_wait(mb + B_P9, par);
     gemm_fma<S, Hc, K1MAX>(wb, DH, rh1, red);
+    gemm_load<2 * Hc, 2 * DH>(Wg2, 2 * DH, wa);
+    gemm_load<Hc, K1MAX>(Wcx2, DH, wb);
     __syncthreads();
     if (e_on) {
-      const float c = tanh_f(red_sum<S, Hc>(red, es, ec) + loccx[tid] + __ldg(w.c1_b + q * Hc + ec));
+      const float c = tanh_f(red_sum<S, Hc>(red, es, ec) + loccx[tid] + b_c1[ec]);
       const float u = locu[tid];
       const float hold = in9[(DH + q * Hc + ec) * S + es];
       const float hn = u * hold + (1.0f - u) * c;
@@ -408,32 +561,30 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
       stage2[ec * S + es] = in9[(q * Hc + ec) * S + es] + hn;     // y1 = y0 + GRU1(y0)  (ResidualWrapper)
     }
     __syncthreads();
-    push_block(in9 + (DH + q * Hc) * S, stage, Hc * S, CS);
-    push_block(in11 + q * Hc * S, stage2, Hc * S, CS);
-    cluster_arrive();
-    gemm_load<2 * Hc, 2 * DH>(Wg2, 2 * DH, wa);
-    gemm_load<Hc, K1MAX>(Wcx2, DH, wb);
-    cluster_wait();
+    push_block(in9 + (DH + q * Hc) * S, stage, Hc * S, CS, mb + B_P10);
+    push_block(in11 + q * Hc * S, stage2, Hc * S, CS, mb + B_P10);
+    mbar_wait(mb + B_P10, par);
     // ================= P11/P12: residual GRU 2 =================
     gemm_fma<S, 2 * Hc, 2 * DH>(wa, 2 * DH, in11, red);
     gemm_fma<S, Hc, K1MAX>(wb, DH, in11, redB);
+    gemm_load<Hc, K1MAX>(Wch2, DH, wb);
     __syncthreads();
     if (e_on) {
-      const float r = sigmoid_f(red_sum<S, 2 * Hc>(red, es, ec) + __ldg(w.g2_b + q * 2 * Hc + ec));
-      const float u = sigmoid_f(red_sum<S, 2 * Hc>(red, es, Hc + ec) + __ldg(w.g2_b + q * 2 * Hc + Hc + ec));
+      const float r = sigmoid_f(red_sum<S, 2 * Hc>(red, es, ec) + b_g2[ec]);
+      const float u = sigmoid_f(red_sum<S, 2 * Hc>(red, es, Hc + ec) + b_g2[Hc + ec]);
       stage[ec * S + es] = r * in11[(DH + q * Hc + ec) * S + es];
       locu[tid] = u;
       loccx[tid] = red_sum<S, Hc>(redB, es, ec);
     }
     __syncthreads();
-    push_block(rh2 + q * Hc * S, stage, Hc * S, CS);
-    cluster_arrive();
-    gemm_load<Hc, K1MAX>(Wch2, DH, wb);
-    cluster_wait();
+    push_block(rh2 + q * Hc * S, stage, Hc * S, CS, mb + B_P11);
+    mbar_wait(mb + B_P11, par);
     gemm_fma<S, Hc, K1MAX>(wb, DH, rh2, red);
+    gemm_load<McO, DH>(Wo, DH, wo);
+    gemm_load<Hc, K1MAX>(W1, K1, wb);
     __syncthreads();
     if (e_on) {
-      const float c = tanh_f(red_sum<S, Hc>(red, es, ec) + loccx[tid] + __ldg(w.c2_b + q * Hc + ec));
+      const float c = tanh_f(red_sum<S, Hc>(red, es, ec) + loccx[tid] + b_c2[ec]);
       const float u = locu[tid];
       const float hold = in11[(DH + q * Hc + ec) * S + es];
       const float hn = u * hold + (1.0f - u) * c;
@@ -441,11 +592,9 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
       stage2[ec * S + es] = in11[(q * Hc + ec) * S + es] + hn;    // y2 = y1 + GRU2(y1)
     }
     __syncthreads();
-    push_block(in11 + (DH + q * Hc) * S, stage, Hc * S, CS);
-    push_block(y2 + q * Hc * S, stage2, Hc * S, CS);
-    cluster_arrive();
-    gemm_load<McO, DH>(Wo, DH, wo);
-    cluster_wait();
+    push_block(in11 + (DH + q * Hc) * S, stage, Hc * S, CS, mb + B_P12);
+    push_block(y2 + q * Hc * S, stage2, Hc * S, CS, mb + B_P12);
+    mbar_wait(mb + B_P12, par);
     // ================= P13: output projection 256 -> 80*r, write frames, feed back =================
     gemm_fma<S, McO, DH>(wo, DH, y2, red);
     __syncthreads();
@@ -454,22 +603,22 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
     if (tid < S * McO) {
       const int s = tid / McO, c = tid % McO, col = q * McO + c, n = n0 + s;
       if (col < Dout) {
-        const float v = red_sum<S, McO>(red, s, c) + __ldg(w.o_b + col);
+        const float v = red_sum<S, McO>(red, s, c) + b_o[c];
         if (n < a.N) a.dec_out[((size_t)n * a.max_steps + t) * Dout + col] = v;
         if (col >= fb0) stage[(col - c_lo) * S + s] = v;
       }
     }
     __syncthreads();
-    if (a.targets == nullptr && c_hi > c_lo) push_block(xin + (c_lo - fb0) * S, stage, (c_hi - c_lo) * S, CS);
-    cluster_arrive();
-    gemm_load<Hc, K1MAX>(W1, K1, wb);
-    cluster_wait();
+    if (free_run && c_hi > c_lo) push_block(xin + (c_lo - fb0) * S, stage, (c_hi - c_lo) * S, CS, mb + B_P13);
   }
+  // nobody may exit while a peer can still write into its shared memory
+  if (free_run && a.steps > 0) mbar_wait(mb + B_P13, (uint32_t)(a.steps - 1) & 1u);
+  cluster_sync_all();
 }
 
 template <int S, int CS>
 cudaError_t launch_decoder_t(const DecoderWeights& w, const DecoderArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)make_layout(S, a.T_in, w.M, CS).total * sizeof(float);
+  const size_t smem = (size_t)make_layout(S, a.T_in, w.M, CS, a.att_res != 0).total * sizeof(float);
   auto kern = decoder_kernel<S, CS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -507,7 +656,7 @@ cudaError_t launch_decoder_cs(const DecoderWeights& w, const DecoderArgs& a, int
 template <int CS>
 int max_active_clusters() {
   auto kern = decoder_kernel<1, CS>;
-  const size_t smem = (size_t)make_layout(1, 128, 80, CS).total * sizeof(float);
+  const size_t smem = (size_t)make_layout(1, 128, 80, CS, false).total * sizeof(float);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     cudaGetLastError();
     return 0;
@@ -537,8 +686,8 @@ int max_active_clusters() {
 
 }  // namespace
 
-size_t decoder_smem_bytes(int S, int T_in, int CS) {
-  return (size_t)make_layout(S, T_in, 80, CS).total * sizeof(float);
+size_t decoder_smem_bytes(int S, int T_in, int M, int CS, bool att_res) {
+  return (size_t)make_layout(S, T_in, M, CS, att_res).total * sizeof(float);
 }
 
 int decoder_pick_cluster_size() {
@@ -548,8 +697,14 @@ int decoder_pick_cluster_size() {
 
 int decoder_max_clusters(int CS) { return CS == 16 ? max_active_clusters<16>() : max_active_clusters<8>(); }
 
-cudaError_t launch_decoder(const DecoderWeights& w, const DecoderArgs& a, int S, cudaStream_t st) {
-  if (a.N <= 0 || a.steps <= 0) return cudaSuccess;
+cudaError_t launch_decoder(const DecoderWeights& w, const DecoderArgs& a_in, int S, cudaStream_t st) {
+  if (a_in.N <= 0 || a_in.steps <= 0) return cudaSuccess;
+  DecoderArgs a = a_in;
+  // keep this CTA's keys rows / memory columns in shared memory when they fit next to the activations
+  const char* env = getenv("TACO_DEC_ATT_RES");
+  a.att_res = decoder_smem_bytes(S, a.T_in, w.M, w.CS, true) <= 227 * 1024 ? 1 : 0;
+  if (env) a.att_res = a.att_res && atoi(env) != 0;
+  if (decoder_smem_bytes(S, a.T_in, w.M, w.CS, a.att_res != 0) > 227 * 1024) return cudaErrorInvalidValue;
   if (w.CS == 16) return launch_decoder_cs<16>(w, a, S, st);
   if (w.CS == 8) return launch_decoder_cs<8>(w, a, S, st);
   return cudaErrorInvalidValue;

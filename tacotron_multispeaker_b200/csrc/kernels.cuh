@@ -75,6 +75,7 @@ struct DecoderArgs {
   const float* keys;     // [N,T_in,256] = memory * W_mem
   const float* targets;  // [N,T_tgt,M] or null (free running)
   int N, T_in, T_tgt, r, steps, max_steps;
+  int att_res;           // keys/memory slices resident in shared memory (set by launch_decoder)
   float* dec_out;        // [N,max_steps,Dout]
   float* align_out;      // [N,T_in,max_steps] or null
 };
@@ -82,6 +83,7 @@ struct DecoderArgs {
 cudaError_t launch_decoder(const DecoderWeights& w, const DecoderArgs& a, int S, cudaStream_t st);
 // Largest cluster size (16 or 8) the device can co-schedule for the decoder kernel.
 int decoder_pick_cluster_size();
-size_t decoder_smem_bytes(int S, int T_in, int CS);
+size_t decoder_smem_bytes(int S, int T_in, int M, int CS, bool att_res);
+int decoder_max_clusters(int CS);
 
 }  // namespace taco

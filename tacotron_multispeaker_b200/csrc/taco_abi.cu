@@ -15,9 +15,6 @@
 #include "../../include/taco_b200.h"
 #include "kernels.cuh"
 
-namespace taco {
-int decoder_max_clusters(int CS);
-}
 using namespace taco;
 
 namespace {
@@ -81,8 +78,8 @@ struct taco_handle {
   int* h_pinned = nullptr;    // [0]=oob, [1]=steps
   int64_t launches = 0;
   bool profiling = false;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  float stage_ms[3] = {0, 0, 0};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [4],[5] bracket the decoder kernel
+  float stage_ms[4] = {0, 0, 0, 0};
 };
 
 namespace {
@@ -578,9 +575,11 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
   DecoderArgs a;
   a.memory = memory; a.keys = keys; a.targets = teacher_force ? mel_targets : nullptr;
   a.N = N; a.T_in = T_in; a.T_tgt = T_tgt; a.r = hp.outputs_per_step; a.steps = max_steps; a.max_steps = max_steps;
-  a.dec_out = dec_out; a.align_out = align_out;
+  a.dec_out = dec_out; a.align_out = align_out; a.att_res = 0;
   const int S = pick_S(h, N);
+  if (h->profiling) cudaEventRecord(h->ev[4], st);
   cudaError_t e = launch_decoder(h->dec, a, S, st);
+  if (h->profiling) cudaEventRecord(h->ev[5], st);
   if (e != cudaSuccess) return fail(h, TACO_ERR_CUDA, std::string("decoder launch: ") + cudaGetErrorString(e));
   h->launches += 1;
   int steps = max_steps;
@@ -641,7 +640,7 @@ int taco_create(const taco_hparams* hp, int device, taco_handle** out) {
   h->names = expected_names(*hp);
   h->emb_dim = hp->embedding_text_channels + (hp->id_num > 1 ? hp->embedding_id_channels : 0);
   if (cudaMallocHost(&h->h_pinned, sizeof(int) * 4) != cudaSuccess) { delete h; return TACO_ERR_CUDA; }
-  for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+  for (int i = 0; i < 6; ++i) cudaEventCreate(&h->ev[i]);
   if (ensure_ints(h, 2 + 1024) != TACO_OK) { taco_destroy(h); return TACO_ERR_CUDA; }
   *out = h;
   return TACO_OK;
@@ -655,7 +654,7 @@ int taco_destroy(taco_handle* h) {
   if (h->ws) cudaFree(h->ws);
   if (h->d_ints) cudaFree(h->d_ints);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
-  for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
   return TACO_OK;
 }
@@ -913,6 +912,7 @@ int taco_forward(taco_handle* h, const int32_t* ids, const int32_t* lengths, con
     cudaEventRecord(h->ev[3], st);
     cudaEventSynchronize(h->ev[3]);
     for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&h->stage_ms[i], h->ev[i], h->ev[i + 1]);
+    cudaEventElapsedTime(&h->stage_ms[3], h->ev[4], h->ev[5]);
   }
   return TACO_OK;
 }
@@ -984,9 +984,9 @@ int taco_set_profiling(taco_handle* h, int on) {
   h->profiling = on != 0;
   return TACO_OK;
 }
-int taco_last_stage_ms(const taco_handle* h, float* ms3_host) {
-  if (!h || !ms3_host) return TACO_ERR_INVALID;
-  for (int i = 0; i < 3; ++i) ms3_host[i] = h->stage_ms[i];
+int taco_last_stage_ms(const taco_handle* h, float* ms4_host) {
+  if (!h || !ms4_host) return TACO_ERR_INVALID;
+  for (int i = 0; i < 4; ++i) ms4_host[i] = h->stage_ms[i];
   return TACO_OK;
 }
 

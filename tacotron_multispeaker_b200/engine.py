@@ -107,9 +107,9 @@ class Engine:
         self._ck(self.lib.taco_set_profiling(self._h, int(on)))
 
     def last_stage_ms(self):
-        buf = (C.c_float * 3)()
+        buf = (C.c_float * 4)()
         self._ck(self.lib.taco_last_stage_ms(self._h, buf))
-        return dict(encoder=buf[0], decoder=buf[1], postnet=buf[2])
+        return dict(encoder=buf[0], decoder=buf[1], postnet=buf[2], decoder_kernel=buf[3])
 
     def check_ids(self):
         self._ck(self.lib.taco_check_ids(self._h, self.stream))
