@@ -146,6 +146,14 @@ int taco_bigru(taco_handle* h, int which, const float* x, const int32_t* lengths
 int taco_conv1d(taco_handle* h, const float* x, int N, int T, int Cin, const float* kernel,
                 const float* bias, int k, int Cout, int act, float* out, void* stream);
 
+/* ---- arithmetic mode of the dense layers ----------------------------------- */
+/* The reference computes in fp32.  0 = fp32 FFMA kernels; 1 (default) = tcgen05 tensor
+ * cores with every operand split into bf16 hi+lo and three products per k-step
+ * (fp32-class accuracy, meets the 1e-3 parity bound); 2 = plain bf16 tensor cores
+ * (looser, separately stated tolerance).  Recurrent kernels always run in fp32. */
+enum { TACO_GEMM_FFMA = 0, TACO_GEMM_BF16X3 = 1, TACO_GEMM_BF16 = 2 };
+int taco_set_gemm_mode(taco_handle* h, int mode);
+
 /* ---- introspection for bench / tests ------------------------------------- */
 /* Kernel launches issued by this handle since creation. */
 int64_t taco_launch_count(const taco_handle* h);

@@ -23,6 +23,7 @@ TACO_ERR_UNSUPPORTED = -6
 BN_MOVING, BN_BATCH = 0, 1
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
 CBHG_ENCODER, CBHG_POST = 0, 1
+GEMM_FFMA, GEMM_BF16X3, GEMM_BF16 = 0, 1, 2
 
 # Every symbol include/taco_b200.h declares (tests check the library exports all of them).
 SYMBOLS = [
@@ -31,7 +32,7 @@ SYMBOLS = [
     "taco_max_steps", "taco_forward", "taco_forward_host",
     "taco_embed", "taco_check_ids", "taco_encoder", "taco_decode", "taco_cbhg", "taco_postnet",
     "taco_bigru", "taco_conv1d",
-    "taco_launch_count", "taco_decoder_geometry", "taco_set_profiling", "taco_last_stage_ms",
+    "taco_set_gemm_mode", "taco_launch_count", "taco_decoder_geometry", "taco_set_profiling", "taco_last_stage_ms",
 ]
 
 
@@ -86,6 +87,7 @@ def load() -> C.CDLL:
     lib.taco_postnet.argtypes = [H, fp, i, i, i, i64, fp, i64, vp]
     lib.taco_bigru.argtypes = [H, i, fp, ip, i, i, fp, vp]
     lib.taco_conv1d.argtypes = [H, fp, i, i, i, fp, fp, i, i, i, fp, vp]
+    lib.taco_set_gemm_mode.argtypes = [H, i]
     lib.taco_launch_count.argtypes = [H]
     lib.taco_launch_count.restype = i64
     lib.taco_decoder_geometry.argtypes = [H, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]

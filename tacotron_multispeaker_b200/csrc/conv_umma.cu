@@ -1,0 +1,385 @@
+// conv1d('same') / dense as a TMA-fed tcgen05 implicit GEMM (sm_100a).
+//
+// Same operator as conv_gemm.cu (reference models/modules.py:93-101, :10,
+// :59-60, :79-89, models/tacotron.py:68,101) on the 5th-generation tensor
+// cores.  D[128 rows (n, t0..t0+127)] x [128 output channels] accumulates in
+// TMEM (fp32) over k-blocks of 64 input channels per filter tap:
+//
+//   A tile  = activations x[n, t0 + j - pad_left + (0..127), c0..c0+63]  (bf16)
+//             one 3-D TMA box per (tap j, channel block); rows outside [0,T)
+//             are zero-filled by the TMA unit -- that IS the 'same' padding,
+//             so no im2col buffer and no boundary code.
+//   B tile  = W^T[out channel o0..o0+127][j*Cp + c0 .. +63]  (bf16, K-major)
+//
+// fp32 parity: the reference computes in fp32, so each operand is split into
+// bf16 hi + bf16 lo (x = hi + lo to ~2^-17) and every k-step issues the three
+// products hi*hi + hi*lo + lo*hi into the same fp32 TMEM accumulator (the
+// dropped lo*lo term is ~2^-18 relative).  NSPLIT=1 is the plain bf16 mode.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one
+// elected thread), warps 2..5 = epilogue (TMEM -> registers -> smem transpose
+// -> coalesced global stores, with bias / activation / folded BN / residual /
+// highway gate).  3-stage smem ring (64 KB per stage) with full/empty
+// mbarriers; tcgen05.commit releases stages and signals the epilogue.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace taco {
+
+namespace {
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3, NTHREADS = 192;
+constexpr uint32_t TILE_BYTES = BM * BK * 2;            // 16 KB: one bf16 operand tile (A or B)
+constexpr uint32_t STAGE_BYTES = 4 * TILE_BYTES;        // A_hi | A_lo | B_hi | B_lo
+constexpr uint32_t EPI_BYTES = 4 * 32 * 33 * 4;         // per-warp 32x33 fp32 transpose staging
+constexpr uint32_t SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + 256;
+
+struct UmmaArgs {
+  int N, T, Cp;            // activation rows / padded channels (Cp % 64 == 0)
+  int taps, bank;          // bank > 1: conv index ci = bank-1-blockIdx.z has ci+1 taps
+  int Cout;                // output channels per conv
+  const float* bias; const float* scale; const float* shift;
+  const float* res; long long res_bs; int ldres;
+  float* out; long long out_bs; int ldo; int col_off;
+  int act, epi;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t mb, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mb, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mb, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(mb), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t mb, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(mb), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t mb, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(mb), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, issued by ONE thread.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mb) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb) : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows are 128 B apart, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                 const UmmaArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* epi = reinterpret_cast<float*>(smem_al + STAGES * STAGE_BYTES);
+  const uint32_t bar0 = smem_base + STAGES * STAGE_BYTES + EPI_BYTES;    // full[S], empty[S], tmem_full, tmem ptr
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  const uint32_t tfull_bar = bar0 + 8u * (2 * STAGES);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + STAGES * STAGE_BYTES + EPI_BYTES + 8 * (2 * STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tps = (p.T + BM - 1) / BM;
+  const int n = blockIdx.x / tps, t0 = (blockIdx.x - n * tps) * BM;
+  const int o0 = blockIdx.y * BN;
+  const int ci = p.bank > 1 ? p.bank - 1 - (int)blockIdx.z : 0;          // heavy convs first
+  const int taps = p.bank > 1 ? ci + 1 : p.taps;
+  const int pl = (taps - 1) >> 1;
+  const int kcb = p.Cp / BK, nkb = taps * kcb;
+  const int brow0 = ci * p.Cout + o0;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB_hi)) : "memory");
+    if (NSPLIT > 1) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA_lo)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB_lo)) : "memory");
+    }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {   // TMEM: 128 fp32 accumulator columns, allocated (and later freed) by this warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(empty_bar(s), ((kb / STAGES) & 1) ^ 1);
+        const uint32_t st = smem_base + s * STAGE_BYTES;
+        mbar_expect_tx(full_bar(s), NSPLIT > 1 ? STAGE_BYTES : 2 * TILE_BYTES);
+        const int j = kb / kcb, c0 = (kb - j * kcb) * BK;
+        const int tt = t0 + j - pl;                                       // may be < 0 or run past T: zero fill
+        tma_load_3d(st, &tmA_hi, full_bar(s), c0, tt, n);
+        tma_load_2d(st + 2 * TILE_BYTES, &tmB_hi, full_bar(s), j * p.Cp + c0, brow0);
+        if (NSPLIT > 1) {
+          tma_load_3d(st + TILE_BYTES, &tmA_lo, full_bar(s), c0, tt, n);
+          tma_load_2d(st + 3 * TILE_BYTES, &tmB_lo, full_bar(s), j * p.Cp + c0, brow0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // kind::f16: C=F32 (bit4), A=BF16 (bit7), B=BF16 (bit10), both K-major, N>>3 at bit17, M>>4 at bit24
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(full_bar(s), (kb / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t st = smem_base + s * STAGE_BYTES;
+        const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + TILE_BYTES);
+        const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES), b_lo = umma_desc(st + 3 * TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          const uint64_t adv = (uint64_t)(kk * 32 >> 4);                  // 16 bf16 = 32 B along K inside the swizzle row
+          umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | kk) != 0);
+          if (NSPLIT > 1) {
+            umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
+          }
+        }
+        umma_commit(empty_bar(s));                                        // stage free once these MMAs have read it
+      }
+      umma_commit(tfull_bar);                                             // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;                                         // TMEM lanes this warp may read
+    float* stg = epi + (warp - 2) * 32 * 33;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const float* bias = p.bias ? p.bias + ci * p.Cout : nullptr;
+    const float* scale = p.scale ? p.scale + ci * p.Cout : nullptr;
+    const float* shift = p.shift ? p.shift + ci * p.Cout : nullptr;
+    const int col_off = p.col_off + ci * p.Cout;
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      const int cbase = o0 + ch * 32;
+      if (cbase >= p.Cout) break;                                         // warp-uniform
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), v);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = __uint_as_float(v[c]);
+      __syncwarp();
+      const int col = cbase + lane;
+      const bool cok = col < p.Cout;
+      float b = 0.f, sc = 1.f, sh = 0.f;
+      if (cok) {
+        if (bias) b = __ldg(bias + col);
+        if (scale) { sc = __ldg(scale + col); sh = __ldg(shift + col); }
+      }
+      for (int r = 0; r < 32; ++r) {
+        const int t = t0 + quarter * 32 + r;
+        if (t >= p.T) break;                                              // warp-uniform
+        float x = stg[r * 33 + lane] + b;
+        if (p.epi == EPI_PLAIN) {
+          x = apply_act(x, p.act);
+          if (scale) x = fmaf(x, sc, sh);
+          if (cok) {
+            if (p.res) x += __ldg(p.res + (long long)n * p.res_bs + (long long)t * p.ldres + col);
+            p.out[(long long)n * p.out_bs + (long long)t * p.ldo + col_off + col] = x;
+          }
+        } else {   // EPI_HIGHWAY: even lane = H_c, odd lane = T_c of channel c = col/2
+          const float tg = __shfl_down_sync(0xffffffffu, x, 1);
+          if (cok && !(lane & 1)) {
+            const int chn = col >> 1;
+            const float H = fmaxf(x, 0.f), Tg = sigmoid_f(tg);
+            const float xin = __ldg(p.res + (long long)n * p.res_bs + (long long)t * p.ldres + chn);
+            p.out[(long long)n * p.out_bs + (long long)t * p.ldo + col_off + chn] = H * Tg + xin * (1.0f - Tg);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
+// fp32 -> bf16 hi + bf16 lo (x ~= hi + lo), channels zero-padded to Cp.
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ x, long long x_bs, int ldx, int N, int T, int C, int Cp,
+                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int Cq = Cp >> 2;
+  const long long total = (long long)N * T * Cq;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % Cq);
+    const long long row = i / Cq;
+    const int t = (int)(row % T), n = (int)(row / T);
+    const int c = q * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c + 3 < C) v = ldg_f4(x + n * x_bs + (long long)t * ldx + c);
+    else if (c < C) {
+      const float* px = x + n * x_bs + (long long)t * ldx;
+      v.x = px[c];
+      if (c + 1 < C) v.y = px[c + 1];
+      if (c + 2 < C) v.z = px[c + 2];
+    }
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
+    const __nv_bfloat16 l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
+    __nv_bfloat162 hA, hB, lA, lB;
+    hA.x = h0; hA.y = h1; hB.x = h2; hB.y = h3; lA.x = l0; lA.y = l1; lB.x = l2; lB.y = l3;
+    uint2 ph, plo;
+    ph.x = *reinterpret_cast<uint32_t*>(&hA); ph.y = *reinterpret_cast<uint32_t*>(&hB);
+    plo.x = *reinterpret_cast<uint32_t*>(&lA); plo.y = *reinterpret_cast<uint32_t*>(&lB);
+    reinterpret_cast<uint2*>(hi)[i] = ph;
+    reinterpret_cast<uint2*>(lo)[i] = plo;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pack_wt_kernel(const float* __restrict__ w, int ldw, int taps, int Cin, int Cout, int Cp, int Kld, int row0,
+               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const long long total = (long long)Cout * taps * Cp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    const int j = (int)((i / Cp) % taps);
+    const int o = (int)(i / ((long long)Cp * taps));
+    const float v = c < Cin ? __ldg(w + (long long)(j * Cin + c) * ldw + o) : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const long long dst = (long long)(row0 + o) * Kld + (long long)j * Cp + c;
+    hi[dst] = h;
+    lo[dst] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// ---- host: tensor maps ------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  return fn;
+}
+bool make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+              const cuuint32_t* box) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint32_t es[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
+
+void launch_split_bf16(const float* x, int64_t x_bs, int ldx, int N, int T, int C, int Cp, void* hi, void* lo,
+                       cudaStream_t st) {
+  const long long total = (long long)N * T * (Cp / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  split_bf16_kernel<<<blocks, 256, 0, st>>>(x, x_bs, ldx, N, T, C, Cp, reinterpret_cast<__nv_bfloat16*>(hi),
+                                            reinterpret_cast<__nv_bfloat16*>(lo));
+}
+
+void launch_pack_wt(const float* w, int ldw, int taps, int Cin, int Cout, int Cp, int Kld, int row0, void* hi,
+                    void* lo, cudaStream_t st) {
+  const long long total = (long long)Cout * taps * Cp;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  pack_wt_kernel<<<blocks, 256, 0, st>>>(w, ldw, taps, Cin, Cout, Cp, Kld, row0, reinterpret_cast<__nv_bfloat16*>(hi),
+                                         reinterpret_cast<__nv_bfloat16*>(lo));
+}
+
+cudaError_t launch_conv_umma(const ConvUmma& c, cudaStream_t st) {
+  if (c.N <= 0 || c.T <= 0) return cudaSuccess;
+  if (c.Cp % BK || c.Kld % BK) return cudaErrorInvalidValue;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  const cuuint64_t adims[3] = {(cuuint64_t)c.Cp, (cuuint64_t)c.T, (cuuint64_t)c.N};
+  const cuuint64_t astr[2] = {(cuuint64_t)c.Cp * 2, (cuuint64_t)c.T * c.Cp * 2};
+  const cuuint32_t abox[3] = {BK, BM, 1};
+  const cuuint64_t bdims[2] = {(cuuint64_t)c.Kld, (cuuint64_t)c.b_rows};
+  const cuuint64_t bstr[1] = {(cuuint64_t)c.Kld * 2};
+  const cuuint32_t bbox[2] = {BK, BN};
+  const bool split = c.nsplit > 1;
+  if (!make_map(&ma_hi, c.a_hi, 3, adims, astr, abox) || !make_map(&mb_hi, c.b_hi, 2, bdims, bstr, bbox) ||
+      !make_map(&ma_lo, split ? c.a_lo : c.a_hi, 3, adims, astr, abox) ||
+      !make_map(&mb_lo, split ? c.b_lo : c.b_hi, 2, bdims, bstr, bbox))
+    return cudaErrorInvalidValue;
+  UmmaArgs p;
+  p.N = c.N; p.T = c.T; p.Cp = c.Cp; p.taps = c.taps; p.bank = c.bank; p.Cout = c.Cout;
+  p.bias = c.bias; p.scale = c.scale; p.shift = c.shift; p.res = c.res; p.res_bs = c.res_bs; p.ldres = c.ldres;
+  p.out = c.out; p.out_bs = c.out_bs; p.ldo = c.ldo; p.col_off = c.col_off; p.act = c.act; p.epi = c.epi;
+  dim3 grid(c.N * ((c.T + BM - 1) / BM), (c.Cout + BN - 1) / BN, c.bank > 1 ? c.bank : 1);
+  cudaError_t e;
+  if (split) {
+    e = cudaFuncSetAttribute(conv_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    conv_umma_kernel<3><<<grid, NTHREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  } else {
+    e = cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    conv_umma_kernel<1><<<grid, NTHREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace taco

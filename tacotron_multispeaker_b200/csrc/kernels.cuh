@@ -29,6 +29,31 @@ struct ConvGemm {
 };
 void launch_conv_gemm(const ConvGemm& p, cudaStream_t st);
 
+// ---- conv1d-as-GEMM on tcgen05 tensor cores (conv_umma.cu) -------------------
+// Same operator as ConvGemm with bf16 operands staged by TMA (fp32 accumulate in TMEM).
+// a_hi/a_lo: activations split into bf16 hi+lo, dense [N][T][Cp] (Cp % 64 == 0, zero padded);
+// b_hi/b_lo: W^T split likewise, [b_rows][Kld] with Kld = taps*Cp (K contiguous).
+// nsplit = 3: hi*hi + hi*lo + lo*hi (fp32-class accuracy); nsplit = 1: plain bf16 (lo unused).
+// bank > 1: `bank` convolutions of Cout channels each in one launch (grid.z); conv ci has ci+1
+// taps, weight rows [ci*Cout, (ci+1)*Cout), bias/scale/shift offset ci*Cout, output column
+// offset col_off + ci*Cout  (the CBHG conv bank, reference modules.py:39-42).
+struct ConvUmma {
+  const void* a_hi; const void* a_lo; int N, T, Cp;
+  const void* b_hi; const void* b_lo; int b_rows, Kld;
+  int taps, bank, Cout, nsplit;
+  const float* bias; const float* scale; const float* shift;
+  const float* res; int64_t res_bs; int ldres;
+  float* out; int64_t out_bs; int ldo; int col_off;
+  int act, epi;
+};
+cudaError_t launch_conv_umma(const ConvUmma& c, cudaStream_t st);
+// x [N,T,C] fp32 (batch stride x_bs, row stride ldx) -> hi/lo bf16 [N][T][Cp], zero padded channels.
+void launch_split_bf16(const float* x, int64_t x_bs, int ldx, int N, int T, int C, int Cp, void* hi, void* lo,
+                       cudaStream_t st);
+// w fp32 [taps*Cin][ldw] -> W^T hi/lo bf16 rows [row0, row0+Cout) of a [*, Kld] matrix, tap j at columns j*Cp.
+void launch_pack_wt(const float* w, int ldw, int taps, int Cin, int Cout, int Cp, int Kld, int row0, void* hi,
+                    void* lo, cudaStream_t st);
+
 // ---- elementwise / statistics (elementwise.cu) -----------------------------
 // Per-channel batch statistics over all (n,t) rows -> scale/shift of
 // tf.layers.batch_normalization(training=True): biased variance, eps.

@@ -34,6 +34,22 @@ struct HostVar {
   bool set = false;
 };
 
+// One GEMM-shaped weight: fp32 [taps*Cin][ldw] for the FFMA path and W^T split into bf16 hi/lo
+// ([b_rows][Kld], K contiguous) for the tcgen05 path.
+struct GemmW {
+  size_t w = 0; int ldw = 0;
+  size_t bt = 0;                       // bf16 element offset of the hi matrix (lo follows at + b_rows*Kld)
+  int taps = 1, Cin = 0, Cout = 0, Cp = 0, Kld = 0, b_rows = 0, bank = 1;
+};
+GemmW make_gemmw(size_t w, int ldw, int taps, int Cin, int Cout, int bank = 1) {
+  GemmW g;
+  g.w = w; g.ldw = ldw; g.taps = taps; g.Cin = Cin; g.Cout = Cout; g.bank = bank;
+  g.Cp = (Cin + 63) & ~63;
+  g.Kld = taps * g.Cp;
+  g.b_rows = bank > 1 ? bank * Cout : Cout;
+  return g;
+}
+
 struct CbhgDev {   // offsets (floats) into the device weight arena
   int K = 0, Cin = 0, P1 = 0, P2 = 0;
   std::vector<size_t> bank_w, bank_b;
@@ -43,6 +59,8 @@ struct CbhgDev {   // offsets (floats) into the device weight arena
   size_t dense_w = 0, dense_b = 0;
   size_t hw_w[4] = {0, 0, 0, 0}, hw_b[4] = {0, 0, 0, 0};
   size_t gru_wx = 0, gru_bx = 0, gru_ug = 0, gru_uc = 0;
+  size_t bank_bias = 0;                // biases of the K bank convolutions back to back
+  GemmW g_bank, g_p1, g_p2, g_dense, g_hw[4], g_xproj;
 };
 
 struct Arena {   // host staging of the packed weights
@@ -67,6 +85,9 @@ struct taco_handle {
   float* dW = nullptr;
   size_t emb = 0, emb_id = 0, pre1_w = 0, pre1_b = 0, pre2_w = 0, pre2_b = 0, mem_w = 0, lin_w = 0, lin_b = 0;
   int lin_ld = 0, emb_dim = 0;
+  GemmW g_pre1, g_pre2, g_mem, g_lin;
+  uint16_t* dB = nullptr;              // bf16 arena: W^T hi/lo for the tensor-core path
+  int gemm_mode = 1;                   // 0 = fp32 FFMA, 1 = bf16x3 tcgen05 (fp32-class), 2 = bf16 tcgen05
   CbhgDev enc, post;
   DecoderWeights dec;
   int CS = 16, max_clusters = 8;
@@ -217,6 +238,7 @@ bool pack_cbhg(taco_handle* h, Arena& A, const std::string& s, int K, int Cin, i
   const int BC = K * 128;
   D.bank_scale = A.alloc(BC); D.bank_shift = A.alloc(BC); D.bank_gamma = A.alloc(BC); D.bank_beta = A.alloc(BC);
   D.bank_w.resize(K); D.bank_b.resize(K);
+  D.bank_bias = A.alloc(BC);
   for (int k = 1; k <= K; ++k) {
     const std::string sc = s + "/conv_bank/conv1d_" + std::to_string(k);
     GETV(w, sc + "/conv1d/kernel", k, Cin, 128);
@@ -224,6 +246,7 @@ bool pack_cbhg(taco_handle* h, Arena& A, const std::string& s, int K, int Cin, i
     D.bank_w[k - 1] = put_matrix(A, w->data.data(), k * Cin, 128, 128);
     D.bank_b[k - 1] = put_vec(A, b->data.data(), 128);
     const int o = (k - 1) * 128;
+    memcpy(&A.buf[D.bank_bias + o], b->data.data(), sizeof(float) * 128);
     if (!pack_bn(h, sc, 128, &A.buf[D.bank_scale + o], &A.buf[D.bank_shift + o], &A.buf[D.bank_gamma + o],
                  &A.buf[D.bank_beta + o], err))
       return false;
@@ -292,6 +315,12 @@ bool pack_cbhg(taco_handle* h, Arena& A, const std::string& s, int K, int Cin, i
     memcpy(&A.buf[D.gru_bx + d * 384 + 256], bc->data.data(), sizeof(float) * 128);
     ++d;
   }
+  D.g_bank = make_gemmw(0, 128, K, Cin, 128, K);
+  D.g_p1 = make_gemmw(D.p1_w, P1, 3, BC, P1);
+  D.g_p2 = make_gemmw(D.p2_w, P2, 3, P1, P2);
+  if (P2 != 128) D.g_dense = make_gemmw(D.dense_w, 128, 1, P2, 128);
+  for (int i = 0; i < 4; ++i) D.g_hw[i] = make_gemmw(D.hw_w[i], 256, 1, 128, 256);
+  D.g_xproj = make_gemmw(D.gru_wx, 768, 1, 128, 768);
   return true;
 }
 
@@ -394,7 +423,7 @@ struct Bump {
 
 size_t cbhg_ws_floats(int K, int P1, int P2, int64_t rows) {
   // bank + pooled + p1 + p2 + dense + 2 highway + xproj, plus slack for alignment
-  return (size_t)rows * ((size_t)2 * K * 128 + P1 + P2 + 128 + 256 + 768) + 32768;
+  return (size_t)rows * ((size_t)3 * K * 128 + P1 + P2 + 128 + 256 + 768) + 32768;   // + bf16 hi/lo staging
 }
 
 int ensure_ws(taco_handle* h, size_t bytes) {
@@ -431,6 +460,37 @@ void conv(Ctx& c, const float* x, int64_t x_bs, int ldx, int N, int T, int Cin, 
   c.h->launches += 1;
 }
 
+// bf16 hi/lo staging of a GEMM's activation operand (tcgen05 path)
+struct BfScratch { uint16_t* hi = nullptr; uint16_t* lo = nullptr; };
+BfScratch take_bf(Bump& ws, int64_t rows, int maxCp) {
+  BfScratch s;
+  s.hi = ws.take<uint16_t>((size_t)rows * maxCp);
+  s.lo = ws.take<uint16_t>((size_t)rows * maxCp);
+  return s;
+}
+
+// One conv1d/dense site: tensor cores (default) or the fp32 FFMA kernel (gemm_mode 0).
+void gemm(Ctx& c, const GemmW& g, const BfScratch& sc, const float* x, int64_t x_bs, int ldx, int N, int T,
+          const float* bias, const float* scale, const float* shift, const float* res, int64_t res_bs, int ldres,
+          float* out, int64_t out_bs, int ldo, int col_off, int act, int epi = EPI_PLAIN) {
+  taco_handle* h = c.h;
+  if (h->gemm_mode == 0) {
+    conv(c, x, x_bs, ldx, N, T, g.Cin, g.taps, c.W(g.w), g.ldw, bias, scale, shift, res, res_bs, ldres, out, out_bs, ldo,
+         col_off, g.Cout, act, epi);
+    return;
+  }
+  launch_split_bf16(x, x_bs, ldx, N, T, g.Cin, g.Cp, sc.hi, sc.lo, c.st);
+  ConvUmma u;
+  u.a_hi = sc.hi; u.a_lo = sc.lo; u.N = N; u.T = T; u.Cp = g.Cp;
+  u.b_hi = h->dB + g.bt; u.b_lo = h->dB + g.bt + (size_t)g.b_rows * g.Kld; u.b_rows = g.b_rows; u.Kld = g.Kld;
+  u.taps = g.taps; u.bank = g.bank; u.Cout = g.Cout; u.nsplit = h->gemm_mode == 2 ? 1 : 3;
+  u.bias = bias; u.scale = scale; u.shift = shift; u.res = res; u.res_bs = res_bs; u.ldres = ldres;
+  u.out = out; u.out_bs = out_bs; u.ldo = ldo; u.col_off = col_off; u.act = act; u.epi = epi;
+  cudaError_t e = launch_conv_umma(u, c.st);
+  if (e != cudaSuccess && h->err.empty()) h->err = std::string("conv_umma launch: ") + cudaGetErrorString(e);
+  h->launches += 2;
+}
+
 // reference cbhg() (models/modules.py:35-74).  x: [N,T,Cin] with batch stride x_bs; out [N,T,256] dense.
 void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, const int32_t* lengths, int N,
               int T, int bn_mode, float* out) {
@@ -445,14 +505,21 @@ void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, 
   float* xproj = ws.take<float>(rows * 768);
   float* bnv = ws.take<float>(2 * 2048);          // batch-mode scale | shift
   double* bnacc = ws.take<double>(2 * 2048);
+  BfScratch sc;
+  if (c.h->gemm_mode != 0) sc = take_bf(ws, rows, BC);
   if (ws.overflow) return;
   const bool batch = bn_mode == TACO_BN_BATCH;
   // conv bank: K convolutions written side by side (tf.concat, modules.py:39-42)
-  for (int k = 1; k <= K; ++k) {
-    const int o = (k - 1) * 128;
-    conv(c, x, x_bs, Cin, N, T, Cin, k, c.W(D.bank_w[k - 1]), 128, c.W(D.bank_b[k - 1]),
-         batch ? nullptr : c.W(D.bank_scale + o), batch ? nullptr : c.W(D.bank_shift + o), nullptr, 0, 0, bank,
-         (int64_t)T * BC, BC, o, 128, TACO_ACT_RELU);
+  if (c.h->gemm_mode != 0) {   // one launch for the whole bank
+    gemm(c, D.g_bank, sc, x, x_bs, Cin, N, T, c.W(D.bank_bias), batch ? nullptr : c.W(D.bank_scale),
+         batch ? nullptr : c.W(D.bank_shift), nullptr, 0, 0, bank, (int64_t)T * BC, BC, 0, TACO_ACT_RELU);
+  } else {
+    for (int k = 1; k <= K; ++k) {
+      const int o = (k - 1) * 128;
+      conv(c, x, x_bs, Cin, N, T, Cin, k, c.W(D.bank_w[k - 1]), 128, c.W(D.bank_b[k - 1]),
+           batch ? nullptr : c.W(D.bank_scale + o), batch ? nullptr : c.W(D.bank_shift + o), nullptr, 0, 0, bank,
+           (int64_t)T * BC, BC, o, 128, TACO_ACT_RELU);
+    }
   }
   if (batch) {
     launch_bn_batch_stats(bank, (int64_t)T * BC, BC, 0, N, T, BC, c.W(D.bank_gamma), c.W(D.bank_beta), kBnEps,
@@ -464,9 +531,8 @@ void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, 
     c.h->launches += 1;
   }
   // proj_1: conv k=3 + ReLU + BN
-  conv(c, pooled, (int64_t)T * BC, BC, N, T, BC, 3, c.W(D.p1_w), D.P1, c.W(D.p1_b),
-       batch ? nullptr : c.W(D.p1_scale), batch ? nullptr : c.W(D.p1_shift), nullptr, 0, 0, p1,
-       (int64_t)T * D.P1, D.P1, 0, D.P1, TACO_ACT_RELU);
+  gemm(c, D.g_p1, sc, pooled, (int64_t)T * BC, BC, N, T, c.W(D.p1_b), batch ? nullptr : c.W(D.p1_scale),
+       batch ? nullptr : c.W(D.p1_shift), nullptr, 0, 0, p1, (int64_t)T * D.P1, D.P1, 0, TACO_ACT_RELU);
   if (batch) {
     launch_bn_batch_stats(p1, (int64_t)T * D.P1, D.P1, 0, N, T, D.P1, c.W(D.p1_gamma), c.W(D.p1_beta), kBnEps,
                           bnacc, bnv, bnv + 2048, c.st);
@@ -474,9 +540,9 @@ void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, 
     c.h->launches += 3;
   }
   // proj_2: conv k=3 + BN (no activation) + residual (modules.py:53,56)
-  conv(c, p1, (int64_t)T * D.P1, D.P1, N, T, D.P1, 3, c.W(D.p2_w), D.P2, c.W(D.p2_b),
-       batch ? nullptr : c.W(D.p2_scale), batch ? nullptr : c.W(D.p2_shift), batch ? nullptr : x, x_bs, Cin, p2,
-       (int64_t)T * D.P2, D.P2, 0, D.P2, TACO_ACT_NONE);
+  gemm(c, D.g_p2, sc, p1, (int64_t)T * D.P1, D.P1, N, T, c.W(D.p2_b), batch ? nullptr : c.W(D.p2_scale),
+       batch ? nullptr : c.W(D.p2_shift), batch ? nullptr : x, x_bs, Cin, p2, (int64_t)T * D.P2, D.P2, 0,
+       TACO_ACT_NONE);
   if (batch) {
     launch_bn_batch_stats(p2, (int64_t)T * D.P2, D.P2, 0, N, T, D.P2, c.W(D.p2_gamma), c.W(D.p2_beta), kBnEps,
                           bnacc, bnv, bnv + 2048, c.st);
@@ -485,8 +551,8 @@ void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, 
   }
   const float* hin = p2;
   if (D.P2 != 128) {   // modules.py:59-60
-    conv(c, p2, (int64_t)T * D.P2, D.P2, N, T, D.P2, 1, c.W(D.dense_w), 128, c.W(D.dense_b), nullptr, nullptr,
-         nullptr, 0, 0, hwb, (int64_t)T * 128, 128, 0, 128, TACO_ACT_NONE);
+    gemm(c, D.g_dense, sc, p2, (int64_t)T * D.P2, D.P2, N, T, c.W(D.dense_b), nullptr, nullptr, nullptr, 0, 0, hwb,
+         (int64_t)T * 128, 128, 0, TACO_ACT_NONE);
     hin = hwb;
   }
   // 4 highway layers (modules.py:63-64)
@@ -494,14 +560,14 @@ void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, 
   int cur = 0;   // first output goes to hwa (hin is p2 or hwb)
   for (int i = 0; i < 4; ++i) {
     float* o = bufs[cur];
-    conv(c, hin, (int64_t)T * 128, 128, N, T, 128, 1, c.W(D.hw_w[i]), 256, c.W(D.hw_b[i]), nullptr, nullptr, hin,
-         (int64_t)T * 128, 128, o, (int64_t)T * 128, 128, 0, 256, TACO_ACT_NONE, EPI_HIGHWAY);
+    gemm(c, D.g_hw[i], sc, hin, (int64_t)T * 128, 128, N, T, c.W(D.hw_b[i]), nullptr, nullptr, hin, (int64_t)T * 128,
+         128, o, (int64_t)T * 128, 128, 0, TACO_ACT_NONE, EPI_HIGHWAY);
     hin = o;
     cur ^= 1;
   }
   // hoisted GRU input projection for both directions, then the recurrence
-  conv(c, hin, (int64_t)T * 128, 128, N, T, 128, 1, c.W(D.gru_wx), 768, c.W(D.gru_bx), nullptr, nullptr, nullptr,
-       0, 0, xproj, (int64_t)T * 768, 768, 0, 768, TACO_ACT_NONE);
+  gemm(c, D.g_xproj, sc, hin, (int64_t)T * 128, 128, N, T, c.W(D.gru_bx), nullptr, nullptr, nullptr, 0, 0, xproj,
+       (int64_t)T * 768, 768, 0, TACO_ACT_NONE);
   launch_bigru(xproj, c.W(D.gru_ug), c.W(D.gru_uc), lengths, N, T, out, (int64_t)T * 256, c.st);
   c.h->launches += 1;
 }
@@ -536,15 +602,17 @@ int do_encoder(taco_handle* h, Bump& ws, const int32_t* ids, const int32_t* leng
   float* emb = ws.take<float>(rows * (E + Es));
   float* a1 = ws.take<float>(rows * 256);
   float* a2 = ws.take<float>(rows * 128);
+  BfScratch sc;
+  if (h->gemm_mode != 0) sc = take_bf(ws, rows, 512);
   if (ws.overflow) return fail(h, TACO_ERR_INVALID, "workspace overflow (encoder)");
   launch_gather_concat(ids, multi ? spk : nullptr, c.W(h->emb), hp.num_symbols, E, multi ? c.W(h->emb_id) : nullptr,
                        hp.id_num, Es, N, T_in, emb, h->d_ints, st);
   h->launches += 1;
   // encoder prenet (modules.py:5-12; dropout is the identity)
-  conv(c, emb, (int64_t)T_in * (E + Es), E + Es, N, T_in, E + Es, 1, c.W(h->pre1_w), 256, c.W(h->pre1_b), nullptr,
-       nullptr, nullptr, 0, 0, a1, (int64_t)T_in * 256, 256, 0, 256, TACO_ACT_RELU);
-  conv(c, a1, (int64_t)T_in * 256, 256, N, T_in, 256, 1, c.W(h->pre2_w), 128, c.W(h->pre2_b), nullptr, nullptr,
-       nullptr, 0, 0, a2, (int64_t)T_in * 128, 128, 0, 128, TACO_ACT_RELU);
+  gemm(c, h->g_pre1, sc, emb, (int64_t)T_in * (E + Es), E + Es, N, T_in, c.W(h->pre1_b), nullptr, nullptr, nullptr, 0, 0,
+       a1, (int64_t)T_in * 256, 256, 0, TACO_ACT_RELU);
+  gemm(c, h->g_pre2, sc, a1, (int64_t)T_in * 256, 256, N, T_in, c.W(h->pre2_b), nullptr, nullptr, nullptr, 0, 0, a2,
+       (int64_t)T_in * 128, 128, 0, TACO_ACT_RELU);
   run_cbhg(c, h->enc, ws, a2, (int64_t)T_in * 128, lengths, N, T_in, bn_mode, memory_out);
   if (ws.overflow) return fail(h, TACO_ERR_INVALID, "workspace overflow (encoder cbhg)");
   return check_launch(h, "encoder");
@@ -552,11 +620,11 @@ int do_encoder(taco_handle* h, Bump& ws, const int32_t* ids, const int32_t* leng
 
 size_t encoder_ws_bytes(const taco_handle* h, int N, int T_in) {
   const int64_t rows = (int64_t)N * T_in;
-  return sizeof(float) * ((size_t)rows * (h->emb_dim + 256 + 128) + cbhg_ws_floats(16, 128, 128, rows)) + 65536;
+  return sizeof(float) * ((size_t)rows * (h->emb_dim + 256 + 128 + 512) + cbhg_ws_floats(16, 128, 128, rows)) + 65536;
 }
 size_t postnet_ws_bytes(const taco_handle* h, int N, int T) {
   const int64_t rows = (int64_t)N * T;
-  return sizeof(float) * ((size_t)rows * 256 + cbhg_ws_floats(8, 256, h->hp.num_mels, rows)) + 65536;
+  return sizeof(float) * ((size_t)rows * 512 + cbhg_ws_floats(8, 256, h->hp.num_mels, rows)) + 65536;
 }
 
 int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, const float* mel_targets, int T_tgt,
@@ -568,10 +636,12 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
   const int max_steps = taco_max_steps(h, teacher_force, T_tgt);
   if (max_steps <= 0) return fail(h, TACO_ERR_INVALID, "no decoder steps (T_tgt < r?)");
   float* keys = ws.take<float>((size_t)N * T_in * 256);
+  BfScratch sc;
+  if (h->gemm_mode != 0) sc = take_bf(ws, (int64_t)N * T_in, 256);
   if (ws.overflow) return fail(h, TACO_ERR_INVALID, "workspace overflow (decoder)");
   // BahdanauAttention memory_layer (no bias), once per utterance (tacotron.py:68)
-  conv(c, memory, (int64_t)T_in * 256, 256, N, T_in, 256, 1, c.W(h->mem_w), 256, nullptr, nullptr, nullptr, nullptr,
-       0, 0, keys, (int64_t)T_in * 256, 256, 0, 256, TACO_ACT_NONE);
+  gemm(c, h->g_mem, sc, memory, (int64_t)T_in * 256, 256, N, T_in, nullptr, nullptr, nullptr, nullptr, 0, 0, keys,
+       (int64_t)T_in * 256, 256, 0, TACO_ACT_NONE);
   DecoderArgs a;
   a.memory = memory; a.keys = keys; a.targets = teacher_force ? mel_targets : nullptr;
   a.N = N; a.T_in = T_in; a.T_tgt = T_tgt; a.r = hp.outputs_per_step; a.steps = max_steps; a.max_steps = max_steps;
@@ -601,12 +671,14 @@ int do_postnet(taco_handle* h, Bump& ws, const float* mel, int N, int T, int bn_
   Ctx c{h, st};
   const taco_hparams& hp = h->hp;
   float* post = ws.take<float>((size_t)N * T * 256);
+  BfScratch sc;
+  if (h->gemm_mode != 0) sc = take_bf(ws, (int64_t)N * T, 256);
   if (ws.overflow) return fail(h, TACO_ERR_INVALID, "workspace overflow (postnet)");
   run_cbhg(c, h->post, ws, mel, mel_bs, nullptr, N, T, bn_mode, post);
   if (ws.overflow) return fail(h, TACO_ERR_INVALID, "workspace overflow (postnet cbhg)");
   // linear_outputs = tf.layers.dense(post_outputs, num_freq)  (tacotron.py:101)
-  conv(c, post, (int64_t)T * 256, 256, N, T, 256, 1, c.W(h->lin_w), h->lin_ld, c.W(h->lin_b), nullptr, nullptr,
-       nullptr, 0, 0, linear_out, lin_bs, hp.num_freq, 0, hp.num_freq, TACO_ACT_NONE);
+  gemm(c, h->g_lin, sc, post, (int64_t)T * 256, 256, N, T, c.W(h->lin_b), nullptr, nullptr, nullptr, 0, 0, linear_out,
+       lin_bs, hp.num_freq, 0, TACO_ACT_NONE);
   return check_launch(h, "postnet");
 }
 
@@ -651,6 +723,7 @@ int taco_destroy(taco_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   if (h->dW) cudaFree(h->dW);
+  if (h->dB) cudaFree(h->dB);
   if (h->ws) cudaFree(h->ws);
   if (h->d_ints) cudaFree(h->d_ints);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -716,6 +789,10 @@ int taco_finalize_weights(taco_handle* h) {
     h->lin_ld = (hp.num_freq + 3) & ~3;
     h->lin_w = put_matrix(A, lw->data.data(), 256, hp.num_freq, h->lin_ld);
     h->lin_b = put_vec(A, lb->data.data(), hp.num_freq);
+    h->g_pre1 = make_gemmw(h->pre1_w, 256, 1, h->emb_dim, 256);
+    h->g_pre2 = make_gemmw(h->pre2_w, 128, 1, 256, 128);
+    h->g_mem = make_gemmw(h->mem_w, 256, 1, 256, 256);
+    h->g_lin = make_gemmw(h->lin_w, h->lin_ld, 1, 256, hp.num_freq);
     return true;
   };
   if (!build()) return bad(err.rfind("missing", 0) == 0 ? TACO_ERR_MISSING_WEIGHT : TACO_ERR_INVALID);
@@ -732,6 +809,34 @@ int taco_finalize_weights(taco_handle* h) {
   if (h->dW) { cudaDeviceSynchronize(); cudaFree(h->dW); h->dW = nullptr; }
   CUDA_OK(h, cudaMalloc(&h->dW, sizeof(float) * A.buf.size()));
   CUDA_OK(h, cudaMemcpy(h->dW, A.buf.data(), sizeof(float) * A.buf.size(), cudaMemcpyHostToDevice));
+  {   // bf16 W^T hi/lo copies for the tcgen05 GEMMs, packed on the device from the fp32 arena
+    std::vector<GemmW*> gs = {&h->g_pre1, &h->g_pre2, &h->g_mem, &h->g_lin};
+    for (CbhgDev* D : {&h->enc, &h->post}) {
+      gs.push_back(&D->g_bank); gs.push_back(&D->g_p1); gs.push_back(&D->g_p2);
+      if (D->P2 != 128) gs.push_back(&D->g_dense);
+      for (int i = 0; i < 4; ++i) gs.push_back(&D->g_hw[i]);
+      gs.push_back(&D->g_xproj);
+    }
+    size_t nb = 0;
+    for (GemmW* g : gs) { g->bt = nb; nb += ((size_t)2 * g->b_rows * g->Kld + 127) & ~size_t(127); }
+    if (h->dB) { cudaDeviceSynchronize(); cudaFree(h->dB); h->dB = nullptr; }
+    CUDA_OK(h, cudaMalloc(&h->dB, sizeof(uint16_t) * nb));
+    CUDA_OK(h, cudaMemset(h->dB, 0, sizeof(uint16_t) * nb));
+    for (GemmW* g : gs) {
+      uint16_t* hi = h->dB + g->bt;
+      uint16_t* lo = hi + (size_t)g->b_rows * g->Kld;
+      if (g->bank > 1) {
+        const CbhgDev& D = (g == &h->enc.g_bank) ? h->enc : h->post;
+        for (int ci = 0; ci < g->bank; ++ci)
+          launch_pack_wt(h->dW + D.bank_w[ci], 128, ci + 1, g->Cin, g->Cout, g->Cp, g->Kld, ci * g->Cout, hi, lo, 0);
+      } else {
+        launch_pack_wt(h->dW + g->w, g->ldw, g->taps, g->Cin, g->Cout, g->Cp, g->Kld, 0, hi, lo, 0);
+      }
+    }
+    CUDA_OK(h, cudaDeviceSynchronize());
+    const char* gm = getenv("TACO_GEMM");
+    if (gm) h->gemm_mode = !strcmp(gm, "ffma") ? 0 : (!strcmp(gm, "bf16") ? 2 : 1);
+  }
   DecoderWeights& d = h->dec;
   const float* B = h->dW;
   d.CS = cs; d.M = hp.num_mels; d.Dout = hp.num_mels * hp.outputs_per_step; d.McO = McO;
@@ -796,7 +901,7 @@ int taco_decode(taco_handle* h, const float* memory, int N, int T_in, const floa
                 int teacher_force, float* dec_out, float* align_out, int32_t* steps_out_host, void* stream) {
   REQUIRE_READY(h);
   if (!memory || !dec_out || N <= 0 || T_in <= 0) return fail(h, TACO_ERR_INVALID, "bad argument");
-  int rc = ensure_ws(h, sizeof(float) * (size_t)N * T_in * 256 + 65536);
+  int rc = ensure_ws(h, sizeof(float) * (size_t)N * T_in * 512 + 65536);
   if (rc) return rc;
   Bump ws(h->ws, h->ws_bytes);
   return do_decode(h, ws, memory, N, T_in, mel_targets, T_tgt, teacher_force, dec_out, align_out, steps_out_host,
@@ -836,13 +941,15 @@ int taco_bigru(taco_handle* h, int which, const float* x, const int32_t* lengths
   REQUIRE_READY(h);
   if (!x || !out || N <= 0 || T <= 0) return fail(h, TACO_ERR_INVALID, "bad argument");
   const CbhgDev& D = which == TACO_CBHG_ENCODER ? h->enc : h->post;
-  int rc = ensure_ws(h, sizeof(float) * (size_t)N * T * 768 + 65536);
+  int rc = ensure_ws(h, sizeof(float) * (size_t)N * T * 1024 + 65536);
   if (rc) return rc;
   Bump ws(h->ws, h->ws_bytes);
   Ctx c{h, (cudaStream_t)stream};
   float* xproj = ws.take<float>((size_t)N * T * 768);
-  conv(c, x, (int64_t)T * 128, 128, N, T, 128, 1, c.W(D.gru_wx), 768, c.W(D.gru_bx), nullptr, nullptr, nullptr, 0, 0,
-       xproj, (int64_t)T * 768, 768, 0, 768, TACO_ACT_NONE);
+  BfScratch sc;
+  if (h->gemm_mode != 0) sc = take_bf(ws, (int64_t)N * T, 128);
+  gemm(c, D.g_xproj, sc, x, (int64_t)T * 128, 128, N, T, c.W(D.gru_bx), nullptr, nullptr, nullptr, 0, 0, xproj,
+       (int64_t)T * 768, 768, 0, TACO_ACT_NONE);
   launch_bigru(xproj, c.W(D.gru_ug), c.W(D.gru_uc), lengths, N, T, out, (int64_t)T * 256, c.st);
   h->launches += 1;
   return check_launch(h, "bigru");
@@ -855,6 +962,31 @@ int taco_conv1d(taco_handle* h, const float* x, int N, int T, int Cin, const flo
   if (!x || !kernel || !out || N <= 0 || T <= 0 || Cin <= 0 || Cin % 4 || k <= 0 || Cout <= 0)
     return fail(h, TACO_ERR_INVALID, "bad argument (Cin must be a multiple of 4)");
   cudaStream_t st = (cudaStream_t)stream;
+  Ctx c{h, st};
+  if (h->gemm_mode != 0) {   // tensor-core path: pack W^T hi/lo and split x on the device, then one UMMA launch
+    GemmW g = make_gemmw(0, Cout, k, Cin, Cout);
+    const size_t nb = (size_t)g.b_rows * g.Kld, na = (size_t)N * T * g.Cp;
+    int rc = ensure_ws(h, sizeof(uint16_t) * 2 * (nb + na) + 65536);
+    if (rc) return rc;
+    Bump ws(h->ws, h->ws_bytes);
+    uint16_t* bhi = ws.take<uint16_t>(nb);
+    uint16_t* blo = ws.take<uint16_t>(nb);
+    BfScratch sc;
+    sc.hi = ws.take<uint16_t>(na);
+    sc.lo = ws.take<uint16_t>(na);
+    launch_pack_wt(kernel, Cout, k, Cin, Cout, g.Cp, g.Kld, 0, bhi, blo, st);
+    launch_split_bf16(x, (int64_t)T * Cin, Cin, N, T, Cin, g.Cp, sc.hi, sc.lo, st);
+    ConvUmma u;
+    u.a_hi = sc.hi; u.a_lo = sc.lo; u.N = N; u.T = T; u.Cp = g.Cp;
+    u.b_hi = bhi; u.b_lo = blo; u.b_rows = g.b_rows; u.Kld = g.Kld;
+    u.taps = k; u.bank = 1; u.Cout = Cout; u.nsplit = h->gemm_mode == 2 ? 1 : 3;
+    u.bias = bias; u.scale = nullptr; u.shift = nullptr; u.res = nullptr; u.res_bs = 0; u.ldres = 0;
+    u.out = out; u.out_bs = (int64_t)T * Cout; u.ldo = Cout; u.col_off = 0; u.act = act; u.epi = EPI_PLAIN;
+    cudaError_t e = launch_conv_umma(u, st);
+    if (e != cudaSuccess) return fail(h, TACO_ERR_CUDA, std::string("conv_umma launch: ") + cudaGetErrorString(e));
+    h->launches += 3;
+    return check_launch(h, "conv1d");
+  }
   const int ldw = (Cout + 3) & ~3;
   const float* w = kernel;
   if (ldw != Cout) {   // pad the leading dimension for 128-bit weight loads
@@ -865,7 +997,6 @@ int taco_conv1d(taco_handle* h, const float* x, int N, int T, int Cin, const flo
                                  (size_t)k * Cin, cudaMemcpyDeviceToDevice, st));
     w = reinterpret_cast<const float*>(h->ws);
   }
-  Ctx c{h, st};
   conv(c, x, (int64_t)T * Cin, Cin, N, T, Cin, k, w, ldw, bias, nullptr, nullptr, nullptr, 0, 0, out, (int64_t)T * Cout,
        Cout, 0, Cout, act);
   return check_launch(h, "conv1d");
@@ -882,8 +1013,8 @@ int taco_forward(taco_handle* h, const int32_t* ids, const int32_t* lengths, con
   const int max_steps = taco_max_steps(h, teacher_force, T_tgt);
   if (max_steps <= 0) return fail(h, TACO_ERR_INVALID, "no decoder steps");
   const int maxT = max_steps * r;
-  size_t need = encoder_ws_bytes(h, N, T_in) + sizeof(float) * (size_t)N * T_in * 512 + 65536;
-  const size_t need_post = postnet_ws_bytes(h, N, maxT) + sizeof(float) * (size_t)N * T_in * 512 + 65536;
+  size_t need = encoder_ws_bytes(h, N, T_in) + sizeof(float) * (size_t)N * T_in * 768 + 65536;
+  const size_t need_post = postnet_ws_bytes(h, N, maxT) + sizeof(float) * (size_t)N * T_in * 768 + 65536;
   if (linear_out && need_post > need) need = need_post;
   int rc = ensure_ws(h, need);
   if (rc) return rc;
@@ -976,6 +1107,12 @@ int taco_decoder_geometry(const taco_handle* h, int N, int* cluster_size, int* s
   if (cluster_size) *cluster_size = h->CS;
   if (samples_per_cluster) *samples_per_cluster = S;
   if (num_clusters) *num_clusters = (N + S - 1) / S;
+  return TACO_OK;
+}
+
+int taco_set_gemm_mode(taco_handle* h, int mode) {
+  if (!h || mode < 0 || mode > 2) return TACO_ERR_INVALID;
+  h->gemm_mode = mode;
   return TACO_OK;
 }
 

@@ -103,6 +103,10 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.taco_launch_count(self._h))
 
+    def set_gemm_mode(self, mode: int):
+        """0 = fp32 FFMA, 1 = bf16x3 tcgen05 (default, fp32-class), 2 = plain bf16 tcgen05."""
+        self._ck(self.lib.taco_set_gemm_mode(self._h, int(mode)))
+
     def set_profiling(self, on: bool):
         self._ck(self.lib.taco_set_profiling(self._h, int(on)))
 
