@@ -30,11 +30,14 @@
 namespace taco {
 
 namespace {
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3, NTHREADS = 192;
+constexpr int BM = 128, BN = 128, BK = 64, MAX_STAGES = 3, NTHREADS = 192;
 constexpr uint32_t TILE_BYTES = BM * BK * 2;            // 16 KB: one bf16 operand tile (A or B)
 constexpr uint32_t STAGE_BYTES = 4 * TILE_BYTES;        // A_hi | A_lo | B_hi | B_lo
 constexpr uint32_t EPI_BYTES = 4 * 32 * 33 * 4;         // per-warp 32x33 fp32 transpose staging
-constexpr uint32_t SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + 256;
+// dynamic smem: 1024 (alignment slack) + stages * 64 KB + [transpose staging] + barriers
+__host__ __device__ constexpr uint32_t smem_bytes(int stages, bool transpose_epi) {
+  return 1024u + (uint32_t)stages * STAGE_BYTES + (transpose_epi ? EPI_BYTES : 0u) + 256u;
+}
 
 struct UmmaArgs {
   int N, T, Cp;            // activation rows / padded channels (Cp % 64 == 0)
@@ -44,6 +47,8 @@ struct UmmaArgs {
   const float* res; long long res_bs; int ldres;
   float* out; long long out_bs; int ldo; int col_off;
   int act, epi;
+  int stages;              // smem ring depth (1..3): short-K launches use fewer so that 2-3 CTAs share an SM
+  int vec_epi;             // 1: rows are 16 B aligned -> direct 128-bit stores from the TMEM registers
 };
 
 // ---- PTX wrappers -------------------------------------------------------------
@@ -115,14 +120,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                  const UmmaArgs p) {
   extern __shared__ uint8_t smem_raw[];
+  const int STAGES = p.stages;
+  const uint32_t epi_bytes = p.vec_epi ? 0u : EPI_BYTES;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   float* epi = reinterpret_cast<float*>(smem_al + STAGES * STAGE_BYTES);
-  const uint32_t bar0 = smem_base + STAGES * STAGE_BYTES + EPI_BYTES;    // full[S], empty[S], tmem_full, tmem ptr
+  const uint32_t bar0 = smem_base + STAGES * STAGE_BYTES + epi_bytes;    // full[S], empty[S], tmem_full, tmem ptr
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-  const uint32_t tfull_bar = bar0 + 8u * (2 * STAGES);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + STAGES * STAGE_BYTES + EPI_BYTES + 8 * (2 * STAGES + 1));
+  auto empty_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+  const uint32_t tfull_bar = bar0 + 8u * (2 * MAX_STAGES);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + STAGES * STAGE_BYTES + epi_bytes + 8 * (2 * MAX_STAGES + 1));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tps = (p.T + BM - 1) / BM;
@@ -141,7 +148,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA_lo)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB_lo)) : "memory");
     }
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -200,51 +207,115 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;                                         // TMEM lanes this warp may read
-    float* stg = epi + (warp - 2) * 32 * 33;
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     const float* bias = p.bias ? p.bias + ci * p.Cout : nullptr;
     const float* scale = p.scale ? p.scale + ci * p.Cout : nullptr;
     const float* shift = p.shift ? p.shift + ci * p.Cout : nullptr;
     const int col_off = p.col_off + ci * p.Cout;
+    if (p.vec_epi) {
+      // ---- direct path: thread = row, 32 consecutive columns per TMEM load, 128-bit global accesses ----
+      const int t = t0 + quarter * 32 + lane;
+      const bool rowok = t < p.T;
+      float* orow = p.out + (long long)n * p.out_bs + (long long)(rowok ? t : 0) * p.ldo + col_off;
+      const float* rrow = p.res ? p.res + (long long)n * p.res_bs + (long long)(rowok ? t : 0) * p.ldres : nullptr;
 #pragma unroll 1
-    for (int ch = 0; ch < BN / 32; ++ch) {
-      const int cbase = o0 + ch * 32;
-      if (cbase >= p.Cout) break;                                         // warp-uniform
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), v);
-#pragma unroll
-      for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = __uint_as_float(v[c]);
-      __syncwarp();
-      const int col = cbase + lane;
-      const bool cok = col < p.Cout;
-      float b = 0.f, sc = 1.f, sh = 0.f;
-      if (cok) {
-        if (bias) b = __ldg(bias + col);
-        if (scale) { sc = __ldg(scale + col); sh = __ldg(shift + col); }
-      }
-      for (int r = 0; r < 32; ++r) {
-        const int t = t0 + quarter * 32 + r;
-        if (t >= p.T) break;                                              // warp-uniform
-        float x = stg[r * 33 + lane] + b;
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int cbase = o0 + ch * 32;
+        if (cbase >= p.Cout) break;                                       // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), v);
         if (p.epi == EPI_PLAIN) {
-          x = apply_act(x, p.act);
-          if (scale) x = fmaf(x, sc, sh);
-          if (cok) {
-            if (p.res) x += __ldg(p.res + (long long)n * p.res_bs + (long long)t * p.ldres + col);
-            p.out[(long long)n * p.out_bs + (long long)t * p.ldo + col_off + col] = x;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int col = cbase + 4 * g;
+            if (col >= p.Cout) break;                                     // Cout % 4 == 0 on this path
+            float4 x = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                   __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+            if (bias) { const float4 b = ldg_f4(bias + col); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
+            x.x = apply_act(x.x, p.act); x.y = apply_act(x.y, p.act); x.z = apply_act(x.z, p.act); x.w = apply_act(x.w, p.act);
+            if (scale) {
+              const float4 sc = ldg_f4(scale + col), sh = ldg_f4(shift + col);
+              x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y); x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+            }
+            if (rowok) {
+              if (rrow) { const float4 r4 = ldg_f4(rrow + col); x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w; }
+              *reinterpret_cast<float4*>(orow + col) = x;
+            }
           }
-        } else {   // EPI_HIGHWAY: even lane = H_c, odd lane = T_c of channel c = col/2
-          const float tg = __shfl_down_sync(0xffffffffu, x, 1);
-          if (cok && !(lane & 1)) {
-            const int chn = col >> 1;
-            const float H = fmaxf(x, 0.f), Tg = sigmoid_f(tg);
-            const float xin = __ldg(p.res + (long long)n * p.res_bs + (long long)t * p.ldres + chn);
-            p.out[(long long)n * p.out_bs + (long long)t * p.ldo + col_off + chn] = H * Tg + xin * (1.0f - Tg);
+        } else {   // EPI_HIGHWAY: columns (2c, 2c+1) = (H_c, T_c); 16 channels per 32-column load
+          const int chn0 = cbase >> 1;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = cbase + 8 * g;
+            if (col >= p.Cout) break;
+            const float4 b0 = ldg_f4(bias + col), b1 = ldg_f4(bias + col + 4);
+            float4 xin = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rowok) xin = ldg_f4(rrow + chn0 + 4 * g);
+            float4 o;
+            {
+              const float H = fmaxf(__uint_as_float(v[8 * g + 0]) + b0.x, 0.f), Tg = sigmoid_f(__uint_as_float(v[8 * g + 1]) + b0.y);
+              o.x = H * Tg + xin.x * (1.0f - Tg);
+            }
+            {
+              const float H = fmaxf(__uint_as_float(v[8 * g + 2]) + b0.z, 0.f), Tg = sigmoid_f(__uint_as_float(v[8 * g + 3]) + b0.w);
+              o.y = H * Tg + xin.y * (1.0f - Tg);
+            }
+            {
+              const float H = fmaxf(__uint_as_float(v[8 * g + 4]) + b1.x, 0.f), Tg = sigmoid_f(__uint_as_float(v[8 * g + 5]) + b1.y);
+              o.z = H * Tg + xin.z * (1.0f - Tg);
+            }
+            {
+              const float H = fmaxf(__uint_as_float(v[8 * g + 6]) + b1.z, 0.f), Tg = sigmoid_f(__uint_as_float(v[8 * g + 7]) + b1.w);
+              o.w = H * Tg + xin.w * (1.0f - Tg);
+            }
+            if (rowok) *reinterpret_cast<float4*>(orow + chn0 + 4 * g) = o;
           }
         }
       }
-      __syncwarp();
+    } else {
+      // ---- transpose path (rows not 16 B aligned, e.g. ldo = 1025): smem transpose -> coalesced scalar stores ----
+      float* stg = epi + (warp - 2) * 32 * 33;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int cbase = o0 + ch * 32;
+        if (cbase >= p.Cout) break;                                       // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = __uint_as_float(v[c]);
+        __syncwarp();
+        const int col = cbase + lane;
+        const bool cok = col < p.Cout;
+        float b = 0.f, sc = 1.f, sh = 0.f;
+        if (cok) {
+          if (bias) b = __ldg(bias + col);
+          if (scale) { sc = __ldg(scale + col); sh = __ldg(shift + col); }
+        }
+        const int rmax = min(32, p.T - (t0 + quarter * 32));
+#pragma unroll 4
+        for (int r = 0; r < rmax; ++r) {
+          const int t = t0 + quarter * 32 + r;
+          float x = stg[r * 33 + lane] + b;
+          if (p.epi == EPI_PLAIN) {
+            x = apply_act(x, p.act);
+            if (scale) x = fmaf(x, sc, sh);
+            if (cok) {
+              if (p.res) x += __ldg(p.res + (long long)n * p.res_bs + (long long)t * p.ldres + col);
+              p.out[(long long)n * p.out_bs + (long long)t * p.ldo + col_off + col] = x;
+            }
+          } else {   // EPI_HIGHWAY: even lane = H_c, odd lane = T_c of channel c = col/2
+            const float tg = __shfl_down_sync(0xffffffffu, x, 1);
+            if (cok && !(lane & 1)) {
+              const int chn = col >> 1;
+              const float H = fmaxf(x, 0.f), Tg = sigmoid_f(tg);
+              const float xin = __ldg(p.res + (long long)n * p.res_bs + (long long)t * p.ldres + chn);
+              p.out[(long long)n * p.out_bs + (long long)t * p.ldo + col_off + chn] = H * Tg + xin * (1.0f - Tg);
+            }
+          }
+        }
+        __syncwarp();
+      }
     }
     tc_fence_before();
   }
@@ -369,16 +440,32 @@ cudaError_t launch_conv_umma(const ConvUmma& c, cudaStream_t st) {
   p.bias = c.bias; p.scale = c.scale; p.shift = c.shift; p.res = c.res; p.res_bs = c.res_bs; p.ldres = c.ldres;
   p.out = c.out; p.out_bs = c.out_bs; p.ldo = c.ldo; p.col_off = c.col_off; p.act = c.act; p.epi = c.epi;
   dim3 grid(c.N * ((c.T + BM - 1) / BM), (c.Cout + BN - 1) / BN, c.bank > 1 ? c.bank : 1);
-  cudaError_t e;
-  if (split) {
-    e = cudaFuncSetAttribute(conv_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    conv_umma_kernel<3><<<grid, NTHREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
-  } else {
-    e = cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    conv_umma_kernel<1><<<grid, NTHREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  // ring depth: deep for long K; short-K launches are epilogue/launch bound and gain from 2-3 CTAs per SM
+  const int nkb_max = c.taps * (c.Cp / BK);
+  p.stages = nkb_max >= 6 ? 3 : (nkb_max >= 3 ? 2 : 1);
+  const int chn = c.epi == EPI_HIGHWAY ? 2 : 1;
+  auto al4 = [](long long v) { return (v & 3) == 0; };
+  p.vec_epi = (al4(c.ldo) && al4(c.col_off) && al4(c.out_bs) && al4(c.Cout / chn) && (c.Cout % (4 * chn) == 0) &&
+               (reinterpret_cast<uintptr_t>(c.out) & 15) == 0 &&
+               (c.res == nullptr || (al4(c.ldres) && al4(c.res_bs) && (reinterpret_cast<uintptr_t>(c.res) & 15) == 0)) &&
+               (c.bias == nullptr || (reinterpret_cast<uintptr_t>(c.bias) & 15) == 0) &&
+               (c.scale == nullptr || ((reinterpret_cast<uintptr_t>(c.scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.shift) & 15) == 0)))
+                  ? 1 : 0;
+  if (c.epi == EPI_HIGHWAY && (c.bias == nullptr || c.res == nullptr)) return cudaErrorInvalidValue;
+  const uint32_t smem = smem_bytes(p.stages, !p.vec_epi);
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& attr_set = attr_done[dev & 63];
+  if (!attr_set) {
+    cudaError_t e1 = cudaFuncSetAttribute(conv_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_STAGES, true));
+    cudaError_t e2 = cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_STAGES, true));
+    if (e1 != cudaSuccess) return e1;
+    if (e2 != cudaSuccess) return e2;
+    attr_set = true;
   }
+  if (split) conv_umma_kernel<3><<<grid, NTHREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  else conv_umma_kernel<1><<<grid, NTHREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   return cudaGetLastError();
 }
 

@@ -74,16 +74,23 @@ def test_embed_oob_id_flags_error(eng):
 @pytest.mark.parametrize("k,cin,cout,act", [(1, 128, 128, 1), (2, 80, 128, 1), (3, 256, 80, 0),
                                             (4, 128, 128, 1), (7, 80, 128, 3), (16, 128, 128, 1),
                                             (1, 256, 1025, 0), (3, 2048, 128, 2), (1, 320, 256, 1)])
-def test_conv1d_same(eng, k, cin, cout, act):
+@pytest.mark.parametrize("mode,tol", [(0, 2e-5), (1, 1e-4), (2, 6e-2)])
+def test_conv1d_same(eng, k, cin, cout, act, mode, tol):
+    """tf.layers.conv1d('same') + bias + activation.  mode 0 = fp32 FFMA kernel, 1 = tcgen05 with
+    bf16 hi/lo split operands (default; fp32-class), 2 = plain bf16 tcgen05 (stated looser tolerance)."""
     rng = np.random.default_rng(k * 1000 + cin + cout)
     N, T = 3, 37
     x = rng.standard_normal((N, T, cin)).astype(np.float32)
     w = (rng.standard_normal((k, cin, cout)) / np.sqrt(k * cin)).astype(np.float32)
     b = rng.standard_normal((cout,)).astype(np.float32)
-    got = eng.conv1d(x, w, b, act)
+    eng.set_gemm_mode(mode)
+    try:
+        got = eng.conv1d(x, w, b, act)
+    finally:
+        eng.set_gemm_mode(1)
     ref = O.conv1d_same(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b))
     ref = [lambda v: v, torch.relu, torch.sigmoid, torch.tanh][act](ref)
-    assert maxabs(got, ref) < 2e-5
+    assert maxabs(got, ref) < tol
 
 
 def test_conv1d_even_kernel_padding_kat(eng):
@@ -94,7 +101,11 @@ def test_conv1d_even_kernel_padding_kat(eng):
     w = np.zeros((k, 4, 4), np.float32)
     for j in range(k):
         w[j, 0, 0] = j + 1
-    got = eng.conv1d(x, w, None, 0)[0, :, 0].cpu().numpy()
+    eng.set_gemm_mode(0)
+    got0 = eng.conv1d(x, w, None, 0)[0, :, 0].cpu().numpy()
+    eng.set_gemm_mode(1)
+    got = eng.conv1d(x, w, None, 0)[0, :, 0].cpu().numpy()   # small integers are exact in bf16 too
+    assert np.array_equal(got, got0)
     exp = np.zeros(T, np.float32)
     for j in range(k):           # y[t] = sum_j x[t + j - 1] w[j]  -> impulse at t = 4 - j + 1
         exp[4 - j + 1] = j + 1
@@ -208,6 +219,25 @@ def test_forward_whole_path(eng, small_hp, small_weights, mode):
     assert maxabs(al, ref["alignments"]) < 1e-4
     if mode != "free":
         assert torch.equal(al.cpu().argmax(dim=1), ref["alignments"].argmax(dim=1))
+
+
+@pytest.mark.parametrize("mode,tol", [(0, 1e-3), (2, 5e-2)])
+def test_forward_other_gemm_modes(eng, small_hp, small_weights, mode, tol):
+    """fp32 FFMA mode meets the same 1e-3 bound; plain-bf16 tensor-core mode is the stated looser
+    tolerance (5e-2 max-abs on mel/linear, teacher-forced)."""
+    hp = small_hp
+    ids, lengths, spk = make_inputs(3, 20, 6, 13)
+    rng = np.random.default_rng(3)
+    mel_t = rng.uniform(0, 1, (3, hp.max_iters * hp.outputs_per_step, hp.num_mels)).astype(np.float32)
+    ref = O.tacotron_forward(small_weights, hp, ids, lengths, mel_targets=mel_t, identities=spk, id_num=6,
+                             teacher_force=True, bn_mode="moving")
+    eng.set_gemm_mode(mode)
+    try:
+        mel, lin, al, steps = eng.forward(ids, lengths, spk, mel_t, True, 0)
+    finally:
+        eng.set_gemm_mode(1)
+    assert steps == ref["steps"]
+    assert maxabs(mel, ref["mel_outputs"]) < tol and maxabs(lin, ref["linear_outputs"]) < tol
 
 
 def test_tacotron_initialize_contract(small_hp, small_weights):
