@@ -89,11 +89,14 @@ struct taco_handle {
   uint16_t* dB = nullptr;              // bf16 arena: W^T hi/lo for the tensor-core path
   int gemm_mode = 1;                   // 0 = fp32 FFMA, 1 = bf16x3 tcgen05 (fp32-class), 2 = bf16 tcgen05
   CbhgDev enc, post;
-  DecoderWeights dec;
-  int CS = 16, max_clusters = 8;
+  DecoderWeights dec[2];               // slices cut for clusters of 8 ([0]) and 16 ([1]) CTAs
+  int max_clusters[2] = {0, 0};        // co-resident clusters of each size on this device
+  int force_cs = 0;
   // workspace
   char* ws = nullptr;
   size_t ws_bytes = 0;
+  char* stg = nullptr;                 // device staging of taco_forward_host (grow-only)
+  size_t stg_bytes = 0;
   int* d_ints = nullptr;      // [0]=oob flag, [1]=steps, [2..]=first_fin[N]
   int d_ints_n = 0;
   int* h_pinned = nullptr;    // [0]=oob, [1]=steps
@@ -572,15 +575,32 @@ void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, 
   c.h->launches += 1;
 }
 
-int pick_S(const taco_handle* h, int N) {
-  const char* env = getenv("TACO_DEC_S");
-  if (env) {
-    int s = atoi(env);
-    if (s == 1 || s == 2 || s == 4 || s == 8) return s;
+// Decoder launch geometry: (cluster size, samples per cluster).  A cluster streams the whole
+// decoder weight set once per step, so fewer/larger clusters save L2 bandwidth while more
+// clusters shorten the per-sample work; clusters beyond the co-resident maximum run as extra
+// waves.  Per-wave step times (us) measured on B200 (tools/dec_sweep.py, round 1).
+void pick_geometry(const taco_handle* h, int N, int* cs_out, int* s_out) {
+  static const float t_wave[2][4] = {{12.3f, 15.6f, 20.2f, 35.2f},    // CS = 8 : S = 1,2,4,8
+                                     {11.2f, 12.7f, 15.5f, 25.6f}};   // CS = 16
+  const char* es = getenv("TACO_DEC_S");
+  const int force_s = es ? atoi(es) : 0;
+  float best = 1e30f;
+  int bcs = 16, bs = 8;
+  for (int ci = 0; ci < 2; ++ci) {
+    const int cs = ci ? 16 : 8;
+    if (h->force_cs && h->force_cs != cs) continue;
+    if (h->max_clusters[ci] < 1) continue;
+    for (int si = 0; si < 4; ++si) {
+      const int S = 1 << si;
+      if (force_s && force_s != S) continue;
+      const int clusters = (N + S - 1) / S;
+      const int waves = (clusters + h->max_clusters[ci] - 1) / h->max_clusters[ci];
+      const float t = waves * t_wave[ci][si];
+      if (t < best - 1e-3f) { best = t; bcs = cs; bs = S; }
+    }
   }
-  for (int s : {1, 2, 4, 8})
-    if ((N + s - 1) / s <= h->max_clusters) return s;
-  return 8;
+  *cs_out = bcs;
+  *s_out = bs;
 }
 
 int check_launch(taco_handle* h, const char* what) {
@@ -646,9 +666,10 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
   a.memory = memory; a.keys = keys; a.targets = teacher_force ? mel_targets : nullptr;
   a.N = N; a.T_in = T_in; a.T_tgt = T_tgt; a.r = hp.outputs_per_step; a.steps = max_steps; a.max_steps = max_steps;
   a.dec_out = dec_out; a.align_out = align_out; a.att_res = 0;
-  const int S = pick_S(h, N);
+  int CS = 16, S = 8;
+  pick_geometry(h, N, &CS, &S);
   if (h->profiling) cudaEventRecord(h->ev[4], st);
-  cudaError_t e = launch_decoder(h->dec, a, S, st);
+  cudaError_t e = launch_decoder(h->dec[CS == 16 ? 1 : 0], a, S, st);
   if (h->profiling) cudaEventRecord(h->ev[5], st);
   if (e != cudaSuccess) return fail(h, TACO_ERR_CUDA, std::string("decoder launch: ") + cudaGetErrorString(e));
   h->launches += 1;
@@ -725,6 +746,7 @@ int taco_destroy(taco_handle* h) {
   if (h->dW) cudaFree(h->dW);
   if (h->dB) cudaFree(h->dB);
   if (h->ws) cudaFree(h->ws);
+  if (h->stg) cudaFree(h->stg);
   if (h->d_ints) cudaFree(h->d_ints);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -796,16 +818,19 @@ int taco_finalize_weights(taco_handle* h) {
     return true;
   };
   if (!build()) return bad(err.rfind("missing", 0) == 0 ? TACO_ERR_MISSING_WEIGHT : TACO_ERR_INVALID);
-  // decoder geometry: largest cluster the device schedules; slices are cut for it
+  // decoder weight slices for both cluster sizes; the launch picks per batch size (pick_geometry)
   const char* env = getenv("TACO_DEC_CS");
-  int cs = env ? atoi(env) : 0;
-  if (cs != 8 && cs != 16) cs = decoder_pick_cluster_size();
-  h->CS = cs;
-  h->max_clusters = decoder_max_clusters(cs);
-  if (h->max_clusters < 1) return fail(h, TACO_ERR_UNSUPPORTED, "decoder cluster cannot be scheduled on this device");
-  DecOff O;
-  int McO = 0;
-  if (!pack_decoder(h, A, cs, O, McO, err)) return bad(err.rfind("missing", 0) == 0 ? TACO_ERR_MISSING_WEIGHT : TACO_ERR_INVALID);
+  h->force_cs = env ? atoi(env) : 0;
+  if (h->force_cs != 8 && h->force_cs != 16) h->force_cs = 0;
+  h->max_clusters[0] = decoder_max_clusters(8);
+  h->max_clusters[1] = decoder_max_clusters(16);
+  if (h->max_clusters[0] < 1 && h->max_clusters[1] < 1)
+    return fail(h, TACO_ERR_UNSUPPORTED, "decoder cluster cannot be scheduled on this device");
+  DecOff O[2];
+  int McO[2] = {0, 0};
+  for (int ci = 0; ci < 2; ++ci)
+    if (!pack_decoder(h, A, ci ? 16 : 8, O[ci], McO[ci], err))
+      return bad(err.rfind("missing", 0) == 0 ? TACO_ERR_MISSING_WEIGHT : TACO_ERR_INVALID);
   if (h->dW) { cudaDeviceSynchronize(); cudaFree(h->dW); h->dW = nullptr; }
   CUDA_OK(h, cudaMalloc(&h->dW, sizeof(float) * A.buf.size()));
   CUDA_OK(h, cudaMemcpy(h->dW, A.buf.data(), sizeof(float) * A.buf.size(), cudaMemcpyHostToDevice));
@@ -837,15 +862,18 @@ int taco_finalize_weights(taco_handle* h) {
     const char* gm = getenv("TACO_GEMM");
     if (gm) h->gemm_mode = !strcmp(gm, "ffma") ? 0 : (!strcmp(gm, "bf16") ? 2 : 1);
   }
-  DecoderWeights& d = h->dec;
   const float* B = h->dW;
-  d.CS = cs; d.M = hp.num_mels; d.Dout = hp.num_mels * hp.outputs_per_step; d.McO = McO;
-  d.p1_s = B + O.p1_s; d.p1_b = B + O.p1_b; d.p2_s = B + O.p2_s; d.p2_b = B + O.p2_b;
-  d.ga_s = B + O.ga_s; d.ga_b = B + O.ga_b; d.cxa_s = B + O.cxa_s; d.cha_s = B + O.cha_s; d.ca_b = B + O.ca_b;
-  d.qp_s = B + O.qp_s; d.att_v = B + O.att_v; d.pc_s = B + O.pc_s; d.pc_b = B + O.pc_b;
-  d.g1_s = B + O.g1_s; d.g1_b = B + O.g1_b; d.cx1_s = B + O.cx1_s; d.ch1_s = B + O.ch1_s; d.c1_b = B + O.c1_b;
-  d.g2_s = B + O.g2_s; d.g2_b = B + O.g2_b; d.cx2_s = B + O.cx2_s; d.ch2_s = B + O.ch2_s; d.c2_b = B + O.c2_b;
-  d.o_s = B + O.o_s; d.o_b = B + O.o_b;
+  for (int ci = 0; ci < 2; ++ci) {
+    DecoderWeights& d = h->dec[ci];
+    const DecOff& o = O[ci];
+    d.CS = ci ? 16 : 8; d.M = hp.num_mels; d.Dout = hp.num_mels * hp.outputs_per_step; d.McO = McO[ci];
+    d.p1_s = B + o.p1_s; d.p1_b = B + o.p1_b; d.p2_s = B + o.p2_s; d.p2_b = B + o.p2_b;
+    d.ga_s = B + o.ga_s; d.ga_b = B + o.ga_b; d.cxa_s = B + o.cxa_s; d.cha_s = B + o.cha_s; d.ca_b = B + o.ca_b;
+    d.qp_s = B + o.qp_s; d.att_v = B + o.att_v; d.pc_s = B + o.pc_s; d.pc_b = B + o.pc_b;
+    d.g1_s = B + o.g1_s; d.g1_b = B + o.g1_b; d.cx1_s = B + o.cx1_s; d.ch1_s = B + o.ch1_s; d.c1_b = B + o.c1_b;
+    d.g2_s = B + o.g2_s; d.g2_b = B + o.g2_b; d.cx2_s = B + o.cx2_s; d.ch2_s = B + o.ch2_s; d.c2_b = B + o.c2_b;
+    d.o_s = B + o.o_s; d.o_b = B + o.o_b;
+  }
   h->finalized = true;
   return TACO_OK;
 }
@@ -1064,9 +1092,12 @@ int taco_forward_host(taco_handle* h, const int32_t* ids_host, const int32_t* le
   const size_t n_mel = (size_t)N * maxT * hp.num_mels, n_lin = linear_out_host ? (size_t)N * maxT * hp.num_freq : 0;
   const size_t n_al = align_out_host ? (size_t)N * T_in * max_steps : 0;
   size_t bytes = 256 * 8 + sizeof(int32_t) * (n_ids + 2 * (size_t)N) + sizeof(float) * (n_tgt + n_mel + n_lin + n_al);
-  char* stg = nullptr;
-  CUDA_OK(h, cudaMalloc(&stg, bytes));
-  Bump b(stg, bytes);
+  if (bytes > h->stg_bytes) {
+    if (h->stg) { cudaDeviceSynchronize(); cudaFree(h->stg); h->stg = nullptr; h->stg_bytes = 0; }
+    CUDA_OK(h, cudaMalloc(&h->stg, bytes));
+    h->stg_bytes = bytes;
+  }
+  Bump b(h->stg, h->stg_bytes);
   int32_t* d_ids = b.take<int32_t>(n_ids);
   int32_t* d_len = b.take<int32_t>(N);
   int32_t* d_spk = b.take<int32_t>(N);
@@ -1092,7 +1123,6 @@ int taco_forward_host(taco_handle* h, const int32_t* ids_host, const int32_t* le
     if (n_al) cp(align_out_host, d_al, sizeof(float) * n_al, cudaMemcpyDeviceToHost);
   }
   cudaError_t e = cudaStreamSynchronize(st);
-  cudaFree(stg);
   if (rc == TACO_OK && e != cudaSuccess) rc = fail(h, TACO_ERR_CUDA, std::string("sync: ") + cudaGetErrorString(e));
   if (rc == TACO_OK) rc = taco_check_ids(h, stream);
   if (steps_out_host) *steps_out_host = steps;
@@ -1103,8 +1133,9 @@ int64_t taco_launch_count(const taco_handle* h) { return h ? h->launches : 0; }
 
 int taco_decoder_geometry(const taco_handle* h, int N, int* cluster_size, int* samples_per_cluster, int* num_clusters) {
   if (!h || !h->finalized) return TACO_ERR_STATE;
-  const int S = pick_S(h, N);
-  if (cluster_size) *cluster_size = h->CS;
+  int CS = 16, S = 8;
+  pick_geometry(h, N, &CS, &S);
+  if (cluster_size) *cluster_size = CS;
   if (samples_per_cluster) *samples_per_cluster = S;
   if (num_clusters) *num_clusters = (N + S - 1) / S;
   return TACO_OK;
