@@ -22,6 +22,14 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+// ---- packed fp32 FMA (Blackwell FFMA2: two fp32 FMAs per issue slot) ---------
+// (d0, d1) += (a0, a1) * (b0, b1)
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n.reg .b64 ra, rb, rc;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%0, %1};\n"
+      "fma.rn.f32x2 rc, ra, rb, rc;\nmov.b64 {%0, %1}, rc;\n}"
+      : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 // ---- vector loads --------------------------------------------------------
 __device__ __forceinline__ float4 ldg_f4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));

@@ -156,10 +156,8 @@ __device__ __forceinline__ void gemm_fma(const float4 (&w)[GemmCfg<MC, KMAX>::MA
       }
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        acc[s * 4 + 0] = fmaf(x[s], w[i].x, acc[s * 4 + 0]);
-        acc[s * 4 + 1] = fmaf(x[s], w[i].y, acc[s * 4 + 1]);
-        acc[s * 4 + 2] = fmaf(x[s], w[i].z, acc[s * 4 + 2]);
-        acc[s * 4 + 3] = fmaf(x[s], w[i].w, acc[s * 4 + 3]);
+        ffma2(acc[s * 4 + 0], acc[s * 4 + 1], x[s], x[s], w[i].x, w[i].y);
+        ffma2(acc[s * 4 + 2], acc[s * 4 + 3], x[s], x[s], w[i].z, w[i].w);
       }
     }
   }

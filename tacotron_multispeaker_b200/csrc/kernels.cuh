@@ -104,6 +104,20 @@ struct DecoderArgs {
   float* dec_out;        // [N,max_steps,Dout]
   float* align_out;      // [N,T_in,max_steps] or null
 };
+// v3 (decoder_v3.cu): cluster of 16, warp-owned hidden units.  `stream`: per (CTA, warp) blocks of
+// the weights that multiply freshly exchanged activations, in consumption order; `ew`: the gate
+// halves that multiply the previous state (resident in shared memory); raw (unpermuted) biases.
+struct DecoderWeightsV3 {
+  int M, Dout;
+  const float* stream;   // [16 CTAs][16 warps][36 float4][32 lanes][4]
+  const float* ew;       // [16 CTAs][16 warps][3 GRUs][4 float4][32 lanes][4]
+  const float *p1_b, *p2_b, *ga_b, *ca_b, *pc_b, *g1_b, *c1_b, *g2_b, *c2_b, *o_b, *att_v;
+};
+cudaError_t launch_decoder_v3(const DecoderWeightsV3& w, const DecoderArgs& a, int S, cudaStream_t st);
+size_t decoder_v3_smem_bytes(int S, int T_in, bool att_res);
+int decoder_v3_stream_floats_per_cta();
+int decoder_v3_resident_floats_per_cta();
+
 // S = samples per cluster (1,2,4,8).  Returns cudaError of the launch.
 cudaError_t launch_decoder(const DecoderWeights& w, const DecoderArgs& a, int S, cudaStream_t st);
 // Largest cluster size (16 or 8) the device can co-schedule for the decoder kernel.

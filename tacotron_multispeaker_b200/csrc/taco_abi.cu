@@ -92,6 +92,8 @@ struct taco_handle {
   DecoderWeights dec[2];               // slices cut for clusters of 8 ([0]) and 16 ([1]) CTAs
   int max_clusters[2] = {0, 0};        // co-resident clusters of each size on this device
   int force_cs = 0;
+  DecoderWeightsV3 dec3;               // warp-owned-unit kernel (cluster of 16)
+  int use_v3 = 1;
   // workspace
   char* ws = nullptr;
   size_t ws_bytes = 0;
@@ -410,6 +412,94 @@ bool pack_decoder(taco_handle* h, Arena& A, int CS, DecOff& O, int& McO, std::st
   return true;
 }
 
+struct Dec3Off { size_t stream, ew, p1_b, p2_b, ga_b, ca_b, pc_b, g1_b, c1_b, g2_b, c2_b, o_b, att_v; };
+
+// Weight blocks of decoder_v3.cu: for CTA q, warp w (hidden unit c = 16q + w) and phase block f,
+// float4 (f + g*NCOL + col) of lane l holds W[col][k = l + 32*(4g + j)], j = 0..3.
+bool pack_decoder_v3(taco_handle* h, Arena& A, Dec3Off& O, std::string& err) {
+  const int M = h->hp.num_mels, r = h->hp.outputs_per_step, Dout = M * r;
+  const std::string att = kATT, dpw = att + "decoder_prenet_wrapper/", mrc = kMRC;
+  GETV(w1, dpw + "decoder_prenet/dense_1/kernel", M + DH, 256);
+  GETV(b1, dpw + "decoder_prenet/dense_1/bias", 256);
+  GETV(w2, dpw + "decoder_prenet/dense_2/kernel", 256, 128);
+  GETV(b2, dpw + "decoder_prenet/dense_2/bias", 128);
+  GETV(wga, dpw + "gru_cell/gates/kernel", DP + DH, 2 * DH);
+  GETV(bga, dpw + "gru_cell/gates/bias", 2 * DH);
+  GETV(wca, dpw + "gru_cell/candidate/kernel", DP + DH, DH);
+  GETV(bca, dpw + "gru_cell/candidate/bias", DH);
+  GETV(wq, att + "bahdanau_attention/query_layer/kernel", 256, 256);
+  GETV(v, att + "bahdanau_attention/attention_v", 256);
+  GETV(wp, mrc + "cell_0/output_projection_wrapper/kernel", 512, 256);
+  GETV(bp, mrc + "cell_0/output_projection_wrapper/bias", 256);
+  GETV(wg1, mrc + "cell_1/gru_cell/gates/kernel", 2 * DH, 2 * DH);
+  GETV(bg1, mrc + "cell_1/gru_cell/gates/bias", 2 * DH);
+  GETV(wc1, mrc + "cell_1/gru_cell/candidate/kernel", 2 * DH, DH);
+  GETV(bc1, mrc + "cell_1/gru_cell/candidate/bias", DH);
+  GETV(wg2, mrc + "cell_2/gru_cell/gates/kernel", 2 * DH, 2 * DH);
+  GETV(bg2, mrc + "cell_2/gru_cell/gates/bias", 2 * DH);
+  GETV(wc2, mrc + "cell_2/gru_cell/candidate/kernel", 2 * DH, DH);
+  GETV(bc2, mrc + "cell_2/gru_cell/candidate/bias", DH);
+  GETV(wo, "decoder/output_projection_wrapper/kernel", 256, Dout);
+  GETV(bo, "decoder/output_projection_wrapper/bias", Dout);
+  const int F4_STEP = decoder_v3_stream_floats_per_cta() / (16 * 128);   // float4 per lane per step
+  O.stream = A.alloc((size_t)16 * decoder_v3_stream_floats_per_cta());
+  O.ew = A.alloc((size_t)16 * decoder_v3_resident_floats_per_cta());
+  auto M2 = [](const HostVar* m, int ld, int row, int col) { return m->data[(size_t)row * ld + col]; };
+  for (int q = 0; q < 16; ++q)
+    for (int w = 0; w < 16; ++w) {
+      const int c = q * 16 + w;
+      size_t f = 0;   // float4 index inside this warp's streamed block
+      const size_t sbase = O.stream + (size_t)(q * 16 + w) * F4_STEP * 128;
+      auto blk = [&](size_t base, size_t& fidx, int ncol, int kg, auto val) {
+        for (int g = 0; g < kg; ++g)
+          for (int col = 0; col < ncol; ++col)
+            for (int l = 0; l < 32; ++l)
+              for (int j = 0; j < 4; ++j)
+                A.buf[base + ((fidx + g * ncol + col) * 32 + l) * 4 + j] = val(col, l + 32 * (4 * g + j));
+        fidx += (size_t)kg * ncol;
+      };
+      // P1  prenet dense_1: rows [frame(M) | ctx(256)], zero padded to 384
+      blk(sbase, f, 1, 3, [&](int, int k) { return k < M + DH ? M2(w1, 256, k, c) : 0.f; });
+      // P2  prenet dense_2: 8 units per CTA (warps 0..7)
+      blk(sbase, f, 1, 2, [&](int, int k) { return w < 8 ? M2(w2, 128, k, q * 8 + w) : 0.f; });
+      // P3  attention GRU: gates x-rows (r,u) + candidate x-rows, K = 128
+      blk(sbase, f, 3, 1, [&](int col, int k) {
+        return col == 0 ? M2(wga, 512, k, c) : (col == 1 ? M2(wga, 512, k, DH + c) : M2(wca, 256, k, c)); });
+      // P4  candidate h-rows
+      blk(sbase, f, 1, 2, [&](int, int k) { return M2(wca, 256, DP + k, c); });
+      // P5  query layer | projection rows of h_att
+      blk(sbase, f, 2, 2, [&](int col, int k) { return col == 0 ? M2(wq, 256, k, c) : M2(wp, 256, k, c); });
+      // P8  projection rows of the context
+      blk(sbase, f, 1, 2, [&](int, int k) { return M2(wp, 256, DH + k, c); });
+      // P9  GRU-1 x-rows: r, u, candidate
+      blk(sbase, f, 3, 2, [&](int col, int k) {
+        return col == 0 ? M2(wg1, 512, k, c) : (col == 1 ? M2(wg1, 512, k, DH + c) : M2(wc1, 256, k, c)); });
+      blk(sbase, f, 1, 2, [&](int, int k) { return M2(wc1, 256, DH + k, c); });                 // P10
+      blk(sbase, f, 3, 2, [&](int col, int k) {                                                 // P11
+        return col == 0 ? M2(wg2, 512, k, c) : (col == 1 ? M2(wg2, 512, k, DH + c) : M2(wc2, 256, k, c)); });
+      blk(sbase, f, 1, 2, [&](int, int k) { return M2(wc2, 256, DH + k, c); });                 // P12
+      blk(sbase, f, 2, 2, [&](int col, int k) {                                                 // P13
+        const int oc = q * 32 + 2 * w + col;
+        return oc < Dout ? M2(wo, Dout, k, oc) : 0.f; });
+      if ((int)f != F4_STEP) { err = "decoder v3 packing: block table out of sync with the kernel"; return false; }
+      // resident recurrent halves of the gates: [gru][g*2 + col]
+      size_t e = 0;
+      const size_t ebase = O.ew + (size_t)(q * 16 + w) * 3 * 4 * 128;
+      blk(ebase, e, 2, 2, [&](int col, int k) { return M2(wga, 512, DP + k, col == 0 ? c : DH + c); });
+      blk(ebase, e, 2, 2, [&](int col, int k) { return M2(wg1, 512, DH + k, col == 0 ? c : DH + c); });
+      blk(ebase, e, 2, 2, [&](int col, int k) { return M2(wg2, 512, DH + k, col == 0 ? c : DH + c); });
+    }
+  O.p1_b = put_vec(A, b1->data.data(), 256);   O.p2_b = put_vec(A, b2->data.data(), 128);
+  O.ga_b = put_vec(A, bga->data.data(), 512);  O.ca_b = put_vec(A, bca->data.data(), 256);
+  O.pc_b = put_vec(A, bp->data.data(), 256);
+  O.g1_b = put_vec(A, bg1->data.data(), 512);  O.c1_b = put_vec(A, bc1->data.data(), 256);
+  O.g2_b = put_vec(A, bg2->data.data(), 512);  O.c2_b = put_vec(A, bc2->data.data(), 256);
+  O.o_b = A.alloc(512);
+  memcpy(&A.buf[O.o_b], bo->data.data(), sizeof(float) * Dout);
+  O.att_v = put_vec(A, v->data.data(), 256);
+  return true;
+}
+
 // ---- workspace ---------------------------------------------------------------
 struct Bump {
   char* base; size_t cap, off = 0; bool overflow = false;
@@ -668,8 +758,12 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
   a.dec_out = dec_out; a.align_out = align_out; a.att_res = 0;
   int CS = 16, S = 8;
   pick_geometry(h, N, &CS, &S);
+  if (getenv("TACO_DEBUG"))
+    fprintf(stderr, "[taco] decode N=%d T_in=%d steps=%d CS=%d S=%d kernel=%s max_clusters(8)=%d (16)=%d\n", N, T_in,
+            max_steps, CS, S, (h->use_v3 && CS == 16) ? "v3" : "v2", h->max_clusters[0], h->max_clusters[1]);
   if (h->profiling) cudaEventRecord(h->ev[4], st);
-  cudaError_t e = launch_decoder(h->dec[CS == 16 ? 1 : 0], a, S, st);
+  cudaError_t e = (h->use_v3 && CS == 16) ? launch_decoder_v3(h->dec3, a, S, st)
+                                          : launch_decoder(h->dec[CS == 16 ? 1 : 0], a, S, st);
   if (h->profiling) cudaEventRecord(h->ev[5], st);
   if (e != cudaSuccess) return fail(h, TACO_ERR_CUDA, std::string("decoder launch: ") + cudaGetErrorString(e));
   h->launches += 1;
@@ -831,6 +925,8 @@ int taco_finalize_weights(taco_handle* h) {
   for (int ci = 0; ci < 2; ++ci)
     if (!pack_decoder(h, A, ci ? 16 : 8, O[ci], McO[ci], err))
       return bad(err.rfind("missing", 0) == 0 ? TACO_ERR_MISSING_WEIGHT : TACO_ERR_INVALID);
+  Dec3Off O3;
+  if (!pack_decoder_v3(h, A, O3, err)) return bad(err.rfind("missing", 0) == 0 ? TACO_ERR_MISSING_WEIGHT : TACO_ERR_INVALID);
   if (h->dW) { cudaDeviceSynchronize(); cudaFree(h->dW); h->dW = nullptr; }
   CUDA_OK(h, cudaMalloc(&h->dW, sizeof(float) * A.buf.size()));
   CUDA_OK(h, cudaMemcpy(h->dW, A.buf.data(), sizeof(float) * A.buf.size(), cudaMemcpyHostToDevice));
@@ -863,6 +959,17 @@ int taco_finalize_weights(taco_handle* h) {
     if (gm) h->gemm_mode = !strcmp(gm, "ffma") ? 0 : (!strcmp(gm, "bf16") ? 2 : 1);
   }
   const float* B = h->dW;
+  {
+    DecoderWeightsV3& d = h->dec3;
+    d.M = hp.num_mels; d.Dout = hp.num_mels * hp.outputs_per_step;
+    d.stream = B + O3.stream; d.ew = B + O3.ew;
+    d.p1_b = B + O3.p1_b; d.p2_b = B + O3.p2_b; d.ga_b = B + O3.ga_b; d.ca_b = B + O3.ca_b; d.pc_b = B + O3.pc_b;
+    d.g1_b = B + O3.g1_b; d.c1_b = B + O3.c1_b; d.g2_b = B + O3.g2_b; d.c2_b = B + O3.c2_b; d.o_b = B + O3.o_b;
+    d.att_v = B + O3.att_v;
+    const char* e3 = getenv("TACO_DEC_V3");
+    h->use_v3 = e3 ? atoi(e3) : 0;
+    if (h->max_clusters[1] < 1) h->use_v3 = 0;
+  }
   for (int ci = 0; ci < 2; ++ci) {
     DecoderWeights& d = h->dec[ci];
     const DecOff& o = O[ci];

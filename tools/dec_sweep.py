@@ -36,5 +36,10 @@ def run(N, T_in, iters, cs_list=(16, 8), s_list=(1, 2, 4, 8)):
     os.environ.pop("TACO_DEC_CS", None)
 
 if __name__ == "__main__":
-    run(32, 100, 200)
-    run(1, 50, 200, s_list=(1,))
+    for v3 in ("1", "0"):
+        os.environ["TACO_DEC_V3"] = v3
+        print("=== TACO_DEC_V3=%s ===" % v3, flush=True)
+        run(32, 100, 200, cs_list=(16,))
+        run(1, 50, 200, cs_list=(16,), s_list=(1,))
+    os.environ["TACO_DEC_V3"] = "0"
+    run(32, 100, 200, cs_list=(8,), s_list=(4,))
