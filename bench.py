@@ -83,7 +83,7 @@ class ClockSampler:
             return
         try:
             self.proc = subprocess.Popen([exe, "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -190,53 +190,92 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     hp = HParams(outputs_per_step=R, max_iters=MAX_ITERS)
-    eng = Engine(hp, ID_NUM, local)
-    eng.load_weights(random_init(hp, ID_NUM, seed=1234))
-    ids_h, len_h, spk_h = make_batch(1 + rank)
+    weights = random_init(hp, ID_NUM, seed=1234)
     dev = torch.device("cuda", local)
-    ids = torch.from_numpy(ids_h).to(dev)
-    lengths = torch.from_numpy(len_h).to(dev)
-    spk = torch.from_numpy(spk_h).to(dev)
     T_out = MAX_ITERS * R
-    outs = (torch.zeros(BATCH, T_out, hp.num_mels, device=dev),
-            torch.zeros(BATCH, T_out, hp.num_freq, device=dev),
-            torch.zeros(BATCH, T_IN, MAX_ITERS, device=dev))
+    n_lanes = max(1, args.inflight)
+    # One handle (own weights copy, workspace and CUDA stream) per batch in flight: the decoder loop
+    # occupies 64 of the 148 SMs, so a second batch's encoder / post-net fills the rest.
+    lanes = []
+    for li in range(n_lanes):
+        e = Engine(hp, ID_NUM, local)
+        e.load_weights(weights)
+        ids_h, len_h, spk_h = make_batch(1 + rank + 100 * li)
+        lanes.append(dict(
+            eng=e, stream=torch.cuda.Stream(device=dev),
+            ids=torch.from_numpy(ids_h).to(dev), lengths=torch.from_numpy(len_h).to(dev),
+            spk=torch.from_numpy(spk_h).to(dev), host=(ids_h, len_h, spk_h),
+            outs=(torch.zeros(BATCH, T_out, hp.num_mels, device=dev),
+                  torch.zeros(BATCH, T_out, hp.num_freq, device=dev),
+                  torch.zeros(BATCH, T_IN, MAX_ITERS, device=dev))))
+    eng = lanes[0]["eng"]
+    ids_h, len_h, spk_h = lanes[0]["host"]
 
-    def step():
-        return eng.forward(ids, lengths, spk, out=outs)
+    def step(l):
+        return l["eng"].forward(l["ids"], l["lengths"], l["spk"], out=l["outs"])
+
+    def timed(active, n_steps):
+        """n_steps forward passes spread over the lanes in `active` (one host thread + stream each);
+        device time from a common start event to the last lane's end event."""
+        barrier()
+        start = torch.cuda.Event(enable_timing=True)
+        start.record()
+        ends, taken = [], []
+
+        def work(l, k):
+            with torch.cuda.stream(l["stream"]):
+                l["stream"].wait_event(start)
+                st = 0
+                for _ in range(k):
+                    st = step(l)[3]
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                ends.append(ev)
+                taken.append(st)
+        share = [n_steps // len(active) + (1 if i < n_steps % len(active) else 0) for i in range(len(active))]
+        if len(active) == 1:
+            work(active[0], share[0])
+        else:
+            ths = [threading.Thread(target=work, args=(l, k)) for l, k in zip(active, share) if k > 0]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        barrier()
+        ms = max(start.elapsed_time(ev) for ev in ends)
+        if dist is not None:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms, taken[0]
 
     # ---- device-resident throughput ----
-    for _ in range(max(args.warmup, 3)):
-        step()
-    eng.check_ids()
+    for l in lanes:
+        with torch.cuda.stream(l["stream"]):
+            for _ in range(max(args.warmup, 3)):
+                step(l)
+        l["eng"].check_ids()
+    timed(lanes, 2 * n_lanes)                        # warm the concurrent schedule too
     sampler = ClockSampler(local) if rank == 0 else None
-    barrier()
-    launches0 = eng.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = sum(l["eng"].launch_count() for l in lanes)
     t_wall0 = time.time()
-    e0.record()
-    steps_taken = 0
-    for _ in range(args.steps):
-        _, _, _, steps_taken = step()
-    e1.record()
-    barrier()
-    t_wall1 = time.time()
-    launches = eng.launch_count() - launches0
-    ms_total = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    ms_total, steps_taken = timed(lanes, args.steps)
+    launches = sum(l["eng"].launch_count() for l in lanes) - launches0
     ms_per_step = ms_total / args.steps
     frames_per_step = BATCH * steps_taken * R * world
     value = frames_per_step / (ms_per_step / 1e3)
+    # the same K steps strictly one after the other on one stream (step latency)
+    ms_single, _ = timed(lanes[:1], args.steps)
+    single = {"ms_per_step": ms_single / args.steps, "value": frames_per_step / (ms_single / args.steps / 1e3),
+              "unit": UNIT, "note": "one batch in flight (step latency)"}
+    t_wall1 = time.time()                            # clocks sampled over both timed regions (GPU busy throughout)
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
 
     # ---- decoder-kernel roofline (measured live, CUDA events on the launch stream) ----
     eng.set_profiling(True)
     dk = []
     for _ in range(3):
-        step()
+        step(lanes[0])
         dk.append(eng.last_stage_ms())
     eng.set_profiling(False)
     stage = {k: float(np.mean([d[k] for d in dk])) for k in dk[0]}
@@ -260,27 +299,55 @@ def run_ours(args):
     # ---- end to end through the C-ABI host entry point (pinned host buffers) ----
     def pinned(shape, dtype):
         return torch.empty(shape, dtype=dtype).pin_memory().numpy()
-    ids_p, len_p, spk_p = pinned((BATCH, T_IN), torch.int32), pinned((BATCH,), torch.int32), pinned((BATCH,), torch.int32)
-    ids_p[:], len_p[:], spk_p[:] = ids_h, len_h, spk_h
-    mel_p, lin_p = pinned((BATCH, T_out, hp.num_mels), torch.float32), pinned((BATCH, T_out, hp.num_freq), torch.float32)
-    al_p = pinned((BATCH, T_IN, MAX_ITERS), torch.float32)
-    for _ in range(2):
-        eng.forward_host(ids_p, len_p, spk_p, None, False, _abi.BN_MOVING, mel_p, lin_p, al_p)
-    barrier()
-    k_e2e = max(2, min(args.steps, 10))
-    t0 = time.perf_counter()
-    for _ in range(k_e2e):
-        eng.forward_host(ids_p, len_p, spk_p, None, False, _abi.BN_MOVING, mel_p, lin_p, al_p)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / k_e2e
-    if dist is not None:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    for l in lanes:
+        hi, hl, hs = l["host"]
+        l["pin"] = dict(ids=pinned((BATCH, T_IN), torch.int32), lens=pinned((BATCH,), torch.int32),
+                        spk=pinned((BATCH,), torch.int32), mel=pinned((BATCH, T_out, hp.num_mels), torch.float32),
+                        lin=pinned((BATCH, T_out, hp.num_freq), torch.float32),
+                        al=pinned((BATCH, T_IN, MAX_ITERS), torch.float32))
+        l["pin"]["ids"][:], l["pin"]["lens"][:], l["pin"]["spk"][:] = hi, hl, hs
+
+    def e2e_step(l):
+        b = l["pin"]
+        return l["eng"].forward_host(b["ids"], b["lens"], b["spk"], None, False, _abi.BN_MOVING, b["mel"], b["lin"], b["al"])
+
+    def e2e_timed(active, n_steps):
+        barrier()
+        share = [n_steps // len(active) + (1 if i < n_steps % len(active) else 0) for i in range(len(active))]
+
+        def work(l, k):
+            with torch.cuda.stream(l["stream"]):
+                for _ in range(k):
+                    e2e_step(l)
+        t0 = time.perf_counter()
+        if len(active) == 1:
+            work(active[0], share[0])
+        else:
+            ths = [threading.Thread(target=work, args=(l, k)) for l, k in zip(active, share) if k > 0]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            tt = torch.tensor([dt], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        return dt / n_steps
+    for l in lanes:
+        with torch.cuda.stream(l["stream"]):
+            e2e_step(l)
+    k_e2e = max(2 * n_lanes, min(args.steps, 10))
+    e2e_timed(lanes, 2 * n_lanes)
+    e2e_s = e2e_timed(lanes, k_e2e)
+    e2e_single_s = e2e_timed(lanes[:1], max(2, k_e2e // 2))
+    pb = lanes[0]["pin"]
     e2e = {"value": frames_per_step / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s,
-           "h2d_bytes_per_step": int(ids_p.nbytes + len_p.nbytes + spk_p.nbytes),
-           "d2h_bytes_per_step": int(mel_p.nbytes + lin_p.nbytes + al_p.nbytes),
-           "api": "taco_forward_host (C ABI, pinned host buffers)"}
+           "single_stream_ms_per_step": 1e3 * e2e_single_s,
+           "h2d_bytes_per_step": int(pb["ids"].nbytes + pb["lens"].nbytes + pb["spk"].nbytes),
+           "d2h_bytes_per_step": int(pb["mel"].nbytes + pb["lin"].nbytes + pb["al"].nbytes),
+           "api": "taco_forward_host (C ABI, pinned host buffers; H2D + forward + D2H per step)"}
 
     # ---- CPU restatement on the host cores (rank 0, N=1 only) ----
     cpu = None
@@ -296,12 +363,15 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world), "e2e": e2e, "gpu_launches": int(launches),
+            "config": dict(workload_config(world), inflight="%d batches in flight per GPU (one handle + CUDA stream "
+                                                            "each); single_stream = one at a time" % n_lanes),
+            "single_stream": single, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "decoder_geometry": geo,
         }
         print(json.dumps(line))
-    eng.close()
+    for l in lanes:
+        l["eng"].close()
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -314,6 +384,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU restatement leg")
+    ap.add_argument("--inflight", type=int, default=2, help="batches in flight per GPU (handles/streams)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
