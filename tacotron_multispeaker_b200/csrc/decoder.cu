@@ -249,6 +249,9 @@ __host__ __device__ inline Layout make_layout(int S, int T_in, int M, int CS, bo
 // barrier slots: mb[p] completes when the outputs of phase p have landed in this CTA
 enum { B_P1 = 0, B_P2, B_P3, B_P4, B_P5, B_P6, B_P7, B_P8, B_P9, B_P10, B_P11, B_P12, B_P13 };
 
+// developer aid: clock stamps of (CTA 0, thread 0) at step TRACE_STEP, 64 slots
+#define TR(i) do { if (a.trace != nullptr && t == 8 && blockIdx.x == 0 && tid == 0) a.trace[i] = clock64(); } while (0)
+
 template <int S, int CS>
 __global__ void __launch_bounds__(NT, 1)
 decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
@@ -375,31 +378,42 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
       }
       __syncthreads();
     }
+    TR(0);
     // ================= P1: decoder prenet dense_1 + ReLU  [frame|ctx] -> 256 =================
     gemm_fma<S, Hc, K1MAX>(wb, K1, xin, red);
+    TR(1);
     gemm_load<Pc, DH>(W2, DH, w2);
     __syncthreads();
+    TR(2);
     if (e_on) stage[ec * S + es] = fmaxf(red_sum<S, Hc>(red, es, ec) + b_p1[ec], 0.f);
     __syncthreads();
+    TR(3);
     push_block(p1 + q * Hc * S, stage, Hc * S, CS, mb + B_P1);
     mbar_wait(mb + B_P1, par);
+    TR(4);
     // ================= P2: prenet dense_2 + ReLU  256 -> 128 =================
     gemm_fma<S, Pc, DH>(w2, DH, p1, red);
+    TR(5);
     gemm_load<2 * Hc, 2 * DH>(WgA, DP + DH, wa);
     gemm_load<Hc, K1MAX>(WcxA, DP, wb);
     __syncthreads();
+    TR(6);
     if (tid < S * Pc) {
       const int s = tid / Pc, c = tid % Pc;
       stage[c * S + s] = fmaxf(red_sum<S, Pc>(red, s, c) + b_p2[c], 0.f);
     }
     __syncthreads();
+    TR(7);
     push_block(in3 + q * Pc * S, stage, Pc * S, CS, mb + B_P2);
     mbar_wait(mb + B_P2, par);
+    TR(8);
     // ================= P3: attention GRU gates + candidate x-part =================
     gemm_fma<S, 2 * Hc, 2 * DH>(wa, DP + DH, in3, red);
     gemm_fma<S, Hc, K1MAX>(wb, DP, in3, redB);
+    TR(9);
     gemm_load<Hc, K1MAX>(WchA, DH, wb);
     __syncthreads();
+    TR(10);
     if (e_on) {
       const float r = sigmoid_f(red_sum<S, 2 * Hc>(red, es, ec) + b_ga[ec]);
       const float u = sigmoid_f(red_sum<S, 2 * Hc>(red, es, Hc + ec) + b_ga[Hc + ec]);
@@ -409,12 +423,16 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
       loccx[tid] = red_sum<S, Hc>(redB, es, ec);
     }
     __syncthreads();
+    TR(11);
     push_block(rhA + q * Hc * S, stage, Hc * S, CS, mb + B_P3);
     mbar_wait(mb + B_P3, par);
+    TR(12);
     // ================= P4: attention GRU candidate h-part -> h_att' =================
     gemm_fma<S, Hc, K1MAX>(wb, DH, rhA, red);
+    TR(13);
     gemm_load<2 * Hc, 2 * DH>(Wqp, DH, wa);
     __syncthreads();
+    TR(14);
     if (e_on) {
       const float c = tanh_f(red_sum<S, Hc>(red, es, ec) + loccx[tid] + b_ca[ec]);
       const float u = locu[tid];
@@ -422,20 +440,26 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
       stage[ec * S + es] = u * hold + (1.0f - u) * c;
     }
     __syncthreads();
+    TR(15);
     push_block(in3 + (DP + q * Hc) * S, stage, Hc * S, CS, mb + B_P4);
     mbar_wait(mb + B_P4, par);
+    TR(16);
     // ================= P5: query layer + h_att' part of the 512->256 projection =================
     gemm_fma<S, 2 * Hc, 2 * DH>(wa, DH, in3 + DP * S, red);
+    TR(17);
     gemm_load<Hc, K1MAX>(Wpc, DH, wb);
     __syncthreads();
+    TR(18);
     if (e_on) {
       stage[es * Hc + ec] = red_sum<S, 2 * Hc>(red, es, ec);          // layout [S][Hc] for pqT
       locy0h[tid] = red_sum<S, 2 * Hc>(red, es, Hc + ec);
     }
     __syncthreads();
+    TR(19);
 #pragma unroll
     for (int s = 0; s < S; ++s) push_block(pqT + s * DH + q * Hc, stage + s * Hc, Hc, CS, mb + B_P5);
     mbar_wait(mb + B_P5, par);
+    TR(20);
     // ================= P6: Bahdanau scores for positions [j0,j1) =================
     {
       const int npairs = S * (j1 - j0);
@@ -460,8 +484,10 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
       }
     }
     __syncthreads();
+    TR(21);
     if (j1 > j0) push_block(sc + j0 * S, stage, (j1 - j0) * S, CS, mb + B_P6);
     mbar_wait(mb + B_P6, par);
+    TR(22);
     // ================= P7: softmax over all T_in (no mask) + context slice =================
     if (warp < S) {
       const int s = warp;
@@ -479,6 +505,7 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
       for (int j = lane; j < T_in; j += 32) sc[j * S + s] *= inv;
     }
     __syncthreads();
+    TR(23);
     if (a.align_out != nullptr) {
       for (int i = tid; i < S * (j1 - j0); i += NT) {
         const int jj = i / S, s = i - jj * S, n = n0 + s;
@@ -520,22 +547,30 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
       }
     }
     __syncthreads();
+    TR(24);
     push_block(xin + (M + q * Hc) * S, stage, Hc * S, CS, mb + B_P7);
     mbar_wait(mb + B_P7, par);
+    TR(25);
     // ================= P8: y0 = [h_att'|ctx] W_p + b  (ctx part; h part from P5) =================
     gemm_fma<S, Hc, K1MAX>(wb, DH, xin + M * S, red);
+    TR(26);
     gemm_load<2 * Hc, 2 * DH>(Wg1, 2 * DH, wa);
     gemm_load<Hc, K1MAX>(Wcx1, DH, wb);
     __syncthreads();
+    TR(27);
     if (e_on) stage[ec * S + es] = red_sum<S, Hc>(red, es, ec) + locy0h[tid] + b_pc[ec];
     __syncthreads();
+    TR(28);
     push_block(in9 + q * Hc * S, stage, Hc * S, CS, mb + B_P8);
     mbar_wait(mb + B_P8, par);
+    TR(29);
     // ================= P9/P10: residual GRU 1 =================
     gemm_fma<S, 2 * Hc, 2 * DH>(wa, 2 * DH, in9, red);
     gemm_fma<S, Hc, K1MAX>(wb, DH, in9, redB);
+    TR(30);
     gemm_load<Hc, K1MAX>(Wch1, DH, wb);
     __syncthreads();
+    TR(31);
     if (e_on) {
       const float r = sigmoid_f(red_sum<S, 2 * Hc>(red, es, ec) + b_g1[ec]);
       const float u = sigmoid_f(red_sum<S, 2 * Hc>(red, es, Hc + ec) + b_g1[Hc + ec]);
@@ -544,12 +579,16 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
       loccx[tid] = red_sum<S, Hc>(redB, es, ec);
     }
     __syncthreads();
+    TR(32);
     push_block(rh1 + q * Hc * S, stage, Hc * S, CS, mb + B_P9);
     mbar_wait(mb + B_P9, par);
+    TR(33);
     gemm_fma<S, Hc, K1MAX>(wb, DH, rh1, red);
+    TR(34);
     gemm_load<2 * Hc, 2 * DH>(Wg2, 2 * DH, wa);
     gemm_load<Hc, K1MAX>(Wcx2, DH, wb);
     __syncthreads();
+    TR(35);
     if (e_on) {
       const float c = tanh_f(red_sum<S, Hc>(red, es, ec) + loccx[tid] + b_c1[ec]);
       const float u = locu[tid];
@@ -559,14 +598,18 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
       stage2[ec * S + es] = in9[(q * Hc + ec) * S + es] + hn;     // y1 = y0 + GRU1(y0)  (ResidualWrapper)
     }
     __syncthreads();
+    TR(36);
     push_block(in9 + (DH + q * Hc) * S, stage, Hc * S, CS, mb + B_P10);
     push_block(in11 + q * Hc * S, stage2, Hc * S, CS, mb + B_P10);
     mbar_wait(mb + B_P10, par);
+    TR(37);
     // ================= P11/P12: residual GRU 2 =================
     gemm_fma<S, 2 * Hc, 2 * DH>(wa, 2 * DH, in11, red);
     gemm_fma<S, Hc, K1MAX>(wb, DH, in11, redB);
+    TR(38);
     gemm_load<Hc, K1MAX>(Wch2, DH, wb);
     __syncthreads();
+    TR(39);
     if (e_on) {
       const float r = sigmoid_f(red_sum<S, 2 * Hc>(red, es, ec) + b_g2[ec]);
       const float u = sigmoid_f(red_sum<S, 2 * Hc>(red, es, Hc + ec) + b_g2[Hc + ec]);
@@ -575,12 +618,16 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
       loccx[tid] = red_sum<S, Hc>(redB, es, ec);
     }
     __syncthreads();
+    TR(40);
     push_block(rh2 + q * Hc * S, stage, Hc * S, CS, mb + B_P11);
     mbar_wait(mb + B_P11, par);
+    TR(41);
     gemm_fma<S, Hc, K1MAX>(wb, DH, rh2, red);
+    TR(42);
     gemm_load<McO, DH>(Wo, DH, wo);
     gemm_load<Hc, K1MAX>(W1, K1, wb);
     __syncthreads();
+    TR(43);
     if (e_on) {
       const float c = tanh_f(red_sum<S, Hc>(red, es, ec) + loccx[tid] + b_c2[ec]);
       const float u = locu[tid];
@@ -590,12 +637,15 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
       stage2[ec * S + es] = in11[(q * Hc + ec) * S + es] + hn;    // y2 = y1 + GRU2(y1)
     }
     __syncthreads();
+    TR(44);
     push_block(in11 + (DH + q * Hc) * S, stage, Hc * S, CS, mb + B_P12);
     push_block(y2 + q * Hc * S, stage2, Hc * S, CS, mb + B_P12);
     mbar_wait(mb + B_P12, par);
+    TR(45);
     // ================= P13: output projection 256 -> 80*r, write frames, feed back =================
     gemm_fma<S, McO, DH>(wo, DH, y2, red);
     __syncthreads();
+    TR(46);
     const int fb0 = Dout - M;                                  // first fed-back column (helpers.py:37)
     const int c_lo = max(q * McO, fb0), c_hi = min((q + 1) * McO, Dout);
     if (tid < S * McO) {
@@ -607,6 +657,7 @@ decoder_kernel(const DecoderWeights w, const DecoderArgs a) {
       }
     }
     __syncthreads();
+    TR(47);
     if (free_run && c_hi > c_lo) push_block(xin + (c_lo - fb0) * S, stage, (c_hi - c_lo) * S, CS, mb + B_P13);
   }
   // nobody may exit while a peer can still write into its shared memory

@@ -94,6 +94,9 @@ struct taco_handle {
   int force_cs = 0;
   DecoderWeightsV3 dec3;               // warp-owned-unit kernel (cluster of 16)
   int use_v3 = 1;
+  DecoderMmaWeights dec4;              // mma.sync kernel (decoder_mma.cu): the default decoder
+  int use_mma = 0;
+  int max_clusters_mma = 0;
   // workspace
   char* ws = nullptr;
   size_t ws_bytes = 0;
@@ -500,6 +503,172 @@ bool pack_decoder_v3(taco_handle* h, Arena& A, Dec3Off& O, std::string& err) {
   return true;
 }
 
+
+// ---- decoder_mma.cu packing -------------------------------------------------------------------
+// Work table of the MMA decoder: which 16-row chunks of which activation buffer every warp
+// multiplies in every phase (see decoder_mma.cu).  Entry = count | chunk0 << 3 | buffer << 8 | tile << 12.
+struct DmItem { int tile = 0, buf = 0, c0 = 0, cnt = 0; };
+void dm_table(int FC, DmItem (&tab)[DM_NPHASE][16]) {
+  for (auto& ph : tab) for (auto& e : ph) e = DmItem();
+  auto single = [&](int ph, int buf) { for (int w = 0; w < 8; ++w) tab[ph][w] = {0, buf, 2 * w, 2}; };
+  auto two = [&](int ph, int buf) {
+    for (int w = 0; w < 8; ++w) { tab[ph][w] = {0, buf, 2 * w, 2}; tab[ph][8 + w] = {1, buf, 2 * w, 2}; }
+  };
+  // P1: context chunks on warps 0..7, frame chunks on warps 8..10
+  single(0, DM_BC);
+  for (int i = 0, c = 0; i < 3; ++i) { const int n = FC / 3 + (i < FC % 3 ? 1 : 0); tab[0][8 + i] = {0, DM_BF, c, n}; c += n; }
+  single(1, DM_BP1);                                   // P2
+  for (int tile = 0; tile < 2; ++tile) {               // P3: r, u over [prenet(8 chunks) | h_att(16 chunks)]
+    tab[2][tile * 6 + 0] = {tile, DM_BP2, 0, 4};
+    tab[2][tile * 6 + 1] = {tile, DM_BP2, 4, 4};
+    for (int i = 0; i < 4; ++i) tab[2][tile * 6 + 2 + i] = {tile, DM_BHA, 4 * i, 4};
+  }
+  for (int i = 0; i < 4; ++i) tab[2][12 + i] = {2, DM_BP2, 2 * i, 2};
+  single(3, DM_BRA);                                   // P4
+  two(4, DM_BHA);                                      // P5: query | projection(h_att)
+  single(5, DM_BC);                                    // P8
+  auto gru = [&](int ph, int bx, int bh) {             // P9 / P11
+    const int c0[3] = {0, 6, 11}, n[3] = {6, 5, 5};
+    for (int tile = 0; tile < 2; ++tile)
+      for (int i = 0; i < 3; ++i) {
+        tab[ph][tile * 6 + i] = {tile, bx, c0[i], n[i]};
+        tab[ph][tile * 6 + 3 + i] = {tile, bh, c0[i], n[i]};
+      }
+    for (int i = 0; i < 4; ++i) tab[ph][12 + i] = {2, bx, 4 * i, 4};
+  };
+  gru(6, DM_BY0, DM_BH1);
+  single(7, DM_BR1);                                   // P10
+  gru(8, DM_BY1, DM_BH2);
+  single(9, DM_BR2);                                   // P12
+  two(10, DM_BY2);                                     // P13
+}
+
+inline uint16_t bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float bf16_f(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
+inline int dm_pos16(int c) { return ((c & 7) >> 1) * 4 + (c >> 3) * 2 + (c & 1); }
+
+struct DmOff { size_t stream, bias, att_v; };
+
+bool pack_decoder_mma(taco_handle* h, Arena& A, DmOff& O, uint32_t (&tabw)[DM_NPHASE][16], std::string& err) {
+  const int M = h->hp.num_mels, r = h->hp.outputs_per_step, Dout = M * r, FC = M / 16;
+  const std::string att = kATT, dpw = att + "decoder_prenet_wrapper/", mrc = kMRC;
+  GETV(w1, dpw + "decoder_prenet/dense_1/kernel", M + DH, 256);
+  GETV(b1, dpw + "decoder_prenet/dense_1/bias", 256);
+  GETV(w2, dpw + "decoder_prenet/dense_2/kernel", 256, 128);
+  GETV(b2, dpw + "decoder_prenet/dense_2/bias", 128);
+  GETV(wga, dpw + "gru_cell/gates/kernel", DP + DH, 2 * DH);
+  GETV(bga, dpw + "gru_cell/gates/bias", 2 * DH);
+  GETV(wca, dpw + "gru_cell/candidate/kernel", DP + DH, DH);
+  GETV(bca, dpw + "gru_cell/candidate/bias", DH);
+  GETV(wq, att + "bahdanau_attention/query_layer/kernel", 256, 256);
+  GETV(v, att + "bahdanau_attention/attention_v", 256);
+  GETV(wp, mrc + "cell_0/output_projection_wrapper/kernel", 512, 256);
+  GETV(bp, mrc + "cell_0/output_projection_wrapper/bias", 256);
+  GETV(wg1, mrc + "cell_1/gru_cell/gates/kernel", 2 * DH, 2 * DH);
+  GETV(bg1, mrc + "cell_1/gru_cell/gates/bias", 2 * DH);
+  GETV(wc1, mrc + "cell_1/gru_cell/candidate/kernel", 2 * DH, DH);
+  GETV(bc1, mrc + "cell_1/gru_cell/candidate/bias", DH);
+  GETV(wg2, mrc + "cell_2/gru_cell/gates/kernel", 2 * DH, 2 * DH);
+  GETV(bg2, mrc + "cell_2/gru_cell/gates/bias", 2 * DH);
+  GETV(wc2, mrc + "cell_2/gru_cell/candidate/kernel", 2 * DH, DH);
+  GETV(bc2, mrc + "cell_2/gru_cell/candidate/bias", DH);
+  GETV(wo, "decoder/output_projection_wrapper/kernel", 256, Dout);
+  GETV(bo, "decoder/output_projection_wrapper/bias", Dout);
+  DmItem tab[DM_NPHASE][16];
+  dm_table(FC, tab);
+  static const int nch[DM_NPHASE] = {DM_NCH1, 2, 4, 2, 2, 2, 6, 2, 6, 2, 2};
+  int off[DM_NPHASE + 1];
+  off[0] = 0;
+  for (int p = 0; p < DM_NPHASE; ++p) off[p + 1] = off[p] + 2 * nch[p];
+  if (off[DM_NPHASE] != DM_F4_STEP) { err = "decoder_mma packing: stream table out of sync"; return false; }
+  for (int p = 0; p < DM_NPHASE; ++p)
+    for (int wp = 0; wp < 16; ++wp) {
+      const DmItem& e = tab[p][wp];
+      if (e.cnt > nch[p] || e.cnt > 7 || e.c0 > 31) { err = "decoder_mma packing: work table overflow"; return false; }
+      tabw[p][wp] = (uint32_t)e.cnt | ((uint32_t)e.c0 << 3) | ((uint32_t)e.buf << 8) | ((uint32_t)e.tile << 12);
+    }
+  auto M2 = [](const HostVar* m, int ld, int row, int col) { return m->data[(size_t)row * ld + col]; };
+  // first K row of chunk 0 of buffer `buf` inside the TF kernel of phase `p`
+  auto krow0 = [&](int p, int buf) -> int {
+    switch (p) {
+      case 0: return buf == DM_BF ? 0 : M;          // [frame | ctx]
+      case 2: return buf == DM_BP2 ? 0 : DP;        // [prenet | h_att]
+      case 3: return DP;                            // candidate rows of r*h_att
+      case 5: return DH;                            // projection rows of the context
+      case 6: case 8: return (buf == DM_BY0 || buf == DM_BY1) ? 0 : DH;
+      case 7: case 9: return DH;
+      default: return 0;
+    }
+  };
+  // weight A[c][k] of (phase, tile) for CTA q: TF kernel element (row k, column of tile row c)
+  auto wval = [&](int p, int q, int tile, int k, int c) -> float {
+    const int col = 16 * q + c;
+    switch (p) {
+      case 0: return M2(w1, 256, k, col);
+      case 1: return M2(w2, 128, k, 16 * (q >> 1) + c);
+      case 2: return tile == 0 ? M2(wga, 512, k, col) : (tile == 1 ? M2(wga, 512, k, DH + col) : M2(wca, 256, k, col));
+      case 3: return M2(wca, 256, k, col);
+      case 4: return tile == 0 ? M2(wq, 256, k, col) : M2(wp, 256, k, col);
+      case 5: return M2(wp, 256, k, col);
+      case 6: return tile == 0 ? M2(wg1, 512, k, col) : (tile == 1 ? M2(wg1, 512, k, DH + col) : M2(wc1, 256, k, col));
+      case 7: return M2(wc1, 256, k, col);
+      case 8: return tile == 0 ? M2(wg2, 512, k, col) : (tile == 1 ? M2(wg2, 512, k, DH + col) : M2(wc2, 256, k, col));
+      case 9: return M2(wc2, 256, k, col);
+      default: {
+        const int oc = (2 * q + tile) * 16 + c;
+        return oc < Dout ? M2(wo, Dout, k, oc) : 0.0f;
+      }
+    }
+  };
+  O.stream = A.alloc((size_t)16 * 16 * DM_F4_STEP * 32 * 4);
+  uint32_t* S32 = reinterpret_cast<uint32_t*>(&A.buf[O.stream]);
+  for (int q = 0; q < 16; ++q)
+    for (int wp = 0; wp < 16; ++wp)
+      for (int p = 0; p < DM_NPHASE; ++p) {
+        const DmItem& e = tab[p][wp];
+        for (int i = 0; i < e.cnt; ++i) {
+          const int kbase = krow0(p, e.buf) + (e.c0 + i) * 16;
+          for (int lane = 0; lane < 32; ++lane) {
+            const int g = lane >> 2, t = lane & 3;
+            const int rows[4] = {g, g + 8, g, g + 8}, ks[4] = {2 * t, 2 * t, 2 * t + 8, 2 * t + 8};
+            uint32_t* hi = S32 + ((((size_t)(q * 16 + wp) * DM_F4_STEP) + off[p] + 2 * i) * 32 + lane) * 4;
+            uint32_t* lo = hi + 32 * 4;
+            for (int j = 0; j < 4; ++j) {
+              const float a0 = wval(p, q, e.tile, kbase + ks[j], rows[j]), a1 = wval(p, q, e.tile, kbase + ks[j] + 1, rows[j]);
+              const uint16_t h0 = bf16_rn(a0), h1 = bf16_rn(a1);
+              const uint16_t l0 = bf16_rn(a0 - bf16_f(h0)), l1 = bf16_rn(a1 - bf16_f(h1));
+              hi[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+              lo[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+          }
+        }
+      }
+  O.bias = A.alloc((size_t)16 * DM_NBIAS);
+  for (int q = 0; q < 16; ++q) {
+    float* B = &A.buf[O.bias + (size_t)q * DM_NBIAS];
+    for (int c = 0; c < 16; ++c) {
+      const int col = 16 * q + c, ps = dm_pos16(c);
+      B[0 + ps] = b1->data[col];
+      B[16 + ps] = b2->data[16 * (q >> 1) + c];
+      B[32 + ps] = bga->data[col];   B[48 + ps] = bga->data[DH + col];   B[64 + ps] = bca->data[col];
+      B[80 + ps] = bp->data[col];
+      B[96 + ps] = bg1->data[col];   B[112 + ps] = bg1->data[DH + col];  B[128 + ps] = bc1->data[col];
+      B[144 + ps] = bg2->data[col];  B[160 + ps] = bg2->data[DH + col];  B[176 + ps] = bc2->data[col];
+      const int oa = (2 * q) * 16 + c, ob = (2 * q + 1) * 16 + c;
+      B[192 + ps] = oa < Dout ? bo->data[oa] : 0.0f;
+      B[208 + ps] = ob < Dout ? bo->data[ob] : 0.0f;
+    }
+  }
+  O.att_v = put_vec(A, v->data.data(), 256);
+  return true;
+}
+
 // ---- workspace ---------------------------------------------------------------
 struct Bump {
   char* base; size_t cap, off = 0; bool overflow = false;
@@ -669,6 +838,26 @@ void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, 
 // decoder weight set once per step, so fewer/larger clusters save L2 bandwidth while more
 // clusters shorten the per-sample work; clusters beyond the co-resident maximum run as extra
 // waves.  Per-wave step times (us) measured on B200 (tools/dec_sweep.py, round 1).
+// Clusters for the mma.sync decoder: whole waves of co-resident clusters, <= 8 samples each; the
+// per-wave time grows with the samples per cluster (exchange bytes), roughly 1 + 0.1 S.
+int pick_mma_clusters(const taco_handle* h, int N) {
+  const char* en = getenv("TACO_DEC_NCL");
+  if (en && atoi(en) > 0) return std::min(N, std::max(atoi(en), (N + 7) / 8));
+  const char* es = getenv("TACO_DEC_S");   // samples per cluster (tests sweep it)
+  if (es && atoi(es) > 0) return (N + std::min(atoi(es), 8) - 1) / std::min(atoi(es), 8);
+  const int maxc = std::max(1, h->max_clusters_mma);
+  float best = 1e30f;
+  int bn = (N + 7) / 8;
+  for (int waves = 1; waves <= 64; ++waves) {
+    const int ncl = std::min(N, waves * maxc), S = (N + ncl - 1) / ncl;
+    if (S > 8) continue;
+    const float cost = ((ncl + maxc - 1) / maxc) * (1.0f + 0.1f * S);
+    if (cost < best - 1e-4f) { best = cost; bn = ncl; }
+    if (ncl == N) break;
+  }
+  return bn;
+}
+
 void pick_geometry(const taco_handle* h, int N, int* cs_out, int* s_out) {
   static const float t_wave[2][4] = {{12.3f, 15.6f, 20.2f, 35.2f},    // CS = 8 : S = 1,2,4,8
                                      {11.2f, 12.7f, 15.5f, 25.6f}};   // CS = 16
@@ -755,18 +944,38 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
   DecoderArgs a;
   a.memory = memory; a.keys = keys; a.targets = teacher_force ? mel_targets : nullptr;
   a.N = N; a.T_in = T_in; a.T_tgt = T_tgt; a.r = hp.outputs_per_step; a.steps = max_steps; a.max_steps = max_steps;
-  a.dec_out = dec_out; a.align_out = align_out; a.att_res = 0;
+  a.dec_out = dec_out; a.align_out = align_out; a.att_res = 0; a.s_max = 0; a.trace = nullptr;
+  const char* trace_path = getenv("TACO_DEC_TRACE");   // developer aid: per-phase clock stamps of CTA 0
+  long long* d_trace = nullptr;
+  if (trace_path) {
+    cudaMalloc(&d_trace, 256 * sizeof(long long));
+    cudaMemsetAsync(d_trace, 0, 256 * sizeof(long long), st);
+    a.trace = d_trace;
+  }
   int CS = 16, S = 8;
   pick_geometry(h, N, &CS, &S);
   if (getenv("TACO_DEBUG"))
     fprintf(stderr, "[taco] decode N=%d T_in=%d steps=%d CS=%d S=%d kernel=%s max_clusters(8)=%d (16)=%d\n", N, T_in,
-            max_steps, CS, S, (h->use_v3 && CS == 16) ? "v3" : "v2", h->max_clusters[0], h->max_clusters[1]);
+            max_steps, CS, S, h->use_mma ? "mma" : ((h->use_v3 && CS == 16) ? "v3" : "v2"), h->max_clusters[0], h->max_clusters[1]);
   if (h->profiling) cudaEventRecord(h->ev[4], st);
-  cudaError_t e = (h->use_v3 && CS == 16) ? launch_decoder_v3(h->dec3, a, S, st)
-                                          : launch_decoder(h->dec[CS == 16 ? 1 : 0], a, S, st);
+  const bool use_mma = h->use_mma && (N + pick_mma_clusters(h, N) - 1) / pick_mma_clusters(h, N) <= 8;
+  cudaError_t e = use_mma ? launch_decoder_mma(h->dec4, a, pick_mma_clusters(h, N), st)
+                  : (h->use_v3 && CS == 16) ? launch_decoder_v3(h->dec3, a, S, st)
+                                            : launch_decoder(h->dec[CS == 16 ? 1 : 0], a, S, st);
   if (h->profiling) cudaEventRecord(h->ev[5], st);
   if (e != cudaSuccess) return fail(h, TACO_ERR_CUDA, std::string("decoder launch: ") + cudaGetErrorString(e));
   h->launches += 1;
+  if (d_trace) {
+    long long ht[256];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(ht, d_trace, sizeof(ht), cudaMemcpyDeviceToHost);
+    cudaFree(d_trace);
+    if (FILE* f = fopen(trace_path, "w")) {
+      fprintf(f, "# N=%d T_in=%d CS=%d S=%d\n", N, T_in, CS, S);
+      for (int i = 0; i < 256; ++i) fprintf(f, "%d %lld\n", i, ht[i]);
+      fclose(f);
+    }
+  }
   int steps = max_steps;
   if (!teacher_force) {
     int rc = ensure_ints(h, 2 + N);
@@ -927,6 +1136,11 @@ int taco_finalize_weights(taco_handle* h) {
       return bad(err.rfind("missing", 0) == 0 ? TACO_ERR_MISSING_WEIGHT : TACO_ERR_INVALID);
   Dec3Off O3;
   if (!pack_decoder_v3(h, A, O3, err)) return bad(err.rfind("missing", 0) == 0 ? TACO_ERR_MISSING_WEIGHT : TACO_ERR_INVALID);
+  // mma.sync decoder (default): needs num_mels and num_mels*r to be multiples of the 16-column tile
+  DmOff O4{0, 0, 0};
+  const bool mma_ok = hp.num_mels % 16 == 0 && hp.num_mels <= 128;
+  if (mma_ok && !pack_decoder_mma(h, A, O4, h->dec4.tab, err))
+    return bad(err.rfind("missing", 0) == 0 ? TACO_ERR_MISSING_WEIGHT : TACO_ERR_INVALID);
   if (h->dW) { cudaDeviceSynchronize(); cudaFree(h->dW); h->dW = nullptr; }
   CUDA_OK(h, cudaMalloc(&h->dW, sizeof(float) * A.buf.size()));
   CUDA_OK(h, cudaMemcpy(h->dW, A.buf.data(), sizeof(float) * A.buf.size(), cudaMemcpyHostToDevice));
@@ -969,6 +1183,15 @@ int taco_finalize_weights(taco_handle* h) {
     const char* e3 = getenv("TACO_DEC_V3");
     h->use_v3 = e3 ? atoi(e3) : 0;
     if (h->max_clusters[1] < 1) h->use_v3 = 0;
+  }
+  {
+    DecoderMmaWeights& d = h->dec4;
+    d.M = hp.num_mels; d.Dout = hp.num_mels * hp.outputs_per_step;
+    d.stream = B + O4.stream; d.bias = B + O4.bias; d.att_v = B + O4.att_v;
+    h->max_clusters_mma = mma_ok ? decoder_mma_max_clusters() : 0;
+    const char* ei = getenv("TACO_DEC_IMPL");   // "mma" (default) | "v2" | "v3": developer switch between decoder kernels
+    h->use_mma = mma_ok && h->max_clusters_mma >= 1 && !(ei && strcmp(ei, "mma") != 0);
+    if (ei && strcmp(ei, "v3") == 0 && h->max_clusters[1] >= 1) h->use_v3 = 1;
   }
   for (int ci = 0; ci < 2; ++ci) {
     DecoderWeights& d = h->dec[ci];
@@ -1242,9 +1465,15 @@ int taco_decoder_geometry(const taco_handle* h, int N, int* cluster_size, int* s
   if (!h || !h->finalized) return TACO_ERR_STATE;
   int CS = 16, S = 8;
   pick_geometry(h, N, &CS, &S);
+  int ncl = (N + S - 1) / S;
+  if (h->use_mma && N > 0) {
+    ncl = pick_mma_clusters(h, N);
+    CS = 16;
+    S = (N + ncl - 1) / ncl;
+  }
   if (cluster_size) *cluster_size = CS;
   if (samples_per_cluster) *samples_per_cluster = S;
-  if (num_clusters) *num_clusters = (N + S - 1) / S;
+  if (num_clusters) *num_clusters = ncl;
   return TACO_OK;
 }
 

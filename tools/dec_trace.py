@@ -1,0 +1,54 @@
+"""Developer aid: per-phase clock stamps of the decoder kernel (TACO_DEC_TRACE) for a few geometries."""
+import os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import make_inputs
+from tacotron_multispeaker_b200.engine import Engine
+from tacotron_multispeaker_b200.hparams import HParams
+from tacotron_multispeaker_b200.weights import random_init
+
+def run(N, T_in, cs, S, tag, iters=40):
+    hp = HParams(outputs_per_step=5, max_iters=iters)
+    w = random_init(hp, 60, seed=1234)
+    ids, lengths, spk = make_inputs(N, T_in, 60, 1, min_len=max(1, int(T_in * 0.6)), vocab=(7108, 7325))
+    os.environ["TACO_DEC_CS"] = str(cs); os.environ["TACO_DEC_S"] = str(S)
+    eng = Engine(hp, 60); eng.load_weights(w); eng.set_profiling(True)
+    mem = eng.encoder(ids, lengths, spk, 0)
+    for _ in range(2):
+        eng.decode(mem, None, False, True)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(3):
+        eng.decode(mem, None, False, True)
+    ev1.record(); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / 3
+    path = os.path.join(ROOT, "gpurun_out", "trace_%s.txt" % tag)
+    os.environ["TACO_DEC_TRACE"] = path
+    eng.decode(mem, None, False, True)
+    torch.cuda.synchronize()
+    os.environ.pop("TACO_DEC_TRACE")
+    st = [int(l.split()[1]) for l in open(path) if not l.startswith("#")]
+    n = max(i for i, v in enumerate(st) if v) + 1
+    d = [st[i] - st[i - 1] for i in range(1, n)]
+    n = 39 if st[38] else n
+    d = [st[i] - st[i - 1] for i in range(1, n)]
+    print("%s N=%d CS=%d S=%d: %.2f us/step; traced step %d clk; deltas: %s" % (tag, N, cs, S, ms * 1e3 / iters, st[n - 1] - st[0], d), flush=True)
+    if st[40]:
+        print("   fine stamps 40..: ", [(i, st[i] - st[9]) for i in range(40, 60) if st[i]], " (relative to stamp 9; stamp 10 at %d)" % (st[10] - st[9]), flush=True)
+    eng.close()
+
+if __name__ == "__main__":
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    impl = os.environ.get("TACO_DEC_IMPL", "mma")
+    if impl == "mma":
+        pass
+        for (N, T_in, S) in [(1, 50, 1), (32, 100, 5)]:
+            run(N, T_in, 16, S, "mma_n%d_s%d" % (N, S), iters=200)
+    else:
+        run(1, 50, 16, 1, "n1_cs16_s1")
+        run(4, 100, 16, 4, "n4_cs16_s4")
+        run(4, 100, 8, 4, "n4_cs8_s4")
+        run(32, 100, 8, 4, "n32_cs8_s4")
+        run(28, 100, 16, 4, "n28_cs16_s4")

@@ -16,9 +16,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t mb, uint32_t parity) {
 // mode 2: one warp per peer sends 16 B x 4 lanes (v2 pattern: 64 B block per source CTA)
 // mode 3: barrier.cluster arrive.release + wait.acquire only
 // mode 4: like 0 but only warp 0 sends (16 messages per CTA per round)
+// mode 5: 64 B block staged in local smem, warp 0 lane p bulk-copies it to peer p (cp.async.bulk smem->dsmem)
+// mode 6: like 5 with a 256 B block
+// mode 7: like 2 with 256 B per source CTA (16 lanes x 16 B per peer)
 template <int MODE>
 __global__ void __launch_bounds__(512, 1) k(int iters, long long* out) {
   __shared__ __align__(16) float buf[2][16 * 16 * 4];
+  __shared__ __align__(16) float stg[2][64];
   __shared__ __align__(8) uint64_t mb[2];
   uint32_t nct; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(nct));
   uint32_t q; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(q));
@@ -36,6 +40,8 @@ __global__ void __launch_bounds__(512, 1) k(int iters, long long* out) {
       continue;
     }
     uint32_t bytes = MODE == 0 ? 16 * nct * 4 : (MODE == 1 ? 16 * nct * 16 : (MODE == 2 ? nct * 64 : nct * 4));
+    if (MODE == 5) bytes = nct * 64;
+    if (MODE == 6 || MODE == 7) bytes = nct * 256;
     if (threadIdx.x == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mb[b])), "r"(bytes) : "memory");
     if (MODE == 0 || MODE == 1) {
       if (lane < (int)nct) {
@@ -44,6 +50,21 @@ __global__ void __launch_bounds__(512, 1) k(int iters, long long* out) {
       }
     } else if (MODE == 2) {
       if (wp < (int)nct && lane < 4) {
+        uint32_t ra = mapa(smem_u32(&buf[b][(q * 16 + lane) * 4]), wp), rm = mapa(smem_u32(&mb[b]), wp);
+        st_async4(ra, acc + it, rm);
+      }
+    } else if (MODE == 5 || MODE == 6) {
+      constexpr int NB = MODE == 5 ? 64 : 256;
+      if (threadIdx.x < NB / 4) stg[b][threadIdx.x] = acc + it;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (wp == 0 && lane < (int)nct) {
+        uint32_t ra = mapa(smem_u32(&buf[b][q * (NB / 4)]), lane), rm = mapa(smem_u32(&mb[b]), lane);
+        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(ra), "r"(smem_u32(&stg[b][0])), "r"(NB), "r"(rm) : "memory");
+      }
+    } else if (MODE == 7) {
+      if (wp < (int)nct && lane < 16) {
         uint32_t ra = mapa(smem_u32(&buf[b][(q * 16 + lane) * 4]), wp), rm = mapa(smem_u32(&mb[b]), wp);
         st_async4(ra, acc + it, rm);
       }
@@ -81,6 +102,9 @@ int main() {
     run<2>(cs, "CS warps/CTA: 64 B to one peer each");
     run<0>(cs, "16 warps/CTA: 4 B to each peer");
     run<1>(cs, "16 warps/CTA: 16 B to each peer");
+    run<7>(cs, "CS warps/CTA: 256 B to one peer each");
+    run<5>(cs, "bulk smem->dsmem: 64 B to each peer");
+    run<6>(cs, "bulk smem->dsmem: 256 B to each peer");
   }
   return 0;
 }
