@@ -21,10 +21,14 @@
 //    samples (bf16 hi and lo, one LDS.128 per chunk), D = hi*hi + lo*hi + hi*lo in fp32.
 //    K is reduced inside the tensor core: no shuffle trees, ~10 instructions per chunk;
 //  * warps split the chunks of a phase; their partial tiles meet in shared memory after one
-//    block barrier and ONE warp (warp 0) finishes the phase: sum, bias, gate math with the
-//    fp32 recurrent state it keeps in registers, hi/lo split, and one 16-byte st.async per lane
-//    and peer -- the S*64-byte block of a CTA is contiguous in the receiver's buffer, so a push
-//    is 16 DSMEM transactions instead of 256;
+//    block barrier and a group of four warps finishes the phase, one thread per (sample, column):
+//    sum, bias, gate math on the fp32 recurrent state, hi/lo split, pack.  After a second barrier
+//    warp p sends that S*64-byte block to peer p with one st.async instruction (the block is
+//    contiguous in the receiver's buffer: 16 DSMEM transactions per push instead of 256, and
+//    the 16 sends leave from 16 warps at once);
+//  * nothing on the step path touches local memory or indexed constants: the per-warp work
+//    table and the reducer's state sit in shared memory, the weight stream bypasses L1
+//    (L1::no_allocate), so the ~150-250 clk L1-miss stalls of the first version are gone;
 //  * activations live in shared memory in MMA-fragment order X[chunk][sample][16 words]
 //    (words t*4+{0,1} = hi pairs k=2t,2t+1 / 2t+8,2t+9, words t*4+{2,3} = lo pairs), which is
 //    exactly what the producing lane holds, so nothing is ever transposed;
@@ -42,7 +46,7 @@ namespace {
 constexpr int CS = 16;         // CTAs per cluster
 constexpr int NT = 512;        // threads per CTA
 constexpr int NW = 16;         // warps per CTA
-constexpr int DH = 256, DP = 128;
+constexpr int DH = 256;
 constexpr int RS = 20;         // floats per (sample) row of a partial tile (16 + pad, keeps float4 alignment)
 constexpr int SLOT = 8 * RS;   // floats per partial tile slot
 
@@ -52,11 +56,57 @@ constexpr int O1 = 0, O2 = O1 + 2 * N1, O3 = O2 + 2 * N2, O4 = O3 + 2 * N3, O5 =
               O9 = O8 + 2 * N8, O10 = O9 + 2 * N9, O11 = O10 + 2 * N10, O12 = O11 + 2 * N11, O13 = O12 + 2 * N12,
               F4_STEP = O13 + 2 * N13;
 static_assert(F4_STEP == DM_F4_STEP, "decoder_mma: stream size out of sync with kernels.cuh");
-constexpr int NWB = 2 * N9;    // weight register buffer (uint4)
+constexpr int NWB = 12;        // weight registers: six slots of (hi, lo) uint4
+
+// register slots of the chunks of each phase
+template <int... SL> struct Slots {};
+using SL1 = Slots<4, 5, 0>;
+using SL2 = Slots<1, 2>;
+using SL3 = Slots<3, 4, 5, 0>;
+using SL4 = Slots<1, 2>;
+using SL5 = Slots<3, 4>;
+using SL8 = Slots<0, 1>;
+using SL9 = Slots<2, 3, 4, 5, 0, 1>;
+using SL10 = Slots<0, 1>;
+using SL11 = Slots<2, 3, 4, 5, 0, 1>;
+using SL12 = Slots<0, 1>;
+using SL13 = Slots<2, 3>;
+static_assert(N1 == 3 && N3 == 4 && N9 == 6 && N11 == 6, "slot lists assume these chunk counts");
 
 enum { B_P1 = 0, B_P2, B_P3, B_P4, B_P5, B_P6, B_P7, B_P8, B_P9, B_P10, B_P11, B_P12, B_P13, NBAR = 16 };
 // phase index inside DecoderMmaWeights::tab
 enum { T_P1 = 0, T_P2, T_P3, T_P4, T_P5, T_P8, T_P9, T_P10, T_P11, T_P12, T_P13 };
+// reducer state slots (float4 per lane of warp 0)
+enum { ST_HA = 0, ST_H1, ST_H2, ST_U, ST_CX, ST_Y0H, ST_Y0, ST_Y1, NSTATE };
+
+// ---- shared memory: fixed part at compile-time offsets, then the S-dependent buffers ------------
+constexpr uint32_t OFF_MBAR = 0;
+constexpr uint32_t OFF_WTAB = OFF_MBAR + NBAR * 8;                 // [11][16] (x offset << 3 | count)
+constexpr uint32_t OFF_RED = OFF_WTAB + DM_NPHASE * 16 * 4;        // partial tiles [16][8][RS]
+constexpr uint32_t OFF_REDS = OFF_RED + NW * SLOT * 4;             // partial softmax normalisers [16][8]
+constexpr uint32_t OFF_BIAS = OFF_REDS + NW * 8 * 4;
+constexpr uint32_t OFF_VATT = OFF_BIAS + DM_NBIAS * 4;
+constexpr uint32_t OFF_STATE = OFF_VATT + DH * 4;                  // [NSTATE][8 samples][16 columns] fp32
+constexpr uint32_t OFF_STG = OFF_STATE + NSTATE * 128 * 4;         // two staged blocks of 8 x 64 bytes
+constexpr uint32_t OFF_INV = OFF_STG + 2 * 512;                    // softmax normalisers 1/sum per sample
+constexpr uint32_t OFF_X = OFF_INV + 32;
+static_assert(OFF_X % 16 == 0 && OFF_RED % 16 == 0 && OFF_STATE % 16 == 0 && OFF_BIAS % 16 == 0, "alignment");
+
+// chunks in front of buffer b (order DM_BF, DM_BC, DM_BP1, DM_BP2(8 chunks), DM_BHA, ...)
+__host__ __device__ __forceinline__ int cum_chunks(int b, int FC) { return b == 0 ? 0 : FC + 16 * (b - 1) - (b > DM_BP2 ? 8 : 0); }
+struct Dyn { uint32_t pq, sc, stage, ksl, msl, total; };
+__host__ __device__ inline Dyn make_dyn(int S, int T_in, int FC, bool att_res) {
+  Dyn d;
+  const uint32_t csb = (uint32_t)S * 64u;
+  const uint32_t npq = (uint32_t)(T_in * S) / CS + 1;              // (position, sample) pairs per CTA, upper bound
+  d.pq = OFF_X + (uint32_t)cum_chunks(DM_NBUF, FC) * csb;          // exp(2 * processed query) fp32 [chunk][n][16]
+  d.sc = d.pq + 16 * csb;                                          // exp(score - B)  [j][n]
+  d.stage = d.sc + (((uint32_t)T_in * S * 4 + 15u) & ~15u);        // this CTA's pairs
+  d.ksl = d.stage + ((npq * 4 + 15u) & ~15u);                      // exp(2 * keys) rows of this CTA's pairs
+  d.msl = d.ksl + (att_res ? npq * DH * 4 : 0u);                   // memory columns of this CTA, tile order
+  d.total = d.msl + (att_res ? (uint32_t)S * T_in * 64u : 0u);
+  return d;
+}
 
 // ---- PTX helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t mb, uint32_t count) {
@@ -70,16 +120,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t mb, uint32_t parity) {
       "{\n"
       ".reg .pred P1;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"   // with a suspend-time hint: sleep in hardware, not in a spin
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"   // suspend-time hint: sleep in hardware
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
       "}" ::"r"(mb), "r"(parity), "r"(0x989680u)
       : "memory");
 }
-__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t rmbar) {
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint4 v, uint32_t rmbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
-               ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(rmbar) : "memory");
+               ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rmbar) : "memory");
 }
 __device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t a, uint32_t rmbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
@@ -90,8 +140,41 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// weight stream: read once per step and SM, keep it out of L1
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP: 1/inf = 0, no range fix-ups
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 // D += A(16x16, row) * B(16x8, col), bf16 inputs, fp32 accumulate
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
@@ -107,81 +190,80 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
   hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
   lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
 }
+// the 16-byte word group lane (n, t) contributes to an activation chunk: columns {2t,2t+1,2t+8,2t+9}
+__device__ __forceinline__ uint4 pack_x(float4 v) {
+  uint4 r;
+  split2(v.x, v.y, r.x, r.z);
+  split2(v.z, v.w, r.y, r.w);
+  return r;
+}
 
 // position of column c (0..15) of a tile inside a 16-float row: the four columns
 // {2t, 2t+1, 2t+8, 2t+9} that lane (n, t) finishes sit at floats t*4 .. t*4+3
 __host__ __device__ __forceinline__ int pos16(int c) { return ((c & 7) >> 1) * 4 + (c >> 3) * 2 + (c & 1); }
 
-template <int NCH>
-__device__ __forceinline__ void load_w(uint4 (&wb)[NWB], const uint4* __restrict__ g, int cnt) {
+// The weight registers are six slots of one chunk-tile (hi, lo uint4) each.  Every phase names the slots its chunks
+// use, chosen so that consecutive phases use disjoint slots wherever they fit: the stream of phase p+1 (or p+2) is
+// requested while phase p waits for its exchange, i.e. off the critical path and at least one phase ahead.
+// chunks I0, I0+1, ... of a phase (stream offset OFF, in uint4 per lane) into slots SL...
+template <int OFF, int I0, int... SL>
+__device__ __forceinline__ void load_w(uint4 (&wb)[NWB], const uint4* __restrict__ ws, int cnt, Slots<SL...>) {
+  constexpr int sl[] = {SL...};
 #pragma unroll
-  for (int i = 0; i < NCH; ++i)
-    if (i < cnt) {
-      wb[2 * i] = __ldg(g + (2 * i) * 32);
-      wb[2 * i + 1] = __ldg(g + (2 * i + 1) * 32);
+  for (int k = 0; k < (int)sizeof...(SL); ++k)
+    if (I0 + k < cnt) {
+      wb[2 * sl[k]] = ldg_stream(ws + (OFF + 2 * (I0 + k)) * 32);
+      wb[2 * sl[k] + 1] = ldg_stream(ws + (OFF + 2 * (I0 + k) + 1) * 32);
     }
 }
 
-// one warp's share of a phase: cnt chunks of one tile; partial tile -> red slot of this warp
-template <int NCH>
-__device__ __forceinline__ void mma_chunks(const uint4 (&wb)[NWB], uint32_t xaddr, uint32_t csb, int cnt, float* slot,
-                                           int g, int t, long long* tr = nullptr) {
+// one warp's share of a phase: cnt chunks of one tile (chunk i in slot SL[i]); partial tile -> red slot of this warp
+template <int... SL>
+__device__ __forceinline__ void mma_chunks(const uint4 (&wb)[NWB], uint32_t xaddr, uint32_t csb, int cnt, uint32_t slot,
+                                           int g, int t, Slots<SL...>) {
+  constexpr int sl[] = {SL...};
   float hh[4] = {0.f, 0.f, 0.f, 0.f}, hl[4] = {0.f, 0.f, 0.f, 0.f}, lh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < NCH; ++i)
+  for (int i = 0; i < (int)sizeof...(SL); ++i)
     if (i < cnt) {
       const uint4 xf = lds128(xaddr + i * csb);
-      if (tr) { tr[48 + 2 * i] = clock64() + (xf.x & 1u); }
-      if (tr) { tr[49 + 2 * i] = clock64() + (wb[2 * i].x & 1u) + (wb[2 * i + 1].x & 1u); }
-      mma16816(hh, wb[2 * i], xf.x, xf.y);       // W_hi * x_hi
-      mma16816(lh, wb[2 * i + 1], xf.x, xf.y);   // W_lo * x_hi
-      mma16816(hl, wb[2 * i], xf.z, xf.w);       // W_hi * x_lo
+      mma16816(hh, wb[2 * sl[i]], xf.x, xf.y);       // W_hi * x_hi
+      mma16816(lh, wb[2 * sl[i] + 1], xf.x, xf.y);   // W_lo * x_hi
+      mma16816(hl, wb[2 * sl[i]], xf.z, xf.w);       // W_hi * x_lo
     }
-  // D[row g / g+8 = tile column][col 2t, 2t+1 = sample]  ->  slot[sample][pos16(column)]
+  // D[row g / g+8 = tile column][col 2t, 2t+1 = sample]  ->  slot[sample][column]   (bank-conflict free with RS = 20)
   // (written even when cnt == 0 so that the reducer never sums a stale slot)
-  const int p = (g >> 1) * 4 + (g & 1);
-  if (tr) tr[56] = clock64() + (__float_as_uint(hh[0] + hl[0] + lh[0]) & 1u);
-  slot[(2 * t) * RS + p] = hh[0] + (hl[0] + lh[0]);
-  slot[(2 * t + 1) * RS + p] = hh[1] + (hl[1] + lh[1]);
-  slot[(2 * t) * RS + p + 2] = hh[2] + (hl[2] + lh[2]);
-  slot[(2 * t + 1) * RS + p + 2] = hh[3] + (hl[3] + lh[3]);
+  const uint32_t p = slot + (uint32_t)(((2 * t) * RS + g) * 4);
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(p), "f"(hh[0] + (hl[0] + lh[0])) : "memory");
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(p + RS * 4), "f"(hh[1] + (hl[1] + lh[1])) : "memory");
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(p + 32), "f"(hh[2] + (hl[2] + lh[2])) : "memory");
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(p + RS * 4 + 32), "f"(hh[3] + (hl[3] + lh[3])) : "memory");
 }
 
-// sum of the partial tiles in slots [s0, s0+ns) for lane (n, t): columns {2t, 2t+1, 2t+8, 2t+9}
+// reducer thread (n, c): sum over the partial tiles in slots [s0, s0+NS) of element [n][c]
 template <int NS>
-__device__ __forceinline__ float4 red_tile(const float* red, int s0, int n, int t) {
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+__device__ __forceinline__ float red_sum(uint32_t red_nc, int s0) {
+  float a = 0.f, b = 0.f;
 #pragma unroll
-  for (int s = 0; s < NS; ++s) {
-    const float4 v = *reinterpret_cast<const float4*>(red + (s0 + s) * SLOT + n * RS + t * 4);
-    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  for (int s = 0; s < NS; s += 2) {
+    a += lds_f(red_nc + (s0 + s) * SLOT * 4);
+    if (s + 1 < NS) b += lds_f(red_nc + (s0 + s + 1) * SLOT * 4);
   }
-  return a;
+  return a + b;
 }
-
-struct Smem {   // byte offsets from the start of dynamic shared memory
-  uint32_t buf[DM_NBUF];
-  uint32_t pq, sc, red, reds, stage, bias, vatt, ksl, msl, total;
-};
-__host__ __device__ inline Smem make_smem(int S, int T_in, int FC, bool att_res) {
-  Smem L;
-  uint32_t o = NBAR * 8;
-  auto take = [&](uint32_t bytes) { uint32_t r = o; o += (bytes + 15u) & ~15u; return r; };
-  const uint32_t csb = (uint32_t)S * 64u;
-  const int nch[DM_NBUF] = {FC, 16, 16, 8, 16, 16, 16, 16, 16, 16, 16, 16, 16};
-  for (int b = 0; b < DM_NBUF; ++b) L.buf[b] = take(nch[b] * csb);
-  L.pq = take(16 * csb);                     // processed query, fp32, X-like layout [chunk][n][16 floats]
-  L.sc = take((uint32_t)T_in * S * 4);       // exp(score - B)  [j][n]
-  L.red = take(NW * SLOT * 4);               // partial tiles
-  L.reds = take(NW * 8 * 4);                 // partial softmax normalisers
-  const int Tj = (T_in + CS - 1) / CS;
-  L.stage = take((uint32_t)Tj * S * 4);
-  L.bias = take(DM_NBIAS * 4);
-  L.vatt = take(DH * 4);
-  L.ksl = take(att_res ? (uint32_t)S * Tj * DH * 4 : 0);        // keys rows [j0,j1) of the S samples
-  L.msl = take(att_res ? (uint32_t)S * T_in * 16 * 4 : 0);      // memory columns of this CTA, tile order
-  L.total = o;
-  return L;
+// reducer thread (n, c) holds v = activation [n][16q + c]: split into bf16 hi/lo, pair with the neighbouring column
+// (lane ^ 1) and write the two words of the pair into the staged block row `stg_n` (MMA-fragment order).
+// Must be executed by whole warps.
+__device__ __forceinline__ void stage_x(uint32_t stg_n, int c, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  const uint32_t hv = __bfloat16_as_ushort(h), lv = __bfloat16_as_ushort(l);
+  const uint32_t hn = __shfl_xor_sync(0xffffffffu, hv, 1), ln = __shfl_xor_sync(0xffffffffu, lv, 1);
+  if ((c & 1) == 0) {
+    const uint32_t wa = stg_n + (uint32_t)((((c & 7) >> 1) * 4 + (c >> 3)) * 4);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(wa), "r"(hv | (hn << 16)) : "memory");
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(wa + 8), "r"(lv | (ln << 16)) : "memory");
+  }
 }
 
 // bias table (floats, tile order so that lane t reads one float4 at [t*4])
@@ -204,90 +286,90 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
   const int n0 = cid * base + min(cid, rem);
   const int M = w.M, Dout = w.Dout, FC = M >> 4, T_in = a.T_in;
   const bool att_res = a.att_res != 0;
-  const Smem L = make_smem(a.s_max, T_in, FC, att_res);   // same carve-up in every cluster of the launch
+  const Dyn L = make_dyn(S, T_in, FC, att_res);
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t csb = (uint32_t)S * 64u;
-  float* red = reinterpret_cast<float*>(smem_raw + L.red);
-  float* reds = reinterpret_cast<float*>(smem_raw + L.reds);
-  float* stage = reinterpret_cast<float*>(smem_raw + L.stage);
-  float* bias = reinterpret_cast<float*>(smem_raw + L.bias);
-  float* vatt = reinterpret_cast<float*>(smem_raw + L.vatt);
-  float* sc = reinterpret_cast<float*>(smem_raw + L.sc);
-  float* ksl = reinterpret_cast<float*>(smem_raw + L.ksl);
-  float* msl = reinterpret_cast<float*>(smem_raw + L.msl);
-  const uint32_t mb0 = sbase;
-  if (S == 0) {   // cannot happen (nclusters <= N) but keeps every CTA of a cluster on the same path
+  const uint32_t mb0 = sbase + OFF_MBAR;
+  // attention scores are cut by flattened (position j, sample n) pair index p = j*S + n: 16 balanced ranges
+  const int NP = T_in * S;
+  const int p0 = (q * NP) / CS, npq = ((q + 1) * NP) / CS - p0;
+  const float invS = 1.0f / (float)S;   // j = floor((p + 0.5) / S) is exact for p < 2^20
+  if (S == 0) {   // cannot happen (nclusters <= N); keeps every CTA of a cluster on the same path
     cluster_sync_all();
     cluster_sync_all();
     return;
   }
 
   // ---- prologue -------------------------------------------------------------------------
-  for (uint32_t i = NBAR * 8 + tid * 4; i < L.total; i += NT * 4) *reinterpret_cast<uint32_t*>(smem_raw + i) = 0u;
+  for (uint32_t i = OFF_WTAB + tid * 4; i < L.total; i += NT * 4) *reinterpret_cast<uint32_t*>(smem_raw + i) = 0u;
   if (tid < NBAR) mbar_init(mb0 + tid * 8, 1);
   __syncthreads();
-  if (tid < DM_NBIAS) bias[tid] = __ldg(w.bias + q * DM_NBIAS + tid);
-  if (tid < DH) vatt[tid] = __ldg(w.att_v + tid);
-  const int Tj = (T_in + CS - 1) / CS;
-  const int j0 = min(q * Tj, T_in), j1 = min(j0 + Tj, T_in), nj = j1 - j0;
+  if (tid < DM_NPHASE * 16) {   // per-warp work table: byte offset of the warp's first chunk and its chunk count
+    const uint32_t e = w.tab[tid >> 4][tid & 15];
+    const uint32_t bufi = (e >> 8) & 15u, c0 = (e >> 3) & 31u;
+    reinterpret_cast<uint32_t*>(smem_raw + OFF_WTAB)[tid] = ((OFF_X + ((uint32_t)cum_chunks((int)bufi, FC) + c0) * csb) << 3) | (e & 7u);
+  }
+  if (tid < DM_NBIAS) reinterpret_cast<float*>(smem_raw + OFF_BIAS)[tid] = __ldg(w.bias + q * DM_NBIAS + tid);
+  if (tid < DH) reinterpret_cast<float*>(smem_raw + OFF_VATT)[tid] = __ldg(w.att_v + tid);
   if (att_res) {
-    for (int i = tid; i < S * nj * (DH / 4); i += NT) {
-      const int c4 = i % (DH / 4), r = i / (DH / 4), s = r / nj, jj = r - s * nj;
-      *reinterpret_cast<float4*>(ksl + ((size_t)s * Tj + jj) * DH + c4 * 4) =
-          ldg_f4(a.keys + ((size_t)(n0 + s) * T_in + j0 + jj) * DH + c4 * 4);
+    float* ksl = reinterpret_cast<float*>(smem_raw + L.ksl);
+    float* msl = reinterpret_cast<float*>(smem_raw + L.msl);
+    for (int i = tid; i < npq * (DH / 4); i += NT) {   // exp(2 key): tanh(k + p) = 1 - 2 / (1 + e^{2k} e^{2p})
+      const int c4 = i % (DH / 4), pp = i / (DH / 4), p = p0 + pp, j = p / S, n = p - j * S;   // (prologue only)
+      float4 k4 = ldg_f4(a.keys + ((size_t)(n0 + n) * T_in + j) * DH + c4 * 4);
+      k4.x = __expf(2.0f * fminf(fmaxf(k4.x, -30.f), 30.f)); k4.y = __expf(2.0f * fminf(fmaxf(k4.y, -30.f), 30.f));
+      k4.z = __expf(2.0f * fminf(fmaxf(k4.z, -30.f), 30.f)); k4.w = __expf(2.0f * fminf(fmaxf(k4.w, -30.f), 30.f));
+      *reinterpret_cast<float4*>(ksl + (size_t)pp * DH + c4 * 4) = k4;
     }
     for (int i = tid; i < S * T_in * 16; i += NT) {
       const int c = i & 15, r = i >> 4, s = r / T_in, j = r - s * T_in;
-      msl[(size_t)r * 16 + pos16(c)] = __ldg(a.memory + ((size_t)(n0 + s) * T_in + j) * DH + q * 16 + c);
+      msl[((size_t)j * S + s) * 16 + c] = __ldg(a.memory + ((size_t)(n0 + s) * T_in + j) * DH + q * 16 + c);   // [j][n][16]
     }
   }
-  float vbound = 0.f;   // B = min(||v||_1, 40) >= any score (|tanh| <= 1)
+  float vbound = 0.f, vsum = 0.f;   // B = min(||v||_1, 40) >= any score (|tanh| <= 1); sum_k v_k
 #pragma unroll
-  for (int i = 0; i < 8; ++i) vbound += fabsf(__ldg(w.att_v + lane + 32 * i));
+  for (int i = 0; i < 8; ++i) { const float vv = __ldg(w.att_v + lane + 32 * i); vbound += fabsf(vv); vsum += vv; }
   vbound = fminf(warp_sum(vbound), 40.0f);
+  vsum = warp_sum(vsum);
 
-  // per-warp work table: tile | buf | chunk0 | count
-  auto tab_cnt = [&](int ph) { return (int)(w.tab[ph][warp] & 7u); };
-  auto tab_x = [&](int ph) {   // shared address of this lane's first B fragment of the phase
-    const uint32_t e = w.tab[ph][warp];
-    const uint32_t bufi = (e >> 8) & 15u, c0 = (e >> 3) & 31u;
-    return sbase + L.buf[bufi] + c0 * csb + (uint32_t)min(g, S - 1) * 64u + (uint32_t)t * 16u;
-  };
   const uint4* ws = reinterpret_cast<const uint4*>(w.stream) + ((size_t)(q * NW + warp) * F4_STEP) * 32 + lane;
-  float* myslot = red + warp * SLOT;
-
-  // recurrent state and carried values of the reducer lane (n = g, columns {2t,2t+1,2t+8,2t+9} of this CTA's tile)
-  float4 hA = make_float4(0.f, 0.f, 0.f, 0.f), h1 = hA, h2 = hA, ukeep = hA, cxkeep = hA, y0h = hA, y0 = hA, y1 = hA;
-  const bool red_on = warp == 0 && g < S;
-  // push one finished 4-column group of every active lane into buffer `dst` (byte offset) chunk `chunk` of all peers
-  auto push_x = [&](uint32_t dst, int chunk, float4 v, int bar, int pstep, int pfirst) {
-    uint32_t h01, l01, h23, l23;
-    split2(v.x, v.y, h01, l01);
-    split2(v.z, v.w, h23, l23);
-    const uint32_t la = sbase + dst + (uint32_t)chunk * csb + (uint32_t)lane * 16u, lm = mb0 + bar * 8;
-#pragma unroll
-    for (int p = 0; p < CS; ++p)
-      if ((p - pfirst) % pstep == 0) st_async_v4(mapa_u32(la, p), h01, h23, l01, l23, mapa_u32(lm, p));
+  const uint32_t wtab = sbase + OFF_WTAB + warp * 4;                       // + phase * 64
+  const uint32_t xl = sbase + (uint32_t)min(g, S - 1) * 64u + (uint32_t)t * 16u;   // lane part of a B-fragment address
+  const uint32_t myslot = sbase + OFF_RED + warp * SLOT * 4;
+  // reducer group: warps 0..3, thread (rn, rc) = (sample, column of this CTA's tile)
+  const int rn = (tid >> 4) & 7, rc = tid & 15;
+  const bool red_grp = warp < 4;
+  const uint32_t red_nc = sbase + OFF_RED + (rn * RS + rc) * 4;
+  const uint32_t st_nc = sbase + OFF_STATE + (rn * 16 + rc) * 4;           // + slot * 512
+  const uint32_t bias_c = sbase + OFF_BIAS + rc * 4;                       // + table * 4
+  const uint32_t stg_n = sbase + OFF_STG + rn * 64;                        // + block * 512
+  const uint32_t stg_lane = sbase + OFF_STG + lane * 16;                   // + block * 512
+  const bool snd_on = lane < 4 * S;            // lanes that carry a word group of a staged block
+  const uint32_t rmb0 = mapa_u32(mb0, (uint32_t)warp);                      // peer `warp`: its mbarriers ...
+  const uint32_t rx = mapa_u32(sbase + lane * 16, (uint32_t)warp);          // ... and this lane's slot in a chunk at offset 0
+  // all warps: send staged block `blk` into (byte offset dst + chunk*csb) of peer `warp`
+  auto send_blk = [&](int blk, uint32_t dst, int bar) {
+    if (snd_on) st_async_v4(rx + dst, lds128(stg_lane + blk * 512), rmb0 + bar * 8);
   };
-  auto push_f4 = [&](uint32_t dst, int chunk, float4 v, int bar) {   // fp32 block (processed query)
-    const uint32_t la = sbase + dst + (uint32_t)chunk * csb + (uint32_t)lane * 16u, lm = mb0 + bar * 8;
-#pragma unroll
-    for (int p = 0; p < CS; ++p)
-      st_async_v4(mapa_u32(la, p), __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w),
-                  mapa_u32(lm, p));
-  };
-  auto bias4 = [&](int off) { return *reinterpret_cast<const float4*>(bias + off + t * 4); };
+#define WCNT(ph) (lds32(wtab + (ph) * 64))
+#define XBUF(b) (OFF_X + (uint32_t)cum_chunks((b), FC) * csb)
 
   uint4 wb[NWB];
-  load_w<N1>(wb, ws + O1 * 32, tab_cnt(T_P1));
+  __syncthreads();   // work table visible
+  load_w<O1, 0>(wb, ws, (int)(WCNT(T_P1) & 7u), SL1());
+  load_w<O2, 0>(wb, ws, (int)(WCNT(T_P2) & 7u), SL2());
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
   cluster_sync_all();   // buffers zeroed and mbarriers initialised everywhere before anyone pushes
 
   const bool free_run = a.targets == nullptr;
   const uint32_t BLK = CS * csb;
   const int fb_tile0 = (Dout - M) >> 4, ntiles = Dout >> 4;
 
+// LOADP(phase table index, stream offset, first chunk, slots): request chunks of a later phase (see the slot schedule)
+#define LOADP(TP, OFF, I0, ...) load_w<OFF, I0>(wb, ws, (int)(WCNT(TP) & 7u), Slots<__VA_ARGS__>());
+#define MMA(SL, TP) { const uint32_t e = WCNT(TP); mma_chunks(wb, xl + (e >> 3), csb, e & 7, myslot, g, t, SL()); }
+#define ST(slot) (st_nc + (slot) * 512)
+#define BIAS(tab) lds_f(bias_c + (tab) * 4)
   for (int step = 0; step < a.steps; ++step) {
     const uint32_t par = (uint32_t)step & 1u;
     if (free_run && step > 0) mbar_wait(mb0 + B_P13 * 8, par ^ 1u);   // fed-back frame of step-1 has landed
@@ -312,133 +394,130 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
         const float* src = a.targets + ((size_t)(n0 + n) * a.T_tgt + (size_t)(step - 1) * a.r + a.r - 1) * M + ch * 16;
         const float2 lo2 = __ldg(reinterpret_cast<const float2*>(src + 2 * tt));
         const float2 hi2 = __ldg(reinterpret_cast<const float2*>(src + 2 * tt + 8));
-        uint32_t h01, l01, h23, l23;
-        split2(lo2.x, lo2.y, h01, l01);
-        split2(hi2.x, hi2.y, h23, l23);
-        sts128(sbase + L.buf[DM_BF] + ch * csb + n * 64 + tt * 16, h01, h23, l01, l23);
+        const uint4 pk = pack_x(make_float4(lo2.x, lo2.y, hi2.x, hi2.y));
+        sts128(sbase + XBUF(DM_BF) + ch * csb + n * 64 + tt * 16, pk.x, pk.y, pk.z, pk.w);
       }
       __syncthreads();
     }
     TRM(0);
     // ================= P1: decoder prenet dense_1 + ReLU on [frame | context] =================
-    mma_chunks<N1>(wb, tab_x(T_P1), csb, tab_cnt(T_P1), myslot, g, t);
-    load_w<N2>(wb, ws + O2 * 32, tab_cnt(T_P2));
+    MMA(SL1, T_P1)
     __syncthreads();
     TRM(1);
-    if (red_on) {
-      float4 v = red_tile<DM_P1_SLOTS>(red, 0, g, t);
-      const float4 b = bias4(BI_P1);
-      v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f); v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
-      push_x(L.buf[DM_BP1], q, v, B_P1, 1, 0);
-    }
+    if (red_grp) stage_x(stg_n, rc, fmaxf(red_sum<DM_P1_SLOTS>(red_nc, 0) + BIAS(BI_P1), 0.f));
+    else { LOADP(T_P3, O3, 0, 3, 4, 5, 0) }     // window of P1: P3 (the reducer warps request theirs after the send)
+    __syncthreads();
+    send_blk(0, XBUF(DM_BP1) + q * csb, B_P1);
+    if (red_grp) { LOADP(T_P3, O3, 0, 3, 4, 5, 0) }
     TRM(2);
     mbar_wait(mb0 + B_P1 * 8, par);
     TRM(3);
     // ================= P2: prenet dense_2 + ReLU (CTA pair 2c, 2c+1 computes chunk c; each feeds half the peers) ====
-    mma_chunks<N2>(wb, tab_x(T_P2), csb, tab_cnt(T_P2), myslot, g, t);
-    load_w<N3>(wb, ws + O3 * 32, tab_cnt(T_P3));
+    MMA(SL2, T_P2)
     __syncthreads();
     TRM(4);
-    if (red_on) {
-      float4 v = red_tile<8>(red, 0, g, t);
-      const float4 b = bias4(BI_P2);
-      v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f); v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
-      push_x(L.buf[DM_BP2], q >> 1, v, B_P2, 2, q & 1);
-    }
+    if (red_grp) stage_x(stg_n, rc, fmaxf(red_sum<8>(red_nc, 0) + BIAS(BI_P2), 0.f));
+    else { LOADP(T_P4, O4, 0, 1, 2) }           // window of P2: P4
+    __syncthreads();
+    if (((warp ^ q) & 1) == 0) send_blk(0, XBUF(DM_BP2) + (q >> 1) * csb, B_P2);
+    if (red_grp) { LOADP(T_P4, O4, 0, 1, 2) }
     TRM(5);
     mbar_wait(mb0 + B_P2 * 8, par);
     TRM(6);
-    // ================= P3: attention GRU gates r,u on [prenet | h_att] and candidate x-part =================
-    mma_chunks<N3>(wb, tab_x(T_P3), csb, tab_cnt(T_P3), myslot, g, t);
-    load_w<N4>(wb, ws + O4 * 32, tab_cnt(T_P4));
-    __syncthreads();
-    TRM(7);
-    if (red_on) {
-      const float4 r = red_tile<6>(red, 0, g, t), u = red_tile<6>(red, 6, g, t);
-      cxkeep = red_tile<4>(red, 12, g, t);
-      const float4 br = bias4(BI_RA), bu = bias4(BI_UA);
-      ukeep = make_float4(sigmoid_f(u.x + bu.x), sigmoid_f(u.y + bu.y), sigmoid_f(u.z + bu.z), sigmoid_f(u.w + bu.w));
-      const float4 rh = make_float4(sigmoid_f(r.x + br.x) * hA.x, sigmoid_f(r.y + br.y) * hA.y,
-                                    sigmoid_f(r.z + br.z) * hA.z, sigmoid_f(r.w + br.w) * hA.w);
-      push_x(L.buf[DM_BRA], q, rh, B_P3, 1, 0);
-    }
+    // ================= GRU phases: gates r,u on [x | h] + candidate x-part; then candidate h-part =================
+#define GRU_GATES(SLG, TP, BI_R, BI_U, ST_H, BUF_R, BAR, LOADNEXT)                                   \
+    MMA(SLG, TP)                                                                                    \
+    __syncthreads();                                                                                 \
+    if (red_grp) {                                                                                   \
+      const float r = sigmoid_f(red_sum<6>(red_nc, 0) + BIAS(BI_R));                                 \
+      sts_f(ST(ST_U), sigmoid_f(red_sum<6>(red_nc, 6) + BIAS(BI_U)));                                \
+      sts_f(ST(ST_CX), red_sum<4>(red_nc, 12));                                                      \
+      stage_x(stg_n, rc, r * lds_f(ST(ST_H)));                                                       \
+    } else { LOADNEXT }                                                                              \
+    __syncthreads();                                                                                 \
+    send_blk(0, XBUF(BUF_R) + q * csb, BAR);                                                         \
+    if (red_grp) { LOADNEXT }
+    // candidate: h' = u h + (1-u) tanh(c_h + c_x + b); y_out = y_in + h' (ResidualWrapper) when BUF_Y >= 0
+#define GRU_CAND(SLC, TP, BI_C, ST_H, ST_YIN, ST_YOUT, BUF_H, BUF_Y, BAR, LOADNEXT)                        \
+    MMA(SLC, TP)                                                                                      \
+    __syncthreads();                                                                                 \
+    if (red_grp) {                                                                                   \
+      const float c = tanh_f(red_sum<8>(red_nc, 0) + lds_f(ST(ST_CX)) + BIAS(BI_C));                 \
+      const float u = lds_f(ST(ST_U));                                                               \
+      const float h = u * lds_f(ST(ST_H)) + (1.0f - u) * c;                                          \
+      sts_f(ST(ST_H), h);                                                                            \
+      stage_x(stg_n, rc, h);                                                                         \
+      if (BUF_Y >= 0) {                                                                              \
+        const float y = lds_f(ST(ST_YIN)) + h;                                                       \
+        if (ST_YOUT >= 0) sts_f(ST(ST_YOUT < 0 ? 0 : ST_YOUT), y);                                   \
+        stage_x(stg_n + 512, rc, y);                                                                 \
+      }                                                                                              \
+    } else { LOADNEXT }                                                                              \
+    __syncthreads();                                                                                 \
+    send_blk(0, XBUF(BUF_H) + q * csb, BAR);                                                         \
+    if (BUF_Y >= 0) send_blk(1, XBUF(BUF_Y < 0 ? 0 : BUF_Y) + q * csb, BAR);                         \
+    if (red_grp) { LOADNEXT }
+
+    // ----- P3 / P4: attention GRU on [prenet | h_att] -----
+    GRU_GATES(SL3, T_P3, BI_RA, BI_UA, ST_HA, DM_BRA, B_P3, LOADP(T_P5, O5, 0, 3, 4))
     TRM(8);
     mbar_wait(mb0 + B_P3 * 8, par);
     TRM(9);
-    // ================= P4: candidate h-part -> h_att' =================
-    {
-      const uint32_t xa4 = tab_x(T_P4);
-      const int cn4 = tab_cnt(T_P4);
-      TRM(40);
-      mma_chunks<N4>(wb, xa4, csb, cn4, myslot, g, t, (a.trace != nullptr && step == 8 && blockIdx.x == 0 && tid == 0) ? a.trace : nullptr);
-      TRM(41);
-      load_w<N5>(wb, ws + O5 * 32, tab_cnt(T_P5));
-      TRM(42);
-    }
-    __syncthreads();
-    TRM(10);
-    if (red_on) {
-      const float4 c = red_tile<8>(red, 0, g, t), b = bias4(BI_CA);
-      if (a.trace != nullptr && step == 8 && blockIdx.x == 0 && tid == 0) a.trace[43] = clock64() + (__float_as_uint(c.x) & 1u);
-      hA.x = ukeep.x * hA.x + (1.0f - ukeep.x) * tanh_f(c.x + cxkeep.x + b.x);
-      hA.y = ukeep.y * hA.y + (1.0f - ukeep.y) * tanh_f(c.y + cxkeep.y + b.y);
-      hA.z = ukeep.z * hA.z + (1.0f - ukeep.z) * tanh_f(c.z + cxkeep.z + b.z);
-      hA.w = ukeep.w * hA.w + (1.0f - ukeep.w) * tanh_f(c.w + cxkeep.w + b.w);
-      if (a.trace != nullptr && step == 8 && blockIdx.x == 0 && tid == 0) a.trace[44] = clock64() + (__float_as_uint(hA.x) & 1u);
-      push_x(L.buf[DM_BHA], q, hA, B_P4, 1, 0);
-    }
+    GRU_CAND(SL4, T_P4, BI_CA, ST_HA, ST_HA, -1, DM_BHA, -1, B_P4, LOADP(T_P8, O8, 0, 0, 1))
     TRM(11);
     mbar_wait(mb0 + B_P4 * 8, par);
     TRM(12);
     // ================= P5: query layer (tile A) and h_att' half of the 512->256 projection (tile B) =================
-    mma_chunks<N5>(wb, tab_x(T_P5), csb, tab_cnt(T_P5), myslot, g, t);
-    load_w<N8>(wb, ws + O8 * 32, tab_cnt(T_P8));
+    MMA(SL5, T_P5)
     __syncthreads();
     TRM(13);
-    if (red_on) {
-      const float4 pq = red_tile<8>(red, 0, g, t);
-      y0h = red_tile<8>(red, 8, g, t);
-      push_f4(L.pq, q, pq, B_P5);
-    }
+    if (red_grp) {   // the query is pushed as e^{2 pq} (fp32) for the score phase
+      sts_f(stg_n + rc * 4, __expf(2.0f * fminf(fmaxf(red_sum<8>(red_nc, 0), -30.f), 30.f)));
+      sts_f(ST(ST_Y0H), red_sum<8>(red_nc, 8));
+    } else { LOADP(T_P9, O9, 0, 2, 3) }   // window of P5: first two chunks of P9 (next two in the window of P6)
+    __syncthreads();
+    send_blk(0, L.pq + q * csb, B_P5);
+    if (red_grp) { LOADP(T_P9, O9, 0, 2, 3) }
     TRM(14);
     mbar_wait(mb0 + B_P5 * 8, par);
     TRM(15);
-    // ================= P6: Bahdanau scores of positions [j0,j1): exp(v . tanh(keys + pq) - B) =================
+    // ================= P6: Bahdanau scores of this CTA's (position, sample) pairs: exp(v . tanh(keys + pq) - B) ======
+    // v.tanh(k + p) = sum v - 2 sum_k v_k / (1 + e^{2k} e^{2p}); e^{2k} is resident, e^{2p} was pushed by P5.
     {
-      const int npairs = S * nj;
-      // lane's 8 inputs k = lane + 32 i sit in chunk (lane>>4) + 2i at tile position pos16(lane & 15)
-      const int pqoff = (lane >> 4) * (int)(csb >> 2) + pos16(lane & 15);
-      const float* pqb = reinterpret_cast<const float*>(smem_raw + L.pq);
-      for (int pi = warp; pi < npairs; pi += NW) {
-        const int jj = pi / S, s = pi - jj * S;
-        const float* prow = pqb + pqoff + s * 16;
-        float e = 0.f;
+      // lane's 8 inputs: k = 4 lane + {0..3} (chunk lane>>2, columns 4 (lane&3)..) and 128 + the same (chunk + 8)
+      const uint32_t pq_l = sbase + L.pq + (uint32_t)(lane >> 2) * csb + (uint32_t)(lane & 3) * 16u;
+      const float4 v0 = lds_f4(sbase + OFF_VATT + lane * 16), v1 = lds_f4(sbase + OFF_VATT + 512 + lane * 16);
+      float* stage = reinterpret_cast<float*>(smem_raw + L.stage);
+      for (int pp = warp; pp < npq; pp += NW) {
+        const int p = p0 + pp, j = (int)(((float)p + 0.5f) * invS), n = p - j * S;
+        const float4 e0 = lds_f4(pq_l + n * 64), e1 = lds_f4(pq_l + 8 * csb + n * 64);   // e^{2 pq}
+        float4 k0, k1;                                                                     // e^{2 key}
         if (att_res) {
-          const float* krow = ksl + ((size_t)s * Tj + jj) * DH + lane;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) e = fmaf(vatt[lane + 32 * i], tanh_f(krow[32 * i] + prow[i * 2 * (int)(csb >> 2)]), e);
+          k0 = lds_f4(sbase + L.ksl + (uint32_t)pp * (DH * 4) + lane * 16);
+          k1 = lds_f4(sbase + L.ksl + (uint32_t)pp * (DH * 4) + 512 + lane * 16);
         } else {
-          const float* krow = a.keys + ((size_t)(n0 + s) * T_in + (j0 + jj)) * DH + lane;
-          float kv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) kv[i] = __ldg(krow + 32 * i);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) e = fmaf(vatt[lane + 32 * i], tanh_f(kv[i] + prow[i * 2 * (int)(csb >> 2)]), e);
+          const float* krow = a.keys + ((size_t)(n0 + n) * T_in + j) * DH + 4 * lane;
+          k0 = ldg_f4(krow); k1 = ldg_f4(krow + 128);
+          k0.x = __expf(2.0f * fminf(fmaxf(k0.x, -30.f), 30.f)); k0.y = __expf(2.0f * fminf(fmaxf(k0.y, -30.f), 30.f));
+          k0.z = __expf(2.0f * fminf(fmaxf(k0.z, -30.f), 30.f)); k0.w = __expf(2.0f * fminf(fmaxf(k0.w, -30.f), 30.f));
+          k1.x = __expf(2.0f * fminf(fmaxf(k1.x, -30.f), 30.f)); k1.y = __expf(2.0f * fminf(fmaxf(k1.y, -30.f), 30.f));
+          k1.z = __expf(2.0f * fminf(fmaxf(k1.z, -30.f), 30.f)); k1.w = __expf(2.0f * fminf(fmaxf(k1.w, -30.f), 30.f));
         }
-        e = warp_sum(e);
-        if (lane == 0) stage[jj * S + s] = __expf(fmaxf(e - vbound, -80.0f));
+        // e^{2k} e^{2p} in [0, inf]: inf -> term 0 (tanh = 1), 0 -> term v (tanh = -1)
+        float s0 = v0.x * rcp_approx(fmaf(k0.x, e0.x, 1.0f)), s1 = v0.y * rcp_approx(fmaf(k0.y, e0.y, 1.0f));
+        s0 = fmaf(v0.z, rcp_approx(fmaf(k0.z, e0.z, 1.0f)), s0); s1 = fmaf(v0.w, rcp_approx(fmaf(k0.w, e0.w, 1.0f)), s1);
+        s0 = fmaf(v1.x, rcp_approx(fmaf(k1.x, e1.x, 1.0f)), s0); s1 = fmaf(v1.y, rcp_approx(fmaf(k1.y, e1.y, 1.0f)), s1);
+        s0 = fmaf(v1.z, rcp_approx(fmaf(k1.z, e1.z, 1.0f)), s0); s1 = fmaf(v1.w, rcp_approx(fmaf(k1.w, e1.w, 1.0f)), s1);
+        const float e = vsum - 2.0f * warp_sum(s0 + s1);
+        if (lane == 0) stage[pp] = __expf(fmaxf(e - vbound, -80.0f));
       }
     }
     __syncthreads();
     TRM(16);
-    if (warp == 0 && nj > 0) {
-      const uint32_t la = sbase + L.sc + (uint32_t)(j0 * S) * 4u, lm = mb0 + B_P6 * 8;
-      for (int i = lane; i < nj * S; i += 32) {
-        const uint32_t v = __float_as_uint(stage[i]);
-#pragma unroll
-        for (int p = 0; p < CS; ++p) st_async_b32(mapa_u32(la + i * 4, p), v, mapa_u32(lm, p));
-      }
-    }
+    // warp p -> peer p: this CTA's pairs into sc[p0 ..]
+    for (int i = lane; i < npq; i += 32)
+      st_async_b32(rx - lane * 16 + L.sc + (uint32_t)(p0 + i) * 4u, lds32(sbase + L.stage + i * 4), rmb0 + B_P6 * 8);
+    LOADP(T_P9, O9, 2, 4, 5)           // window of P6: chunks 2, 3 of P9
     TRM(17);
     mbar_wait(mb0 + B_P6 * 8, par);
     TRM(18);
@@ -447,149 +526,112 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       float ssum = 0.f;
       if (g < S) {
-        for (int j = warp; j < T_in; j += NW) {
-          const float p = sc[j * S + g];
-          float4 m;
-          if (att_res) {
-            m = *reinterpret_cast<const float4*>(msl + ((size_t)g * T_in + j) * 16 + t * 4);
-          } else {
-            const float* mp = a.memory + ((size_t)(n0 + g) * T_in + j) * DH + q * 16 + 2 * t;
-            const float2 m01 = __ldg(reinterpret_cast<const float2*>(mp));
-            const float2 m89 = __ldg(reinterpret_cast<const float2*>(mp + 8));
-            m = make_float4(m01.x, m01.y, m89.x, m89.y);
-          }
-          acc.x = fmaf(p, m.x, acc.x); acc.y = fmaf(p, m.y, acc.y); acc.z = fmaf(p, m.z, acc.z); acc.w = fmaf(p, m.w, acc.w);
-          ssum += p;
+        const float* sc = reinterpret_cast<const float*>(smem_raw + L.sc) + g;
+        float4 acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float ssum2 = 0.f;
+        auto mload = [&](int j) -> float4 {
+          if (att_res) return *reinterpret_cast<const float4*>(smem_raw + L.msl + (((size_t)j * S + g) * 16 + t * 4) * 4);
+          return ldg_f4(a.memory + ((size_t)(n0 + g) * T_in + j) * DH + q * 16 + 4 * t);
+        };
+        int j = warp;
+        for (; j + NW < T_in; j += 2 * NW) {
+          const float pa = sc[j * S], pb = sc[(j + NW) * S];
+          const float4 ma = mload(j), mb2 = mload(j + NW);
+          acc.x = fmaf(pa, ma.x, acc.x); acc.y = fmaf(pa, ma.y, acc.y); acc.z = fmaf(pa, ma.z, acc.z); acc.w = fmaf(pa, ma.w, acc.w);
+          acc2.x = fmaf(pb, mb2.x, acc2.x); acc2.y = fmaf(pb, mb2.y, acc2.y); acc2.z = fmaf(pb, mb2.z, acc2.z); acc2.w = fmaf(pb, mb2.w, acc2.w);
+          ssum += pa; ssum2 += pb;
         }
+        if (j < T_in) {
+          const float pa = sc[j * S];
+          const float4 ma = mload(j);
+          acc.x = fmaf(pa, ma.x, acc.x); acc.y = fmaf(pa, ma.y, acc.y); acc.z = fmaf(pa, ma.z, acc.z); acc.w = fmaf(pa, ma.w, acc.w);
+          ssum += pa;
+        }
+        acc.x += acc2.x; acc.y += acc2.y; acc.z += acc2.z; acc.w += acc2.w;
+        ssum += ssum2;
       }
-      *reinterpret_cast<float4*>(myslot + g * RS + t * 4) = acc;
-      if (t == 0) reds[warp * 8 + g] = ssum;
+      sts_f4(myslot + (g * RS + t * 4) * 4, acc);   // partial context of sample g, columns 4t..4t+3
+      if (t == 0) reinterpret_cast<float*>(smem_raw + OFF_REDS)[warp * 8 + g] = ssum;
     }
     __syncthreads();
     TRM(19);
-    if (warp == 0) {
-      float inv = 0.f;
-      if (g < S) {
-        const float4 c = red_tile<16>(red, 0, g, t);
-        float ssum = 0.f;
+    if (red_grp) {
+      const float* reds = reinterpret_cast<const float*>(smem_raw + OFF_REDS) + rn;
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int s = 0; s < NW; ++s) ssum += reds[s * 8 + g];
-        inv = 1.0f / ssum;
-        push_x(L.buf[DM_BC], q, make_float4(c.x * inv, c.y * inv, c.z * inv, c.w * inv), B_P7, 1, 0);
-      }
-      if (a.align_out != nullptr) {   // alignments of this CTA's positions (tacotron.py:104 layout [N,T_in,steps])
-        for (int i0 = 0; i0 < nj * 8; i0 += 32) {
-          const int i = i0 + lane, jj = i >> 3, s = i & 7;
-          const float iv = __shfl_sync(0xffffffffu, inv, (s < S ? s : 0) * 4);
-          if (jj < nj && s < S) a.align_out[((size_t)(n0 + s) * T_in + (j0 + jj)) * a.max_steps + step] = stage[jj * S + s] * iv;
-        }
+      for (int s = 0; s < NW; s += 2) { s0 += reds[s * 8]; s1 += reds[s * 8 + 8]; }
+      const float inv = 1.0f / (s0 + s1);
+      stage_x(stg_n, rc, red_sum<16>(red_nc, 0) * inv);
+      if (rc == 0) reinterpret_cast<float*>(smem_raw + OFF_INV)[rn] = inv;
+    }
+    __syncthreads();
+    send_blk(0, XBUF(DM_BC) + q * csb, B_P7);
+    if (warp == 1 && a.align_out != nullptr) {   // alignments of this CTA's pairs (tacotron.py:104: [N,T_in,steps])
+      const float* stage = reinterpret_cast<const float*>(smem_raw + L.stage);
+      const float* invs = reinterpret_cast<const float*>(smem_raw + OFF_INV);
+      for (int pp = lane; pp < npq; pp += 32) {
+        const int p = p0 + pp, j = (int)(((float)p + 0.5f) * invS), n = p - j * S;
+        a.align_out[((size_t)(n0 + n) * T_in + j) * a.max_steps + step] = stage[pp] * invs[n];
       }
     }
     TRM(20);
     mbar_wait(mb0 + B_P7 * 8, par);
     TRM(21);
     // ================= P8: y0 = [h_att' | ctx] W_p + b (ctx half here, h half from P5) =================
-    mma_chunks<N8>(wb, tab_x(T_P8), csb, tab_cnt(T_P8), myslot, g, t);
-    load_w<N9>(wb, ws + O9 * 32, tab_cnt(T_P9));
+    MMA(SL8, T_P8)
     __syncthreads();
     TRM(22);
-    if (red_on) {
-      const float4 c = red_tile<8>(red, 0, g, t), b = bias4(BI_PC);
-      y0 = make_float4(c.x + y0h.x + b.x, c.y + y0h.y + b.y, c.z + y0h.z + b.z, c.w + y0h.w + b.w);
-      push_x(L.buf[DM_BY0], q, y0, B_P8, 1, 0);
-    }
+    if (red_grp) {
+      const float y0 = red_sum<8>(red_nc, 0) + lds_f(ST(ST_Y0H)) + BIAS(BI_PC);
+      sts_f(ST(ST_Y0), y0);
+      stage_x(stg_n, rc, y0);
+    } else { LOADP(T_P9, O9, 4, 0, 1) }           // window of P8: last two chunks of P9
+    __syncthreads();
+    send_blk(0, XBUF(DM_BY0) + q * csb, B_P8);
+    if (red_grp) { LOADP(T_P9, O9, 4, 0, 1) }
     TRM(23);
     mbar_wait(mb0 + B_P8 * 8, par);
     TRM(24);
-    // ================= P9: decoder GRU 1 gates on [y0 | h1] + candidate x-part =================
-    mma_chunks<N9>(wb, tab_x(T_P9), csb, tab_cnt(T_P9), myslot, g, t);
-    load_w<N10>(wb, ws + O10 * 32, tab_cnt(T_P10));
-    __syncthreads();
-    TRM(25);
-    if (red_on) {
-      const float4 r = red_tile<6>(red, 0, g, t), u = red_tile<6>(red, 6, g, t);
-      cxkeep = red_tile<4>(red, 12, g, t);
-      const float4 br = bias4(BI_R1), bu = bias4(BI_U1);
-      ukeep = make_float4(sigmoid_f(u.x + bu.x), sigmoid_f(u.y + bu.y), sigmoid_f(u.z + bu.z), sigmoid_f(u.w + bu.w));
-      const float4 rh = make_float4(sigmoid_f(r.x + br.x) * h1.x, sigmoid_f(r.y + br.y) * h1.y,
-                                    sigmoid_f(r.z + br.z) * h1.z, sigmoid_f(r.w + br.w) * h1.w);
-      push_x(L.buf[DM_BR1], q, rh, B_P9, 1, 0);
-    }
+    // ----- P9 / P10: decoder GRU 1 on [y0 | h1], y1 = y0 + h1' -----
+    GRU_GATES(SL9, T_P9, BI_R1, BI_U1, ST_H1, DM_BR1, B_P9, LOADP(T_P10, O10, 0, 0, 1) LOADP(T_P11, O11, 0, 2, 3, 4, 5))
     TRM(26);
     mbar_wait(mb0 + B_P9 * 8, par);
     TRM(27);
-    // ================= P10: GRU 1 candidate h-part -> h1', y1 = y0 + h1' (ResidualWrapper) =================
-    mma_chunks<N10>(wb, tab_x(T_P10), csb, tab_cnt(T_P10), myslot, g, t);
-    load_w<N11>(wb, ws + O11 * 32, tab_cnt(T_P11));
-    __syncthreads();
-    TRM(28);
-    if (red_on) {
-      const float4 c = red_tile<8>(red, 0, g, t), b = bias4(BI_C1);
-      h1.x = ukeep.x * h1.x + (1.0f - ukeep.x) * tanh_f(c.x + cxkeep.x + b.x);
-      h1.y = ukeep.y * h1.y + (1.0f - ukeep.y) * tanh_f(c.y + cxkeep.y + b.y);
-      h1.z = ukeep.z * h1.z + (1.0f - ukeep.z) * tanh_f(c.z + cxkeep.z + b.z);
-      h1.w = ukeep.w * h1.w + (1.0f - ukeep.w) * tanh_f(c.w + cxkeep.w + b.w);
-      y1 = make_float4(y0.x + h1.x, y0.y + h1.y, y0.z + h1.z, y0.w + h1.w);
-      push_x(L.buf[DM_BH1], q, h1, B_P10, 1, 0);
-      push_x(L.buf[DM_BY1], q, y1, B_P10, 1, 0);
-    }
+    GRU_CAND(SL10, T_P10, BI_C1, ST_H1, ST_Y0, ST_Y1, DM_BH1, DM_BY1, B_P10, LOADP(T_P11, O11, 4, 0, 1))
     TRM(29);
     mbar_wait(mb0 + B_P10 * 8, par);
     TRM(30);
-    // ================= P11: decoder GRU 2 gates on [y1 | h2] + candidate x-part =================
-    mma_chunks<N11>(wb, tab_x(T_P11), csb, tab_cnt(T_P11), myslot, g, t);
-    load_w<N12>(wb, ws + O12 * 32, tab_cnt(T_P12));
-    __syncthreads();
-    TRM(31);
-    if (red_on) {
-      const float4 r = red_tile<6>(red, 0, g, t), u = red_tile<6>(red, 6, g, t);
-      cxkeep = red_tile<4>(red, 12, g, t);
-      const float4 br = bias4(BI_R2), bu = bias4(BI_U2);
-      ukeep = make_float4(sigmoid_f(u.x + bu.x), sigmoid_f(u.y + bu.y), sigmoid_f(u.z + bu.z), sigmoid_f(u.w + bu.w));
-      const float4 rh = make_float4(sigmoid_f(r.x + br.x) * h2.x, sigmoid_f(r.y + br.y) * h2.y,
-                                    sigmoid_f(r.z + br.z) * h2.z, sigmoid_f(r.w + br.w) * h2.w);
-      push_x(L.buf[DM_BR2], q, rh, B_P11, 1, 0);
-    }
+    // ----- P11 / P12: decoder GRU 2 on [y1 | h2], y2 = y1 + h2' -----
+    GRU_GATES(SL11, T_P11, BI_R2, BI_U2, ST_H2, DM_BR2, B_P11, LOADP(T_P12, O12, 0, 0, 1) LOADP(T_P13, O13, 0, 2, 3) LOADP(T_P1, O1, 0, 4, 5))
     TRM(32);
     mbar_wait(mb0 + B_P11 * 8, par);
     TRM(33);
-    // ================= P12: GRU 2 candidate h-part -> h2', y2 = y1 + h2' =================
-    mma_chunks<N12>(wb, tab_x(T_P12), csb, tab_cnt(T_P12), myslot, g, t);
-    load_w<N13>(wb, ws + O13 * 32, tab_cnt(T_P13));
-    __syncthreads();
-    TRM(34);
-    if (red_on) {
-      const float4 c = red_tile<8>(red, 0, g, t), b = bias4(BI_C2);
-      h2.x = ukeep.x * h2.x + (1.0f - ukeep.x) * tanh_f(c.x + cxkeep.x + b.x);
-      h2.y = ukeep.y * h2.y + (1.0f - ukeep.y) * tanh_f(c.y + cxkeep.y + b.y);
-      h2.z = ukeep.z * h2.z + (1.0f - ukeep.z) * tanh_f(c.z + cxkeep.z + b.z);
-      h2.w = ukeep.w * h2.w + (1.0f - ukeep.w) * tanh_f(c.w + cxkeep.w + b.w);
-      push_x(L.buf[DM_BH2], q, h2, B_P12, 1, 0);
-      push_x(L.buf[DM_BY2], q, make_float4(y1.x + h2.x, y1.y + h2.y, y1.z + h2.z, y1.w + h2.w), B_P12, 1, 0);
-    }
+    GRU_CAND(SL12, T_P12, BI_C2, ST_H2, ST_Y1, -1, DM_BH2, DM_BY2, B_P12, LOADP(T_P1, O1, 2, 0))
     TRM(35);
     mbar_wait(mb0 + B_P12 * 8, par);
     TRM(36);
     // ================= P13: output projection tiles 2q, 2q+1 -> frames, feed the last frame back =================
-    mma_chunks<N13>(wb, tab_x(T_P13), csb, tab_cnt(T_P13), myslot, g, t);
-    load_w<N1>(wb, ws + O1 * 32, tab_cnt(T_P1));
+    MMA(SL13, T_P13)
     __syncthreads();
     TRM(37);
-    if (red_on) {
+    if (red_grp) {
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int tile = 2 * q + half;
-        if (tile < ntiles) {
-          float4 o = red_tile<8>(red, half * 8, g, t);
-          const float4 b = bias4(half ? BI_OB : BI_OA);
-          o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          float* orow = a.dec_out + ((size_t)(n0 + g) * a.max_steps + step) * Dout + tile * 16 + 2 * t;
-          *reinterpret_cast<float2*>(orow) = make_float2(o.x, o.y);
-          *reinterpret_cast<float2*>(orow + 8) = make_float2(o.z, o.w);
-          if (free_run && tile >= fb_tile0) push_x(L.buf[DM_BF], tile - fb_tile0, o, B_P13, 1, 0);   // helpers.py:37
-        }
+        const float o = red_sum<8>(red_nc, half * 8) + BIAS(half ? BI_OB : BI_OA);
+        if (tile < ntiles && rn < S) a.dec_out[((size_t)(n0 + rn) * a.max_steps + step) * Dout + tile * 16 + rc] = o;
+        if (free_run) stage_x(stg_n + half * 512, rc, o);   // next decoder input = last frame of the group (helpers.py:37)
       }
     }
+    if (free_run) {
+      __syncthreads();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int tile = 2 * q + half;
+        if (tile < ntiles && tile >= fb_tile0) send_blk(half, XBUF(DM_BF) + (tile - fb_tile0) * csb, B_P13);
+      }
+    }
+    LOADP(T_P2, O2, 0, 1, 2)           // window of P13: P2
     TRM(38);
   }
   // nobody may exit while a peer can still write into its shared memory
@@ -600,7 +642,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
 }  // namespace
 
 size_t decoder_mma_smem_bytes(int s_max, int T_in, int M, bool att_res) {
-  return make_smem(s_max, T_in, M >> 4, att_res).total;
+  return make_dyn(s_max, T_in, M >> 4, att_res).total;
 }
 
 int decoder_mma_max_clusters() {

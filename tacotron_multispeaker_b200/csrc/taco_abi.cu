@@ -653,7 +653,7 @@ bool pack_decoder_mma(taco_handle* h, Arena& A, DmOff& O, uint32_t (&tabw)[DM_NP
   for (int q = 0; q < 16; ++q) {
     float* B = &A.buf[O.bias + (size_t)q * DM_NBIAS];
     for (int c = 0; c < 16; ++c) {
-      const int col = 16 * q + c, ps = dm_pos16(c);
+      const int col = 16 * q + c, ps = c;
       B[0 + ps] = b1->data[col];
       B[16 + ps] = b2->data[16 * (q >> 1) + c];
       B[32 + ps] = bga->data[col];   B[48 + ps] = bga->data[DH + col];   B[64 + ps] = bca->data[col];

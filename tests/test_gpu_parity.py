@@ -327,3 +327,38 @@ def test_r1_fork_defaults():
     assert maxabs(mel, ref["mel_outputs"]) < 1e-3
     assert maxabs(lin, ref["linear_outputs"]) < 1e-3
     e.close()
+
+
+def test_full_size_free_running_config3():
+    """BASELINE config 3 at full size (batch 32, T_in 100, 200 decoder steps x r=5 = 1000 frames, free running):
+    mel / linear within the north-star 1e-3 of the oracle, alignments within 1e-5 with identical per-step argmax,
+    identical stop step.  The decoder runs on the mma.sync kernel with 7 clusters of 5/4 utterances."""
+    from tacotron_multispeaker_b200.engine import Engine
+    from tacotron_multispeaker_b200.hparams import HParams
+    from tacotron_multispeaker_b200.weights import random_init
+    hp = HParams(outputs_per_step=5, max_iters=200)
+    w = random_init(hp, 60, seed=1234)
+    ids, lengths, spk = make_inputs(32, 100, 60, 1, min_len=60, vocab=(7108, 7325))
+    ref = O.tacotron_forward(w, hp, ids, lengths, identities=spk, id_num=60)
+    e = Engine(hp, 60)
+    e.load_weights(w)
+    mel, lin, al, steps = e.forward(ids, lengths, spk)
+    geo = e.decoder_geometry(32)
+    e.close()
+    assert steps == ref["steps"] == 200
+    assert geo["cluster_size"] == 16 and geo["num_clusters"] * geo["samples_per_cluster"] >= 32
+    assert maxabs(mel, ref["mel_outputs"]) < 1e-3
+    assert maxabs(lin, ref["linear_outputs"]) < 1e-3
+    assert maxabs(al, ref["alignments"]) < 1e-5
+    assert torch.equal(al.cpu().argmax(dim=1), ref["alignments"].argmax(dim=1))
+
+
+@pytest.mark.parametrize("N,S", [(1, 1), (7, 1), (13, 2), (8, 8), (23, 3), (40, 8)])
+def test_decode_mma_cluster_cuts(eng, ow, small_hp, N, S):
+    """The mma.sync decoder cuts a batch into clusters of S <= 8 utterances (uneven cuts, more clusters than fit at
+    once -> several waves): every cut gives the oracle's result."""
+    e_dec, e_al, al, ral = _decode_case(eng, ow, small_hp, N, 37, True, 100 + N, S)
+    assert e_dec < 2e-4 and e_al < 1e-5
+    assert torch.equal(al.cpu().argmax(dim=1), ral.argmax(dim=1))
+    e_dec, e_al, _, _ = _decode_case(eng, ow, small_hp, N, 37, False, 200 + N, S)
+    assert e_dec < 1e-3 and e_al < 1e-4

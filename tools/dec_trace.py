@@ -30,13 +30,13 @@ def run(N, T_in, cs, S, tag, iters=40):
     torch.cuda.synchronize()
     os.environ.pop("TACO_DEC_TRACE")
     st = [int(l.split()[1]) for l in open(path) if not l.startswith("#")]
-    n = max(i for i, v in enumerate(st) if v) + 1
-    d = [st[i] - st[i - 1] for i in range(1, n)]
-    n = 39 if st[38] else n
-    d = [st[i] - st[i - 1] for i in range(1, n)]
-    print("%s N=%d CS=%d S=%d: %.2f us/step; traced step %d clk; deltas: %s" % (tag, N, cs, S, ms * 1e3 / iters, st[n - 1] - st[0], d), flush=True)
-    if st[40]:
-        print("   fine stamps 40..: ", [(i, st[i] - st[9]) for i in range(40, 60) if st[i]], " (relative to stamp 9; stamp 10 at %d)" % (st[10] - st[9]), flush=True)
+    idx = [i for i in range(40) if st[i]]
+    d = ["%d:%d" % (idx[k], st[idx[k]] - st[idx[k - 1]]) for k in range(1, len(idx))]
+    print("%s N=%d CS=%d S=%d: %.2f us/step; traced step %d clk; stamp:delta %s" % (tag, N, cs, S, ms * 1e3 / iters, st[idx[-1]] - st[idx[0]], " ".join(d)), flush=True)
+    if st[64]:
+        for b0, name in ((64, "after wait"), (80, "after mma"), (96, "after load issue")):
+            print("   per-warp %s (rel. stamp 9): %s" % (name, [st[b0 + w] - st[9] for w in range(16)]), flush=True)
+        print("   stamp 10 (after barrier) at %d" % (st[10] - st[9]), flush=True)
     eng.close()
 
 if __name__ == "__main__":
