@@ -113,6 +113,20 @@ int taco_forward_host(taco_handle* h, const int32_t* ids_host, const int32_t* le
                       float* linear_out_host, float* align_out_host, int32_t* steps_out_host,
                       void* stream);
 
+/* The same call in two halves, for callers that keep several batches in flight
+ * (one handle + stream each): _begin copies the inputs, runs the forward (it
+ * blocks only until the decoder's step count is known) and ENQUEUES the output
+ * copies; _end waits for them and returns the step count.  Between the two the
+ * host may start another handle's _begin, so that one batch's 144 MB of D2H
+ * traffic overlaps the next batch's compute.  The host buffers must stay valid
+ * until _end returns.  taco_forward_host == _begin followed by _end. */
+int taco_forward_host_begin(taco_handle* h, const int32_t* ids_host, const int32_t* lengths_host,
+                            const int32_t* spk_host, const float* mel_targets_host, int N,
+                            int T_in, int T_tgt, int bn_mode, int teacher_force,
+                            float* mel_out_host, float* linear_out_host, float* align_out_host,
+                            void* stream);
+int taco_forward_host_end(taco_handle* h, int32_t* steps_out_host, void* stream);
+
 /* ---- stage-level entry points (unit parity against the oracle) ----------- */
 /* tacotron.py:46-55: out [N,T_in,E(+E_id)].  OOB ids write a zero row and make
  * the call return TACO_ERR_OOB_ID at the next taco_check_ids(). */

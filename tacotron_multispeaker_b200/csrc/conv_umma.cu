@@ -24,6 +24,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -443,6 +445,13 @@ cudaError_t launch_conv_umma(const ConvUmma& c, cudaStream_t st) {
   // ring depth: deep for long K; short-K launches are epilogue/launch bound and gain from 2-3 CTAs per SM
   const int nkb_max = c.taps * (c.Cp / BK);
   p.stages = nkb_max >= 6 ? 3 : (nkb_max >= 3 ? 2 : 1);
+  // many more CTAs than SMs: a one-stage CTA (82 KB) lets two or three CTAs share an SM, so one CTA's epilogue
+  // overlaps its neighbours' loads and MMAs -- measured 2.08 -> 1.87 ms on the post-net of config 3
+  if ((long long)grid.x * grid.y * grid.z >= 1024) p.stages = 1;
+  {   // developer switch: TACO_UMMA_STAGES_MAX caps the ring depth (more CTAs per SM, less pipelining per CTA)
+    static const int cap = [] { const char* e = getenv("TACO_UMMA_STAGES_MAX"); return e ? atoi(e) : 0; }();
+    if (cap >= 1 && p.stages > cap) p.stages = cap;
+  }
   const int chn = c.epi == EPI_HIGHWAY ? 2 : 1;
   auto al4 = [](long long v) { return (v & 3) == 0; };
   p.vec_epi = (al4(c.ldo) && al4(c.col_off) && al4(c.out_bs) && al4(c.Cout / chn) && (c.Cout % (4 * chn) == 0) &&

@@ -218,9 +218,11 @@ __device__ __forceinline__ void load_w(uint4 (&wb)[NWB], const uint4* __restrict
 }
 
 // one warp's share of a phase: cnt chunks of one tile (chunk i in slot SL[i]); partial tile -> red slot of this warp
-template <int... SL>
+// NX > 0: the same weight chunks also multiply the chunks at byte offsets d1 (and d2) from xaddr when nx >= 1 (2) --
+// a sum of activation vectors (y1 = y0 + h1', y2 = y0 + h1' + h2') is never formed or exchanged, only its terms are.
+template <int NX, int... SL>
 __device__ __forceinline__ void mma_chunks(const uint4 (&wb)[NWB], uint32_t xaddr, uint32_t csb, int cnt, uint32_t slot,
-                                           int g, int t, Slots<SL...>) {
+                                           int g, int t, Slots<SL...>, int nx = 0, uint32_t d1 = 0, uint32_t d2 = 0) {
   constexpr int sl[] = {SL...};
   float hh[4] = {0.f, 0.f, 0.f, 0.f}, hl[4] = {0.f, 0.f, 0.f, 0.f}, lh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -230,6 +232,18 @@ __device__ __forceinline__ void mma_chunks(const uint4 (&wb)[NWB], uint32_t xadd
       mma16816(hh, wb[2 * sl[i]], xf.x, xf.y);       // W_hi * x_hi
       mma16816(lh, wb[2 * sl[i] + 1], xf.x, xf.y);   // W_lo * x_hi
       mma16816(hl, wb[2 * sl[i]], xf.z, xf.w);       // W_hi * x_lo
+      if (NX >= 1 && nx >= 1) {
+        const uint4 yf = lds128(xaddr + d1 + i * csb);
+        mma16816(hh, wb[2 * sl[i]], yf.x, yf.y);
+        mma16816(lh, wb[2 * sl[i] + 1], yf.x, yf.y);
+        mma16816(hl, wb[2 * sl[i]], yf.z, yf.w);
+      }
+      if (NX >= 2 && nx >= 2) {
+        const uint4 zf = lds128(xaddr + d2 + i * csb);
+        mma16816(hh, wb[2 * sl[i]], zf.x, zf.y);
+        mma16816(lh, wb[2 * sl[i] + 1], zf.x, zf.y);
+        mma16816(hl, wb[2 * sl[i]], zf.z, zf.w);
+      }
     }
   // D[row g / g+8 = tile column][col 2t, 2t+1 = sample]  ->  slot[sample][column]   (bank-conflict free with RS = 20)
   // (written even when cnt == 0 so that the reducer never sums a stale slot)
@@ -307,7 +321,8 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
   if (tid < DM_NPHASE * 16) {   // per-warp work table: byte offset of the warp's first chunk and its chunk count
     const uint32_t e = w.tab[tid >> 4][tid & 15];
     const uint32_t bufi = (e >> 8) & 15u, c0 = (e >> 3) & 31u;
-    reinterpret_cast<uint32_t*>(smem_raw + OFF_WTAB)[tid] = ((OFF_X + ((uint32_t)cum_chunks((int)bufi, FC) + c0) * csb) << 3) | (e & 7u);
+    reinterpret_cast<uint32_t*>(smem_raw + OFF_WTAB)[tid] =
+        (((e >> 14) & 3u) << 28) | ((OFF_X + ((uint32_t)cum_chunks((int)bufi, FC) + c0) * csb) << 3) | (e & 7u);
   }
   if (tid < DM_NBIAS) reinterpret_cast<float*>(smem_raw + OFF_BIAS)[tid] = __ldg(w.bias + q * DM_NBIAS + tid);
   if (tid < DH) reinterpret_cast<float*>(smem_raw + OFF_VATT)[tid] = __ldg(w.att_v + tid);
@@ -363,11 +378,14 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
 
   const bool free_run = a.targets == nullptr;
   const uint32_t BLK = CS * csb;
+  const uint32_t dH1 = (uint32_t)(cum_chunks(DM_BH1, FC) - cum_chunks(DM_BY0, FC)) * csb;   // y0 chunk i -> h1' chunk i
+  const uint32_t dH2 = (uint32_t)(cum_chunks(DM_BH2, FC) - cum_chunks(DM_BY0, FC)) * csb;   // y0 chunk i -> h2' chunk i
   const int fb_tile0 = (Dout - M) >> 4, ntiles = Dout >> 4;
 
 // LOADP(phase table index, stream offset, first chunk, slots): request chunks of a later phase (see the slot schedule)
 #define LOADP(TP, OFF, I0, ...) load_w<OFF, I0>(wb, ws, (int)(WCNT(TP) & 7u), Slots<__VA_ARGS__>());
-#define MMA(SL, TP) { const uint32_t e = WCNT(TP); mma_chunks(wb, xl + (e >> 3), csb, e & 7, myslot, g, t, SL()); }
+#define MMA(SL, TP) { const uint32_t e = WCNT(TP); mma_chunks<0>(wb, xl + ((e & 0x0fffffffu) >> 3), csb, e & 7, myslot, g, t, SL()); }
+#define MMAX(NX, SL, TP) { const uint32_t e = WCNT(TP); mma_chunks<NX>(wb, xl + ((e & 0x0fffffffu) >> 3), csb, e & 7, myslot, g, t, SL(), (int)(e >> 28), dH1, dH2); }
 #define ST(slot) (st_nc + (slot) * 512)
 #define BIAS(tab) lds_f(bias_c + (tab) * 4)
   for (int step = 0; step < a.steps; ++step) {
@@ -383,9 +401,9 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
       mbar_expect_tx(mb0 + B_P7 * 8, BLK);
       mbar_expect_tx(mb0 + B_P8 * 8, BLK);
       mbar_expect_tx(mb0 + B_P9 * 8, BLK);
-      mbar_expect_tx(mb0 + B_P10 * 8, 2 * BLK);
+      mbar_expect_tx(mb0 + B_P10 * 8, BLK);
       mbar_expect_tx(mb0 + B_P11 * 8, BLK);
-      mbar_expect_tx(mb0 + B_P12 * 8, 2 * BLK);
+      mbar_expect_tx(mb0 + B_P12 * 8, BLK);
       if (free_run) mbar_expect_tx(mb0 + B_P13 * 8, (uint32_t)FC * csb);
     }
     if (!free_run) {   // teacher forcing: input = mel_targets[:, (step-1)*r + r-1, :]  (helpers.py:48,75)
@@ -425,8 +443,8 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     mbar_wait(mb0 + B_P2 * 8, par);
     TRM(6);
     // ================= GRU phases: gates r,u on [x | h] + candidate x-part; then candidate h-part =================
-#define GRU_GATES(SLG, TP, BI_R, BI_U, ST_H, BUF_R, BAR, LOADNEXT)                                   \
-    MMA(SLG, TP)                                                                                    \
+#define GRU_GATES(NXG, SLG, TP, BI_R, BI_U, ST_H, BUF_R, BAR, LOADNEXT)                              \
+    MMAX(NXG, SLG, TP)                                                                                  \
     __syncthreads();                                                                                 \
     if (red_grp) {                                                                                   \
       const float r = sigmoid_f(red_sum<6>(red_nc, 0) + BIAS(BI_R));                                 \
@@ -459,7 +477,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     if (red_grp) { LOADNEXT }
 
     // ----- P3 / P4: attention GRU on [prenet | h_att] -----
-    GRU_GATES(SL3, T_P3, BI_RA, BI_UA, ST_HA, DM_BRA, B_P3, LOADP(T_P5, O5, 0, 3, 4))
+    GRU_GATES(0, SL3, T_P3, BI_RA, BI_UA, ST_HA, DM_BRA, B_P3, LOADP(T_P5, O5, 0, 3, 4))
     TRM(8);
     mbar_wait(mb0 + B_P3 * 8, par);
     TRM(9);
@@ -582,9 +600,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     __syncthreads();
     TRM(22);
     if (red_grp) {
-      const float y0 = red_sum<8>(red_nc, 0) + lds_f(ST(ST_Y0H)) + BIAS(BI_PC);
-      sts_f(ST(ST_Y0), y0);
-      stage_x(stg_n, rc, y0);
+      stage_x(stg_n, rc, red_sum<8>(red_nc, 0) + lds_f(ST(ST_Y0H)) + BIAS(BI_PC));
     } else { LOADP(T_P9, O9, 4, 0, 1) }           // window of P8: last two chunks of P9
     __syncthreads();
     send_blk(0, XBUF(DM_BY0) + q * csb, B_P8);
@@ -593,25 +609,25 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     mbar_wait(mb0 + B_P8 * 8, par);
     TRM(24);
     // ----- P9 / P10: decoder GRU 1 on [y0 | h1], y1 = y0 + h1' -----
-    GRU_GATES(SL9, T_P9, BI_R1, BI_U1, ST_H1, DM_BR1, B_P9, LOADP(T_P10, O10, 0, 0, 1) LOADP(T_P11, O11, 0, 2, 3, 4, 5))
+    GRU_GATES(0, SL9, T_P9, BI_R1, BI_U1, ST_H1, DM_BR1, B_P9, LOADP(T_P10, O10, 0, 0, 1) LOADP(T_P11, O11, 0, 2, 3, 4, 5))
     TRM(26);
     mbar_wait(mb0 + B_P9 * 8, par);
     TRM(27);
-    GRU_CAND(SL10, T_P10, BI_C1, ST_H1, ST_Y0, ST_Y1, DM_BH1, DM_BY1, B_P10, LOADP(T_P11, O11, 4, 0, 1))
+    GRU_CAND(SL10, T_P10, BI_C1, ST_H1, ST_H1, -1, DM_BH1, -1, B_P10, LOADP(T_P11, O11, 4, 0, 1))
     TRM(29);
     mbar_wait(mb0 + B_P10 * 8, par);
     TRM(30);
     // ----- P11 / P12: decoder GRU 2 on [y1 | h2], y2 = y1 + h2' -----
-    GRU_GATES(SL11, T_P11, BI_R2, BI_U2, ST_H2, DM_BR2, B_P11, LOADP(T_P12, O12, 0, 0, 1) LOADP(T_P13, O13, 0, 2, 3) LOADP(T_P1, O1, 0, 4, 5))
+    GRU_GATES(1, SL11, T_P11, BI_R2, BI_U2, ST_H2, DM_BR2, B_P11, LOADP(T_P12, O12, 0, 0, 1) LOADP(T_P13, O13, 0, 2, 3) LOADP(T_P1, O1, 0, 4, 5))
     TRM(32);
     mbar_wait(mb0 + B_P11 * 8, par);
     TRM(33);
-    GRU_CAND(SL12, T_P12, BI_C2, ST_H2, ST_Y1, -1, DM_BH2, DM_BY2, B_P12, LOADP(T_P1, O1, 2, 0))
+    GRU_CAND(SL12, T_P12, BI_C2, ST_H2, ST_H2, -1, DM_BH2, -1, B_P12, LOADP(T_P1, O1, 2, 0))
     TRM(35);
     mbar_wait(mb0 + B_P12 * 8, par);
     TRM(36);
     // ================= P13: output projection tiles 2q, 2q+1 -> frames, feed the last frame back =================
-    MMA(SL13, T_P13)
+    MMAX(2, SL13, T_P13)
     __syncthreads();
     TRM(37);
     if (red_grp) {

@@ -104,7 +104,9 @@ struct taco_handle {
   size_t stg_bytes = 0;
   int* d_ints = nullptr;      // [0]=oob flag, [1]=steps, [2..]=first_fin[N]
   int d_ints_n = 0;
-  int* h_pinned = nullptr;    // [0]=oob, [1]=steps
+  int* h_pinned = nullptr;    // [0]=oob, [1]=steps   (mapped pinned memory: kernels write it directly)
+  int* d_pinned = nullptr;    // device address of h_pinned
+  int pending_steps = 0;      // step count of the forward started by taco_forward_host_begin
   int64_t launches = 0;
   bool profiling = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [4],[5] bracket the decoder kernel
@@ -507,7 +509,7 @@ bool pack_decoder_v3(taco_handle* h, Arena& A, Dec3Off& O, std::string& err) {
 // ---- decoder_mma.cu packing -------------------------------------------------------------------
 // Work table of the MMA decoder: which 16-row chunks of which activation buffer every warp
 // multiplies in every phase (see decoder_mma.cu).  Entry = count | chunk0 << 3 | buffer << 8 | tile << 12.
-struct DmItem { int tile = 0, buf = 0, c0 = 0, cnt = 0; };
+struct DmItem { int tile = 0, buf = 0, c0 = 0, cnt = 0, nx = 0; };   // nx: extra activation buffers multiplied by the same weights
 void dm_table(int FC, DmItem (&tab)[DM_NPHASE][16]) {
   for (auto& ph : tab) for (auto& e : ph) e = DmItem();
   auto single = [&](int ph, int buf) { for (int w = 0; w < 8; ++w) tab[ph][w] = {0, buf, 2 * w, 2}; };
@@ -527,20 +529,22 @@ void dm_table(int FC, DmItem (&tab)[DM_NPHASE][16]) {
   single(3, DM_BRA);                                   // P4
   two(4, DM_BHA);                                      // P5: query | projection(h_att)
   single(5, DM_BC);                                    // P8
-  auto gru = [&](int ph, int bx, int bh) {             // P9 / P11
+  auto gru = [&](int ph, int bx, int bh, int nx) {     // P9 / P11
     const int c0[3] = {0, 6, 11}, n[3] = {6, 5, 5};
     for (int tile = 0; tile < 2; ++tile)
       for (int i = 0; i < 3; ++i) {
-        tab[ph][tile * 6 + i] = {tile, bx, c0[i], n[i]};
-        tab[ph][tile * 6 + 3 + i] = {tile, bh, c0[i], n[i]};
+        tab[ph][tile * 6 + i] = {tile, bx, c0[i], n[i], nx};
+        tab[ph][tile * 6 + 3 + i] = {tile, bh, c0[i], n[i], 0};
       }
-    for (int i = 0; i < 4; ++i) tab[ph][12 + i] = {2, bx, 4 * i, 4};
+    for (int i = 0; i < 4; ++i) tab[ph][12 + i] = {2, bx, 4 * i, 4, nx};
   };
-  gru(6, DM_BY0, DM_BH1);
+  gru(6, DM_BY0, DM_BH1, 0);
   single(7, DM_BR1);                                   // P10
-  gru(8, DM_BY1, DM_BH2);
+  // GRU 2 reads y1 = y0 + h1' by linearity: the x rows multiply the y0 buffer AND the h1' buffer (nothing extra is pushed)
+  gru(8, DM_BY0, DM_BH2, 1);
   single(9, DM_BR2);                                   // P12
-  two(10, DM_BY2);                                     // P13
+  two(10, DM_BY0);                                     // P13: y2 = y0 + h1' + h2' the same way
+  for (int w = 0; w < 16; ++w) tab[10][w].nx = 2;
 }
 
 inline uint16_t bf16_rn(float f) {
@@ -591,7 +595,7 @@ bool pack_decoder_mma(taco_handle* h, Arena& A, DmOff& O, uint32_t (&tabw)[DM_NP
     for (int wp = 0; wp < 16; ++wp) {
       const DmItem& e = tab[p][wp];
       if (e.cnt > nch[p] || e.cnt > 7 || e.c0 > 31) { err = "decoder_mma packing: work table overflow"; return false; }
-      tabw[p][wp] = (uint32_t)e.cnt | ((uint32_t)e.c0 << 3) | ((uint32_t)e.buf << 8) | ((uint32_t)e.tile << 12);
+      tabw[p][wp] = (uint32_t)e.cnt | ((uint32_t)e.c0 << 3) | ((uint32_t)e.buf << 8) | ((uint32_t)e.tile << 12) | ((uint32_t)e.nx << 14);
     }
   auto M2 = [](const HostVar* m, int ld, int row, int col) { return m->data[(size_t)row * ld + col]; };
   // first K row of chunk 0 of buffer `buf` inside the TF kernel of phase `p`
@@ -601,7 +605,7 @@ bool pack_decoder_mma(taco_handle* h, Arena& A, DmOff& O, uint32_t (&tabw)[DM_NP
       case 2: return buf == DM_BP2 ? 0 : DP;        // [prenet | h_att]
       case 3: return DP;                            // candidate rows of r*h_att
       case 5: return DH;                            // projection rows of the context
-      case 6: case 8: return (buf == DM_BY0 || buf == DM_BY1) ? 0 : DH;
+      case 6: case 8: return buf == DM_BY0 ? 0 : DH;
       case 7: case 9: return DH;
       default: return 0;
     }
@@ -980,11 +984,12 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
   if (!teacher_force) {
     int rc = ensure_ints(h, 2 + N);
     if (rc) return rc;
-    launch_find_steps(dec_out, N, max_steps, hp.num_mels * hp.outputs_per_step, h->d_ints + 2, h->d_ints + 1, st);
+    // The step count goes straight into mapped pinned memory: a D2H copy here would queue on the copy engine behind
+    // another handle's 144 MB output transfer and stall this forward in the middle (batches in flight on other streams).
+    launch_find_steps(dec_out, N, max_steps, hp.num_mels * hp.outputs_per_step, h->d_ints + 2, h->d_pinned + 1, st);
     h->launches += 3;
-    CUDA_OK(h, cudaMemcpyAsync(h->h_pinned + 1, h->d_ints + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_OK(h, cudaStreamSynchronize(st));
-    steps = h->h_pinned[1];
+    steps = *(volatile int*)(h->h_pinned + 1);
   }
   if (steps_out_host) *steps_out_host = steps;
   return check_launch(h, "decoder");
@@ -1035,7 +1040,8 @@ int taco_create(const taco_hparams* hp, int device, taco_handle** out) {
   h->device = device;
   h->names = expected_names(*hp);
   h->emb_dim = hp->embedding_text_channels + (hp->id_num > 1 ? hp->embedding_id_channels : 0);
-  if (cudaMallocHost(&h->h_pinned, sizeof(int) * 4) != cudaSuccess) { delete h; return TACO_ERR_CUDA; }
+  if (cudaHostAlloc(&h->h_pinned, sizeof(int) * 4, cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer(&h->d_pinned, h->h_pinned, 0) != cudaSuccess) { delete h; return TACO_ERR_CUDA; }
   for (int i = 0; i < 6; ++i) cudaEventCreate(&h->ev[i]);
   if (ensure_ints(h, 2 + 1024) != TACO_OK) { taco_destroy(h); return TACO_ERR_CUDA; }
   *out = h;
@@ -1406,11 +1412,11 @@ int taco_forward(taco_handle* h, const int32_t* ids, const int32_t* lengths, con
   return TACO_OK;
 }
 
-int taco_forward_host(taco_handle* h, const int32_t* ids_host, const int32_t* lengths_host, const int32_t* spk_host,
-                      const float* mel_targets_host, int N, int T_in, int T_tgt, int bn_mode, int teacher_force,
-                      float* mel_out_host, float* linear_out_host, float* align_out_host, int32_t* steps_out_host,
-                      void* stream) {
+int taco_forward_host_begin(taco_handle* h, const int32_t* ids_host, const int32_t* lengths_host, const int32_t* spk_host,
+                            const float* mel_targets_host, int N, int T_in, int T_tgt, int bn_mode, int teacher_force,
+                            float* mel_out_host, float* linear_out_host, float* align_out_host, void* stream) {
   REQUIRE_READY(h);
+  h->pending_steps = 0;
   if (!ids_host || !mel_out_host || N <= 0 || T_in <= 0) return fail(h, TACO_ERR_INVALID, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const taco_hparams& hp = h->hp;
@@ -1452,11 +1458,30 @@ int taco_forward_host(taco_handle* h, const int32_t* ids_host, const int32_t* le
     if (n_lin) cp(linear_out_host, d_lin, sizeof(float) * n_lin, cudaMemcpyDeviceToHost);
     if (n_al) cp(align_out_host, d_al, sizeof(float) * n_al, cudaMemcpyDeviceToHost);
   }
-  cudaError_t e = cudaStreamSynchronize(st);
-  if (rc == TACO_OK && e != cudaSuccess) rc = fail(h, TACO_ERR_CUDA, std::string("sync: ") + cudaGetErrorString(e));
-  if (rc == TACO_OK) rc = taco_check_ids(h, stream);
-  if (steps_out_host) *steps_out_host = steps;
+  h->pending_steps = steps;
+  return rc;   // the output copies are in flight on `stream`: taco_forward_host_end waits for them
+}
+
+int taco_forward_host_end(taco_handle* h, int32_t* steps_out_host, void* stream) {
+  REQUIRE_READY(h);
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(h, TACO_ERR_CUDA, std::string("sync: ") + cudaGetErrorString(e));
+  const int rc = taco_check_ids(h, stream);
+  if (steps_out_host) *steps_out_host = h->pending_steps;
   return rc;
+}
+
+int taco_forward_host(taco_handle* h, const int32_t* ids_host, const int32_t* lengths_host, const int32_t* spk_host,
+                      const float* mel_targets_host, int N, int T_in, int T_tgt, int bn_mode, int teacher_force,
+                      float* mel_out_host, float* linear_out_host, float* align_out_host, int32_t* steps_out_host,
+                      void* stream) {
+  const int rc = taco_forward_host_begin(h, ids_host, lengths_host, spk_host, mel_targets_host, N, T_in, T_tgt, bn_mode,
+                                         teacher_force, mel_out_host, linear_out_host, align_out_host, stream);
+  if (rc != TACO_OK) {
+    if (h) cudaStreamSynchronize((cudaStream_t)stream);
+    return rc;
+  }
+  return taco_forward_host_end(h, steps_out_host, stream);
 }
 
 int64_t taco_launch_count(const taco_handle* h) { return h ? h->launches : 0; }

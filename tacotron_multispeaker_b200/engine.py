@@ -213,6 +213,28 @@ class Engine:
         return (mel[:, :T], lin[:, :T] if lin is not None else None,
                 al[:, :, :s] if al is not None else None, s)
 
+    def forward_host_begin(self, ids: np.ndarray, lengths: np.ndarray, spk: Optional[np.ndarray],
+                           mel_targets: Optional[np.ndarray], teacher_force: bool, bn_mode: int,
+                           mel_out: np.ndarray, linear_out: Optional[np.ndarray], align_out: Optional[np.ndarray]) -> None:
+        """``taco_forward_host_begin``: inputs copied, forward run, output copies ENQUEUED (see ``forward_host_end``)."""
+        N, T_in = ids.shape
+        T_tgt = mel_targets.shape[1] if (teacher_force and mel_targets is not None) else 0
+
+        def hp_(a):
+            return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+        use_spk = spk if (spk is not None and self.id_num > 1) else None
+        self._ck(self.lib.taco_forward_host_begin(self._h, hp_(ids), hp_(lengths), hp_(use_spk),
+                                                  hp_(mel_targets if teacher_force else None), N, T_in, T_tgt, bn_mode,
+                                                  int(teacher_force), hp_(mel_out), hp_(linear_out), hp_(align_out),
+                                                  self.stream))
+
+    def forward_host_end(self) -> int:
+        """``taco_forward_host_end``: wait for the output copies of the forward begun on this handle; step count."""
+        steps = C.c_int32(0)
+        self._ck(self.lib.taco_forward_host_end(self._h, C.byref(steps), self.stream))
+        return steps.value
+
     def forward_host(self, ids: np.ndarray, lengths: np.ndarray, spk: Optional[np.ndarray],
                      mel_targets: Optional[np.ndarray], teacher_force: bool, bn_mode: int,
                      mel_out: np.ndarray, linear_out: Optional[np.ndarray], align_out: Optional[np.ndarray]) -> int:

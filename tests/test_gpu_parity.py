@@ -362,3 +362,20 @@ def test_decode_mma_cluster_cuts(eng, ow, small_hp, N, S):
     assert torch.equal(al.cpu().argmax(dim=1), ral.argmax(dim=1))
     e_dec, e_al, _, _ = _decode_case(eng, ow, small_hp, N, 37, False, 200 + N, S)
     assert e_dec < 1e-3 and e_al < 1e-4
+
+
+def test_forward_host_begin_end(eng, small_hp):
+    """taco_forward_host == taco_forward_host_begin + taco_forward_host_end (outputs land after _end)."""
+    hp = small_hp
+    N, T_in = 3, 14
+    ids, lengths, spk = make_inputs(N, T_in, 6, 21)
+    ms = eng.max_steps(False)
+    shapes = ((N, ms * hp.outputs_per_step, 80), (N, ms * hp.outputs_per_step, 1025), (N, T_in, ms))
+    a = [np.zeros(s, np.float32) for s in shapes]
+    b = [np.zeros(s, np.float32) for s in shapes]
+    s1 = eng.forward_host(ids, lengths, spk, None, False, 0, *a)
+    eng.forward_host_begin(ids, lengths, spk, None, False, 0, *b)
+    s2 = eng.forward_host_end()
+    assert s1 == s2
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
