@@ -175,6 +175,12 @@ int64_t taco_launch_count(const taco_handle* h);
  * cluster used for batch N. */
 int taco_decoder_geometry(const taco_handle* h, int N, int* cluster_size, int* samples_per_cluster,
                           int* num_clusters);
+/* Host-only introspection (no GPU needed): the work table of the mma.sync
+ * decoder for a given num_mels -- which 16-row chunks of which activation
+ * buffer each of the 16 warps multiplies in each of the 11 MMA phases.
+ * out[(phase*16 + warp)*5 + {0..4}] = {tile, buffer, first chunk, chunk count,
+ * extra activation buffers multiplied by the same weights}; out_len >= 880. */
+int taco_decoder_work_table(int num_mels, int32_t* out, int out_len);
 /* Device time (ms, CUDA events on `stream`) of the stages of the last
  * taco_forward when profiling is on: [0]=encoder [1]=decoder stage (memory
  * layer + loop + step count) [2]=postnet [3]=the decoder loop kernel alone. */

@@ -1486,6 +1486,20 @@ int taco_forward_host(taco_handle* h, const int32_t* ids_host, const int32_t* le
 
 int64_t taco_launch_count(const taco_handle* h) { return h ? h->launches : 0; }
 
+// Host-only: the decoder's work table for a given num_mels (no GPU, no handle).  out[phase][warp][5] =
+// {tile, buffer, first chunk, chunk count, extra activation buffers}.
+int taco_decoder_work_table(int num_mels, int32_t* out, int out_len) {
+  if (num_mels <= 0 || num_mels > 128 || (num_mels & 15) || !out || out_len < DM_NPHASE * 16 * 5) return TACO_ERR_INVALID;
+  DmItem tab[DM_NPHASE][16];
+  dm_table(num_mels / 16, tab);
+  for (int p = 0; p < DM_NPHASE; ++p)
+    for (int w = 0; w < 16; ++w) {
+      int32_t* e = out + (p * 16 + w) * 5;
+      e[0] = tab[p][w].tile; e[1] = tab[p][w].buf; e[2] = tab[p][w].c0; e[3] = tab[p][w].cnt; e[4] = tab[p][w].nx;
+    }
+  return TACO_OK;
+}
+
 int taco_decoder_geometry(const taco_handle* h, int N, int* cluster_size, int* samples_per_cluster, int* num_clusters) {
   if (!h || !h->finalized) return TACO_ERR_STATE;
   int CS = 16, S = 8;
