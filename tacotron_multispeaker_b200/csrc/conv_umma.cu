@@ -295,25 +295,38 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           if (scale) { sc = __ldg(scale + col); sh = __ldg(shift + col); }
         }
         const int rmax = min(32, p.T - (t0 + quarter * 32));
-#pragma unroll 4
-        for (int r = 0; r < rmax; ++r) {
-          const int t = t0 + quarter * 32 + r;
-          float x = stg[r * 33 + lane] + b;
-          if (p.epi == EPI_PLAIN) {
-            x = apply_act(x, p.act);
-            if (scale) x = fmaf(x, sc, sh);
+        // row pointers advance by the leading dimension: no 64-bit index arithmetic per element
+        const int tq = t0 + quarter * 32;
+        if (p.epi == EPI_PLAIN) {
+          float* optr = p.out + (long long)n * p.out_bs + (long long)tq * p.ldo + col_off + col;
+          const float* rptr = p.res ? p.res + (long long)n * p.res_bs + (long long)tq * p.ldres + col : nullptr;
+          const bool has_scale = scale != nullptr;
+#pragma unroll 8
+          for (int r = 0; r < rmax; ++r) {
+            float x = apply_act(stg[r * 33 + lane] + b, p.act);
+            if (has_scale) x = fmaf(x, sc, sh);
             if (cok) {
-              if (p.res) x += __ldg(p.res + (long long)n * p.res_bs + (long long)t * p.ldres + col);
-              p.out[(long long)n * p.out_bs + (long long)t * p.ldo + col_off + col] = x;
+              if (rptr) x += __ldg(rptr);
+              *optr = x;
             }
-          } else {   // EPI_HIGHWAY: even lane = H_c, odd lane = T_c of channel c = col/2
+            optr += p.ldo;
+            if (rptr) rptr += p.ldres;
+          }
+        } else {   // EPI_HIGHWAY: even lane = H_c, odd lane = T_c of channel c = col/2
+          const int chn = col >> 1;
+          float* optr = p.out + (long long)n * p.out_bs + (long long)tq * p.ldo + col_off + chn;
+          const float* rptr = p.res + (long long)n * p.res_bs + (long long)tq * p.ldres + chn;
+#pragma unroll 4
+          for (int r = 0; r < rmax; ++r) {
+            const float x = stg[r * 33 + lane] + b;
             const float tg = __shfl_down_sync(0xffffffffu, x, 1);
             if (cok && !(lane & 1)) {
-              const int chn = col >> 1;
               const float H = fmaxf(x, 0.f), Tg = sigmoid_f(tg);
-              const float xin = __ldg(p.res + (long long)n * p.res_bs + (long long)t * p.ldres + chn);
-              p.out[(long long)n * p.out_bs + (long long)t * p.ldo + col_off + chn] = H * Tg + xin * (1.0f - Tg);
+              const float xin = __ldg(rptr);
+              *optr = H * Tg + xin * (1.0f - Tg);
             }
+            optr += p.ldo;
+            rptr += p.ldres;
           }
         }
         __syncwarp();

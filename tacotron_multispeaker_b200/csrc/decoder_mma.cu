@@ -286,6 +286,8 @@ enum { BI_P1 = 0, BI_P2 = 16, BI_RA = 32, BI_UA = 48, BI_CA = 64, BI_PC = 80, BI
 static_assert(BI_OB + 16 == DM_NBIAS, "bias table size");
 
 #define TRM(i) do { if (a.trace != nullptr && step == 8 && blockIdx.x == 0 && tid == 0) a.trace[i] = clock64(); } while (0)
+// per-warp stamp: 16 consecutive entries starting at `base`
+#define TRW(base) do { if (a.trace != nullptr && step == 8 && blockIdx.x == 0 && lane == 0) a.trace[(base) + warp] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(NT, 1)
 decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int nclusters) {
@@ -388,6 +390,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
 #define MMAX(NX, SL, TP) { const uint32_t e = WCNT(TP); mma_chunks<NX>(wb, xl + ((e & 0x0fffffffu) >> 3), csb, e & 7, myslot, g, t, SL(), (int)(e >> 28), dH1, dH2); }
 #define ST(slot) (st_nc + (slot) * 512)
 #define BIAS(tab) lds_f(bias_c + (tab) * 4)
+  int trb = -1;   // developer aid: base of the per-warp stamps inside the GRU macros
   for (int step = 0; step < a.steps; ++step) {
     const uint32_t par = (uint32_t)step & 1u;
     if (free_run && step > 0) mbar_wait(mb0 + B_P13 * 8, par ^ 1u);   // fed-back frame of step-1 has landed
@@ -445,6 +448,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     // ================= GRU phases: gates r,u on [x | h] + candidate x-part; then candidate h-part =================
 #define GRU_GATES(NXG, SLG, TP, BI_R, BI_U, ST_H, BUF_R, BAR, LOADNEXT)                              \
     MMAX(NXG, SLG, TP)                                                                                  \
+    if (trb >= 0) TRW(trb);                                                                          \
     __syncthreads();                                                                                 \
     if (red_grp) {                                                                                   \
       const float r = sigmoid_f(red_sum<6>(red_nc, 0) + BIAS(BI_R));                                 \
@@ -452,12 +456,14 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
       sts_f(ST(ST_CX), red_sum<4>(red_nc, 12));                                                      \
       stage_x(stg_n, rc, r * lds_f(ST(ST_H)));                                                       \
     } else { LOADNEXT }                                                                              \
+    if (trb >= 0) TRW(trb + 16);                                                                     \
     __syncthreads();                                                                                 \
     send_blk(0, XBUF(BUF_R) + q * csb, BAR);                                                         \
     if (red_grp) { LOADNEXT }
     // candidate: h' = u h + (1-u) tanh(c_h + c_x + b); y_out = y_in + h' (ResidualWrapper) when BUF_Y >= 0
 #define GRU_CAND(SLC, TP, BI_C, ST_H, ST_YIN, ST_YOUT, BUF_H, BUF_Y, BAR, LOADNEXT)                        \
     MMA(SLC, TP)                                                                                      \
+    if (trb >= 0) TRW(trb);                                                                          \
     __syncthreads();                                                                                 \
     if (red_grp) {                                                                                   \
       const float c = tanh_f(red_sum<8>(red_nc, 0) + lds_f(ST(ST_CX)) + BIAS(BI_C));                 \
@@ -471,6 +477,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
         stage_x(stg_n + 512, rc, y);                                                                 \
       }                                                                                              \
     } else { LOADNEXT }                                                                              \
+    if (trb >= 0) TRW(trb + 16);                                                                     \
     __syncthreads();                                                                                 \
     send_blk(0, XBUF(BUF_H) + q * csb, BAR);                                                         \
     if (BUF_Y >= 0) send_blk(1, XBUF(BUF_Y < 0 ? 0 : BUF_Y) + q * csb, BAR);                         \
@@ -499,6 +506,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     TRM(14);
     mbar_wait(mb0 + B_P5 * 8, par);
     TRM(15);
+    TRW(160);
     // ================= P6: Bahdanau scores of this CTA's (position, sample) pairs: exp(v . tanh(keys + pq) - B) ======
     // v.tanh(k + p) = sum v - 2 sum_k v_k / (1 + e^{2k} e^{2p}); e^{2k} is resident, e^{2p} was pushed by P5.
     {
@@ -530,6 +538,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
         if (lane == 0) stage[pp] = __expf(fmaxf(e - vbound, -80.0f));
       }
     }
+    TRW(144);
     __syncthreads();
     TRM(16);
     // warp p -> peer p: this CTA's pairs into sc[p0 ..]
@@ -539,6 +548,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     TRM(17);
     mbar_wait(mb0 + B_P6 * 8, par);
     TRM(18);
+    TRW(64);
     // ================= P7: context slice sum_j p_j memory[j][16q..16q+15] / sum_j p_j =================
     {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -568,6 +578,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
         acc.x += acc2.x; acc.y += acc2.y; acc.z += acc2.z; acc.w += acc2.w;
         ssum += ssum2;
       }
+      TRW(80);
       sts_f4(myslot + (g * RS + t * 4) * 4, acc);   // partial context of sample g, columns 4t..4t+3
       if (t == 0) reinterpret_cast<float*>(smem_raw + OFF_REDS)[warp * 8 + g] = ssum;
     }
@@ -608,12 +619,17 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     TRM(23);
     mbar_wait(mb0 + B_P8 * 8, par);
     TRM(24);
+    TRW(192);
+    trb = 208;
     // ----- P9 / P10: decoder GRU 1 on [y0 | h1], y1 = y0 + h1' -----
     GRU_GATES(0, SL9, T_P9, BI_R1, BI_U1, ST_H1, DM_BR1, B_P9, LOADP(T_P10, O10, 0, 0, 1) LOADP(T_P11, O11, 0, 2, 3, 4, 5))
     TRM(26);
     mbar_wait(mb0 + B_P9 * 8, par);
     TRM(27);
+    TRW(96);
+    trb = 112;
     GRU_CAND(SL10, T_P10, BI_C1, ST_H1, ST_H1, -1, DM_BH1, -1, B_P10, LOADP(T_P11, O11, 4, 0, 1))
+    trb = -1;
     TRM(29);
     mbar_wait(mb0 + B_P10 * 8, par);
     TRM(30);

@@ -8,6 +8,9 @@ from tacotron_multispeaker_b200.engine import Engine
 from tacotron_multispeaker_b200.hparams import HParams
 from tacotron_multispeaker_b200.weights import random_init
 
+def impl_mma():
+    return os.environ.get("TACO_DEC_IMPL", "mma") == "mma"
+
 def run(N, T_in, cs, S, tag, iters=40):
     hp = HParams(outputs_per_step=5, max_iters=iters)
     w = random_init(hp, 60, seed=1234)
@@ -33,10 +36,14 @@ def run(N, T_in, cs, S, tag, iters=40):
     idx = [i for i in range(40) if st[i]]
     d = ["%d:%d" % (idx[k], st[idx[k]] - st[idx[k - 1]]) for k in range(1, len(idx))]
     print("%s N=%d CS=%d S=%d: %.2f us/step; traced step %d clk; stamp:delta %s" % (tag, N, cs, S, ms * 1e3 / iters, st[idx[-1]] - st[idx[0]], " ".join(d)), flush=True)
-    if st[64]:
-        for b0, name in ((64, "after wait"), (80, "after mma"), (96, "after load issue")):
-            print("   per-warp %s (rel. stamp 9): %s" % (name, [st[b0 + w] - st[9] for w in range(16)]), flush=True)
-        print("   stamp 10 (after barrier) at %d" % (st[10] - st[9]), flush=True)
+    if impl_mma():
+        names = {160: "P6 start (after wait P5)", 144: "P6 scores done", 64: "P7 start (after wait P6)", 80: "P7 loop done",
+                 192: "P9 start (after wait P8)", 208: "P9 mma done", 224: "P9 reduce/loads done",
+                 96: "P10 start (after wait P9)", 112: "P10 mma done", 128: "P10 reduce/loads done"}
+        stamps = [int(l.split()[1]) for l in open(path) if not l.startswith("#")]
+        for b0 in (160, 144, 64, 80, 192, 208, 224, 96, 112, 128):
+            ref = {160: 15, 144: 15, 64: 18, 80: 18, 192: 24, 208: 24, 224: 24, 96: 27, 112: 27, 128: 27}[b0]
+            print("   per-warp %-28s rel. stamp %d: %s" % (names[b0], ref, [stamps[b0 + w] - stamps[ref] if stamps[b0 + w] else None for w in range(16)]), flush=True)
     eng.close()
 
 if __name__ == "__main__":
