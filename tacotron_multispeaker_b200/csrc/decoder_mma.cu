@@ -72,6 +72,9 @@ using SL11 = Slots<2, 3, 4, 5, 0, 1>;
 using SL12 = Slots<0, 1>;
 using SL13 = Slots<2, 3>;
 static_assert(N1 == 3 && N3 == 4 && N9 == 6 && N11 == 6, "slot lists assume these chunk counts");
+// chunk-tile index of the TMEM-resident phases inside a warp's 128-column slice (8 columns per chunk-tile)
+constexpr int TC9 = 0, TC10 = TC9 + N9, TC11 = TC10 + N10, TC12 = TC11 + N11;
+static_assert(TC12 + N12 == 16, "the four GRU phases fill the 16 chunk-tiles per warp that TMEM holds");
 
 enum { B_P1 = 0, B_P2, B_P3, B_P4, B_P5, B_P6, B_P7, B_P8, B_P9, B_P10, B_P11, B_P12, B_P13, NBAR = 16 };
 // phase index inside DecoderMmaWeights::tab
@@ -89,7 +92,9 @@ constexpr uint32_t OFF_VATT = OFF_BIAS + DM_NBIAS * 4;
 constexpr uint32_t OFF_STATE = OFF_VATT + DH * 4;                  // [NSTATE][8 samples][16 columns] fp32
 constexpr uint32_t OFF_STG = OFF_STATE + NSTATE * 128 * 4;         // two staged blocks of 8 x 64 bytes
 constexpr uint32_t OFF_INV = OFF_STG + 2 * 512;                    // softmax normalisers 1/sum per sample
-constexpr uint32_t OFF_X = OFF_INV + 32;
+constexpr uint32_t OFF_P6T = OFF_INV + 32;                         // per-warp pair geometry of the score phase
+constexpr uint32_t OFF_TMEM = OFF_P6T + 64;                       // TMEM base address written by tcgen05.alloc
+constexpr uint32_t OFF_X = OFF_TMEM + 16;
 static_assert(OFF_X % 16 == 0 && OFF_RED % 16 == 0 && OFF_STATE % 16 == 0 && OFF_BIAS % 16 == 0, "alignment");
 
 // chunks in front of buffer b (order DM_BF, DM_BC, DM_BP1, DM_BP2(8 chunks), DM_BHA, ...)
@@ -176,6 +181,25 @@ __device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP: 1/inf = 0,
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+// ---- tensor memory as a weight store --------------------------------------------------------------------------------
+// The 256 KB of TMEM are not needed for accumulators here (the mat-vecs run on mma.sync), so they hold the A fragments of
+// the four heaviest phases (both decoder GRUs: 16 chunk-tiles of 1 KB per warp).  A warp reads and writes its own lane
+// quarter (warp % 4) with the 32x32b shape: x8 = the eight 32-bit words (hi uint4, lo uint4) of one chunk-tile per lane.
+// Measured (tools/ubench/tmem_ld.cu): 40-50 clk load+wait, ~800 B/clk/SM with 16 warps, and no LSU / L2 traffic.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint4& hi, uint4& lo) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w), "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& hi, const uint4& lo) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "r"(taddr), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the registers of a slot are only defined after tcgen05.wait::ld: make the compiler see them as produced there
+__device__ __forceinline__ void reg_fence(uint4& a, uint4& b) {
+  asm volatile("" : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w), "+r"(b.x), "+r"(b.y), "+r"(b.z), "+r"(b.w));
+}
+
 // D += A(16x16, row) * B(16x8, col), bf16 inputs, fp32 accumulate
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -215,6 +239,22 @@ __device__ __forceinline__ void load_w(uint4 (&wb)[NWB], const uint4* __restrict
       wb[2 * sl[k]] = ldg_stream(ws + (OFF + 2 * (I0 + k)) * 32);
       wb[2 * sl[k] + 1] = ldg_stream(ws + (OFF + 2 * (I0 + k) + 1) * 32);
     }
+}
+
+// the same from tensor memory: chunk-tile I0+k of a phase lives in column group TC0+I0+k of the warp's TMEM slice
+template <int TC0, int I0, int... SL>
+__device__ __forceinline__ void load_t(uint4 (&wb)[NWB], uint32_t tw, int cnt, Slots<SL...>) {
+  constexpr int sl[] = {SL...};
+#pragma unroll
+  for (int k = 0; k < (int)sizeof...(SL); ++k)
+    if (I0 + k < cnt) tmem_ld8(tw + (uint32_t)(TC0 + I0 + k) * 8u, wb[2 * sl[k]], wb[2 * sl[k] + 1]);
+}
+template <int... SL>
+__device__ __forceinline__ void wait_t(uint4 (&wb)[NWB], Slots<SL...>) {
+  constexpr int sl[] = {SL...};
+  tmem_wait_ld();
+#pragma unroll
+  for (int k = 0; k < (int)sizeof...(SL); ++k) reg_fence(wb[2 * sl[k]], wb[2 * sl[k] + 1]);
 }
 
 // one warp's share of a phase: cnt chunks of one tile (chunk i in slot SL[i]); partial tile -> red slot of this warp
@@ -371,8 +411,35 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
 #define WCNT(ph) (lds32(wtab + (ph) * 64))
 #define XBUF(b) (OFF_X + (uint32_t)cum_chunks((b), FC) * csb)
 
+  // P6: a warp works on the pairs of ONE sample; sample, first local pair and pair stride of this warp
+  // (kept in shared memory: the integer divisions are done once, the registers stay free)
+  if (lane == 0) {
+    const int wn = warp % S;
+    reinterpret_cast<uint32_t*>(smem_raw + OFF_P6T)[warp] =
+        (uint32_t)wn | ((uint32_t)((wn - p0 % S + S) % S + (warp / S) * S) << 8) | ((uint32_t)(((NW - wn + S - 1) / S) * S) << 16);
+  }
   uint4 wb[NWB];
-  __syncthreads();   // work table visible
+  if (warp == 0) {   // all 512 TMEM columns: the kernel owns the SM anyway (512 threads x 128 registers)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sbase + OFF_TMEM) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();   // work table and TMEM base visible
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = lds32(sbase + OFF_TMEM);
+  // this warp's slice: lane quarter warp % 4 (hardware rule), 128 columns = 16 chunk-tiles: P9 0-5, P10 6-7, P11 8-13, P12 14-15
+  const uint32_t tw = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * 128u;
+  {
+    auto fill = [&](int tp, int off, int tc0) {
+      const int cnt = (int)(WCNT(tp) & 7u);
+      for (int i = 0; i < cnt; ++i) {
+        const uint4 hi = ldg_stream(ws + (off + 2 * i) * 32), lo = ldg_stream(ws + (off + 2 * i + 1) * 32);
+        tmem_st8(tw + (uint32_t)(tc0 + i) * 8u, hi, lo);
+      }
+    };
+    fill(T_P9, O9, TC9); fill(T_P10, O10, TC10); fill(T_P11, O11, TC11); fill(T_P12, O12, TC12);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
   load_w<O1, 0>(wb, ws, (int)(WCNT(T_P1) & 7u), SL1());
   load_w<O2, 0>(wb, ws, (int)(WCNT(T_P2) & 7u), SL2());
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -386,6 +453,8 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
 
 // LOADP(phase table index, stream offset, first chunk, slots): request chunks of a later phase (see the slot schedule)
 #define LOADP(TP, OFF, I0, ...) load_w<OFF, I0>(wb, ws, (int)(WCNT(TP) & 7u), Slots<__VA_ARGS__>());
+#define TLOADP(TP, TC0, I0, ...) load_t<TC0, I0>(wb, tw, (int)(WCNT(TP) & 7u), Slots<__VA_ARGS__>());
+#define TWAIT(SL) wait_t(wb, SL());
 #define MMA(SL, TP) { const uint32_t e = WCNT(TP); mma_chunks<0>(wb, xl + ((e & 0x0fffffffu) >> 3), csb, e & 7, myslot, g, t, SL()); }
 #define MMAX(NX, SL, TP) { const uint32_t e = WCNT(TP); mma_chunks<NX>(wb, xl + ((e & 0x0fffffffu) >> 3), csb, e & 7, myslot, g, t, SL(), (int)(e >> 28), dH1, dH2); }
 #define ST(slot) (st_nc + (slot) * 512)
@@ -426,10 +495,9 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     __syncthreads();
     TRM(1);
     if (red_grp) stage_x(stg_n, rc, fmaxf(red_sum<DM_P1_SLOTS>(red_nc, 0) + BIAS(BI_P1), 0.f));
-    else { LOADP(T_P3, O3, 0, 3, 4, 5, 0) }     // window of P1: P3 (the reducer warps request theirs after the send)
     __syncthreads();
     send_blk(0, XBUF(DM_BP1) + q * csb, B_P1);
-    if (red_grp) { LOADP(T_P3, O3, 0, 3, 4, 5, 0) }
+    LOADP(T_P3, O3, 0, 3, 4, 5, 0)              // window of P1: P3 (after the send: the reducers' LDS do not queue behind it)
     TRM(2);
     mbar_wait(mb0 + B_P1 * 8, par);
     TRM(3);
@@ -438,31 +506,35 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     __syncthreads();
     TRM(4);
     if (red_grp) stage_x(stg_n, rc, fmaxf(red_sum<8>(red_nc, 0) + BIAS(BI_P2), 0.f));
-    else { LOADP(T_P4, O4, 0, 1, 2) }           // window of P2: P4
     __syncthreads();
     if (((warp ^ q) & 1) == 0) send_blk(0, XBUF(DM_BP2) + (q >> 1) * csb, B_P2);
-    if (red_grp) { LOADP(T_P4, O4, 0, 1, 2) }
+    LOADP(T_P4, O4, 0, 1, 2)                    // window of P2: P4
     TRM(5);
     mbar_wait(mb0 + B_P2 * 8, par);
     TRM(6);
     // ================= GRU phases: gates r,u on [x | h] + candidate x-part; then candidate h-part =================
-#define GRU_GATES(NXG, SLG, TP, BI_R, BI_U, ST_H, BUF_R, BAR, LOADNEXT)                              \
+#define GRU_GATES(NXG, SLG, TP, BI_R, BI_U, ST_H, BUF_R, BAR, URGENT, LATER)                             \
     MMAX(NXG, SLG, TP)                                                                                  \
+    URGENT   /* weights of the NEXT phase go into the slots this phase used last */                  \
     if (trb >= 0) TRW(trb);                                                                          \
     __syncthreads();                                                                                 \
+    /* three reducer groups work side by side: warps 0-3 r (-> r*h staged), 4-7 u, 8-11 the candidate's x part */ \
     if (red_grp) {                                                                                   \
       const float r = sigmoid_f(red_sum<6>(red_nc, 0) + BIAS(BI_R));                                 \
-      sts_f(ST(ST_U), sigmoid_f(red_sum<6>(red_nc, 6) + BIAS(BI_U)));                                \
-      sts_f(ST(ST_CX), red_sum<4>(red_nc, 12));                                                      \
       stage_x(stg_n, rc, r * lds_f(ST(ST_H)));                                                       \
-    } else { LOADNEXT }                                                                              \
+    } else if (warp < 8) {                                                                           \
+      sts_f(ST(ST_U), sigmoid_f(red_sum<6>(red_nc, 6) + BIAS(BI_U)));                                \
+    } else if (warp < 12) {                                                                          \
+      sts_f(ST(ST_CX), red_sum<4>(red_nc, 12));                                                      \
+    }                                                                                                \
     if (trb >= 0) TRW(trb + 16);                                                                     \
     __syncthreads();                                                                                 \
     send_blk(0, XBUF(BUF_R) + q * csb, BAR);                                                         \
-    if (red_grp) { LOADNEXT }
+    LATER
     // candidate: h' = u h + (1-u) tanh(c_h + c_x + b); y_out = y_in + h' (ResidualWrapper) when BUF_Y >= 0
-#define GRU_CAND(SLC, TP, BI_C, ST_H, ST_YIN, ST_YOUT, BUF_H, BUF_Y, BAR, LOADNEXT)                        \
+#define GRU_CAND(SLC, TP, BI_C, ST_H, ST_YIN, ST_YOUT, BUF_H, BUF_Y, BAR, URGENT, LATER)                     \
     MMA(SLC, TP)                                                                                      \
+    URGENT                                                                                           \
     if (trb >= 0) TRW(trb);                                                                          \
     __syncthreads();                                                                                 \
     if (red_grp) {                                                                                   \
@@ -476,19 +548,19 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
         if (ST_YOUT >= 0) sts_f(ST(ST_YOUT < 0 ? 0 : ST_YOUT), y);                                   \
         stage_x(stg_n + 512, rc, y);                                                                 \
       }                                                                                              \
-    } else { LOADNEXT }                                                                              \
+    }                                                                                                \
     if (trb >= 0) TRW(trb + 16);                                                                     \
     __syncthreads();                                                                                 \
     send_blk(0, XBUF(BUF_H) + q * csb, BAR);                                                         \
     if (BUF_Y >= 0) send_blk(1, XBUF(BUF_Y < 0 ? 0 : BUF_Y) + q * csb, BAR);                         \
-    if (red_grp) { LOADNEXT }
+    LATER
 
     // ----- P3 / P4: attention GRU on [prenet | h_att] -----
-    GRU_GATES(0, SL3, T_P3, BI_RA, BI_UA, ST_HA, DM_BRA, B_P3, LOADP(T_P5, O5, 0, 3, 4))
+    GRU_GATES(0, SL3, T_P3, BI_RA, BI_UA, ST_HA, DM_BRA, B_P3, , LOADP(T_P5, O5, 0, 3, 4))
     TRM(8);
     mbar_wait(mb0 + B_P3 * 8, par);
     TRM(9);
-    GRU_CAND(SL4, T_P4, BI_CA, ST_HA, ST_HA, -1, DM_BHA, -1, B_P4, LOADP(T_P8, O8, 0, 0, 1))
+    GRU_CAND(SL4, T_P4, BI_CA, ST_HA, ST_HA, -1, DM_BHA, -1, B_P4, , LOADP(T_P8, O8, 0, 0, 1))
     TRM(11);
     mbar_wait(mb0 + B_P4 * 8, par);
     TRM(12);
@@ -498,44 +570,63 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     TRM(13);
     if (red_grp) {   // the query is pushed as e^{2 pq} (fp32) for the score phase
       sts_f(stg_n + rc * 4, __expf(2.0f * fminf(fmaxf(red_sum<8>(red_nc, 0), -30.f), 30.f)));
+    } else if (warp < 8) {
       sts_f(ST(ST_Y0H), red_sum<8>(red_nc, 8));
-    } else { LOADP(T_P9, O9, 0, 2, 3) }   // window of P5: first two chunks of P9 (next two in the window of P6)
+    }
     __syncthreads();
     send_blk(0, L.pq + q * csb, B_P5);
-    if (red_grp) { LOADP(T_P9, O9, 0, 2, 3) }
     TRM(14);
     mbar_wait(mb0 + B_P5 * 8, par);
     TRM(15);
     TRW(160);
     // ================= P6: Bahdanau scores of this CTA's (position, sample) pairs: exp(v . tanh(keys + pq) - B) ======
     // v.tanh(k + p) = sum v - 2 sum_k v_k / (1 + e^{2k} e^{2p}); e^{2k} is resident, e^{2p} was pushed by P5.
+    // A warp works on ONE sample (warp % S): e^{2p} and v stay in registers and a pair costs two LDS.128 of e^{2k}.
+    // Two elements share one MUFU.RCP: v1/a + v2/b = (v1 b + v2 a) / (a b) with a, b clamped to 2^62 (tanh = 1 there).
     {
+      const uint32_t geo = lds32(sbase + OFF_P6T + warp * 4);
+      const int wn = geo & 0xffu, dpp = geo >> 16;
+      int pp = (geo >> 8) & 0xffu;
       // lane's 8 inputs: k = 4 lane + {0..3} (chunk lane>>2, columns 4 (lane&3)..) and 128 + the same (chunk + 8)
-      const uint32_t pq_l = sbase + L.pq + (uint32_t)(lane >> 2) * csb + (uint32_t)(lane & 3) * 16u;
+      const uint32_t pq_l = sbase + L.pq + (uint32_t)(lane >> 2) * csb + (uint32_t)(lane & 3) * 16u + (uint32_t)wn * 64u;
       const float4 v0 = lds_f4(sbase + OFF_VATT + lane * 16), v1 = lds_f4(sbase + OFF_VATT + 512 + lane * 16);
-      float* stage = reinterpret_cast<float*>(smem_raw + L.stage);
-      for (int pp = warp; pp < npq; pp += NW) {
-        const int p = p0 + pp, j = (int)(((float)p + 0.5f) * invS), n = p - j * S;
-        const float4 e0 = lds_f4(pq_l + n * 64), e1 = lds_f4(pq_l + 8 * csb + n * 64);   // e^{2 pq}
-        float4 k0, k1;                                                                     // e^{2 key}
+      const float4 e0 = lds_f4(pq_l), e1 = lds_f4(pq_l + 8 * csb);                             // e^{2 pq}
+      auto load_keys = [&](int pl, float4& k0, float4& k1) {                                   // e^{2 key} of local pair pl
         if (att_res) {
-          k0 = lds_f4(sbase + L.ksl + (uint32_t)pp * (DH * 4) + lane * 16);
-          k1 = lds_f4(sbase + L.ksl + (uint32_t)pp * (DH * 4) + 512 + lane * 16);
+          k0 = lds_f4(sbase + L.ksl + (uint32_t)pl * (DH * 4) + lane * 16);
+          k1 = lds_f4(sbase + L.ksl + (uint32_t)pl * (DH * 4) + 512 + lane * 16);
         } else {
-          const float* krow = a.keys + ((size_t)(n0 + n) * T_in + j) * DH + 4 * lane;
+          const int j = (p0 + pl) / S;
+          const float* krow = a.keys + ((size_t)(n0 + wn) * T_in + j) * DH + 4 * lane;
           k0 = ldg_f4(krow); k1 = ldg_f4(krow + 128);
           k0.x = __expf(2.0f * fminf(fmaxf(k0.x, -30.f), 30.f)); k0.y = __expf(2.0f * fminf(fmaxf(k0.y, -30.f), 30.f));
           k0.z = __expf(2.0f * fminf(fmaxf(k0.z, -30.f), 30.f)); k0.w = __expf(2.0f * fminf(fmaxf(k0.w, -30.f), 30.f));
           k1.x = __expf(2.0f * fminf(fmaxf(k1.x, -30.f), 30.f)); k1.y = __expf(2.0f * fminf(fmaxf(k1.y, -30.f), 30.f));
           k1.z = __expf(2.0f * fminf(fmaxf(k1.z, -30.f), 30.f)); k1.w = __expf(2.0f * fminf(fmaxf(k1.w, -30.f), 30.f));
         }
-        // e^{2k} e^{2p} in [0, inf]: inf -> term 0 (tanh = 1), 0 -> term v (tanh = -1)
-        float s0 = v0.x * rcp_approx(fmaf(k0.x, e0.x, 1.0f)), s1 = v0.y * rcp_approx(fmaf(k0.y, e0.y, 1.0f));
-        s0 = fmaf(v0.z, rcp_approx(fmaf(k0.z, e0.z, 1.0f)), s0); s1 = fmaf(v0.w, rcp_approx(fmaf(k0.w, e0.w, 1.0f)), s1);
-        s0 = fmaf(v1.x, rcp_approx(fmaf(k1.x, e1.x, 1.0f)), s0); s1 = fmaf(v1.y, rcp_approx(fmaf(k1.y, e1.y, 1.0f)), s1);
-        s0 = fmaf(v1.z, rcp_approx(fmaf(k1.z, e1.z, 1.0f)), s0); s1 = fmaf(v1.w, rcp_approx(fmaf(k1.w, e1.w, 1.0f)), s1);
-        const float e = vsum - 2.0f * warp_sum(s0 + s1);
-        if (lane == 0) stage[pp] = __expf(fmaxf(e - vbound, -80.0f));
+      };
+      constexpr float BIG = 4.611686018427387904e18f;   // 2^62
+      auto pair_rcp = [&](float ka, float ea, float va, float kb, float eb, float vb) -> float {
+        const float da = fminf(fmaf(ka, ea, 1.0f), BIG), db = fminf(fmaf(kb, eb, 1.0f), BIG);
+        return fmaf(va, db, vb * da) * rcp_approx(da * db);
+      };
+      auto partial = [&](const float4& k0, const float4& k1) -> float {
+        return (pair_rcp(k0.x, e0.x, v0.x, k0.y, e0.y, v0.y) + pair_rcp(k0.z, e0.z, v0.z, k0.w, e0.w, v0.w)) +
+               (pair_rcp(k1.x, e1.x, v1.x, k1.y, e1.y, v1.y) + pair_rcp(k1.z, e1.z, v1.z, k1.w, e1.w, v1.w));
+      };
+      for (; pp < npq; pp += 2 * dpp) {   // two pairs per pass: one butterfly reduces both
+        const bool two = pp + dpp < npq;
+        float4 ka0, ka1, kb0, kb1;
+        load_keys(pp, ka0, ka1);
+        load_keys(two ? pp + dpp : pp, kb0, kb1);
+        const float sa = partial(ka0, ka1), sb = partial(kb0, kb1);
+        // lanes 0..15 end up with pair A's sum, lanes 16..31 with pair B's
+        const bool up = lane >= 16;
+        float sv = (up ? sb : sa) + __shfl_xor_sync(0xffffffffu, up ? sa : sb, 16);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        const float ex = __expf(fmaxf(vsum - 2.0f * sv - vbound, -80.0f));
+        if (lane == 0 || (lane == 16 && two)) sts_f(sbase + L.stage + (uint32_t)(up ? pp + dpp : pp) * 4u, ex);
       }
     }
     TRW(144);
@@ -544,43 +635,61 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     // warp p -> peer p: this CTA's pairs into sc[p0 ..]
     for (int i = lane; i < npq; i += 32)
       st_async_b32(rx - lane * 16 + L.sc + (uint32_t)(p0 + i) * 4u, lds32(sbase + L.stage + i * 4), rmb0 + B_P6 * 8);
-    LOADP(T_P9, O9, 2, 4, 5)           // window of P6: chunks 2, 3 of P9
     TRM(17);
     mbar_wait(mb0 + B_P6 * 8, par);
     TRM(18);
     TRW(64);
     // ================= P7: context slice sum_j p_j memory[j][16q..16q+15] / sum_j p_j =================
+    // lane (g, t): sample g, columns 4t..4t+3; warp w takes the positions j = w (mod 16)
     {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      float ssum = 0.f;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float ssum = 0.f, ssum2 = 0.f;
       if (g < S) {
-        const float* sc = reinterpret_cast<const float*>(smem_raw + L.sc) + g;
-        float4 acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float ssum2 = 0.f;
-        auto mload = [&](int j) -> float4 {
-          if (att_res) return *reinterpret_cast<const float4*>(smem_raw + L.msl + (((size_t)j * S + g) * 16 + t * 4) * 4);
-          return ldg_f4(a.memory + ((size_t)(n0 + g) * T_in + j) * DH + q * 16 + 4 * t);
-        };
-        int j = warp;
-        for (; j + NW < T_in; j += 2 * NW) {
-          const float pa = sc[j * S], pb = sc[(j + NW) * S];
-          const float4 ma = mload(j), mb2 = mload(j + NW);
-          acc.x = fmaf(pa, ma.x, acc.x); acc.y = fmaf(pa, ma.y, acc.y); acc.z = fmaf(pa, ma.z, acc.z); acc.w = fmaf(pa, ma.w, acc.w);
-          acc2.x = fmaf(pb, mb2.x, acc2.x); acc2.y = fmaf(pb, mb2.y, acc2.y); acc2.z = fmaf(pb, mb2.z, acc2.z); acc2.w = fmaf(pb, mb2.w, acc2.w);
-          ssum += pa; ssum2 += pb;
-        }
-        if (j < T_in) {
-          const float pa = sc[j * S];
-          const float4 ma = mload(j);
-          acc.x = fmaf(pa, ma.x, acc.x); acc.y = fmaf(pa, ma.y, acc.y); acc.z = fmaf(pa, ma.z, acc.z); acc.w = fmaf(pa, ma.w, acc.w);
-          ssum += pa;
+        const int niter = (T_in - warp + NW - 1) / NW;
+        if (att_res) {
+          uint32_t pa = sbase + L.sc + (uint32_t)(warp * S + g) * 4u;
+          uint32_t ma = sbase + L.msl + (uint32_t)((warp * S + g) * 16 + t * 4) * 4u;
+          const uint32_t dp = (uint32_t)NW * S * 4u, dm = (uint32_t)NW * S * 64u;
+          int i = 0;
+          for (; i + 4 <= niter; i += 4) {
+            const float p0v = lds_f(pa), p1v = lds_f(pa + dp), p2v = lds_f(pa + 2 * dp), p3v = lds_f(pa + 3 * dp);
+            const float4 m0 = lds_f4(ma), m1 = lds_f4(ma + dm), m2 = lds_f4(ma + 2 * dm), m3 = lds_f4(ma + 3 * dm);
+            acc.x = fmaf(p0v, m0.x, acc.x); acc.y = fmaf(p0v, m0.y, acc.y); acc.z = fmaf(p0v, m0.z, acc.z); acc.w = fmaf(p0v, m0.w, acc.w);
+            acc2.x = fmaf(p1v, m1.x, acc2.x); acc2.y = fmaf(p1v, m1.y, acc2.y); acc2.z = fmaf(p1v, m1.z, acc2.z); acc2.w = fmaf(p1v, m1.w, acc2.w);
+            acc.x = fmaf(p2v, m2.x, acc.x); acc.y = fmaf(p2v, m2.y, acc.y); acc.z = fmaf(p2v, m2.z, acc.z); acc.w = fmaf(p2v, m2.w, acc.w);
+            acc2.x = fmaf(p3v, m3.x, acc2.x); acc2.y = fmaf(p3v, m3.y, acc2.y); acc2.z = fmaf(p3v, m3.z, acc2.z); acc2.w = fmaf(p3v, m3.w, acc2.w);
+            ssum += p0v + p2v; ssum2 += p1v + p3v;
+            pa += 4 * dp; ma += 4 * dm;
+          }
+          if (i + 2 <= niter) {
+            const float p0v = lds_f(pa), p1v = lds_f(pa + dp);
+            const float4 m0 = lds_f4(ma), m1 = lds_f4(ma + dm);
+            acc.x = fmaf(p0v, m0.x, acc.x); acc.y = fmaf(p0v, m0.y, acc.y); acc.z = fmaf(p0v, m0.z, acc.z); acc.w = fmaf(p0v, m0.w, acc.w);
+            acc2.x = fmaf(p1v, m1.x, acc2.x); acc2.y = fmaf(p1v, m1.y, acc2.y); acc2.z = fmaf(p1v, m1.z, acc2.z); acc2.w = fmaf(p1v, m1.w, acc2.w);
+            ssum += p0v; ssum2 += p1v;
+            pa += 2 * dp; ma += 2 * dm; i += 2;
+          }
+          if (i < niter) {
+            const float p0v = lds_f(pa);
+            const float4 m0 = lds_f4(ma);
+            acc.x = fmaf(p0v, m0.x, acc.x); acc.y = fmaf(p0v, m0.y, acc.y); acc.z = fmaf(p0v, m0.z, acc.z); acc.w = fmaf(p0v, m0.w, acc.w);
+            ssum += p0v;
+          }
+        } else {
+          const float* sc = reinterpret_cast<const float*>(smem_raw + L.sc) + g;
+          for (int j = warp; j < T_in; j += NW) {
+            const float pv = sc[j * S];
+            const float4 m0 = ldg_f4(a.memory + ((size_t)(n0 + g) * T_in + j) * DH + q * 16 + 4 * t);
+            acc.x = fmaf(pv, m0.x, acc.x); acc.y = fmaf(pv, m0.y, acc.y); acc.z = fmaf(pv, m0.z, acc.z); acc.w = fmaf(pv, m0.w, acc.w);
+            ssum += pv;
+          }
         }
         acc.x += acc2.x; acc.y += acc2.y; acc.z += acc2.z; acc.w += acc2.w;
         ssum += ssum2;
       }
       TRW(80);
       sts_f4(myslot + (g * RS + t * 4) * 4, acc);   // partial context of sample g, columns 4t..4t+3
-      if (t == 0) reinterpret_cast<float*>(smem_raw + OFF_REDS)[warp * 8 + g] = ssum;
+      if (t == 0) sts_f(sbase + OFF_REDS + (uint32_t)(warp * 8 + g) * 4u, ssum);
     }
     __syncthreads();
     TRM(19);
@@ -589,7 +698,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
       float s0 = 0.f, s1 = 0.f;
 #pragma unroll
       for (int s = 0; s < NW; s += 2) { s0 += reds[s * 8]; s1 += reds[s * 8 + 8]; }
-      const float inv = 1.0f / (s0 + s1);
+      const float inv = rcp_approx(s0 + s1);   // >= T_in e^{-80} > 0 (1 ulp; the oracle divides)
       stage_x(stg_n, rc, red_sum<16>(red_nc, 0) * inv);
       if (rc == 0) reinterpret_cast<float*>(smem_raw + OFF_INV)[rn] = inv;
     }
@@ -612,33 +721,37 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     TRM(22);
     if (red_grp) {
       stage_x(stg_n, rc, red_sum<8>(red_nc, 0) + lds_f(ST(ST_Y0H)) + BIAS(BI_PC));
-    } else { LOADP(T_P9, O9, 4, 0, 1) }           // window of P8: last two chunks of P9
+    }
     __syncthreads();
     send_blk(0, XBUF(DM_BY0) + q * csb, B_P8);
-    if (red_grp) { LOADP(T_P9, O9, 4, 0, 1) }
+    TLOADP(T_P9, TC9, 0, 2, 3, 4, 5, 0, 1)   // window of P8: all of P9 from tensor memory
     TRM(23);
     mbar_wait(mb0 + B_P8 * 8, par);
     TRM(24);
     TRW(192);
     trb = 208;
+    TWAIT(SL9)
     // ----- P9 / P10: decoder GRU 1 on [y0 | h1], y1 = y0 + h1' -----
-    GRU_GATES(0, SL9, T_P9, BI_R1, BI_U1, ST_H1, DM_BR1, B_P9, LOADP(T_P10, O10, 0, 0, 1) LOADP(T_P11, O11, 0, 2, 3, 4, 5))
+    GRU_GATES(0, SL9, T_P9, BI_R1, BI_U1, ST_H1, DM_BR1, B_P9, , TLOADP(T_P10, TC10, 0, 0, 1))
     TRM(26);
     mbar_wait(mb0 + B_P9 * 8, par);
     TRM(27);
     TRW(96);
     trb = 112;
-    GRU_CAND(SL10, T_P10, BI_C1, ST_H1, ST_H1, -1, DM_BH1, -1, B_P10, LOADP(T_P11, O11, 4, 0, 1))
+    TWAIT(SL10)
+    GRU_CAND(SL10, T_P10, BI_C1, ST_H1, ST_H1, -1, DM_BH1, -1, B_P10, , TLOADP(T_P11, TC11, 0, 2, 3, 4, 5, 0, 1))
     trb = -1;
     TRM(29);
     mbar_wait(mb0 + B_P10 * 8, par);
     TRM(30);
     // ----- P11 / P12: decoder GRU 2 on [y1 | h2], y2 = y1 + h2' -----
-    GRU_GATES(1, SL11, T_P11, BI_R2, BI_U2, ST_H2, DM_BR2, B_P11, LOADP(T_P12, O12, 0, 0, 1) LOADP(T_P13, O13, 0, 2, 3) LOADP(T_P1, O1, 0, 4, 5))
+    TWAIT(SL11)
+    GRU_GATES(1, SL11, T_P11, BI_R2, BI_U2, ST_H2, DM_BR2, B_P11, , TLOADP(T_P12, TC12, 0, 0, 1) LOADP(T_P13, O13, 0, 2, 3) LOADP(T_P1, O1, 0, 4, 5))
     TRM(32);
     mbar_wait(mb0 + B_P11 * 8, par);
     TRM(33);
-    GRU_CAND(SL12, T_P12, BI_C2, ST_H2, ST_H2, -1, DM_BH2, -1, B_P12, LOADP(T_P1, O1, 2, 0))
+    TWAIT(SL12)
+    GRU_CAND(SL12, T_P12, BI_C2, ST_H2, ST_H2, -1, DM_BH2, -1, B_P12, , LOADP(T_P1, O1, 2, 0))
     TRM(35);
     mbar_wait(mb0 + B_P12 * 8, par);
     TRM(36);
@@ -646,14 +759,11 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     MMAX(2, SL13, T_P13)
     __syncthreads();
     TRM(37);
-    if (red_grp) {
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int tile = 2 * q + half;
-        const float o = red_sum<8>(red_nc, half * 8) + BIAS(half ? BI_OB : BI_OA);
-        if (tile < ntiles && rn < S) a.dec_out[((size_t)(n0 + rn) * a.max_steps + step) * Dout + tile * 16 + rc] = o;
-        if (free_run) stage_x(stg_n + half * 512, rc, o);   // next decoder input = last frame of the group (helpers.py:37)
-      }
+    if (warp < 8) {   // warps 0-3: tile 2q, warps 4-7: tile 2q+1
+      const int half = warp >> 2, tile = 2 * q + half;
+      const float o = red_sum<8>(red_nc, half * 8) + BIAS(half ? BI_OB : BI_OA);
+      if (tile < ntiles && rn < S) a.dec_out[((size_t)(n0 + rn) * a.max_steps + step) * Dout + tile * 16 + rc] = o;
+      if (free_run) stage_x(stg_n + half * 512, rc, o);   // next decoder input = last frame of the group (helpers.py:37)
     }
     if (free_run) {
       __syncthreads();
@@ -668,7 +778,9 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
   }
   // nobody may exit while a peer can still write into its shared memory
   if (free_run && a.steps > 0) mbar_wait(mb0 + B_P13 * 8, (uint32_t)(a.steps - 1) & 1u);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_sync_all();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
 }  // namespace
