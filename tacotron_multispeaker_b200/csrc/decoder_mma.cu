@@ -190,6 +190,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint4& hi, uint4& lo) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w), "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8_if(bool on, uint32_t taddr, uint4& hi, uint4& lo) {   // `on` is warp-uniform
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.u32 p, %9, 0;\n"
+      "@!p bra.uni TLD_SKIP;\n"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+      "TLD_SKIP:\n"
+      "}\n"
+      : "+r"(hi.x), "+r"(hi.y), "+r"(hi.z), "+r"(hi.w), "+r"(lo.x), "+r"(lo.y), "+r"(lo.z), "+r"(lo.w)
+      : "r"(taddr), "r"((uint32_t)on));
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& hi, const uint4& lo) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                :: "r"(taddr), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
@@ -205,6 +217,51 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint4& a, uint32_t
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+// One chunk of a work item: B fragment from shared memory, then hh += W_hi x_hi, lh += W_lo x_hi, hl += W_hi x_lo.
+// `on` is warp-uniform.  The block is skipped with a REAL branch (bra.uni): ptxas otherwise predicates the three HMMAs,
+// and a predicated-off HMMA still occupies the tensor pipe for its 8 cycles -- measured: a warp with no work in a phase
+// took as long as one with six chunks, and slowed the three warps it shares the pipe with.
+__device__ __forceinline__ void mma3_if(bool on, float (&hh)[4], float (&hl)[4], float (&lh)[4], const uint4& a, const uint4& b,
+                                        uint32_t xaddr) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 x0, x1, x2, x3;\n"
+      "setp.ne.u32 p, %21, 0;\n"
+      "@!p bra.uni MMA3_SKIP;\n"
+      "ld.shared.v4.b32 {x0, x1, x2, x3}, [%20];\n"
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%12,%13,%14,%15}, {x0,x1}, {%0,%1,%2,%3};\n"
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%8,%9,%10,%11}, {%16,%17,%18,%19}, {x0,x1}, {%8,%9,%10,%11};\n"
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%4,%5,%6,%7}, {%12,%13,%14,%15}, {x2,x3}, {%4,%5,%6,%7};\n"
+      "MMA3_SKIP:\n"
+      "}\n"
+      : "+f"(hh[0]), "+f"(hh[1]), "+f"(hh[2]), "+f"(hh[3]), "+f"(hl[0]), "+f"(hl[1]), "+f"(hl[2]), "+f"(hl[3]),
+        "+f"(lh[0]), "+f"(lh[1]), "+f"(lh[2]), "+f"(lh[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "r"(xaddr), "r"((uint32_t)on)
+      : "memory");
+}
+// One operand pass of a work item: chunks 0..cnt-1 of the activation buffer at xaddr against the weight slots SL.
+// The B fragment of chunk i+1 is requested before the MMAs of chunk i (two register sets), so that the three
+// accumulator chains run at the tensor pipe's dependent-issue latency instead of LDS + MMA per chunk.
+template <int... SL>
+__device__ __forceinline__ void mma_pass(float (&hh)[4], float (&hl)[4], float (&lh)[4], const uint4 (&wb)[NWB], uint32_t xaddr,
+                                         uint32_t csb, int cnt) {
+  constexpr int sl[] = {SL...};
+  constexpr int MAXC = (int)sizeof...(SL);
+  uint4 xa = lds128(xaddr), xb = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    if (i + 1 < MAXC && i + 1 < cnt) {
+      if (i & 1) xa = lds128(xaddr + (i + 1) * csb); else xb = lds128(xaddr + (i + 1) * csb);
+    }
+    if (i < cnt) {
+      const uint4& xf = (i & 1) ? xb : xa;
+      mma16816(hh, wb[2 * sl[i]], xf.x, xf.y);       // W_hi * x_hi
+      mma16816(lh, wb[2 * sl[i] + 1], xf.x, xf.y);   // W_lo * x_hi
+      mma16816(hl, wb[2 * sl[i]], xf.z, xf.w);       // W_hi * x_lo
+    }
+  }
 }
 // fp32 -> bf16 hi (round to nearest) + bf16 lo (remainder); packs two values per 32-bit word
 __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
@@ -247,7 +304,14 @@ __device__ __forceinline__ void load_t(uint4 (&wb)[NWB], uint32_t tw, int cnt, S
   constexpr int sl[] = {SL...};
 #pragma unroll
   for (int k = 0; k < (int)sizeof...(SL); ++k)
-    if (I0 + k < cnt) tmem_ld8(tw + (uint32_t)(TC0 + I0 + k) * 8u, wb[2 * sl[k]], wb[2 * sl[k] + 1]);
+    tmem_ld8_if(I0 + k < cnt, tw + (uint32_t)(TC0 + I0 + k) * 8u, wb[2 * sl[k]], wb[2 * sl[k] + 1]);
+}
+// chunk-tiles 0..cnt-1 at consecutive column groups from tx (runtime base: the spare columns of another warp's slice)
+template <int... SL>
+__device__ __forceinline__ void load_tx(uint4 (&wb)[NWB], uint32_t tx, int cnt, Slots<SL...>) {
+  constexpr int sl[] = {SL...};
+#pragma unroll
+  for (int k = 0; k < (int)sizeof...(SL); ++k) tmem_ld8_if(k < cnt, tx + (uint32_t)k * 8u, wb[2 * sl[k]], wb[2 * sl[k] + 1]);
 }
 template <int... SL>
 __device__ __forceinline__ void wait_t(uint4 (&wb)[NWB], Slots<SL...>) {
@@ -265,26 +329,16 @@ __device__ __forceinline__ void mma_chunks(const uint4 (&wb)[NWB], uint32_t xadd
                                            int g, int t, Slots<SL...>, int nx = 0, uint32_t d1 = 0, uint32_t d2 = 0) {
   constexpr int sl[] = {SL...};
   float hh[4] = {0.f, 0.f, 0.f, 0.f}, hl[4] = {0.f, 0.f, 0.f, 0.f}, lh[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int i = 0; i < (int)sizeof...(SL); ++i)
-    if (i < cnt) {
-      const uint4 xf = lds128(xaddr + i * csb);
-      mma16816(hh, wb[2 * sl[i]], xf.x, xf.y);       // W_hi * x_hi
-      mma16816(lh, wb[2 * sl[i] + 1], xf.x, xf.y);   // W_lo * x_hi
-      mma16816(hl, wb[2 * sl[i]], xf.z, xf.w);       // W_hi * x_lo
-      if (NX >= 1 && nx >= 1) {
-        const uint4 yf = lds128(xaddr + d1 + i * csb);
-        mma16816(hh, wb[2 * sl[i]], yf.x, yf.y);
-        mma16816(lh, wb[2 * sl[i] + 1], yf.x, yf.y);
-        mma16816(hl, wb[2 * sl[i]], yf.z, yf.w);
-      }
-      if (NX >= 2 && nx >= 2) {
-        const uint4 zf = lds128(xaddr + d2 + i * csb);
-        mma16816(hh, wb[2 * sl[i]], zf.x, zf.y);
-        mma16816(lh, wb[2 * sl[i] + 1], zf.x, zf.y);
-        mma16816(hl, wb[2 * sl[i]], zf.z, zf.w);
-      }
-    }
+  // one branch per operand pass (a block of this size is not if-converted), per-chunk predicates inside
+  if (cnt > 0) {
+    mma_pass<SL...>(hh, hl, lh, wb, xaddr, csb, cnt);
+  }
+  if (NX >= 1 && cnt > 0 && nx >= 1) {
+    mma_pass<SL...>(hh, hl, lh, wb, xaddr + d1, csb, cnt);
+  }
+  if (NX >= 2 && cnt > 0 && nx >= 2) {
+    mma_pass<SL...>(hh, hl, lh, wb, xaddr + d2, csb, cnt);
+  }
   // D[row g / g+8 = tile column][col 2t, 2t+1 = sample]  ->  slot[sample][column]   (bank-conflict free with RS = 20)
   // (written even when cnt == 0 so that the reducer never sums a stale slot)
   const uint32_t p = slot + (uint32_t)(((2 * t) * RS + g) * 4);
@@ -292,6 +346,46 @@ __device__ __forceinline__ void mma_chunks(const uint4 (&wb)[NWB], uint32_t xadd
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(p + RS * 4), "f"(hh[1] + (hl[1] + lh[1])) : "memory");
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(p + 32), "f"(hh[2] + (hl[2] + lh[2])) : "memory");
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(p + RS * 4 + 32), "f"(hh[3] + (hl[3] + lh[3])) : "memory");
+}
+
+// The same work item in two parts.  PART 0 (early) runs in the exchange window BEFORE the phase's mbarrier wait and
+// multiplies every operand that is already complete (the previous recurrent state, the context of the previous step,
+// y0 / h1' for the sums y1, y2); its partial tile stays in four registers.  PART 1 (late) runs after the wait, adds the
+// operand that has just arrived and writes the partial tile.  Work item flags: nx (extra buffers), early (bit 30).
+//   nx == 0: the one buffer is early iff flagged;  nx >= 1: every buffer but the last extra one is early.
+template <int PART, int NX, int... SL>
+__device__ __forceinline__ void mma_split(float (&pre)[4], const uint4 (&wb)[NWB], uint32_t xl, uint32_t csb, uint32_t e,
+                                          uint32_t slot, int g, int t, Slots<SL...>, uint32_t d1 = 0, uint32_t d2 = 0) {
+  constexpr int sl[] = {SL...};
+  const int cnt = (int)(e & 7u), nx = (int)((e >> 28) & 3u);
+  const bool early = ((e >> 30) & 1u) != 0;
+  const uint32_t xaddr = xl + ((e & 0x0fffffffu) >> 3);
+  const bool do0 = PART == 0 ? (nx != 0 || early) : (nx == 0 && !early);
+  const bool do1 = NX >= 1 && (PART == 0 ? nx >= 2 : nx == 1);
+  const bool do2 = NX >= 2 && PART == 1 && nx == 2;
+  float hh[4], hl[4] = {0.f, 0.f, 0.f, 0.f}, lh[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) hh[k] = PART == 0 ? 0.f : pre[k];
+  // one branch per operand pass (a block of this size is not if-converted), per-chunk predicates inside
+  if (do0 && cnt > 0) {
+    mma_pass<SL...>(hh, hl, lh, wb, xaddr, csb, cnt);
+  }
+  if (NX >= 1 && do1 && cnt > 0) {
+    mma_pass<SL...>(hh, hl, lh, wb, xaddr + d1, csb, cnt);
+  }
+  if (NX >= 2 && do2 && cnt > 0) {
+    mma_pass<SL...>(hh, hl, lh, wb, xaddr + d2, csb, cnt);
+  }
+  if (PART == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pre[k] = hh[k] + (hl[k] + lh[k]);
+  } else {
+    const uint32_t p = slot + (uint32_t)(((2 * t) * RS + g) * 4);
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(p), "f"(hh[0] + (hl[0] + lh[0])) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(p + RS * 4), "f"(hh[1] + (hl[1] + lh[1])) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(p + 32), "f"(hh[2] + (hl[2] + lh[2])) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(p + RS * 4 + 32), "f"(hh[3] + (hl[3] + lh[3])) : "memory");
+  }
 }
 
 // reducer thread (n, c): sum over the partial tiles in slots [s0, s0+NS) of element [n][c]
@@ -325,14 +419,16 @@ enum { BI_P1 = 0, BI_P2 = 16, BI_RA = 32, BI_UA = 48, BI_CA = 64, BI_PC = 80, BI
        BI_R2 = 144, BI_U2 = 160, BI_C2 = 176, BI_OA = 192, BI_OB = 208 };
 static_assert(BI_OB + 16 == DM_NBIAS, "bias table size");
 
-#define TRM(i) do { if (a.trace != nullptr && step == 8 && blockIdx.x == 0 && tid == 0) a.trace[i] = clock64(); } while (0)
+#define TRM(i) do { if (a.trace != nullptr && step == 8 && blockIdx.x == a.trace_cta && tid == 0) a.trace[i] = clock64(); } while (0)
 // per-warp stamp: 16 consecutive entries starting at `base`
-#define TRW(base) do { if (a.trace != nullptr && step == 8 && blockIdx.x == 0 && lane == 0) a.trace[(base) + warp] = clock64(); } while (0)
+#define TRW(base) do { if (a.trace != nullptr && step == 8 && blockIdx.x == a.trace_cta && lane == 0) a.trace[(base) + warp] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(NT, 1)
 decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int nclusters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // the warp index through a shuffle from lane 0: ptxas then knows it is warp-uniform (uniform registers and branches
+  // instead of predication, BSSY/BSYNC and WARPSYNC around every per-warp decision)
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int g = lane >> 2, t = lane & 3;       // MMA fragment coordinates; as reducer: sample g, column group t
   const int q = (int)cluster_ctarank();
   const int cid = (int)cluster_id_x();
@@ -364,7 +460,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     const uint32_t e = w.tab[tid >> 4][tid & 15];
     const uint32_t bufi = (e >> 8) & 15u, c0 = (e >> 3) & 31u;
     reinterpret_cast<uint32_t*>(smem_raw + OFF_WTAB)[tid] =
-        (((e >> 14) & 3u) << 28) | ((OFF_X + ((uint32_t)cum_chunks((int)bufi, FC) + c0) * csb) << 3) | (e & 7u);
+        (((e >> 16) & 1u) << 30) | (((e >> 14) & 3u) << 28) | ((OFF_X + ((uint32_t)cum_chunks((int)bufi, FC) + c0) * csb) << 3) | (e & 7u);
   }
   if (tid < DM_NBIAS) reinterpret_cast<float*>(smem_raw + OFF_BIAS)[tid] = __ldg(w.bias + q * DM_NBIAS + tid);
   if (tid < DH) reinterpret_cast<float*>(smem_raw + OFF_VATT)[tid] = __ldg(w.att_v + tid);
@@ -408,7 +504,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
   auto send_blk = [&](int blk, uint32_t dst, int bar) {
     if (snd_on) st_async_v4(rx + dst, lds128(stg_lane + blk * 512), rmb0 + bar * 8);
   };
-#define WCNT(ph) (lds32(wtab + (ph) * 64))
+#define WCNT(ph) ((uint32_t)__shfl_sync(0xffffffffu, lds32(wtab + (ph) * 64), 0))
 #define XBUF(b) (OFF_X + (uint32_t)cum_chunks((b), FC) * csb)
 
   // P6: a warp works on the pairs of ONE sample; sample, first local pair and pair stride of this warp
@@ -438,9 +534,31 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
       }
     };
     fill(T_P9, O9, TC9); fill(T_P10, O10, TC10); fill(T_P11, O11, TC11); fill(T_P12, O12, TC12);
+  }
+  // Warps 8..15 leave 4-8 of their 16 chunk-tiles unused, and the four warps of a lane quarter can read each other's
+  // columns.  The spare ones hold the operands of the EARLY parts that would otherwise come from L2 one phase sooner
+  // than the slot schedule can request them (measured: up to 1 k clk of L2-latency spread on the slowest CTA):
+  //   the h_att rows of the attention GRU's gates (P3, warps 2-5 and 8-11, 4 chunk-tiles each)
+  //       -> slice of warp 12 + (warp % 4), chunk-tiles 4-7 (first h-warp of the lane quarter) or 12-15 (second);
+  //   the context rows of the prenet (P1, warps 0-7, 2 chunk-tiles each)
+  //       -> slice of warp 8 + (warp % 4), chunk-tiles 6-7 (warps 0-3) or 14-15 (warps 4-7).
+  const bool early1 = ((WCNT(T_P1) >> 30) & 1u) != 0, early3 = ((WCNT(T_P3) >> 30) & 1u) != 0;
+  const uint32_t tq = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t tx1 = tq + 2u * 128u + (warp < 4 ? 6u : 14u) * 8u;
+  const uint32_t tx3 = tq + 3u * 128u + (warp < 8 ? 4u : 12u) * 8u;
+  {
+    auto fillx = [&](int tp, int off, uint32_t tx) {
+      const int cnt = (int)(WCNT(tp) & 7u);
+      for (int i = 0; i < cnt; ++i) {
+        const uint4 hi = ldg_stream(ws + (off + 2 * i) * 32), lo = ldg_stream(ws + (off + 2 * i + 1) * 32);
+        tmem_st8(tx + (uint32_t)i * 8u, hi, lo);
+      }
+    };
+    if (early1) fillx(T_P1, O1, tx1);
+    if (early3) fillx(T_P3, O3, tx3);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
-  load_w<O1, 0>(wb, ws, (int)(WCNT(T_P1) & 7u), SL1());
+  if (!early1) load_w<O1, 0>(wb, ws, (int)(WCNT(T_P1) & 7u), SL1());
   load_w<O2, 0>(wb, ws, (int)(WCNT(T_P2) & 7u), SL2());
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   cluster_sync_all();   // buffers zeroed and mbarriers initialised everywhere before anyone pushes
@@ -457,8 +575,11 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
 #define TWAIT(SL) wait_t(wb, SL());
 #define MMA(SL, TP) { const uint32_t e = WCNT(TP); mma_chunks<0>(wb, xl + ((e & 0x0fffffffu) >> 3), csb, e & 7, myslot, g, t, SL()); }
 #define MMAX(NX, SL, TP) { const uint32_t e = WCNT(TP); mma_chunks<NX>(wb, xl + ((e & 0x0fffffffu) >> 3), csb, e & 7, myslot, g, t, SL(), (int)(e >> 28), dH1, dH2); }
+#define MMA_PRE(NX, SL, TP) mma_split<0, NX>(pre, wb, xl, csb, WCNT(TP), myslot, g, t, SL(), dH1, dH2);
+#define MMA_POST(NX, SL, TP) mma_split<1, NX>(pre, wb, xl, csb, WCNT(TP), myslot, g, t, SL(), dH1, dH2);
 #define ST(slot) (st_nc + (slot) * 512)
 #define BIAS(tab) lds_f(bias_c + (tab) * 4)
+  float pre[4] = {0.f, 0.f, 0.f, 0.f};   // early part of the next phase's partial tile (step 0, P1: the context is zero)
   int trb = -1;   // developer aid: base of the per-warp stamps inside the GRU macros
   for (int step = 0; step < a.steps; ++step) {
     const uint32_t par = (uint32_t)step & 1u;
@@ -491,13 +612,13 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     }
     TRM(0);
     // ================= P1: decoder prenet dense_1 + ReLU on [frame | context] =================
-    MMA(SL1, T_P1)
+    MMA_POST(0, SL1, T_P1)                      // frame chunks; the context chunks were multiplied in the window of P13
     __syncthreads();
     TRM(1);
     if (red_grp) stage_x(stg_n, rc, fmaxf(red_sum<DM_P1_SLOTS>(red_nc, 0) + BIAS(BI_P1), 0.f));
     __syncthreads();
     send_blk(0, XBUF(DM_BP1) + q * csb, B_P1);
-    LOADP(T_P3, O3, 0, 3, 4, 5, 0)              // window of P1: P3 (after the send: the reducers' LDS do not queue behind it)
+    if (!early3) { LOADP(T_P3, O3, 0, 3, 4, 5, 0) }   // window of P1: the x rows of P3 (the h_att rows live in TMEM)
     TRM(2);
     mbar_wait(mb0 + B_P1 * 8, par);
     TRM(3);
@@ -509,12 +630,17 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     __syncthreads();
     if (((warp ^ q) & 1) == 0) send_blk(0, XBUF(DM_BP2) + (q >> 1) * csb, B_P2);
     LOADP(T_P4, O4, 0, 1, 2)                    // window of P2: P4
+    if (early3) {                               // ... and the h_att rows of the attention GRU's gates, from TMEM
+      load_tx(wb, tx3, (int)(WCNT(T_P3) & 7u), SL3());
+      TWAIT(SL3)
+      MMA_PRE(0, SL3, T_P3)
+    } else { pre[0] = pre[1] = pre[2] = pre[3] = 0.f; }
     TRM(5);
     mbar_wait(mb0 + B_P2 * 8, par);
     TRM(6);
     // ================= GRU phases: gates r,u on [x | h] + candidate x-part; then candidate h-part =================
 #define GRU_GATES(NXG, SLG, TP, BI_R, BI_U, ST_H, BUF_R, BAR, URGENT, LATER)                             \
-    MMAX(NXG, SLG, TP)                                                                                  \
+    MMA_POST(NXG, SLG, TP)                                                                              \
     URGENT   /* weights of the NEXT phase go into the slots this phase used last */                  \
     if (trb >= 0) TRW(trb);                                                                          \
     __syncthreads();                                                                                 \
@@ -556,7 +682,10 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     LATER
 
     // ----- P3 / P4: attention GRU on [prenet | h_att] -----
+    TRW(192);
+    trb = 208;
     GRU_GATES(0, SL3, T_P3, BI_RA, BI_UA, ST_HA, DM_BRA, B_P3, , LOADP(T_P5, O5, 0, 3, 4))
+    trb = -1;
     TRM(8);
     mbar_wait(mb0 + B_P3 * 8, par);
     TRM(9);
@@ -578,7 +707,6 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     TRM(14);
     mbar_wait(mb0 + B_P5 * 8, par);
     TRM(15);
-    TRW(160);
     // ================= P6: Bahdanau scores of this CTA's (position, sample) pairs: exp(v . tanh(keys + pq) - B) ======
     // v.tanh(k + p) = sum v - 2 sum_k v_k / (1 + e^{2k} e^{2p}); e^{2k} is resident, e^{2p} was pushed by P5.
     // A warp works on ONE sample (warp % S): e^{2p} and v stay in registers and a pair costs two LDS.128 of e^{2k}.
@@ -629,7 +757,6 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
         if (lane == 0 || (lane == 16 && two)) sts_f(sbase + L.stage + (uint32_t)(up ? pp + dpp : pp) * 4u, ex);
       }
     }
-    TRW(144);
     __syncthreads();
     TRM(16);
     // warp p -> peer p: this CTA's pairs into sc[p0 ..]
@@ -638,7 +765,6 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     TRM(17);
     mbar_wait(mb0 + B_P6 * 8, par);
     TRM(18);
-    TRW(64);
     // ================= P7: context slice sum_j p_j memory[j][16q..16q+15] / sum_j p_j =================
     // lane (g, t): sample g, columns 4t..4t+3; warp w takes the positions j = w (mod 16)
     {
@@ -687,7 +813,6 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
         acc.x += acc2.x; acc.y += acc2.y; acc.z += acc2.z; acc.w += acc2.w;
         ssum += ssum2;
       }
-      TRW(80);
       sts_f4(myslot + (g * RS + t * 4) * 4, acc);   // partial context of sample g, columns 4t..4t+3
       if (t == 0) sts_f(sbase + OFF_REDS + (uint32_t)(warp * 8 + g) * 4u, ssum);
     }
@@ -724,13 +849,16 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     }
     __syncthreads();
     send_blk(0, XBUF(DM_BY0) + q * csb, B_P8);
-    TLOADP(T_P9, TC9, 0, 2, 3, 4, 5, 0, 1)   // window of P8: all of P9 from tensor memory
+    TRW(160);
+    TLOADP(T_P9, TC9, 0, 2, 3, 4, 5, 0, 1)   // window of P8: all of P9 from tensor memory, then its h1 rows
+    TRW(144);
+    TWAIT(SL9)
+    TRW(64);
+    MMA_PRE(0, SL9, T_P9)
+    TRW(80);
     TRM(23);
     mbar_wait(mb0 + B_P8 * 8, par);
     TRM(24);
-    TRW(192);
-    trb = 208;
-    TWAIT(SL9)
     // ----- P9 / P10: decoder GRU 1 on [y0 | h1], y1 = y0 + h1' -----
     GRU_GATES(0, SL9, T_P9, BI_R1, BI_U1, ST_H1, DM_BR1, B_P9, , TLOADP(T_P10, TC10, 0, 0, 1))
     TRM(26);
@@ -739,24 +867,23 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     TRW(96);
     trb = 112;
     TWAIT(SL10)
-    GRU_CAND(SL10, T_P10, BI_C1, ST_H1, ST_H1, -1, DM_BH1, -1, B_P10, , TLOADP(T_P11, TC11, 0, 2, 3, 4, 5, 0, 1))
+    GRU_CAND(SL10, T_P10, BI_C1, ST_H1, ST_H1, -1, DM_BH1, -1, B_P10, , TLOADP(T_P11, TC11, 0, 2, 3, 4, 5, 0, 1) TWAIT(SL11) MMA_PRE(1, SL11, T_P11))
     trb = -1;
     TRM(29);
     mbar_wait(mb0 + B_P10 * 8, par);
     TRM(30);
     // ----- P11 / P12: decoder GRU 2 on [y1 | h2], y2 = y1 + h2' -----
-    TWAIT(SL11)
-    GRU_GATES(1, SL11, T_P11, BI_R2, BI_U2, ST_H2, DM_BR2, B_P11, , TLOADP(T_P12, TC12, 0, 0, 1) LOADP(T_P13, O13, 0, 2, 3) LOADP(T_P1, O1, 0, 4, 5))
+    GRU_GATES(1, SL11, T_P11, BI_R2, BI_U2, ST_H2, DM_BR2, B_P11, , TLOADP(T_P12, TC12, 0, 0, 1) LOADP(T_P13, O13, 0, 2, 3) if (!early1) { LOADP(T_P1, O1, 0, 4, 5) })
     TRM(32);
     mbar_wait(mb0 + B_P11 * 8, par);
     TRM(33);
     TWAIT(SL12)
-    GRU_CAND(SL12, T_P12, BI_C2, ST_H2, ST_H2, -1, DM_BH2, -1, B_P12, , LOADP(T_P1, O1, 2, 0))
+    GRU_CAND(SL12, T_P12, BI_C2, ST_H2, ST_H2, -1, DM_BH2, -1, B_P12, , if (!early1) { LOADP(T_P1, O1, 2, 0) } MMA_PRE(2, SL13, T_P13))
     TRM(35);
     mbar_wait(mb0 + B_P12 * 8, par);
     TRM(36);
     // ================= P13: output projection tiles 2q, 2q+1 -> frames, feed the last frame back =================
-    MMAX(2, SL13, T_P13)
+    MMA_POST(2, SL13, T_P13)
     __syncthreads();
     TRM(37);
     if (warp < 8) {   // warps 0-3: tile 2q, warps 4-7: tile 2q+1
@@ -774,6 +901,11 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
       }
     }
     LOADP(T_P2, O2, 0, 1, 2)           // window of P13: P2
+    if (early1) {                      // ... and the context rows of the next step's prenet, from TMEM
+      load_tx(wb, tx1, (int)(WCNT(T_P1) & 7u), SL1());
+      TWAIT(SL1)
+      MMA_PRE(0, SL1, T_P1)
+    } else { pre[0] = pre[1] = pre[2] = pre[3] = 0.f; }
     TRM(38);
   }
   // nobody may exit while a peer can still write into its shared memory

@@ -104,7 +104,8 @@ struct DecoderArgs {
   int s_max;             // decoder_mma: largest number of samples per cluster in this launch (set by the launcher)
   float* dec_out;        // [N,max_steps,Dout]
   float* align_out;      // [N,T_in,max_steps] or null
-  long long* trace;      // developer aid: per-phase clock stamps of CTA 0 (TACO_DEC_TRACE), or null
+  long long* trace;      // developer aid: per-phase clock stamps of one CTA (TACO_DEC_TRACE), or null
+  int trace_cta;         // which CTA writes them (TACO_DEC_TRACE_CTA, default 0)
 };
 // v3 (decoder_v3.cu): cluster of 16, warp-owned hidden units.  `stream`: per (CTA, warp) blocks of
 // the weights that multiply freshly exchanged activations, in consumption order; `ew`: the gate

@@ -509,7 +509,7 @@ bool pack_decoder_v3(taco_handle* h, Arena& A, Dec3Off& O, std::string& err) {
 // ---- decoder_mma.cu packing -------------------------------------------------------------------
 // Work table of the MMA decoder: which 16-row chunks of which activation buffer every warp
 // multiplies in every phase (see decoder_mma.cu).  Entry = count | chunk0 << 3 | buffer << 8 | tile << 12.
-struct DmItem { int tile = 0, buf = 0, c0 = 0, cnt = 0, nx = 0; };   // nx: extra activation buffers multiplied by the same weights
+struct DmItem { int tile = 0, buf = 0, c0 = 0, cnt = 0, nx = 0, early = 0; };   // early: operand complete before the phase's exchange   // nx: extra activation buffers multiplied by the same weights
 void dm_table(int FC, DmItem (&tab)[DM_NPHASE][16]) {
   for (auto& ph : tab) for (auto& e : ph) e = DmItem();
   auto single = [&](int ph, int buf) { for (int w = 0; w < 8; ++w) tab[ph][w] = {0, buf, 2 * w, 2}; };
@@ -545,6 +545,13 @@ void dm_table(int FC, DmItem (&tab)[DM_NPHASE][16]) {
   single(9, DM_BR2);                                   // P12
   two(10, DM_BY0);                                     // P13: y2 = y0 + h1' + h2' the same way
   for (int w = 0; w < 16; ++w) tab[10][w].nx = 2;
+  // operands that are complete one exchange earlier: the context of the previous step (P1) and the recurrent states
+  for (int w = 0; w < 16; ++w) {
+    if (tab[0][w].cnt && tab[0][w].buf == DM_BC) tab[0][w].early = 1;
+    if (tab[2][w].cnt && tab[2][w].buf == DM_BHA) tab[2][w].early = 1;
+    if (tab[6][w].cnt && tab[6][w].buf == DM_BH1) tab[6][w].early = 1;
+    if (tab[8][w].cnt && tab[8][w].buf == DM_BH2) tab[8][w].early = 1;
+  }
 }
 
 inline uint16_t bf16_rn(float f) {
@@ -595,7 +602,7 @@ bool pack_decoder_mma(taco_handle* h, Arena& A, DmOff& O, uint32_t (&tabw)[DM_NP
     for (int wp = 0; wp < 16; ++wp) {
       const DmItem& e = tab[p][wp];
       if (e.cnt > nch[p] || e.cnt > 7 || e.c0 > 31) { err = "decoder_mma packing: work table overflow"; return false; }
-      tabw[p][wp] = (uint32_t)e.cnt | ((uint32_t)e.c0 << 3) | ((uint32_t)e.buf << 8) | ((uint32_t)e.tile << 12) | ((uint32_t)e.nx << 14);
+      tabw[p][wp] = (uint32_t)e.cnt | ((uint32_t)e.c0 << 3) | ((uint32_t)e.buf << 8) | ((uint32_t)e.tile << 12) | ((uint32_t)e.nx << 14) | ((uint32_t)e.early << 16);
     }
   auto M2 = [](const HostVar* m, int ld, int row, int col) { return m->data[(size_t)row * ld + col]; };
   // first K row of chunk 0 of buffer `buf` inside the TF kernel of phase `p`
@@ -948,13 +955,14 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
   DecoderArgs a;
   a.memory = memory; a.keys = keys; a.targets = teacher_force ? mel_targets : nullptr;
   a.N = N; a.T_in = T_in; a.T_tgt = T_tgt; a.r = hp.outputs_per_step; a.steps = max_steps; a.max_steps = max_steps;
-  a.dec_out = dec_out; a.align_out = align_out; a.att_res = 0; a.s_max = 0; a.trace = nullptr;
+  a.dec_out = dec_out; a.align_out = align_out; a.att_res = 0; a.s_max = 0; a.trace = nullptr; a.trace_cta = 0;
   const char* trace_path = getenv("TACO_DEC_TRACE");   // developer aid: per-phase clock stamps of CTA 0
   long long* d_trace = nullptr;
   if (trace_path) {
     cudaMalloc(&d_trace, 256 * sizeof(long long));
     cudaMemsetAsync(d_trace, 0, 256 * sizeof(long long), st);
     a.trace = d_trace;
+    if (const char* tc = getenv("TACO_DEC_TRACE_CTA")) a.trace_cta = atoi(tc);
   }
   int CS = 16, S = 8;
   pick_geometry(h, N, &CS, &S);

@@ -37,12 +37,12 @@ def run(N, T_in, cs, S, tag, iters=40):
     d = ["%d:%d" % (idx[k], st[idx[k]] - st[idx[k - 1]]) for k in range(1, len(idx))]
     print("%s N=%d CS=%d S=%d: %.2f us/step; traced step %d clk; stamp:delta %s" % (tag, N, cs, S, ms * 1e3 / iters, st[idx[-1]] - st[idx[0]], " ".join(d)), flush=True)
     if impl_mma():
-        names = {160: "P6 start (after wait P5)", 144: "P6 scores done", 64: "P7 start (after wait P6)", 80: "P7 loop done",
-                 192: "P9 start (after wait P8)", 208: "P9 mma done", 224: "P9 reduce/loads done",
+        names = {160: "P8 sent, before TLOADP(P9)", 144: "TLOADP(P9) issued", 64: "TWAIT(P9) done", 80: "PRE(P9) done",
+                 192: "P3 start (after wait P2)", 208: "P3 mma done", 224: "P3 reduce done",
                  96: "P10 start (after wait P9)", 112: "P10 mma done", 128: "P10 reduce/loads done"}
         stamps = [int(l.split()[1]) for l in open(path) if not l.startswith("#")]
         for b0 in (160, 144, 64, 80, 192, 208, 224, 96, 112, 128):
-            ref = {160: 15, 144: 15, 64: 18, 80: 18, 192: 24, 208: 24, 224: 24, 96: 27, 112: 27, 128: 27}[b0]
+            ref = {160: 22, 144: 22, 64: 22, 80: 22, 192: 6, 208: 6, 224: 6, 96: 27, 112: 27, 128: 27}[b0]
             print("   per-warp %-28s rel. stamp %d: %s" % (names[b0], ref, [stamps[b0 + w] - stamps[ref] if stamps[b0 + w] else None for w in range(16)]), flush=True)
     eng.close()
 
@@ -51,8 +51,11 @@ if __name__ == "__main__":
     impl = os.environ.get("TACO_DEC_IMPL", "mma")
     if impl == "mma":
         pass
-        for (N, T_in, S) in [(1, 50, 1), (32, 100, 5)]:
-            run(N, T_in, 16, S, "mma_n%d_s%d" % (N, S), iters=200)
+        ctas = [int(c) for c in os.environ.get("TRACE_CTAS", "0").split(",")]
+        for cta in ctas:
+            os.environ["TACO_DEC_TRACE_CTA"] = str(cta)
+            for (N, T_in, S) in ([(1, 50, 1), (32, 100, 5)] if cta == 0 else [(32, 100, 5)]):
+                run(N, T_in, 16, S, "mma_n%d_s%d_cta%d" % (N, S, cta), iters=200)
     else:
         run(1, 50, 16, 1, "n1_cs16_s1")
         run(4, 100, 16, 4, "n4_cs16_s4")
