@@ -94,13 +94,14 @@ constexpr uint32_t OFF_STG = OFF_STATE + NSTATE * 128 * 4;         // two staged
 constexpr uint32_t OFF_INV = OFF_STG + 2 * 512;                    // softmax normalisers 1/sum per sample
 constexpr uint32_t OFF_P6T = OFF_INV + 32;                         // per-warp pair geometry of the score phase
 constexpr uint32_t OFF_TMEM = OFF_P6T + 64;                       // TMEM base address written by tcgen05.alloc
-constexpr uint32_t OFF_X = OFF_TMEM + 16;
+constexpr uint32_t OFF_SEQ = OFF_TMEM + 16;                       // per-warp order of the streamed chunk-tiles [16][16]
+constexpr uint32_t OFF_X = OFF_SEQ + NW * 16 * 4;
 static_assert(OFF_X % 16 == 0 && OFF_RED % 16 == 0 && OFF_STATE % 16 == 0 && OFF_BIAS % 16 == 0, "alignment");
 
 // chunks in front of buffer b (order DM_BF, DM_BC, DM_BP1, DM_BP2(8 chunks), DM_BHA, ...)
 __host__ __device__ __forceinline__ int cum_chunks(int b, int FC) { return b == 0 ? 0 : FC + 16 * (b - 1) - (b > DM_BP2 ? 8 : 0); }
-struct Dyn { uint32_t pq, sc, stage, ksl, msl, total; };
-__host__ __device__ inline Dyn make_dyn(int S, int T_in, int FC, bool att_res) {
+struct Dyn { uint32_t pq, sc, stage, ksl, msl, ring, total; };
+__host__ __device__ inline Dyn make_dyn(int S, int T_in, int FC, bool att_res, int d0, int d1) {
   Dyn d;
   const uint32_t csb = (uint32_t)S * 64u;
   const uint32_t npq = (uint32_t)(T_in * S) / CS + 1;              // (position, sample) pairs per CTA, upper bound
@@ -109,7 +110,8 @@ __host__ __device__ inline Dyn make_dyn(int S, int T_in, int FC, bool att_res) {
   d.stage = d.sc + (((uint32_t)T_in * S * 4 + 15u) & ~15u);        // this CTA's pairs
   d.ksl = d.stage + ((npq * 4 + 15u) & ~15u);                      // exp(2 * keys) rows of this CTA's pairs
   d.msl = d.ksl + (att_res ? npq * DH * 4 : 0u);                   // memory columns of this CTA, tile order
-  d.total = d.msl + (att_res ? (uint32_t)S * T_in * 64u : 0u);
+  d.ring = d.msl + (att_res ? (uint32_t)S * T_in * 64u : 0u);      // weight ring: d0 KB for each of warps 0-7, d1 KB for 8-15
+  d.total = d.ring + (uint32_t)(8 * d0 + 8 * d1) * 1024u;
   return d;
 }
 
@@ -181,6 +183,46 @@ __device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP: 1/inf = 0,
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+// ---- the streamed weights: a per-warp ring in shared memory, filled by cp.async ------------------------------------------
+// Chunk-tiles that fit neither in tensor memory nor in registers are re-read from L2 every step.  Loading them straight
+// into registers (the first version) ties their arrival to the register scoreboards: a phase that waits for the chunks
+// it requested two phases ago also waits for everything requested since, so the effective prefetch distance was one
+// exchange window and the slowest CTA of a cluster ate the L2 latency in every streamed phase.  cp.async groups are
+// counted explicitly: the ring is always D chunk-tiles (1 KB = hi + lo fragments of 32 lanes) ahead of the consumer, each
+// lane copies and later reads only its own 32 bytes (no cross-lane visibility needed), and `wait_group D - cnt` waits for
+// exactly the oldest cnt entries.
+struct Ring { uint32_t base, seq; int D, n, rp, rf, kf; };   // base: this lane's 16 bytes of slot 0; seq: smem address of the order table
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int pend) {   // pend is warp-uniform, 0..7
+  switch (pend) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+  }
+}
+// request the next cnt chunk-tiles of this warp's order into the slots that were consumed last
+__device__ __forceinline__ void ring_refill(Ring& r, const uint4* __restrict__ ws, int cnt) {
+  for (int k = 0; k < cnt; ++k) {
+    uint32_t off;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(off) : "r"(r.seq + (uint32_t)r.kf * 4u));
+    const uint4* src = ws + (size_t)off * 32;
+    const uint32_t dst = r.base + (uint32_t)r.rf * 1024u;
+    cp_async16(dst, src);
+    cp_async16(dst + 512u, src + 32);
+    cp_async_commit();
+    r.rf = r.rf + 1 == r.D ? 0 : r.rf + 1;
+    r.kf = r.kf + 1 == r.n ? 0 : r.kf + 1;
+  }
+}
+
 // ---- tensor memory as a weight store --------------------------------------------------------------------------------
 // The 256 KB of TMEM are not needed for accumulators here (the mat-vecs run on mma.sync), so they hold the A fragments of
 // the four heaviest phases (both decoder GRUs: 16 chunk-tiles of 1 KB per warp).  A warp reads and writes its own lane
@@ -313,6 +355,21 @@ __device__ __forceinline__ void load_tx(uint4 (&wb)[NWB], uint32_t tx, int cnt, 
 #pragma unroll
   for (int k = 0; k < (int)sizeof...(SL); ++k) tmem_ld8_if(k < cnt, tx + (uint32_t)k * 8u, wb[2 * sl[k]], wb[2 * sl[k] + 1]);
 }
+// the oldest cnt chunk-tiles of the ring into the register slots SL
+template <int... SL>
+__device__ __forceinline__ void ring_take(uint4 (&wb)[NWB], Ring& r, int cnt, Slots<SL...>) {
+  constexpr int sl[] = {SL...};
+  if (cnt == 0) return;
+  cp_async_wait_pending(r.D - cnt);
+#pragma unroll
+  for (int k = 0; k < (int)sizeof...(SL); ++k)
+    if (k < cnt) {
+      const uint32_t src = r.base + (uint32_t)r.rp * 1024u;
+      wb[2 * sl[k]] = lds128(src);
+      wb[2 * sl[k] + 1] = lds128(src + 512u);
+      r.rp = r.rp + 1 == r.D ? 0 : r.rp + 1;
+    }
+}
 template <int... SL>
 __device__ __forceinline__ void wait_t(uint4 (&wb)[NWB], Slots<SL...>) {
   constexpr int sl[] = {SL...};
@@ -438,7 +495,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
   const int n0 = cid * base + min(cid, rem);
   const int M = w.M, Dout = w.Dout, FC = M >> 4, T_in = a.T_in;
   const bool att_res = a.att_res != 0;
-  const Dyn L = make_dyn(S, T_in, FC, att_res);
+  const Dyn L = make_dyn(S, T_in, FC, att_res, a.ring_d0, a.ring_d1);
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t csb = (uint32_t)S * 64u;
   const uint32_t mb0 = sbase + OFF_MBAR;
@@ -558,8 +615,32 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     if (early3) fillx(T_P3, O3, tx3);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
-  if (!early1) load_w<O1, 0>(wb, ws, (int)(WCNT(T_P1) & 7u), SL1());
-  load_w<O2, 0>(wb, ws, (int)(WCNT(T_P2) & 7u), SL2());
+  // the streamed chunk-tiles of this warp in consumption order (stream offsets in 512-byte rows)
+  Ring rg;
+  rg.seq = sbase + OFF_SEQ + (uint32_t)warp * 64u;
+  rg.n = 0;
+  {
+    auto add = [&](int tp, int off) {
+      const int cnt = (int)(WCNT(tp) & 7u);
+      for (int i = 0; i < cnt; ++i) {
+        if (lane == 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(rg.seq + (uint32_t)rg.n * 4u), "r"((uint32_t)(off + 2 * i)) : "memory");
+        ++rg.n;
+      }
+    };
+    if (!early1) add(T_P1, O1);
+    add(T_P2, O2);
+    if (!early3) add(T_P3, O3);
+    add(T_P4, O4); add(T_P5, O5); add(T_P8, O8); add(T_P13, O13);
+  }
+  __syncwarp();
+  {
+    const int dmax = warp < 8 ? a.ring_d0 : a.ring_d1;
+    rg.D = rg.n < dmax ? rg.n : dmax;
+    rg.base = sbase + L.ring + (uint32_t)(warp < 8 ? warp * a.ring_d0 : 8 * a.ring_d0 + (warp - 8) * a.ring_d1) * 1024u + (uint32_t)lane * 16u;
+    rg.rp = 0; rg.rf = 0; rg.kf = 0;
+    ring_refill(rg, ws, rg.D);   // rf wraps back to 0 = rp: the ring is full
+  }
+  if (!early1) ring_take(wb, rg, (int)(WCNT(T_P1) & 7u), SL1());
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   cluster_sync_all();   // buffers zeroed and mbarriers initialised everywhere before anyone pushes
 
@@ -569,12 +650,11 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
   const uint32_t dH2 = (uint32_t)(cum_chunks(DM_BH2, FC) - cum_chunks(DM_BY0, FC)) * csb;   // y0 chunk i -> h2' chunk i
   const int fb_tile0 = (Dout - M) >> 4, ntiles = Dout >> 4;
 
-// LOADP(phase table index, stream offset, first chunk, slots): request chunks of a later phase (see the slot schedule)
-#define LOADP(TP, OFF, I0, ...) load_w<OFF, I0>(wb, ws, (int)(WCNT(TP) & 7u), Slots<__VA_ARGS__>());
+#define RTAKE(TP, SL) ring_take(wb, rg, (int)(WCNT(TP) & 7u), SL());
+#define RFILL(TP) ring_refill(rg, ws, (int)(WCNT(TP) & 7u));
 #define TLOADP(TP, TC0, I0, ...) load_t<TC0, I0>(wb, tw, (int)(WCNT(TP) & 7u), Slots<__VA_ARGS__>());
 #define TWAIT(SL) wait_t(wb, SL());
 #define MMA(SL, TP) { const uint32_t e = WCNT(TP); mma_chunks<0>(wb, xl + ((e & 0x0fffffffu) >> 3), csb, e & 7, myslot, g, t, SL()); }
-#define MMAX(NX, SL, TP) { const uint32_t e = WCNT(TP); mma_chunks<NX>(wb, xl + ((e & 0x0fffffffu) >> 3), csb, e & 7, myslot, g, t, SL(), (int)(e >> 28), dH1, dH2); }
 #define MMA_PRE(NX, SL, TP) mma_split<0, NX>(pre, wb, xl, csb, WCNT(TP), myslot, g, t, SL(), dH1, dH2);
 #define MMA_POST(NX, SL, TP) mma_split<1, NX>(pre, wb, xl, csb, WCNT(TP), myslot, g, t, SL(), dH1, dH2);
 #define ST(slot) (st_nc + (slot) * 512)
@@ -618,7 +698,8 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     if (red_grp) stage_x(stg_n, rc, fmaxf(red_sum<DM_P1_SLOTS>(red_nc, 0) + BIAS(BI_P1), 0.f));
     __syncthreads();
     send_blk(0, XBUF(DM_BP1) + q * csb, B_P1);
-    if (!early3) { LOADP(T_P3, O3, 0, 3, 4, 5, 0) }   // window of P1: the x rows of P3 (the h_att rows live in TMEM)
+    if (!early1) { RFILL(T_P1) }                // window of P1: refill the ring, P2's chunks into registers
+    RTAKE(T_P2, SL2)
     TRM(2);
     mbar_wait(mb0 + B_P1 * 8, par);
     TRM(3);
@@ -629,7 +710,8 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     if (red_grp) stage_x(stg_n, rc, fmaxf(red_sum<8>(red_nc, 0) + BIAS(BI_P2), 0.f));
     __syncthreads();
     if (((warp ^ q) & 1) == 0) send_blk(0, XBUF(DM_BP2) + (q >> 1) * csb, B_P2);
-    LOADP(T_P4, O4, 0, 1, 2)                    // window of P2: P4
+    RFILL(T_P2)                                 // window of P2: the x rows of P3 from the ring ...
+    if (!early3) { RTAKE(T_P3, SL3) }
     if (early3) {                               // ... and the h_att rows of the attention GRU's gates, from TMEM
       load_tx(wb, tx3, (int)(WCNT(T_P3) & 7u), SL3());
       TWAIT(SL3)
@@ -684,12 +766,12 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     // ----- P3 / P4: attention GRU on [prenet | h_att] -----
     TRW(192);
     trb = 208;
-    GRU_GATES(0, SL3, T_P3, BI_RA, BI_UA, ST_HA, DM_BRA, B_P3, , LOADP(T_P5, O5, 0, 3, 4))
+    GRU_GATES(0, SL3, T_P3, BI_RA, BI_UA, ST_HA, DM_BRA, B_P3, , if (!early3) { RFILL(T_P3) } RTAKE(T_P4, SL4))
     trb = -1;
     TRM(8);
     mbar_wait(mb0 + B_P3 * 8, par);
     TRM(9);
-    GRU_CAND(SL4, T_P4, BI_CA, ST_HA, ST_HA, -1, DM_BHA, -1, B_P4, , LOADP(T_P8, O8, 0, 0, 1))
+    GRU_CAND(SL4, T_P4, BI_CA, ST_HA, ST_HA, -1, DM_BHA, -1, B_P4, , RFILL(T_P4) RTAKE(T_P5, SL5))
     TRM(11);
     mbar_wait(mb0 + B_P4 * 8, par);
     TRM(12);
@@ -704,6 +786,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     }
     __syncthreads();
     send_blk(0, L.pq + q * csb, B_P5);
+    RFILL(T_P5)                           // window of P5: refill
     TRM(14);
     mbar_wait(mb0 + B_P5 * 8, par);
     TRM(15);
@@ -829,6 +912,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     }
     __syncthreads();
     send_blk(0, XBUF(DM_BC) + q * csb, B_P7);
+    RTAKE(T_P8, SL8)                      // window of P7: P8's chunks into registers
     if (warp == 1 && a.align_out != nullptr) {   // alignments of this CTA's pairs (tacotron.py:104: [N,T_in,steps])
       const float* stage = reinterpret_cast<const float*>(smem_raw + L.stage);
       const float* invs = reinterpret_cast<const float*>(smem_raw + OFF_INV);
@@ -849,6 +933,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     }
     __syncthreads();
     send_blk(0, XBUF(DM_BY0) + q * csb, B_P8);
+    RFILL(T_P8)
     TRW(160);
     TLOADP(T_P9, TC9, 0, 2, 3, 4, 5, 0, 1)   // window of P8: all of P9 from tensor memory, then its h1 rows
     TRW(144);
@@ -873,12 +958,12 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     mbar_wait(mb0 + B_P10 * 8, par);
     TRM(30);
     // ----- P11 / P12: decoder GRU 2 on [y1 | h2], y2 = y1 + h2' -----
-    GRU_GATES(1, SL11, T_P11, BI_R2, BI_U2, ST_H2, DM_BR2, B_P11, , TLOADP(T_P12, TC12, 0, 0, 1) LOADP(T_P13, O13, 0, 2, 3) if (!early1) { LOADP(T_P1, O1, 0, 4, 5) })
+    GRU_GATES(1, SL11, T_P11, BI_R2, BI_U2, ST_H2, DM_BR2, B_P11, , TLOADP(T_P12, TC12, 0, 0, 1))
     TRM(32);
     mbar_wait(mb0 + B_P11 * 8, par);
     TRM(33);
     TWAIT(SL12)
-    GRU_CAND(SL12, T_P12, BI_C2, ST_H2, ST_H2, -1, DM_BH2, -1, B_P12, , if (!early1) { LOADP(T_P1, O1, 2, 0) } MMA_PRE(2, SL13, T_P13))
+    GRU_CAND(SL12, T_P12, BI_C2, ST_H2, ST_H2, -1, DM_BH2, -1, B_P12, , RTAKE(T_P13, SL13) MMA_PRE(2, SL13, T_P13))
     TRM(35);
     mbar_wait(mb0 + B_P12 * 8, par);
     TRM(36);
@@ -900,7 +985,8 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
         if (tile < ntiles && tile >= fb_tile0) send_blk(half, XBUF(DM_BF) + (tile - fb_tile0) * csb, B_P13);
       }
     }
-    LOADP(T_P2, O2, 0, 1, 2)           // window of P13: P2
+    RFILL(T_P13)                       // window of P13: refill, the frame rows of the next step's prenet into registers
+    if (!early1) { RTAKE(T_P1, SL1) }
     if (early1) {                      // ... and the context rows of the next step's prenet, from TMEM
       load_tx(wb, tx1, (int)(WCNT(T_P1) & 7u), SL1());
       TWAIT(SL1)
@@ -910,6 +996,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
   }
   // nobody may exit while a peer can still write into its shared memory
   if (free_run && a.steps > 0) mbar_wait(mb0 + B_P13 * 8, (uint32_t)(a.steps - 1) & 1u);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");   // nothing may still be in flight into this CTA's shared memory
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_sync_all();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -917,8 +1004,8 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
 
 }  // namespace
 
-size_t decoder_mma_smem_bytes(int s_max, int T_in, int M, bool att_res) {
-  return make_dyn(s_max, T_in, M >> 4, att_res).total;
+size_t decoder_mma_smem_bytes(int s_max, int T_in, int M, bool att_res, int ring_d0, int ring_d1) {
+  return make_dyn(s_max, T_in, M >> 4, att_res, ring_d0, ring_d1).total;
 }
 
 int decoder_mma_max_clusters() {
@@ -952,11 +1039,19 @@ cudaError_t launch_decoder_mma(const DecoderMmaWeights& w, const DecoderArgs& a_
   DecoderArgs a = a_in;
   a.s_max = (a.N + nclusters - 1) / nclusters;
   if (a.s_max > 8 || (w.M & 15) || (w.Dout & 15) || w.M > 128) return cudaErrorInvalidValue;
+  // shared memory: the attention operands resident if they fit, then the deepest weight ring that fits
+  // (warps 0-7 consume up to 14 streamed chunk-tiles per step, 4 of them in one phase; warps 8-15 at most 6, 2 at a time)
   const char* env = getenv("TACO_DEC_ATT_RES");
-  a.att_res = decoder_mma_smem_bytes(a.s_max, a.T_in, w.M, true) <= 227 * 1024 ? 1 : 0;
-  if (env) a.att_res = a.att_res && atoi(env) != 0;
-  const size_t smem = decoder_mma_smem_bytes(a.s_max, a.T_in, w.M, a.att_res != 0);
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  const bool want_res = !env || atoi(env) != 0;
+  static const int rings[3][2] = {{6, 3}, {5, 3}, {4, 2}};
+  size_t smem = 0;
+  bool ok = false;
+  for (int res = want_res ? 1 : 0; res >= 0 && !ok; --res)
+    for (int k = 0; k < 3 && !ok; ++k) {
+      smem = decoder_mma_smem_bytes(a.s_max, a.T_in, w.M, res != 0, rings[k][0], rings[k][1]);
+      if (smem <= 227 * 1024) { a.att_res = res; a.ring_d0 = rings[k][0]; a.ring_d1 = rings[k][1]; ok = true; }
+    }
+  if (!ok) return cudaErrorInvalidValue;
   auto kern = decoder_mma_kernel;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

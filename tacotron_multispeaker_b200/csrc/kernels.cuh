@@ -106,6 +106,7 @@ struct DecoderArgs {
   float* align_out;      // [N,T_in,max_steps] or null
   long long* trace;      // developer aid: per-phase clock stamps of one CTA (TACO_DEC_TRACE), or null
   int trace_cta;         // which CTA writes them (TACO_DEC_TRACE_CTA, default 0)
+  int ring_d0, ring_d1;  // decoder_mma: depth (KB = chunk-tiles) of the weight ring of warps 0-7 / 8-15 (set by the launcher)
 };
 // v3 (decoder_v3.cu): cluster of 16, warp-owned hidden units.  `stream`: per (CTA, warp) blocks of
 // the weights that multiply freshly exchanged activations, in consumption order; `ew`: the gate
@@ -138,7 +139,7 @@ struct DecoderMmaWeights {
   uint32_t tab[DM_NPHASE][16];
 };
 cudaError_t launch_decoder_mma(const DecoderMmaWeights& w, const DecoderArgs& a, int nclusters, cudaStream_t st);
-size_t decoder_mma_smem_bytes(int s_max, int T_in, int M, bool att_res);
+size_t decoder_mma_smem_bytes(int s_max, int T_in, int M, bool att_res, int ring_d0, int ring_d1);
 int decoder_mma_max_clusters();
 
 // S = samples per cluster (1,2,4,8).  Returns cudaError of the launch.
