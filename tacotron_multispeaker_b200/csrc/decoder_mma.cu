@@ -476,10 +476,13 @@ enum { BI_P1 = 0, BI_P2 = 16, BI_RA = 32, BI_UA = 48, BI_CA = 64, BI_PC = 80, BI
        BI_R2 = 144, BI_U2 = 160, BI_C2 = 176, BI_OA = 192, BI_OB = 208 };
 static_assert(BI_OB + 16 == DM_NBIAS, "bias table size");
 
-#define TRM(i) do { if (a.trace != nullptr && step == 8 && blockIdx.x == a.trace_cta && tid == 0) a.trace[i] = clock64(); } while (0)
+#define TRM(i) do { if (TRACE && a.trace != nullptr && step == 8 && blockIdx.x == a.trace_cta && tid == 0) a.trace[i] = clock64(); } while (0)
 // per-warp stamp: 16 consecutive entries starting at `base`
-#define TRW(base) do { if (a.trace != nullptr && step == 8 && blockIdx.x == a.trace_cta && lane == 0) a.trace[(base) + warp] = clock64(); } while (0)
+#define TRW(base) do { if (TRACE && a.trace != nullptr && step == 8 && blockIdx.x == a.trace_cta && lane == 0) a.trace[(base) + warp] = clock64(); } while (0)
 
+// TRACE: clock stamps of one CTA (developer aid).  A separate instantiation: even predicated off, the stamp
+// instructions (LDC of the pointer, CS2R, STG) took ~10 % of the stall samples of the production kernel.
+template <bool TRACE>
 __global__ void __launch_bounds__(NT, 1)
 decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int nclusters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -724,7 +727,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
 #define GRU_GATES(NXG, SLG, TP, BI_R, BI_U, ST_H, BUF_R, BAR, URGENT, LATER)                             \
     MMA_POST(NXG, SLG, TP)                                                                              \
     URGENT   /* weights of the NEXT phase go into the slots this phase used last */                  \
-    if (trb >= 0) TRW(trb);                                                                          \
+    if (TRACE && trb >= 0) TRW(trb);                                                                          \
     __syncthreads();                                                                                 \
     /* three reducer groups work side by side: warps 0-3 r (-> r*h staged), 4-7 u, 8-11 the candidate's x part */ \
     if (red_grp) {                                                                                   \
@@ -735,7 +738,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     } else if (warp < 12) {                                                                          \
       sts_f(ST(ST_CX), red_sum<4>(red_nc, 12));                                                      \
     }                                                                                                \
-    if (trb >= 0) TRW(trb + 16);                                                                     \
+    if (TRACE && trb >= 0) TRW(trb + 16);                                                                     \
     __syncthreads();                                                                                 \
     send_blk(0, XBUF(BUF_R) + q * csb, BAR);                                                         \
     LATER
@@ -743,7 +746,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
 #define GRU_CAND(SLC, TP, BI_C, ST_H, ST_YIN, ST_YOUT, BUF_H, BUF_Y, BAR, URGENT, LATER)                     \
     MMA(SLC, TP)                                                                                      \
     URGENT                                                                                           \
-    if (trb >= 0) TRW(trb);                                                                          \
+    if (TRACE && trb >= 0) TRW(trb);                                                                          \
     __syncthreads();                                                                                 \
     if (red_grp) {                                                                                   \
       const float c = tanh_f(red_sum<8>(red_nc, 0) + lds_f(ST(ST_CX)) + BIAS(BI_C));                 \
@@ -757,7 +760,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
         stage_x(stg_n + 512, rc, y);                                                                 \
       }                                                                                              \
     }                                                                                                \
-    if (trb >= 0) TRW(trb + 16);                                                                     \
+    if (TRACE && trb >= 0) TRW(trb + 16);                                                                     \
     __syncthreads();                                                                                 \
     send_blk(0, XBUF(BUF_H) + q * csb, BAR);                                                         \
     if (BUF_Y >= 0) send_blk(1, XBUF(BUF_Y < 0 ? 0 : BUF_Y) + q * csb, BAR);                         \
@@ -1009,7 +1012,7 @@ size_t decoder_mma_smem_bytes(int s_max, int T_in, int M, bool att_res, int ring
 }
 
 int decoder_mma_max_clusters() {
-  auto kern = decoder_mma_kernel;
+  auto kern = decoder_mma_kernel<false>;
   const int smem = 200 * 1024;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
@@ -1052,7 +1055,7 @@ cudaError_t launch_decoder_mma(const DecoderMmaWeights& w, const DecoderArgs& a_
       if (smem <= 227 * 1024) { a.att_res = res; a.ring_d0 = rings[k][0]; a.ring_d1 = rings[k][1]; ok = true; }
     }
   if (!ok) return cudaErrorInvalidValue;
-  auto kern = decoder_mma_kernel;
+  auto kern = a.trace != nullptr ? decoder_mma_kernel<true> : decoder_mma_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);

@@ -12,8 +12,9 @@ runs the forward path.
 Scope: the path ends at the post-net linear spectrogram, so
 ``synthesize`` returns / saves the spectrogram and alignment instead of a
 Griffin-Lim waveform (``util/audio.py:39-46`` is the next row, not built yet).
-Checkpoints are ``.npz`` archives keyed by TF variable names; without one,
-``load(None, id_num=...)`` uses random-init weights.
+Checkpoints are TensorFlow V2 bundles (``model.ckpt-N.index`` + ``.data-*``, read by
+``tf_checkpoint.py`` without TensorFlow) or ``.npz`` archives keyed by TF variable
+names; without one, ``load(None, id_num=...)`` uses random-init weights.
 """
 from __future__ import annotations
 
@@ -25,6 +26,7 @@ import numpy as np
 from .hparams import HParams, hparams as default_hparams
 from .tacotron import create_model
 from .text import sequence_to_text2, text_to_sequence2
+from .tf_checkpoint import load_weights
 from .weights import PREFIX, random_init
 
 
@@ -48,8 +50,8 @@ class Synthesizer:
             weights = random_init(hp, id_num, seed=seed)
         else:
             print("Loading checkpoint: %s" % checkpoint_path)
-            with np.load(checkpoint_path) as z:
-                weights = {k: z[k] for k in z.files}
+            # a TF V2 checkpoint prefix ("model.ckpt-1000"), a log directory with a `checkpoint` state file, or .npz
+            weights = load_weights(checkpoint_path)
         var_to_shape_map = {k: tuple(v.shape) for k, v in weights.items()}
         self.id_num = var_to_shape_map[PREFIX + "embedding_id"][0]   # KeyError if single-speaker: synthesizer.py:25
         self.model.load_weights(weights)
