@@ -40,6 +40,17 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
+// A/B switches (same-box comparisons with tools/ab): all on by default
+#ifndef TACO_DEC_REBAL
+#define TACO_DEC_REBAL 1   // early parts of P11 / P13 spread over the windows with slack
+#endif
+#ifndef TACO_DEC_QUADS
+#define TACO_DEC_QUADS 1   // exp(score) blocks cut at multiples of four pairs, sent as 16-byte words
+#endif
+#ifndef TACO_DEC_P8W6
+#define TACO_DEC_P8W6 1    // P8's streamed chunk-tiles are taken from the ring in the window of P6
+#endif
+
 namespace taco {
 
 namespace {
@@ -94,8 +105,9 @@ constexpr uint32_t OFF_STG = OFF_STATE + NSTATE * 128 * 4;         // two staged
 constexpr uint32_t OFF_INV = OFF_STG + 2 * 512;                    // softmax normalisers 1/sum per sample
 constexpr uint32_t OFF_P6T = OFF_INV + 32;                         // per-warp pair geometry of the score phase
 constexpr uint32_t OFF_TMEM = OFF_P6T + 64;                       // TMEM base address written by tcgen05.alloc
+constexpr uint32_t OFF_VB = OFF_TMEM + 4;                         // sum_k v_k - min(||v||_1, 40) (read once per step)
 constexpr uint32_t OFF_SEQ = OFF_TMEM + 16;                       // per-warp order of the streamed chunk-tiles [16][16]
-constexpr uint32_t OFF_X = OFF_SEQ + NW * 16 * 4;
+constexpr uint32_t OFF_X = (OFF_SEQ + NW * 16 * 4 + 127u) & ~127u;
 static_assert(OFF_X % 16 == 0 && OFF_RED % 16 == 0 && OFF_STATE % 16 == 0 && OFF_BIAS % 16 == 0, "alignment");
 
 // chunks in front of buffer b (order DM_BF, DM_BC, DM_BP1, DM_BP2(8 chunks), DM_BHA, ...)
@@ -104,13 +116,16 @@ struct Dyn { uint32_t pq, sc, stage, ksl, msl, ring, total; };
 __host__ __device__ inline Dyn make_dyn(int S, int T_in, int FC, bool att_res, int d0, int d1) {
   Dyn d;
   const uint32_t csb = (uint32_t)S * 64u;
-  const uint32_t npq = (uint32_t)(T_in * S) / CS + 1;              // (position, sample) pairs per CTA, upper bound
-  d.pq = OFF_X + (uint32_t)cum_chunks(DM_NBUF, FC) * csb;          // exp(2 * processed query) fp32 [chunk][n][16]
-  d.sc = d.pq + 16 * csb;                                          // exp(score - B)  [j][n]
-  d.stage = d.sc + (((uint32_t)T_in * S * 4 + 15u) & ~15u);        // this CTA's pairs
-  d.ksl = d.stage + ((npq * 4 + 15u) & ~15u);                      // exp(2 * keys) rows of this CTA's pairs
-  d.msl = d.ksl + (att_res ? npq * DH * 4 : 0u);                   // memory columns of this CTA, tile order
-  d.ring = d.msl + (att_res ? (uint32_t)S * T_in * 64u : 0u);      // weight ring: d0 KB for each of warps 0-7, d1 KB for 8-15
+  const uint32_t npq = (uint32_t)(T_in * S) / CS + 4;              // (position, sample) pairs per CTA, upper bound
+  // every region starts on a 128-byte line: a warp-wide LDS.128 / cp.async of 512 contiguous bytes then touches four
+  // lines, not five (measured: +-7 % of the step time depending on where the ring happened to land)
+  auto up = [](uint32_t v) { return (v + 127u) & ~127u; };
+  d.pq = up(OFF_X + (uint32_t)cum_chunks(DM_NBUF, FC) * csb);      // exp(2 * processed query) fp32 [chunk][n][16]
+  d.sc = up(d.pq + 16 * csb);                                      // exp(score - B)  [j][n]
+  d.stage = up(d.sc + (uint32_t)T_in * S * 4 + 16u);               // this CTA's pairs
+  d.ksl = up(d.stage + npq * 4);                                   // exp(2 * keys) rows of this CTA's pairs
+  d.msl = up(d.ksl + (att_res ? npq * DH * 4 : 0u));               // memory columns of this CTA, tile order
+  d.ring = up(d.msl + (att_res ? (uint32_t)S * T_in * 64u : 0u));  // weight ring: d0 KB for each of warps 0-7, d1 KB for 8-15
   d.total = d.ring + (uint32_t)(8 * d0 + 8 * d1) * 1024u;
   return d;
 }
@@ -191,7 +206,7 @@ __device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP: 1/inf = 0,
 // counted explicitly: the ring is always D chunk-tiles (1 KB = hi + lo fragments of 32 lanes) ahead of the consumer, each
 // lane copies and later reads only its own 32 bytes (no cross-lane visibility needed), and `wait_group D - cnt` waits for
 // exactly the oldest cnt entries.
-struct Ring { uint32_t base, seq; int D, n, rp, rf, kf; };   // base: this lane's 16 bytes of slot 0; seq: smem address of the order table
+struct Ring { uint32_t base, seq; int D, n, rp, kf; };   // base: this lane's 16 bytes of slot 0; seq: smem address of the order table
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
 }
@@ -210,15 +225,17 @@ __device__ __forceinline__ void cp_async_wait_pending(int pend) {   // pend is w
 }
 // request the next cnt chunk-tiles of this warp's order into the slots that were consumed last
 __device__ __forceinline__ void ring_refill(Ring& r, const uint4* __restrict__ ws, int cnt) {
+  int rf = r.rp - cnt;   // the slots consumed last (nothing was taken since)
+  if (rf < 0) rf += r.D;
   for (int k = 0; k < cnt; ++k) {
     uint32_t off;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(off) : "r"(r.seq + (uint32_t)r.kf * 4u));
     const uint4* src = ws + (size_t)off * 32;
-    const uint32_t dst = r.base + (uint32_t)r.rf * 1024u;
+    const uint32_t dst = r.base + (uint32_t)rf * 1024u;
     cp_async16(dst, src);
     cp_async16(dst + 512u, src + 32);
     cp_async_commit();
-    r.rf = r.rf + 1 == r.D ? 0 : r.rf + 1;
+    rf = rf + 1 == r.D ? 0 : rf + 1;
     r.kf = r.kf + 1 == r.n ? 0 : r.kf + 1;
   }
 }
@@ -286,14 +303,17 @@ __device__ __forceinline__ void mma3_if(bool on, float (&hh)[4], float (&hl)[4],
 // One operand pass of a work item: chunks 0..cnt-1 of the activation buffer at xaddr against the weight slots SL.
 // The B fragment of chunk i+1 is requested before the MMAs of chunk i (two register sets), so that the three
 // accumulator chains run at the tensor pipe's dependent-issue latency instead of LDS + MMA per chunk.
-template <int... SL>
+// (I0, I1: the chunk range of this call, for work items whose early part is spread over two windows; the caller
+// guarantees I0 < cnt)
+template <int I0, int I1, int... SL>
 __device__ __forceinline__ void mma_pass(float (&hh)[4], float (&hl)[4], float (&lh)[4], const uint4 (&wb)[NWB], uint32_t xaddr,
                                          uint32_t csb, int cnt) {
   constexpr int sl[] = {SL...};
-  constexpr int MAXC = (int)sizeof...(SL);
-  uint4 xa = lds128(xaddr), xb = make_uint4(0u, 0u, 0u, 0u);
+  constexpr int MAXC = (int)sizeof...(SL) < I1 ? (int)sizeof...(SL) : I1;
+  uint4 xa = make_uint4(0u, 0u, 0u, 0u), xb = make_uint4(0u, 0u, 0u, 0u);
+  if (I0 & 1) xb = lds128(xaddr + I0 * csb); else xa = lds128(xaddr + I0 * csb);
 #pragma unroll
-  for (int i = 0; i < MAXC; ++i) {
+  for (int i = I0; i < MAXC; ++i) {
     if (i + 1 < MAXC && i + 1 < cnt) {
       if (i & 1) xa = lds128(xaddr + (i + 1) * csb); else xb = lds128(xaddr + (i + 1) * csb);
     }
@@ -385,16 +405,17 @@ template <int NX, int... SL>
 __device__ __forceinline__ void mma_chunks(const uint4 (&wb)[NWB], uint32_t xaddr, uint32_t csb, int cnt, uint32_t slot,
                                            int g, int t, Slots<SL...>, int nx = 0, uint32_t d1 = 0, uint32_t d2 = 0) {
   constexpr int sl[] = {SL...};
+  constexpr int I0 = 0, I1 = 8;
   float hh[4] = {0.f, 0.f, 0.f, 0.f}, hl[4] = {0.f, 0.f, 0.f, 0.f}, lh[4] = {0.f, 0.f, 0.f, 0.f};
   // one branch per operand pass (a block of this size is not if-converted), per-chunk predicates inside
   if (cnt > 0) {
-    mma_pass<SL...>(hh, hl, lh, wb, xaddr, csb, cnt);
+    mma_pass<I0, I1, SL...>(hh, hl, lh, wb, xaddr, csb, cnt);
   }
   if (NX >= 1 && cnt > 0 && nx >= 1) {
-    mma_pass<SL...>(hh, hl, lh, wb, xaddr + d1, csb, cnt);
+    mma_pass<I0, I1, SL...>(hh, hl, lh, wb, xaddr + d1, csb, cnt);
   }
   if (NX >= 2 && cnt > 0 && nx >= 2) {
-    mma_pass<SL...>(hh, hl, lh, wb, xaddr + d2, csb, cnt);
+    mma_pass<I0, I1, SL...>(hh, hl, lh, wb, xaddr + d2, csb, cnt);
   }
   // D[row g / g+8 = tile column][col 2t, 2t+1 = sample]  ->  slot[sample][column]   (bank-conflict free with RS = 20)
   // (written even when cnt == 0 so that the reducer never sums a stale slot)
@@ -410,7 +431,8 @@ __device__ __forceinline__ void mma_chunks(const uint4 (&wb)[NWB], uint32_t xadd
 // y0 / h1' for the sums y1, y2); its partial tile stays in four registers.  PART 1 (late) runs after the wait, adds the
 // operand that has just arrived and writes the partial tile.  Work item flags: nx (extra buffers), early (bit 30).
 //   nx == 0: the one buffer is early iff flagged;  nx >= 1: every buffer but the last extra one is early.
-template <int PART, int NX, int... SL>
+// I0, I1: chunk range of this call; ACC: the early part continues one started in an earlier window.
+template <int PART, int NX, int I0, int I1, bool ACC, int... SL>
 __device__ __forceinline__ void mma_split(float (&pre)[4], const uint4 (&wb)[NWB], uint32_t xl, uint32_t csb, uint32_t e,
                                           uint32_t slot, int g, int t, Slots<SL...>, uint32_t d1 = 0, uint32_t d2 = 0) {
   constexpr int sl[] = {SL...};
@@ -422,16 +444,16 @@ __device__ __forceinline__ void mma_split(float (&pre)[4], const uint4 (&wb)[NWB
   const bool do2 = NX >= 2 && PART == 1 && nx == 2;
   float hh[4], hl[4] = {0.f, 0.f, 0.f, 0.f}, lh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int k = 0; k < 4; ++k) hh[k] = PART == 0 ? 0.f : pre[k];
+  for (int k = 0; k < 4; ++k) hh[k] = (PART == 0 && !ACC) ? 0.f : pre[k];
   // one branch per operand pass (a block of this size is not if-converted), per-chunk predicates inside
-  if (do0 && cnt > 0) {
-    mma_pass<SL...>(hh, hl, lh, wb, xaddr, csb, cnt);
+  if (do0 && cnt > I0) {
+    mma_pass<I0, I1, SL...>(hh, hl, lh, wb, xaddr, csb, cnt);
   }
-  if (NX >= 1 && do1 && cnt > 0) {
-    mma_pass<SL...>(hh, hl, lh, wb, xaddr + d1, csb, cnt);
+  if (NX >= 1 && do1 && cnt > I0) {
+    mma_pass<I0, I1, SL...>(hh, hl, lh, wb, xaddr + d1, csb, cnt);
   }
-  if (NX >= 2 && do2 && cnt > 0) {
-    mma_pass<SL...>(hh, hl, lh, wb, xaddr + d2, csb, cnt);
+  if (NX >= 2 && do2 && cnt > I0) {
+    mma_pass<I0, I1, SL...>(hh, hl, lh, wb, xaddr + d2, csb, cnt);
   }
   if (PART == 0) {
 #pragma unroll
@@ -485,7 +507,7 @@ static_assert(BI_OB + 16 == DM_NBIAS, "bias table size");
 template <bool TRACE>
 __global__ void __launch_bounds__(NT, 1)
 decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int nclusters) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   // the warp index through a shuffle from lane 0: ptxas then knows it is warp-uniform (uniform registers and branches
   // instead of predication, BSSY/BSYNC and WARPSYNC around every per-warp decision)
   const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -503,9 +525,13 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
   const uint32_t csb = (uint32_t)S * 64u;
   const uint32_t mb0 = sbase + OFF_MBAR;
   // attention scores are cut by flattened (position j, sample n) pair index p = j*S + n: 16 balanced ranges
-  const int NP = T_in * S;
+  // (cut at multiples of four pairs: a CTA's exp(score) block goes out as 16-byte words)
+  const int NP = T_in * S, NQ = (NP + 3) >> 2;
+#if TACO_DEC_QUADS
+  const int p0 = 4 * ((q * NQ) / CS), npq = min(NP, 4 * (((q + 1) * NQ) / CS)) - p0;
+#else
   const int p0 = (q * NP) / CS, npq = ((q + 1) * NP) / CS - p0;
-  const float invS = 1.0f / (float)S;   // j = floor((p + 0.5) / S) is exact for p < 2^20
+#endif
   if (S == 0) {   // cannot happen (nclusters <= N); keeps every CTA of a cluster on the same path
     cluster_sync_all();
     cluster_sync_all();
@@ -544,6 +570,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
   for (int i = 0; i < 8; ++i) { const float vv = __ldg(w.att_v + lane + 32 * i); vbound += fabsf(vv); vsum += vv; }
   vbound = fminf(warp_sum(vbound), 40.0f);
   vsum = warp_sum(vsum);
+  if (tid == 0) sts_f(sbase + OFF_VB, vsum - vbound);   // written before the barriers of the prologue
 
   const uint4* ws = reinterpret_cast<const uint4*>(w.stream) + ((size_t)(q * NW + warp) * F4_STEP) * 32 + lane;
   const uint32_t wtab = sbase + OFF_WTAB + warp * 4;                       // + phase * 64
@@ -603,9 +630,8 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
   //   the context rows of the prenet (P1, warps 0-7, 2 chunk-tiles each)
   //       -> slice of warp 8 + (warp % 4), chunk-tiles 6-7 (warps 0-3) or 14-15 (warps 4-7).
   const bool early1 = ((WCNT(T_P1) >> 30) & 1u) != 0, early3 = ((WCNT(T_P3) >> 30) & 1u) != 0;
-  const uint32_t tq = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-  const uint32_t tx1 = tq + 2u * 128u + (warp < 4 ? 6u : 14u) * 8u;
-  const uint32_t tx3 = tq + 3u * 128u + (warp < 8 ? 4u : 12u) * 8u;
+  #define TX1 (tw - (uint32_t)(warp >> 2) * 128u + 2u * 128u + (warp < 4 ? 6u : 14u) * 8u)
+#define TX3 (tw - (uint32_t)(warp >> 2) * 128u + 3u * 128u + (warp < 8 ? 4u : 12u) * 8u)
   {
     auto fillx = [&](int tp, int off, uint32_t tx) {
       const int cnt = (int)(WCNT(tp) & 7u);
@@ -614,8 +640,8 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
         tmem_st8(tx + (uint32_t)i * 8u, hi, lo);
       }
     };
-    if (early1) fillx(T_P1, O1, tx1);
-    if (early3) fillx(T_P3, O3, tx3);
+    if (early1) fillx(T_P1, O1, TX1);
+    if (early3) fillx(T_P3, O3, TX3);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
   // the streamed chunk-tiles of this warp in consumption order (stream offsets in 512-byte rows)
@@ -640,8 +666,8 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     const int dmax = warp < 8 ? a.ring_d0 : a.ring_d1;
     rg.D = rg.n < dmax ? rg.n : dmax;
     rg.base = sbase + L.ring + (uint32_t)(warp < 8 ? warp * a.ring_d0 : 8 * a.ring_d0 + (warp - 8) * a.ring_d1) * 1024u + (uint32_t)lane * 16u;
-    rg.rp = 0; rg.rf = 0; rg.kf = 0;
-    ring_refill(rg, ws, rg.D);   // rf wraps back to 0 = rp: the ring is full
+    rg.rp = 0; rg.kf = 0;
+    ring_refill(rg, ws, rg.D);   // rp - D = rp (mod D): fills every slot once, the ring is full
   }
   if (!early1) ring_take(wb, rg, (int)(WCNT(T_P1) & 7u), SL1());
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -658,8 +684,22 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
 #define TLOADP(TP, TC0, I0, ...) load_t<TC0, I0>(wb, tw, (int)(WCNT(TP) & 7u), Slots<__VA_ARGS__>());
 #define TWAIT(SL) wait_t(wb, SL());
 #define MMA(SL, TP) { const uint32_t e = WCNT(TP); mma_chunks<0>(wb, xl + ((e & 0x0fffffffu) >> 3), csb, e & 7, myslot, g, t, SL()); }
-#define MMA_PRE(NX, SL, TP) mma_split<0, NX>(pre, wb, xl, csb, WCNT(TP), myslot, g, t, SL(), dH1, dH2);
-#define MMA_POST(NX, SL, TP) mma_split<1, NX>(pre, wb, xl, csb, WCNT(TP), myslot, g, t, SL(), dH1, dH2);
+#define MMA_PRE(NX, SL, TP) mma_split<0, NX, 0, 8, false>(pre, wb, xl, csb, WCNT(TP), myslot, g, t, SL(), dH1, dH2);
+#define MMA_PRE_R(NX, SL, TP, I0, I1, ACC) mma_split<0, NX, I0, I1, ACC>(pre, wb, xl, csb, WCNT(TP), myslot, g, t, SL(), dH1, dH2);
+#define MMA_POST(NX, SL, TP) mma_split<1, NX, 0, 8, false>(pre, wb, xl, csb, WCNT(TP), myslot, g, t, SL(), dH1, dH2);
+// where the early parts of the two decoder GRUs' successors run (TACO_DEC_REBAL: spread over the windows with slack)
+
+#if TACO_DEC_REBAL
+#define W9_WORK TLOADP(T_P10, TC10, 0, 0, 1) TLOADP(T_P11, TC11, 0, 2, 3, 4, 5) TWAIT(SL11) MMA_PRE_R(1, SL11, T_P11, 0, 4, false)
+#define W10_WORK TLOADP(T_P11, TC11, 4, 0, 1) TWAIT(SL11) MMA_PRE_R(1, SL11, T_P11, 4, 6, true)
+#define W11_WORK TLOADP(T_P12, TC12, 0, 0, 1) RTAKE(T_P13, SL13) MMA_PRE(2, SL13, T_P13)
+#define W12_WORK
+#else
+#define W9_WORK TLOADP(T_P10, TC10, 0, 0, 1)
+#define W10_WORK TLOADP(T_P11, TC11, 0, 2, 3, 4, 5, 0, 1) TWAIT(SL11) MMA_PRE(1, SL11, T_P11)
+#define W11_WORK TLOADP(T_P12, TC12, 0, 0, 1)
+#define W12_WORK RTAKE(T_P13, SL13) MMA_PRE(2, SL13, T_P13)
+#endif
 #define ST(slot) (st_nc + (slot) * 512)
 #define BIAS(tab) lds_f(bias_c + (tab) * 4)
   float pre[4] = {0.f, 0.f, 0.f, 0.f};   // early part of the next phase's partial tile (step 0, P1: the context is zero)
@@ -673,7 +713,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
       mbar_expect_tx(mb0 + B_P3 * 8, BLK);
       mbar_expect_tx(mb0 + B_P4 * 8, BLK);
       mbar_expect_tx(mb0 + B_P5 * 8, BLK);
-      mbar_expect_tx(mb0 + B_P6 * 8, (uint32_t)T_in * S * 4u);
+      mbar_expect_tx(mb0 + B_P6 * 8, TACO_DEC_QUADS ? (uint32_t)NQ * 16u : (uint32_t)NP * 4u);
       mbar_expect_tx(mb0 + B_P7 * 8, BLK);
       mbar_expect_tx(mb0 + B_P8 * 8, BLK);
       mbar_expect_tx(mb0 + B_P9 * 8, BLK);
@@ -716,7 +756,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     RFILL(T_P2)                                 // window of P2: the x rows of P3 from the ring ...
     if (!early3) { RTAKE(T_P3, SL3) }
     if (early3) {                               // ... and the h_att rows of the attention GRU's gates, from TMEM
-      load_tx(wb, tx3, (int)(WCNT(T_P3) & 7u), SL3());
+      load_tx(wb, TX3, (int)(WCNT(T_P3) & 7u), SL3());
       TWAIT(SL3)
       MMA_PRE(0, SL3, T_P3)
     } else { pre[0] = pre[1] = pre[2] = pre[3] = 0.f; }
@@ -839,15 +879,22 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
         float sv = (up ? sb : sa) + __shfl_xor_sync(0xffffffffu, up ? sa : sb, 16);
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
-        const float ex = __expf(fmaxf(vsum - 2.0f * sv - vbound, -80.0f));
+        const float ex = __expf(fmaxf(fmaf(-2.0f, sv, lds_f(sbase + OFF_VB)), -80.0f));
         if (lane == 0 || (lane == 16 && two)) sts_f(sbase + L.stage + (uint32_t)(up ? pp + dpp : pp) * 4u, ex);
       }
     }
     __syncthreads();
     TRM(16);
-    // warp p -> peer p: this CTA's pairs into sc[p0 ..]
+    // warp p -> peer p: this CTA's pairs into sc[p0 ..], four per DSMEM transaction (the tail of the last quad is padding)
+#if TACO_DEC_QUADS
+    if (lane < ((npq + 3) >> 2)) st_async_v4(rx + L.sc + (uint32_t)p0 * 4u, lds128(sbase + L.stage + lane * 16), rmb0 + B_P6 * 8);
+#else
     for (int i = lane; i < npq; i += 32)
       st_async_b32(rx - lane * 16 + L.sc + (uint32_t)(p0 + i) * 4u, lds32(sbase + L.stage + i * 4), rmb0 + B_P6 * 8);
+#endif
+#if TACO_DEC_P8W6
+    RTAKE(T_P8, SL8)                      // window of P6: P8's chunks into registers
+#endif
     TRM(17);
     mbar_wait(mb0 + B_P6 * 8, par);
     TRM(18);
@@ -915,10 +962,13 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     }
     __syncthreads();
     send_blk(0, XBUF(DM_BC) + q * csb, B_P7);
+#if !TACO_DEC_P8W6
     RTAKE(T_P8, SL8)                      // window of P7: P8's chunks into registers
+#endif
     if (warp == 1 && a.align_out != nullptr) {   // alignments of this CTA's pairs (tacotron.py:104: [N,T_in,steps])
       const float* stage = reinterpret_cast<const float*>(smem_raw + L.stage);
       const float* invs = reinterpret_cast<const float*>(smem_raw + OFF_INV);
+      const float invS = 1.0f / (float)S;   // j = floor((p + 0.5) / S) is exact for p < 2^20
       for (int pp = lane; pp < npq; pp += 32) {
         const int p = p0 + pp, j = (int)(((float)p + 0.5f) * invS), n = p - j * S;
         a.align_out[((size_t)(n0 + n) * T_in + j) * a.max_steps + step] = stage[pp] * invs[n];
@@ -948,25 +998,25 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     mbar_wait(mb0 + B_P8 * 8, par);
     TRM(24);
     // ----- P9 / P10: decoder GRU 1 on [y0 | h1], y1 = y0 + h1' -----
-    GRU_GATES(0, SL9, T_P9, BI_R1, BI_U1, ST_H1, DM_BR1, B_P9, , TLOADP(T_P10, TC10, 0, 0, 1))
+    GRU_GATES(0, SL9, T_P9, BI_R1, BI_U1, ST_H1, DM_BR1, B_P9, , W9_WORK)
     TRM(26);
     mbar_wait(mb0 + B_P9 * 8, par);
     TRM(27);
     TRW(96);
     trb = 112;
     TWAIT(SL10)
-    GRU_CAND(SL10, T_P10, BI_C1, ST_H1, ST_H1, -1, DM_BH1, -1, B_P10, , TLOADP(T_P11, TC11, 0, 2, 3, 4, 5, 0, 1) TWAIT(SL11) MMA_PRE(1, SL11, T_P11))
+    GRU_CAND(SL10, T_P10, BI_C1, ST_H1, ST_H1, -1, DM_BH1, -1, B_P10, , W10_WORK)
     trb = -1;
     TRM(29);
     mbar_wait(mb0 + B_P10 * 8, par);
     TRM(30);
     // ----- P11 / P12: decoder GRU 2 on [y1 | h2], y2 = y1 + h2' -----
-    GRU_GATES(1, SL11, T_P11, BI_R2, BI_U2, ST_H2, DM_BR2, B_P11, , TLOADP(T_P12, TC12, 0, 0, 1))
+    GRU_GATES(1, SL11, T_P11, BI_R2, BI_U2, ST_H2, DM_BR2, B_P11, , W11_WORK)
     TRM(32);
     mbar_wait(mb0 + B_P11 * 8, par);
     TRM(33);
     TWAIT(SL12)
-    GRU_CAND(SL12, T_P12, BI_C2, ST_H2, ST_H2, -1, DM_BH2, -1, B_P12, , RTAKE(T_P13, SL13) MMA_PRE(2, SL13, T_P13))
+    GRU_CAND(SL12, T_P12, BI_C2, ST_H2, ST_H2, -1, DM_BH2, -1, B_P12, , W12_WORK)
     TRM(35);
     mbar_wait(mb0 + B_P12 * 8, par);
     TRM(36);
@@ -991,7 +1041,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     RFILL(T_P13)                       // window of P13: refill, the frame rows of the next step's prenet into registers
     if (!early1) { RTAKE(T_P1, SL1) }
     if (early1) {                      // ... and the context rows of the next step's prenet, from TMEM
-      load_tx(wb, tx1, (int)(WCNT(T_P1) & 7u), SL1());
+      load_tx(wb, TX1, (int)(WCNT(T_P1) & 7u), SL1());
       TWAIT(SL1)
       MMA_PRE(0, SL1, T_P1)
     } else { pre[0] = pre[1] = pre[2] = pre[3] = 0.f; }
@@ -1002,7 +1052,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
   asm volatile("cp.async.wait_group 0;" ::: "memory");   // nothing may still be in flight into this CTA's shared memory
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_sync_all();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(lds32(sbase + OFF_TMEM)) : "memory");
 }
 
 }  // namespace
