@@ -112,7 +112,7 @@ static_assert(OFF_X % 16 == 0 && OFF_RED % 16 == 0 && OFF_STATE % 16 == 0 && OFF
 
 // chunks in front of buffer b (order DM_BF, DM_BC, DM_BP1, DM_BP2(8 chunks), DM_BHA, ...)
 __host__ __device__ __forceinline__ int cum_chunks(int b, int FC) { return b == 0 ? 0 : FC + 16 * (b - 1) - (b > DM_BP2 ? 8 : 0); }
-struct Dyn { uint32_t pq, sc, stage, ksl, msl, ring, total; };
+struct Dyn { uint32_t pq, sc, stage, pn, ksl, msl, ring, total; };
 __host__ __device__ inline Dyn make_dyn(int S, int T_in, int FC, bool att_res, int d0, int d1) {
   Dyn d;
   const uint32_t csb = (uint32_t)S * 64u;
@@ -123,7 +123,8 @@ __host__ __device__ inline Dyn make_dyn(int S, int T_in, int FC, bool att_res, i
   d.pq = up(OFF_X + (uint32_t)cum_chunks(DM_NBUF, FC) * csb);      // exp(2 * processed query) fp32 [chunk][n][16]
   d.sc = up(d.pq + 16 * csb);                                      // exp(score - B)  [j][n]
   d.stage = up(d.sc + (uint32_t)T_in * S * 4 + 16u);               // this CTA's pairs
-  d.ksl = up(d.stage + npq * 4);                                   // exp(2 * keys) rows of this CTA's pairs
+  d.pn = d.stage + ((npq * 4 + 15u) & ~15u);                       // sample index of this CTA's pairs (bytes)
+  d.ksl = up(d.pn + npq);                                          // exp(2 * keys) rows of this CTA's pairs
   d.msl = up(d.ksl + (att_res ? npq * DH * 4 : 0u));               // memory columns of this CTA, tile order
   d.ring = up(d.msl + (att_res ? (uint32_t)S * T_in * 64u : 0u));  // weight ring: d0 KB for each of warps 0-7, d1 KB for 8-15
   d.total = d.ring + (uint32_t)(8 * d0 + 8 * d1) * 1024u;
@@ -560,9 +561,10 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
       k4.z = __expf(2.0f * fminf(fmaxf(k4.z, -30.f), 30.f)); k4.w = __expf(2.0f * fminf(fmaxf(k4.w, -30.f), 30.f));
       *reinterpret_cast<float4*>(ksl + (size_t)pp * DH + c4 * 4) = k4;
     }
-    for (int i = tid; i < S * T_in * 16; i += NT) {
-      const int c = i & 15, r = i >> 4, s = r / T_in, j = r - s * T_in;
-      msl[((size_t)j * S + s) * 16 + c] = __ldg(a.memory + ((size_t)(n0 + s) * T_in + j) * DH + q * 16 + c);   // [j][n][16]
+    for (int i = tid; i < S * T_in * 4; i += NT) {   // 16 columns = four float4 per (sample, position)
+      const int c4 = i & 3, r = i >> 2, s = r / T_in, j = r - s * T_in;
+      *reinterpret_cast<float4*>(msl + ((size_t)j * S + s) * 16 + c4 * 4) =
+          ldg_f4(a.memory + ((size_t)(n0 + s) * T_in + j) * DH + q * 16 + c4 * 4);   // [j][n][16]
     }
   }
   float vbound = 0.f, vsum = 0.f;   // B = min(||v||_1, 40) >= any score (|tanh| <= 1); sum_k v_k
@@ -594,13 +596,8 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
 #define WCNT(ph) ((uint32_t)__shfl_sync(0xffffffffu, lds32(wtab + (ph) * 64), 0))
 #define XBUF(b) (OFF_X + (uint32_t)cum_chunks((b), FC) * csb)
 
-  // P6: a warp works on the pairs of ONE sample; sample, first local pair and pair stride of this warp
-  // (kept in shared memory: the integer divisions are done once, the registers stay free)
-  if (lane == 0) {
-    const int wn = warp % S;
-    reinterpret_cast<uint32_t*>(smem_raw + OFF_P6T)[warp] =
-        (uint32_t)wn | ((uint32_t)((wn - p0 % S + S) % S + (warp / S) * S) << 8) | ((uint32_t)(((NW - wn + S - 1) / S) * S) << 16);
-  }
+  // P6: sample index of every local pair (one integer division each, once)
+  for (int pp = tid; pp < npq; pp += NT) smem_raw[L.pn + pp] = (unsigned char)((p0 + pp) % S);
   uint4 wb[NWB];
   if (warp == 0) {   // all 512 TMEM columns: the kernel owns the SM anyway (512 threads x 128 registers)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sbase + OFF_TMEM) : "memory");
@@ -615,9 +612,14 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
   {
     auto fill = [&](int tp, int off, int tc0) {
       const int cnt = (int)(WCNT(tp) & 7u);
-      for (int i = 0; i < cnt; ++i) {
-        const uint4 hi = ldg_stream(ws + (off + 2 * i) * 32), lo = ldg_stream(ws + (off + 2 * i + 1) * 32);
-        tmem_st8(tw + (uint32_t)(tc0 + i) * 8u, hi, lo);
+      for (int i0 = 0; i0 < cnt; i0 += 3) {   // three chunk-tiles in flight: the L2 latency is paid twice, not six times
+        uint4 hi[3], lo[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (i0 + k < cnt) { hi[k] = ldg_stream(ws + (off + 2 * (i0 + k)) * 32); lo[k] = ldg_stream(ws + (off + 2 * (i0 + k) + 1) * 32); }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (i0 + k < cnt) tmem_st8(tw + (uint32_t)(tc0 + i0 + k) * 8u, hi[k], lo[k]);
       }
     };
     fill(T_P9, O9, TC9); fill(T_P10, O10, TC10); fill(T_P11, O11, TC11); fill(T_P12, O12, TC12);
@@ -835,52 +837,49 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     TRM(15);
     // ================= P6: Bahdanau scores of this CTA's (position, sample) pairs: exp(v . tanh(keys + pq) - B) ======
     // v.tanh(k + p) = sum v - 2 sum_k v_k / (1 + e^{2k} e^{2p}); e^{2k} is resident, e^{2p} was pushed by P5.
-    // A warp works on ONE sample (warp % S): e^{2p} and v stay in registers and a pair costs two LDS.128 of e^{2k}.
-    // Two elements share one MUFU.RCP: v1/a + v2/b = (v1 b + v2 a) / (a b) with a, b clamped to 2^62 (tanh = 1 there).
+    // Warp w takes the local pairs 2w, 2w+1 (+32, ...): two per pass, one butterfly reduces both.
+    // Four elements share one MUFU.RCP: v1/a + v2/b + v3/c + v4/d = (N_ab cd + N_cd ab) / (ab cd) with N_ab = v1 b + v2 a and
+    // the denominators clamped to 2^30 (tanh = 1 - 2^-29 there: below fp32 resolution of the score).
     {
-      const uint32_t geo = lds32(sbase + OFF_P6T + warp * 4);
-      const int wn = geo & 0xffu, dpp = geo >> 16;
-      int pp = (geo >> 8) & 0xffu;
       // lane's 8 inputs: k = 4 lane + {0..3} (chunk lane>>2, columns 4 (lane&3)..) and 128 + the same (chunk + 8)
-      const uint32_t pq_l = sbase + L.pq + (uint32_t)(lane >> 2) * csb + (uint32_t)(lane & 3) * 16u + (uint32_t)wn * 64u;
+      const uint32_t pq_l = sbase + L.pq + (uint32_t)(lane >> 2) * csb + (uint32_t)(lane & 3) * 16u;
       const float4 v0 = lds_f4(sbase + OFF_VATT + lane * 16), v1 = lds_f4(sbase + OFF_VATT + 512 + lane * 16);
-      const float4 e0 = lds_f4(pq_l), e1 = lds_f4(pq_l + 8 * csb);                             // e^{2 pq}
-      auto load_keys = [&](int pl, float4& k0, float4& k1) {                                   // e^{2 key} of local pair pl
+      constexpr float BIG = 1073741824.0f;   // 2^30
+      auto quad = [&](const float4& k, const float4& e, const float4& v) -> float {
+        const float da = fminf(fmaf(k.x, e.x, 1.0f), BIG), db = fminf(fmaf(k.y, e.y, 1.0f), BIG);
+        const float dc = fminf(fmaf(k.z, e.z, 1.0f), BIG), dd = fminf(fmaf(k.w, e.w, 1.0f), BIG);
+        const float ab = da * db, cd = dc * dd;
+        const float nab = fmaf(v.x, db, v.y * da), ncd = fmaf(v.z, dd, v.w * dc);
+        return fmaf(nab, cd, ncd * ab) * rcp_approx(ab * cd);
+      };
+      auto pair_sum = [&](int pl) -> float {   // sum_k v_k / (1 + e^{2k} e^{2p}) over this lane's 8 inputs of local pair pl
+        const int n = smem_raw[L.pn + pl];
+        const float4 e0 = lds_f4(pq_l + (uint32_t)n * 64u), e1 = lds_f4(pq_l + (uint32_t)n * 64u + 8 * csb);   // e^{2 pq}
+        float4 k0, k1;                                                                                     // e^{2 key}
         if (att_res) {
           k0 = lds_f4(sbase + L.ksl + (uint32_t)pl * (DH * 4) + lane * 16);
           k1 = lds_f4(sbase + L.ksl + (uint32_t)pl * (DH * 4) + 512 + lane * 16);
         } else {
           const int j = (p0 + pl) / S;
-          const float* krow = a.keys + ((size_t)(n0 + wn) * T_in + j) * DH + 4 * lane;
+          const float* krow = a.keys + ((size_t)(n0 + n) * T_in + j) * DH + 4 * lane;
           k0 = ldg_f4(krow); k1 = ldg_f4(krow + 128);
           k0.x = __expf(2.0f * fminf(fmaxf(k0.x, -30.f), 30.f)); k0.y = __expf(2.0f * fminf(fmaxf(k0.y, -30.f), 30.f));
           k0.z = __expf(2.0f * fminf(fmaxf(k0.z, -30.f), 30.f)); k0.w = __expf(2.0f * fminf(fmaxf(k0.w, -30.f), 30.f));
           k1.x = __expf(2.0f * fminf(fmaxf(k1.x, -30.f), 30.f)); k1.y = __expf(2.0f * fminf(fmaxf(k1.y, -30.f), 30.f));
           k1.z = __expf(2.0f * fminf(fmaxf(k1.z, -30.f), 30.f)); k1.w = __expf(2.0f * fminf(fmaxf(k1.w, -30.f), 30.f));
         }
+        return quad(k0, e0, v0) + quad(k1, e1, v1);
       };
-      constexpr float BIG = 4.611686018427387904e18f;   // 2^62
-      auto pair_rcp = [&](float ka, float ea, float va, float kb, float eb, float vb) -> float {
-        const float da = fminf(fmaf(ka, ea, 1.0f), BIG), db = fminf(fmaf(kb, eb, 1.0f), BIG);
-        return fmaf(va, db, vb * da) * rcp_approx(da * db);
-      };
-      auto partial = [&](const float4& k0, const float4& k1) -> float {
-        return (pair_rcp(k0.x, e0.x, v0.x, k0.y, e0.y, v0.y) + pair_rcp(k0.z, e0.z, v0.z, k0.w, e0.w, v0.w)) +
-               (pair_rcp(k1.x, e1.x, v1.x, k1.y, e1.y, v1.y) + pair_rcp(k1.z, e1.z, v1.z, k1.w, e1.w, v1.w));
-      };
-      for (; pp < npq; pp += 2 * dpp) {   // two pairs per pass: one butterfly reduces both
-        const bool two = pp + dpp < npq;
-        float4 ka0, ka1, kb0, kb1;
-        load_keys(pp, ka0, ka1);
-        load_keys(two ? pp + dpp : pp, kb0, kb1);
-        const float sa = partial(ka0, ka1), sb = partial(kb0, kb1);
+      for (int pp = 2 * warp; pp < npq; pp += 2 * NW) {
+        const bool two = pp + 1 < npq;
+        const float sa = pair_sum(pp), sb = pair_sum(two ? pp + 1 : pp);
         // lanes 0..15 end up with pair A's sum, lanes 16..31 with pair B's
         const bool up = lane >= 16;
         float sv = (up ? sb : sa) + __shfl_xor_sync(0xffffffffu, up ? sa : sb, 16);
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
         const float ex = __expf(fmaxf(fmaf(-2.0f, sv, lds_f(sbase + OFF_VB)), -80.0f));
-        if (lane == 0 || (lane == 16 && two)) sts_f(sbase + L.stage + (uint32_t)(up ? pp + dpp : pp) * 4u, ex);
+        if (lane == 0 || (lane == 16 && two)) sts_f(sbase + L.stage + (uint32_t)(up ? pp + 1 : pp) * 4u, ex);
       }
     }
     __syncthreads();
