@@ -580,18 +580,32 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
   const uint32_t myslot = sbase + OFF_RED + warp * SLOT * 4;
   // reducer group: warps 0..3, thread (rn, rc) = (sample, column of this CTA's tile)
   const int rn = (tid >> 4) & 7, rc = tid & 15;
-  const bool red_grp = warp < 4;
+  // Reducer groups sit on the warps with the least MMA / weight-ring work (the work table loads warps 0-7 most):
+  // group 0 (sums, gate math, staging, the exchange) = warps 12-15, group 1 = warps 8-11, group 2 = warps 4-7.
+  const bool red_grp = warp >= 12, red_grp1 = (warp >> 2) == 2, red_grp2 = (warp >> 2) == 1;
   const uint32_t red_nc = sbase + OFF_RED + (rn * RS + rc) * 4;
   const uint32_t st_nc = sbase + OFF_STATE + (rn * 16 + rc) * 4;           // + slot * 512
   const uint32_t bias_c = sbase + OFF_BIAS + rc * 4;                       // + table * 4
   const uint32_t stg_n = sbase + OFF_STG + rn * 64;                        // + block * 512
-  const uint32_t stg_lane = sbase + OFF_STG + lane * 16;                   // + block * 512
-  const bool snd_on = lane < 4 * S;            // lanes that carry a word group of a staged block
   const uint32_t rmb0 = mapa_u32(mb0, (uint32_t)warp);                      // peer `warp`: its mbarriers ...
   const uint32_t rx = mapa_u32(sbase + lane * 16, (uint32_t)warp);          // ... and this lane's slot in a chunk at offset 0
-  // all warps: send staged block `blk` into (byte offset dst + chunk*csb) of peer `warp`
-  auto send_blk = [&](int blk, uint32_t dst, int bar) {
-    if (snd_on) st_async_v4(rx + dst, lds128(stg_lane + blk * 512), rmb0 + bar * 8);
+  // A reducer warp sends what it staged itself: warp r of a reducer group owns the rows of samples 2r, 2r+1 of staged
+  // block `blk` (8 word groups of 16 bytes) and pushes them to all 16 peers (or, `pair`, to the 8 peers of this CTA's
+  // parity) -- no block barrier between the reduction and the exchange, and the other 12 warps are already in the window.
+  auto send_rows = [&](int blk, uint32_t dst, int bar, bool pair) {
+    __syncwarp();
+    const int wg = lane & 7, sn = 2 * (warp & 3) + (wg >> 2);
+    if (sn < S) {
+      const uint32_t off = (uint32_t)sn * 64u + (uint32_t)(wg & 3) * 16u;
+      const uint4 v = lds128(sbase + OFF_STG + (uint32_t)blk * 512u + off);
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        if (pair && it >= 2) break;
+        const uint32_t k = (uint32_t)(it * 4 + (lane >> 3));
+        const uint32_t peer = pair ? 2u * k + (uint32_t)(q & 1) : k;
+        st_async_v4(mapa_u32(sbase + dst + off, peer), v, mapa_u32(mb0 + (uint32_t)bar * 8u, peer));
+      }
+    }
   };
 #define WCNT(ph) ((uint32_t)__shfl_sync(0xffffffffu, lds32(wtab + (ph) * 64), 0))
 #define XBUF(b) (OFF_X + (uint32_t)cum_chunks((b), FC) * csb)
@@ -740,9 +754,10 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     MMA_POST(0, SL1, T_P1)                      // frame chunks; the context chunks were multiplied in the window of P13
     __syncthreads();
     TRM(1);
-    if (red_grp) stage_x(stg_n, rc, fmaxf(red_sum<DM_P1_SLOTS>(red_nc, 0) + BIAS(BI_P1), 0.f));
-    __syncthreads();
-    send_blk(0, XBUF(DM_BP1) + q * csb, B_P1);
+    if (red_grp) {
+      stage_x(stg_n, rc, fmaxf(red_sum<DM_P1_SLOTS>(red_nc, 0) + BIAS(BI_P1), 0.f));
+      send_rows(0, XBUF(DM_BP1) + q * csb, B_P1, false);
+    }
     if (!early1) { RFILL(T_P1) }                // window of P1: refill the ring, P2's chunks into registers
     RTAKE(T_P2, SL2)
     TRM(2);
@@ -752,9 +767,10 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     MMA(SL2, T_P2)
     __syncthreads();
     TRM(4);
-    if (red_grp) stage_x(stg_n, rc, fmaxf(red_sum<8>(red_nc, 0) + BIAS(BI_P2), 0.f));
-    __syncthreads();
-    if (((warp ^ q) & 1) == 0) send_blk(0, XBUF(DM_BP2) + (q >> 1) * csb, B_P2);
+    if (red_grp) {
+      stage_x(stg_n, rc, fmaxf(red_sum<8>(red_nc, 0) + BIAS(BI_P2), 0.f));
+      send_rows(0, XBUF(DM_BP2) + (q >> 1) * csb, B_P2, true);
+    }
     RFILL(T_P2)                                 // window of P2: the x rows of P3 from the ring ...
     if (!early3) { RTAKE(T_P3, SL3) }
     if (early3) {                               // ... and the h_att rows of the attention GRU's gates, from TMEM
@@ -775,14 +791,17 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     if (red_grp) {                                                                                   \
       const float r = sigmoid_f(red_sum<6>(red_nc, 0) + BIAS(BI_R));                                 \
       stage_x(stg_n, rc, r * lds_f(ST(ST_H)));                                                       \
-    } else if (warp < 8) {                                                                           \
+      /* the exchange must not complete before groups 1, 2 have read their partial tiles (the next phase overwrites them) */ \
+      asm volatile("bar.sync 1, 384;" ::: "memory");                                                 \
+      send_rows(0, XBUF(BUF_R) + q * csb, BAR, false);                                               \
+    } else if (red_grp1) {                                                                           \
       sts_f(ST(ST_U), sigmoid_f(red_sum<6>(red_nc, 6) + BIAS(BI_U)));                                \
-    } else if (warp < 12) {                                                                          \
+      asm volatile("bar.arrive 1, 384;" ::: "memory");                                               \
+    } else if (red_grp2) {                                                                           \
       sts_f(ST(ST_CX), red_sum<4>(red_nc, 12));                                                      \
+      asm volatile("bar.arrive 1, 384;" ::: "memory");                                               \
     }                                                                                                \
     if (TRACE && trb >= 0) TRW(trb + 16);                                                                     \
-    __syncthreads();                                                                                 \
-    send_blk(0, XBUF(BUF_R) + q * csb, BAR);                                                         \
     LATER
     // candidate: h' = u h + (1-u) tanh(c_h + c_x + b); y_out = y_in + h' (ResidualWrapper) when BUF_Y >= 0
 #define GRU_CAND(SLC, TP, BI_C, ST_H, ST_YIN, ST_YOUT, BUF_H, BUF_Y, BAR, URGENT, LATER)                     \
@@ -801,11 +820,10 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
         if (ST_YOUT >= 0) sts_f(ST(ST_YOUT < 0 ? 0 : ST_YOUT), y);                                   \
         stage_x(stg_n + 512, rc, y);                                                                 \
       }                                                                                              \
+      send_rows(0, XBUF(BUF_H) + q * csb, BAR, false);                                               \
+      if (BUF_Y >= 0) send_rows(1, XBUF(BUF_Y < 0 ? 0 : BUF_Y) + q * csb, BAR, false);               \
     }                                                                                                \
     if (TRACE && trb >= 0) TRW(trb + 16);                                                                     \
-    __syncthreads();                                                                                 \
-    send_blk(0, XBUF(BUF_H) + q * csb, BAR);                                                         \
-    if (BUF_Y >= 0) send_blk(1, XBUF(BUF_Y < 0 ? 0 : BUF_Y) + q * csb, BAR);                         \
     LATER
 
     // ----- P3 / P4: attention GRU on [prenet | h_att] -----
@@ -826,11 +844,10 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     TRM(13);
     if (red_grp) {   // the query is pushed as e^{2 pq} (fp32) for the score phase
       sts_f(stg_n + rc * 4, __expf(2.0f * fminf(fmaxf(red_sum<8>(red_nc, 0), -30.f), 30.f)));
-    } else if (warp < 8) {
+      send_rows(0, L.pq + q * csb, B_P5, false);
+    } else if (red_grp1) {
       sts_f(ST(ST_Y0H), red_sum<8>(red_nc, 8));
     }
-    __syncthreads();
-    send_blk(0, L.pq + q * csb, B_P5);
     RFILL(T_P5)                           // window of P5: refill
     TRM(14);
     mbar_wait(mb0 + B_P5 * 8, par);
@@ -958,21 +975,11 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
       const float inv = rcp_approx(s0 + s1);   // >= T_in e^{-80} > 0 (1 ulp; the oracle divides)
       stage_x(stg_n, rc, red_sum<16>(red_nc, 0) * inv);
       if (rc == 0) reinterpret_cast<float*>(smem_raw + OFF_INV)[rn] = inv;
+      send_rows(0, XBUF(DM_BC) + q * csb, B_P7, false);
     }
-    __syncthreads();
-    send_blk(0, XBUF(DM_BC) + q * csb, B_P7);
 #if !TACO_DEC_P8W6
     RTAKE(T_P8, SL8)                      // window of P7: P8's chunks into registers
 #endif
-    if (warp == 1 && a.align_out != nullptr) {   // alignments of this CTA's pairs (tacotron.py:104: [N,T_in,steps])
-      const float* stage = reinterpret_cast<const float*>(smem_raw + L.stage);
-      const float* invs = reinterpret_cast<const float*>(smem_raw + OFF_INV);
-      const float invS = 1.0f / (float)S;   // j = floor((p + 0.5) / S) is exact for p < 2^20
-      for (int pp = lane; pp < npq; pp += 32) {
-        const int p = p0 + pp, j = (int)(((float)p + 0.5f) * invS), n = p - j * S;
-        a.align_out[((size_t)(n0 + n) * T_in + j) * a.max_steps + step] = stage[pp] * invs[n];
-      }
-    }
     TRM(20);
     mbar_wait(mb0 + B_P7 * 8, par);
     TRM(21);
@@ -982,9 +989,16 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     TRM(22);
     if (red_grp) {
       stage_x(stg_n, rc, red_sum<8>(red_nc, 0) + lds_f(ST(ST_Y0H)) + BIAS(BI_PC));
+      send_rows(0, XBUF(DM_BY0) + q * csb, B_P8, false);
+    } else if (warp == 0 && a.align_out != nullptr) {
+      // alignments of this CTA's pairs (tacotron.py:104: [N,T_in,steps]); the normalisers were written in P7 before the barrier above
+      const float* stage = reinterpret_cast<const float*>(smem_raw + L.stage);
+      const float* invs = reinterpret_cast<const float*>(smem_raw + OFF_INV);
+      for (int pp = lane; pp < npq; pp += 32) {
+        const int n = smem_raw[L.pn + pp], j = (p0 + pp - n) / S;
+        a.align_out[((size_t)(n0 + n) * T_in + j) * a.max_steps + step] = stage[pp] * invs[n];
+      }
     }
-    __syncthreads();
-    send_blk(0, XBUF(DM_BY0) + q * csb, B_P8);
     RFILL(T_P8)
     TRW(160);
     TLOADP(T_P9, TC9, 0, 2, 3, 4, 5, 0, 1)   // window of P8: all of P9 from tensor memory, then its h1 rows
@@ -1023,20 +1037,18 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     MMA_POST(2, SL13, T_P13)
     __syncthreads();
     TRM(37);
-    if (warp < 8) {   // warps 0-3: tile 2q, warps 4-7: tile 2q+1
-      const int half = warp >> 2, tile = 2 * q + half;
+    if (warp >= 8) {   // warps 12-15: tile 2q, warps 8-11: tile 2q+1
+      const int half = red_grp ? 0 : 1, tile = 2 * q + half;
       const float o = red_sum<8>(red_nc, half * 8) + BIAS(half ? BI_OB : BI_OA);
       if (tile < ntiles && rn < S) a.dec_out[((size_t)(n0 + rn) * a.max_steps + step) * Dout + tile * 16 + rc] = o;
-      if (free_run) stage_x(stg_n + half * 512, rc, o);   // next decoder input = last frame of the group (helpers.py:37)
-    }
-    if (free_run) {
-      __syncthreads();
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int tile = 2 * q + half;
-        if (tile < ntiles && tile >= fb_tile0) send_blk(half, XBUF(DM_BF) + (tile - fb_tile0) * csb, B_P13);
+      if (free_run) {   // next decoder input = last frame of the group (helpers.py:37)
+        stage_x(stg_n + half * 512, rc, o);
+        if (tile < ntiles && tile >= fb_tile0) send_rows(half, XBUF(DM_BF) + (tile - fb_tile0) * csb, B_P13, false);
       }
     }
+    // the only second block barrier of a step: the next step's P1 overwrites the partial tiles, and in most CTAs (no
+    // feedback tile) nothing else orders it after this reduction
+    __syncthreads();
     RFILL(T_P13)                       // window of P13: refill, the frame rows of the next step's prenet into registers
     if (!early1) { RTAKE(T_P1, SL1) }
     if (early1) {                      // ... and the context rows of the next step's prenet, from TMEM
