@@ -47,6 +47,9 @@
 #ifndef TACO_DEC_QUADS
 #define TACO_DEC_QUADS 1   // exp(score) blocks cut at multiples of four pairs, sent as 16-byte words
 #endif
+#ifndef TACO_DEC_P13W12
+#define TACO_DEC_P13W12 1  // the early part of P13 runs in the window of P12 (1) or P11 (0)
+#endif
 #ifndef TACO_DEC_P8W6
 #define TACO_DEC_P8W6 1    // P8's streamed chunk-tiles are taken from the ring in the window of P6
 #endif
@@ -708,8 +711,13 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
 #if TACO_DEC_REBAL
 #define W9_WORK TLOADP(T_P10, TC10, 0, 0, 1) TLOADP(T_P11, TC11, 0, 2, 3, 4, 5) TWAIT(SL11) MMA_PRE_R(1, SL11, T_P11, 0, 4, false)
 #define W10_WORK TLOADP(T_P11, TC11, 4, 0, 1) TWAIT(SL11) MMA_PRE_R(1, SL11, T_P11, 4, 6, true)
+#if TACO_DEC_P13W12
+#define W11_WORK TLOADP(T_P12, TC12, 0, 0, 1)
+#define W12_WORK RTAKE(T_P13, SL13) MMA_PRE(2, SL13, T_P13)
+#else
 #define W11_WORK TLOADP(T_P12, TC12, 0, 0, 1) RTAKE(T_P13, SL13) MMA_PRE(2, SL13, T_P13)
 #define W12_WORK
+#endif
 #else
 #define W9_WORK TLOADP(T_P10, TC10, 0, 0, 1)
 #define W10_WORK TLOADP(T_P11, TC11, 0, 2, 3, 4, 5, 0, 1) TWAIT(SL11) MMA_PRE(1, SL11, T_P11)
