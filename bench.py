@@ -70,6 +70,16 @@ def workload_config(n_gpus: int):
     }
 
 
+_JSON_OUT = None
+
+
+def emit(line) -> None:
+    """The one JSON line of the run, on the process's original stdout."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -162,7 +172,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -385,7 +395,7 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "decoder_geometry": geo,
         }
-        print(json.dumps(line))
+        emit(line)
     for l in lanes:
         l["eng"].close()
     if dist is not None:
@@ -402,6 +412,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU restatement leg")
     ap.add_argument("--inflight", type=int, default=2, help="batches in flight per GPU (handles/streams)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on stdout when
+    # NCCL_DEBUG is set): file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved one.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
