@@ -11,9 +11,10 @@ utterance), mel + post-net linear output.  Metric: mel frames/s (whole job).
 
  * value : inputs already resident in HBM, K back-to-back steps between CUDA
            events, barrier + synchronize on both sides, max over ranks.
- * e2e   : the same step through the C-ABI host call (taco_forward_host) with
-           HOST buffers: H2D of ids/lengths/speakers and D2H of mel, linear and
-           alignments inside the timed region.
+ * e2e   : the same step through the C-ABI host calls (taco_forward_host_begin /
+           _wait / _end) with HOST buffers: H2D of ids/lengths/speakers and D2H of
+           mel, linear and alignments inside the timed region; several batches in
+           flight (one handle, stream and pinned buffer set each).
  * roofline : the decoder loop kernel (the dominant kernel): algorithmic bytes
            per launch (12.90 MB/step fp32 at N=32,T_in=100) over
            its CUDA-event duration, against the measured HBM copy peak.
@@ -203,9 +204,10 @@ def run_ours(args):
     weights = random_init(hp, ID_NUM, seed=1234)
     dev = torch.device("cuda", local)
     T_out = MAX_ITERS * R
-    n_lanes = max(1, args.inflight)
+    n_dev = max(1, args.inflight)            # lanes of the device-resident measurement
+    n_lanes = max(n_dev, args.e2e_lanes)     # lanes of the end-to-end measurement (their D2H traffic needs more of them)
     # One handle (own weights copy, workspace and CUDA stream) per batch in flight: the decoder loop
-    # occupies 64 of the 148 SMs, so a second batch's encoder / post-net fills the rest.
+    # occupies 112 of the 148 SMs for 2.2 ms, another batch's encoder / post-net (GEMMs, 64-CTA BiGRU) fills the rest and the gaps.
     lanes = []
     for li in range(n_lanes):
         e = Engine(hp, ID_NUM, local)
@@ -265,11 +267,12 @@ def run_ours(args):
             for _ in range(max(args.warmup, 3)):
                 step(l)
         l["eng"].check_ids()
-    timed(lanes, 2 * n_lanes)                        # warm the concurrent schedule too
+    dev_lanes = lanes[:n_dev]
+    timed(dev_lanes, 2 * n_dev)                      # warm the concurrent schedule too
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = sum(l["eng"].launch_count() for l in lanes)
     t_wall0 = time.time()
-    ms_total, steps_taken = timed(lanes, args.steps)
+    ms_total, steps_taken = timed(dev_lanes, args.steps)
     launches = sum(l["eng"].launch_count() for l in lanes) - launches0
     ms_per_step = ms_total / args.steps
     frames_per_step = BATCH * steps_taken * R * world
@@ -326,14 +329,19 @@ def run_ours(args):
                         al=pinned((BATCH, T_IN, MAX_ITERS), torch.float32))
         l["pin"]["ids"][:], l["pin"]["lens"][:], l["pin"]["spk"][:] = hi, hl, hs
 
-    # Lanes must not fall into lockstep (all computing, then all copying): at most n_lanes-1 of them are inside the
-    # compute half (taco_forward_host_begin) at any time, so one lane's 144 MB of D2H overlaps the others' kernels.
-    compute_slots = threading.Semaphore(max(1, n_lanes - 1))
+    # Lanes must not fall into lockstep (all computing, then all copying).  taco_forward_host_begin only enqueues; a lane
+    # holds one of the compute slots until its decoder loop is done (its post-net then fills the SMs the next lane's
+    # decoder leaves free) and gives it up before its 144 MB of D2H.  Measured on B200 (lanes, slots -> M frames/s):
+    # (2,1) 6.2-7.2, (3,2) 6.4, (4,2) 8.3-8.4, (5,2) 8.3, (6,2) 8.8, (6,3) 8.7, (8,2) 8.5.
+    n_slots = int(os.environ.get("TACO_E2E_SLOTS", 2 if n_lanes >= 3 else 1))
+    release_stage = int(os.environ.get("TACO_E2E_RELEASE", 0))   # 0: when the decoder loop is done, 1: all kernels
+    compute_slots = threading.Semaphore(n_slots)
 
     def e2e_step(l):
         b = l["pin"]
         with compute_slots:
             l["eng"].forward_host_begin(b["ids"], b["lens"], b["spk"], None, False, _abi.BN_MOVING, b["mel"], b["lin"], b["al"])
+            l["eng"].forward_host_wait(release_stage)
         return l["eng"].forward_host_end()
 
     def e2e_timed(active, n_steps):
@@ -372,8 +380,8 @@ def run_ours(args):
            "single_stream_ms_per_step": 1e3 * e2e_single_s,
            "h2d_bytes_per_step": int(pb["ids"].nbytes + pb["lens"].nbytes + pb["spk"].nbytes),
            "d2h_bytes_per_step": int(pb["mel"].nbytes + pb["lin"].nbytes + pb["al"].nbytes),
-           "api": "taco_forward_host_begin/_end (C ABI, pinned host buffers; H2D + forward + D2H per step; at most "
-                  "%d of the %d lanes in the compute half at once)" % (max(1, n_lanes - 1), n_lanes)}
+           "api": "taco_forward_host_begin/_wait/_end (C ABI, pinned host buffers; H2D + forward + D2H per step; %d lanes, "
+                  "at most %d of them between _begin and the end of their decoder loop)" % (n_lanes, n_slots)}
 
     # ---- CPU restatement on the host cores (rank 0, N=1 only) ----
     cpu = None
@@ -390,7 +398,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(world), inflight="%d batches in flight per GPU (one handle + CUDA stream "
-                                                            "each); single_stream = one at a time" % n_lanes),
+                                                            "each); single_stream = one at a time" % n_dev),
             "single_stream": single, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "decoder_geometry": geo,
@@ -410,7 +418,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU restatement leg")
-    ap.add_argument("--inflight", type=int, default=2, help="batches in flight per GPU (handles/streams)")
+    ap.add_argument("--inflight", type=int, default=4, help="batches in flight per GPU (handles/streams), device-resident leg")
+    ap.add_argument("--e2e-lanes", type=int, default=6, help="batches in flight per GPU in the end-to-end leg")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on stdout when
     # NCCL_DEBUG is set): file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved one.

@@ -114,17 +114,25 @@ int taco_forward_host(taco_handle* h, const int32_t* ids_host, const int32_t* le
                       void* stream);
 
 /* The same call in two halves, for callers that keep several batches in flight
- * (one handle + stream each): _begin copies the inputs, runs the forward (it
- * blocks only until the decoder's step count is known) and ENQUEUES the output
- * copies; _end waits for them and returns the step count.  Between the two the
- * host may start another handle's _begin, so that one batch's 144 MB of D2H
- * traffic overlaps the next batch's compute.  The host buffers must stay valid
- * until _end returns.  taco_forward_host == _begin followed by _end. */
+ * (one handle + stream each): _begin ENQUEUES the input copies, the forward and
+ * the output copies and returns without waiting for anything -- a free-running
+ * decode is enqueued for max_iters steps and its step count is read at the end
+ * (only an early stop, i.e. an exactly-zero frame, makes _end redo the post-net
+ * on the shorter length); _wait blocks until the decoder loop of that forward
+ * (TACO_STAGE_DECODER) or its last kernel (TACO_STAGE_COMPUTE) has finished --
+ * the post-net resp. the output copies may still be running -- so that a caller
+ * can start another handle's forward while this one's post-net fills the SMs
+ * the next decoder leaves free and its 144 MB of D2H traffic drains; _end
+ * waits for the copies and returns the step count.  The
+ * host buffers must stay valid until _end returns.  taco_forward_host == _begin
+ * followed by _end. */
 int taco_forward_host_begin(taco_handle* h, const int32_t* ids_host, const int32_t* lengths_host,
                             const int32_t* spk_host, const float* mel_targets_host, int N,
                             int T_in, int T_tgt, int bn_mode, int teacher_force,
                             float* mel_out_host, float* linear_out_host, float* align_out_host,
                             void* stream);
+enum { TACO_STAGE_DECODER = 0, TACO_STAGE_COMPUTE = 1 };
+int taco_forward_host_wait(taco_handle* h, int stage);
 int taco_forward_host_end(taco_handle* h, int32_t* steps_out_host, void* stream);
 
 /* ---- stage-level entry points (unit parity against the oracle) ----------- */

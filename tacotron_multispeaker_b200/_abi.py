@@ -29,7 +29,8 @@ GEMM_FFMA, GEMM_BF16X3, GEMM_BF16 = 0, 1, 2
 SYMBOLS = [
     "taco_create", "taco_destroy", "taco_last_error", "taco_version",
     "taco_set_weight", "taco_finalize_weights", "taco_num_weights", "taco_weight_name",
-    "taco_max_steps", "taco_forward", "taco_forward_host", "taco_forward_host_begin", "taco_forward_host_end",
+    "taco_max_steps", "taco_forward", "taco_forward_host", "taco_forward_host_begin", "taco_forward_host_wait",
+    "taco_forward_host_end",
     "taco_embed", "taco_check_ids", "taco_encoder", "taco_decode", "taco_cbhg", "taco_postnet",
     "taco_bigru", "taco_conv1d",
     "taco_set_gemm_mode", "taco_launch_count", "taco_decoder_geometry", "taco_decoder_work_table", "taco_set_profiling", "taco_last_stage_ms",
@@ -80,6 +81,7 @@ def load() -> C.CDLL:
     lib.taco_forward.argtypes = [H, ip, ip, ip, fp, i, i, i, i, i, fp, fp, fp, C.POINTER(C.c_int32), vp]
     lib.taco_forward_host.argtypes = [H, ip, ip, ip, fp, i, i, i, i, i, fp, fp, fp, C.POINTER(C.c_int32), vp]
     lib.taco_forward_host_begin.argtypes = [H, ip, ip, ip, fp, i, i, i, i, i, fp, fp, fp, vp]
+    lib.taco_forward_host_wait.argtypes = [H, i]
     lib.taco_forward_host_end.argtypes = [H, C.POINTER(C.c_int32), vp]
     lib.taco_decoder_work_table.argtypes = [i, C.POINTER(C.c_int32), i]
     lib.taco_embed.argtypes = [H, ip, ip, i, i, fp, vp]

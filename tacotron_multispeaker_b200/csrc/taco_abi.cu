@@ -107,9 +107,20 @@ struct taco_handle {
   int* h_pinned = nullptr;    // [0]=oob, [1]=steps   (mapped pinned memory: kernels write it directly)
   int* d_pinned = nullptr;    // device address of h_pinned
   int pending_steps = 0;      // step count of the forward started by taco_forward_host_begin
+  // Free-running decodes almost always run max_iters steps (the stop condition is an exact-zero frame), so the forward
+  // does not wait for the count in the middle: the post-net is enqueued for max_steps and the count is read from mapped
+  // pinned memory at the end.  Only if it came out smaller is the post-net redone on the right length.
+  struct Spec {
+    bool active = false;
+    int N = 0, T_in = 0, max_steps = 0, bn_mode = 0;
+    float *d_mel = nullptr, *d_lin = nullptr, *lin_host = nullptr;
+    size_t lin_bytes = 0;
+  } spec;
   int64_t launches = 0;
   bool profiling = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [4],[5] bracket the decoder kernel
+  cudaEvent_t ev_compute = nullptr;   // taco_forward_host_begin: last kernel enqueued, output copies not yet
+  cudaEvent_t ev_decoder = nullptr;   // ... and the end of the decoder loop (the post-net follows)
   float stage_ms[4] = {0, 0, 0, 0};
 };
 
@@ -938,7 +949,8 @@ size_t postnet_ws_bytes(const taco_handle* h, int N, int T) {
 }
 
 int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, const float* mel_targets, int T_tgt,
-              int teacher_force, float* dec_out, float* align_out, int32_t* steps_out_host, cudaStream_t st) {
+              int teacher_force, float* dec_out, float* align_out, int32_t* steps_out_host, cudaStream_t st,
+              bool defer_count = false) {
   Ctx c{h, st};
   const taco_hparams& hp = h->hp;
   if (T_in > 512) return fail(h, TACO_ERR_UNSUPPORTED, "T_in > 512 not supported by the decoder kernel");
@@ -996,8 +1008,10 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
     // another handle's 144 MB output transfer and stall this forward in the middle (batches in flight on other streams).
     launch_find_steps(dec_out, N, max_steps, hp.num_mels * hp.outputs_per_step, h->d_ints + 2, h->d_pinned + 1, st);
     h->launches += 3;
-    CUDA_OK(h, cudaStreamSynchronize(st));
-    steps = *(volatile int*)(h->h_pinned + 1);
+    if (!defer_count) {
+      CUDA_OK(h, cudaStreamSynchronize(st));
+      steps = *(volatile int*)(h->h_pinned + 1);
+    }   // else: optimistic max_steps; the caller reads h_pinned[1] after its own synchronisation
   }
   if (steps_out_host) *steps_out_host = steps;
   return check_launch(h, "decoder");
@@ -1051,6 +1065,8 @@ int taco_create(const taco_hparams* hp, int device, taco_handle** out) {
   if (cudaHostAlloc(&h->h_pinned, sizeof(int) * 4, cudaHostAllocMapped) != cudaSuccess ||
       cudaHostGetDevicePointer(&h->d_pinned, h->h_pinned, 0) != cudaSuccess) { delete h; return TACO_ERR_CUDA; }
   for (int i = 0; i < 6; ++i) cudaEventCreate(&h->ev[i]);
+  cudaEventCreateWithFlags(&h->ev_compute, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_decoder, cudaEventDisableTiming);
   if (ensure_ints(h, 2 + 1024) != TACO_OK) { taco_destroy(h); return TACO_ERR_CUDA; }
   *out = h;
   return TACO_OK;
@@ -1067,6 +1083,8 @@ int taco_destroy(taco_handle* h) {
   if (h->d_ints) cudaFree(h->d_ints);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->ev_compute) cudaEventDestroy(h->ev_compute);
+  if (h->ev_decoder) cudaEventDestroy(h->ev_decoder);
   delete h;
   return TACO_OK;
 }
@@ -1374,9 +1392,24 @@ int taco_conv1d(taco_handle* h, const float* x, int N, int T, int Cin, const flo
   return check_launch(h, "conv1d");
 }
 
-int taco_forward(taco_handle* h, const int32_t* ids, const int32_t* lengths, const int32_t* spk,
-                 const float* mel_targets, int N, int T_in, int T_tgt, int bn_mode, int teacher_force, float* mel_out,
-                 float* linear_out, float* align_out, int32_t* steps_out_host, void* stream) {
+// Post-net again on the true length after an early stop (the all-zero frame case): rare, synchronous.
+static int redo_postnet(taco_handle* h, int N, int T_in, int max_steps, int steps, int bn_mode, const float* mel,
+                        float* linear_out, cudaStream_t st) {
+  const taco_hparams& hp = h->hp;
+  const int r = hp.outputs_per_step, maxT = max_steps * r;
+  Bump ws(h->ws, h->ws_bytes);
+  ws.take<float>((size_t)N * T_in * 256);   // same carve-up as the forward: encoder memory first
+  int rc = do_postnet(h, ws, mel, N, steps * r, bn_mode, (int64_t)maxT * hp.num_mels, linear_out,
+                      (int64_t)maxT * hp.num_freq, st);
+  if (rc) return rc;
+  CUDA_OK(h, cudaStreamSynchronize(st));
+  return TACO_OK;
+}
+
+// defer_final: do not synchronise at all (taco_forward_host_begin); the caller finishes with finish_spec().
+static int forward_impl(taco_handle* h, const int32_t* ids, const int32_t* lengths, const int32_t* spk,
+                        const float* mel_targets, int N, int T_in, int T_tgt, int bn_mode, int teacher_force, float* mel_out,
+                        float* linear_out, float* align_out, int32_t* steps_out_host, void* stream, bool defer_final) {
   REQUIRE_READY(h);
   if (!ids || !mel_out || N <= 0 || T_in <= 0) return fail(h, TACO_ERR_INVALID, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1401,9 +1434,11 @@ int taco_forward(taco_handle* h, const int32_t* ids, const int32_t* lengths, con
   if (h->profiling) cudaEventRecord(h->ev[1], st);
   ws.off = mark;   // encoder scratch is dead; stream order keeps reuse safe
   int steps = 0;
-  rc = do_decode(h, ws, memory, N, T_in, mel_targets, T_tgt, teacher_force, mel_out, align_out, &steps, st);
+  rc = do_decode(h, ws, memory, N, T_in, mel_targets, T_tgt, teacher_force, mel_out, align_out, &steps, st,
+                 /*defer_count=*/true);
   if (rc) return rc;
   if (h->profiling) cudaEventRecord(h->ev[2], st);
+  if (defer_final) cudaEventRecord(h->ev_decoder, st);
   if (steps_out_host) *steps_out_host = steps;
   if (linear_out) {
     ws.off = mark;
@@ -1411,13 +1446,36 @@ int taco_forward(taco_handle* h, const int32_t* ids, const int32_t* lengths, con
                     (int64_t)maxT * hp.num_freq, st);
     if (rc) return rc;
   }
-  if (h->profiling) {
-    cudaEventRecord(h->ev[3], st);
+  if (h->profiling) cudaEventRecord(h->ev[3], st);
+  h->spec.active = false;
+  if (!teacher_force) {
+    if (defer_final) {
+      h->spec.active = true;
+      h->spec.N = N; h->spec.T_in = T_in; h->spec.max_steps = max_steps; h->spec.bn_mode = bn_mode;
+      h->spec.d_mel = mel_out; h->spec.d_lin = linear_out;
+    } else {
+      CUDA_OK(h, cudaStreamSynchronize(st));
+      steps = *(volatile int*)(h->h_pinned + 1);
+      if (steps != max_steps && linear_out) {
+        rc = redo_postnet(h, N, T_in, max_steps, steps, bn_mode, mel_out, linear_out, st);
+        if (rc) return rc;
+      }
+      if (steps_out_host) *steps_out_host = steps;
+    }
+  }
+  if (h->profiling && !defer_final) {
     cudaEventSynchronize(h->ev[3]);
     for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&h->stage_ms[i], h->ev[i], h->ev[i + 1]);
     cudaEventElapsedTime(&h->stage_ms[3], h->ev[4], h->ev[5]);
   }
   return TACO_OK;
+}
+
+int taco_forward(taco_handle* h, const int32_t* ids, const int32_t* lengths, const int32_t* spk,
+                 const float* mel_targets, int N, int T_in, int T_tgt, int bn_mode, int teacher_force, float* mel_out,
+                 float* linear_out, float* align_out, int32_t* steps_out_host, void* stream) {
+  return forward_impl(h, ids, lengths, spk, mel_targets, N, T_in, T_tgt, bn_mode, teacher_force, mel_out, linear_out,
+                      align_out, steps_out_host, stream, /*defer_final=*/false);
 }
 
 int taco_forward_host_begin(taco_handle* h, const int32_t* ids_host, const int32_t* lengths_host, const int32_t* spk_host,
@@ -1459,21 +1517,48 @@ int taco_forward_host_begin(taco_handle* h, const int32_t* ids_host, const int32
   if (n_tgt) cp(d_tgt, mel_targets_host, sizeof(float) * n_tgt, cudaMemcpyHostToDevice);
   int steps = 0;
   if (rc == TACO_OK)
-    rc = taco_forward(h, d_ids, lengths_host ? d_len : nullptr, spk_host ? d_spk : nullptr, d_tgt, N, T_in, T_tgt,
-                      bn_mode, teacher_force, d_mel, d_lin, d_al, &steps, stream);
+    rc = forward_impl(h, d_ids, lengths_host ? d_len : nullptr, spk_host ? d_spk : nullptr, d_tgt, N, T_in, T_tgt,
+                      bn_mode, teacher_force, d_mel, d_lin, d_al, &steps, stream, /*defer_final=*/true);
   if (rc == TACO_OK) {
+    cudaEventRecord(h->ev_compute, st);
     cp(mel_out_host, d_mel, sizeof(float) * n_mel, cudaMemcpyDeviceToHost);
     if (n_lin) cp(linear_out_host, d_lin, sizeof(float) * n_lin, cudaMemcpyDeviceToHost);
     if (n_al) cp(align_out_host, d_al, sizeof(float) * n_al, cudaMemcpyDeviceToHost);
   }
   h->pending_steps = steps;
-  return rc;   // the output copies are in flight on `stream`: taco_forward_host_end waits for them
+  h->spec.lin_host = linear_out_host;
+  h->spec.lin_bytes = sizeof(float) * n_lin;
+  return rc;   // nothing was waited for: kernels and output copies are in flight on `stream` (taco_forward_host_end)
+}
+
+int taco_forward_host_wait(taco_handle* h, int stage) {
+  REQUIRE_READY(h);
+  if (stage != TACO_STAGE_DECODER && stage != TACO_STAGE_COMPUTE) return fail(h, TACO_ERR_INVALID, "bad stage");
+  const cudaError_t e = cudaEventSynchronize(stage == TACO_STAGE_DECODER ? h->ev_decoder : h->ev_compute);
+  if (e != cudaSuccess) return fail(h, TACO_ERR_CUDA, std::string("event sync: ") + cudaGetErrorString(e));
+  return TACO_OK;
 }
 
 int taco_forward_host_end(taco_handle* h, int32_t* steps_out_host, void* stream) {
   REQUIRE_READY(h);
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   if (e != cudaSuccess) return fail(h, TACO_ERR_CUDA, std::string("sync: ") + cudaGetErrorString(e));
+  if (h->spec.active) {   // free-running forward enqueued with the optimistic step count
+    h->spec.active = false;
+    const int steps = *(volatile int*)(h->h_pinned + 1);
+    if (steps != h->spec.max_steps && h->spec.d_lin) {
+      int rc2 = redo_postnet(h, h->spec.N, h->spec.T_in, h->spec.max_steps, steps, h->spec.bn_mode, h->spec.d_mel,
+                             h->spec.d_lin, (cudaStream_t)stream);
+      if (rc2) return rc2;
+      if (cudaMemcpy(h->spec.lin_host, h->spec.d_lin, h->spec.lin_bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail(h, TACO_ERR_CUDA, "memcpy failed");
+    }
+    h->pending_steps = steps;
+    if (h->profiling) {
+      for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&h->stage_ms[i], h->ev[i], h->ev[i + 1]);
+      cudaEventElapsedTime(&h->stage_ms[3], h->ev[4], h->ev[5]);
+    }
+  }
   const int rc = taco_check_ids(h, stream);
   if (steps_out_host) *steps_out_host = h->pending_steps;
   return rc;

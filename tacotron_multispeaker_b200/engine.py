@@ -229,6 +229,11 @@ class Engine:
                                                   int(teacher_force), hp_(mel_out), hp_(linear_out), hp_(align_out),
                                                   self.stream))
 
+    def forward_host_wait(self, stage: int = 1) -> None:
+        """``taco_forward_host_wait``: block until the decoder loop (stage 0) or all kernels (stage 1) of the forward
+        begun on this handle are done (its post-net resp. output copies may still be in flight)."""
+        self._ck(self.lib.taco_forward_host_wait(self._h, stage))
+
     def forward_host_end(self) -> int:
         """``taco_forward_host_end``: wait for the output copies of the forward begun on this handle; step count."""
         steps = C.c_int32(0)
