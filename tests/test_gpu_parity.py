@@ -295,6 +295,35 @@ def test_stop_token_kat(small_hp):
     e.close()
 
 
+def test_stop_token_kat_host_path(small_hp):
+    """The same early stop through taco_forward_host_begin/_wait/_end: the forward is enqueued for max_iters steps
+    (optimistic), _end finds steps == 1 and redoes the post-net on the true length before returning."""
+    from tacotron_multispeaker_b200.engine import Engine
+    from tacotron_multispeaker_b200.weights import random_init
+    hp = small_hp
+    w = random_init(hp, 0, seed=9)
+    w["model/inference/decoder/output_projection_wrapper/kernel"][:] = 0.0
+    w["model/inference/decoder/output_projection_wrapper/bias"][:] = 0.0
+    e = Engine(hp, 0)
+    e.load_weights(w)
+    N, T_in = 3, 9
+    ids, lengths, _ = make_inputs(N, T_in, 1, 6)
+    ms = e.max_steps(False, 0)
+    mel = np.full((N, ms * hp.outputs_per_step, 80), 7.0, np.float32)
+    lin = np.full((N, ms * hp.outputs_per_step, 1025), 7.0, np.float32)
+    al = np.zeros((N, T_in, ms), np.float32)
+    e.forward_host_begin(ids, lengths, None, None, False, 0, mel, lin, al)
+    e.forward_host_wait(0)
+    e.forward_host_wait(1)
+    steps = e.forward_host_end()
+    assert steps == 1
+    ref = O.tacotron_forward(w, hp, ids, lengths)
+    r = hp.outputs_per_step
+    assert float(np.abs(mel[:, :r]).max()) == 0.0
+    assert maxabs(torch.from_numpy(lin[:, :r]), ref["linear_outputs"]) < 1e-3
+    e.close()
+
+
 def test_forward_host_matches_device(eng, small_hp):
     hp = small_hp
     N, T_in = 3, 14
