@@ -49,8 +49,10 @@ struct UmmaArgs {
   const float* res; long long res_bs; int ldres;
   float* out; long long out_bs; int ldo; int col_off;
   int act, epi;
-  int stages;              // smem ring depth (1..3): short-K launches use fewer so that 2-3 CTAs share an SM
+  int stages;              // smem ring depth (1..3)
   int vec_epi;             // 1: rows are 16 B aligned -> direct 128-bit stores from the TMEM registers
+  int nx, ny, ntiles;      // tile list: nx = N * ceil(T / 128) row tiles, ny column tiles, ntiles = nx * ny * bank
+  int acc_cols;            // TMEM columns to allocate: 256 (two accumulators, persistent CTAs) or 128 (one tile per CTA)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------
@@ -59,6 +61,9 @@ __device__ __forceinline__ void mbar_init(uint32_t mb, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t mb, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mb) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t mb, uint32_t parity) {
   asm volatile(
@@ -127,21 +132,32 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   float* epi = reinterpret_cast<float*>(smem_al + STAGES * STAGE_BYTES);
-  const uint32_t bar0 = smem_base + STAGES * STAGE_BYTES + epi_bytes;    // full[S], empty[S], tmem_full, tmem ptr
+  const uint32_t bar0 = smem_base + STAGES * STAGE_BYTES + epi_bytes;    // full[S], empty[S], tmem_full[2], tmem_empty[2], tmem ptr
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
-  const uint32_t tfull_bar = bar0 + 8u * (2 * MAX_STAGES);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + STAGES * STAGE_BYTES + epi_bytes + 8 * (2 * MAX_STAGES + 1));
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 2 + b); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + STAGES * STAGE_BYTES + epi_bytes + 8 * (2 * MAX_STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tps = (p.T + BM - 1) / BM;
-  const int n = blockIdx.x / tps, t0 = (blockIdx.x - n * tps) * BM;
-  const int o0 = blockIdx.y * BN;
-  const int ci = p.bank > 1 ? p.bank - 1 - (int)blockIdx.z : 0;          // heavy convs first
-  const int taps = p.bank > 1 ? ci + 1 : p.taps;
-  const int pl = (taps - 1) >> 1;
-  const int kcb = p.Cp / BK, nkb = taps * kcb;
-  const int brow0 = ci * p.Cout + o0;
+  const int kcb = p.Cp / BK;
+  // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... in the order (conv of the bank, heavy first; column
+  // tile; row tile fastest, so that the CTAs working at the same time share their weight tiles in L2).  The TMA, MMA and
+  // epilogue roles each walk the same list; the accumulator alternates between two 128-column TMEM buffers, so the
+  // epilogue of tile i overlaps the loads and MMAs of tile i+1.
+  struct Tile { int n, t0, o0, ci, taps, pl, nkb, brow0; };
+  auto decode = [&](int L) {
+    Tile q;
+    const int x = L % p.nx, r = L / p.nx, y = r % p.ny, z = r / p.ny;   // row tile fastest: neighbours share the weight tile
+    q.n = x / tps; q.t0 = (x - q.n * tps) * BM; q.o0 = y * BN;
+    q.ci = p.bank > 1 ? p.bank - 1 - z : 0;                               // heavy convs first
+    q.taps = p.bank > 1 ? q.ci + 1 : p.taps;
+    q.pl = (q.taps - 1) >> 1;
+    q.nkb = q.taps * kcb;
+    q.brow0 = q.ci * p.Cout + q.o0;
+    return q;
+  };
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA_hi)) : "memory");
@@ -151,11 +167,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB_lo)) : "memory");
     }
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tfull_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }   // 4 epilogue warps release a buffer
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {   // TMEM: 128 fp32 accumulator columns, allocated (and later freed) by this warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(128u) : "memory");
+  if (warp == 2) {   // TMEM: two 128-column fp32 accumulators, allocated (and later freed) by this warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)p.acc_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -166,18 +182,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(empty_bar(s), ((kb / STAGES) & 1) ^ 1);
-        const uint32_t st = smem_base + s * STAGE_BYTES;
-        mbar_expect_tx(full_bar(s), NSPLIT > 1 ? STAGE_BYTES : 2 * TILE_BYTES);
-        const int j = kb / kcb, c0 = (kb - j * kcb) * BK;
-        const int tt = t0 + j - pl;                                       // may be < 0 or run past T: zero fill
-        tma_load_3d(st, &tmA_hi, full_bar(s), c0, tt, n);
-        tma_load_2d(st + 2 * TILE_BYTES, &tmB_hi, full_bar(s), j * p.Cp + c0, brow0);
-        if (NSPLIT > 1) {
-          tma_load_3d(st + TILE_BYTES, &tmA_lo, full_bar(s), c0, tt, n);
-          tma_load_2d(st + 3 * TILE_BYTES, &tmB_lo, full_bar(s), j * p.Cp + c0, brow0);
+      int it = 0;                                                         // k-block counter over all tiles of this CTA
+      for (int L = blockIdx.x; L < p.ntiles; L += gridDim.x) {
+        const Tile q = decode(L);
+        for (int kb = 0; kb < q.nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
+          const uint32_t st = smem_base + s * STAGE_BYTES;
+          mbar_expect_tx(full_bar(s), NSPLIT > 1 ? STAGE_BYTES : 2 * TILE_BYTES);
+          const int j = kb / kcb, c0 = (kb - j * kcb) * BK;
+          const int tt = q.t0 + j - q.pl;                                 // may be < 0 or run past T: zero fill
+          tma_load_3d(st, &tmA_hi, full_bar(s), c0, tt, q.n);
+          tma_load_2d(st + 2 * TILE_BYTES, &tmB_hi, full_bar(s), j * p.Cp + c0, q.brow0);
+          if (NSPLIT > 1) {
+            tma_load_3d(st + TILE_BYTES, &tmA_lo, full_bar(s), c0, tt, q.n);
+            tma_load_2d(st + 3 * TILE_BYTES, &tmB_lo, full_bar(s), j * p.Cp + c0, q.brow0);
+          }
         }
       }
     }
@@ -186,30 +206,44 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     if (lane == 0) {
       // kind::f16: C=F32 (bit4), A=BF16 (bit7), B=BF16 (bit10), both K-major, N>>3 at bit17, M>>4 at bit24
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(full_bar(s), (kb / STAGES) & 1);
+      int it = 0, i = 0;
+      for (int L = blockIdx.x; L < p.ntiles; L += gridDim.x, ++i) {
+        const Tile q = decode(L);
+        const int b = i & 1;
+        mbar_wait(tempty_bar(b), ((i >> 1) & 1) ^ 1);                     // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t st = smem_base + s * STAGE_BYTES;
-        const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + TILE_BYTES);
-        const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES), b_lo = umma_desc(st + 3 * TILE_BYTES);
+        const uint32_t acc = tmem_base + (uint32_t)(b * BN);
+        for (int kb = 0; kb < q.nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(full_bar(s), (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t st = smem_base + s * STAGE_BYTES;
+          const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + TILE_BYTES);
+          const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES), b_lo = umma_desc(st + 3 * TILE_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          const uint64_t adv = (uint64_t)(kk * 32 >> 4);                  // 16 bf16 = 32 B along K inside the swizzle row
-          umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | kk) != 0);
-          if (NSPLIT > 1) {
-            umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-            umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 32 >> 4);                // 16 bf16 = 32 B along K inside the swizzle row
+            umma_bf16(acc, a_hi + adv, b_hi + adv, idesc, (kb | kk) != 0);
+            if (NSPLIT > 1) {
+              umma_bf16(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_bf16(acc, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
           }
+          umma_commit(empty_bar(s));                                      // stage free once these MMAs have read it
         }
-        umma_commit(empty_bar(s));                                        // stage free once these MMAs have read it
+        umma_commit(tfull_bar(b));                                        // accumulator complete
       }
-      umma_commit(tfull_bar);                                             // accumulator complete
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;                                         // TMEM lanes this warp may read
-    mbar_wait(tfull_bar, 0);
+    int i = 0;
+    for (int L = blockIdx.x; L < p.ntiles; L += gridDim.x, ++i) {
+    const Tile q = decode(L);
+    const int n = q.n, t0 = q.t0, o0 = q.o0, ci = q.ci;
+    const int ab = i & 1;
+    const uint32_t acc = tmem_base + (uint32_t)(ab * BN);
+    mbar_wait(tfull_bar(ab), (i >> 1) & 1);
     tc_fence_after();
     const float* bias = p.bias ? p.bias + ci * p.Cout : nullptr;
     const float* scale = p.scale ? p.scale + ci * p.Cout : nullptr;
@@ -226,7 +260,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int cbase = o0 + ch * 32;
         if (cbase >= p.Cout) break;                                       // warp-uniform
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), v);
+        tmem_ld32(acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), v);
         if (p.epi == EPI_PLAIN) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
@@ -283,7 +317,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int cbase = o0 + ch * 32;
         if (cbase >= p.Cout) break;                                       // warp-uniform
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), v);
+        tmem_ld32(acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), v);
 #pragma unroll
         for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = __uint_as_float(v[c]);
         __syncwarp();
@@ -332,12 +366,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         __syncwarp();
       }
     }
+    // this warp has read its lanes of the accumulator: hand the buffer back to the MMA issuer
     tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty_bar(ab));
+    }   // tile loop
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.acc_cols) : "memory");
   }
 }
 
@@ -454,17 +493,43 @@ cudaError_t launch_conv_umma(const ConvUmma& c, cudaStream_t st) {
   p.N = c.N; p.T = c.T; p.Cp = c.Cp; p.taps = c.taps; p.bank = c.bank; p.Cout = c.Cout;
   p.bias = c.bias; p.scale = c.scale; p.shift = c.shift; p.res = c.res; p.res_bs = c.res_bs; p.ldres = c.ldres;
   p.out = c.out; p.out_bs = c.out_bs; p.ldo = c.ldo; p.col_off = c.col_off; p.act = c.act; p.epi = c.epi;
-  dim3 grid(c.N * ((c.T + BM - 1) / BM), (c.Cout + BN - 1) / BN, c.bank > 1 ? c.bank : 1);
-  // ring depth: deep for long K; short-K launches are epilogue/launch bound and gain from 2-3 CTAs per SM
+  // Persistent grid: one CTA per SM (three 64 KB stages), each walking its share of the tiles.
+  p.nx = c.N * ((c.T + BM - 1) / BM);
+  p.ny = (c.Cout + BN - 1) / BN;
+  const long long ntiles = (long long)p.nx * p.ny * (c.bank > 1 ? c.bank : 1);
+  if (ntiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+  p.ntiles = (int)ntiles;
+  // Long-K launches (the 3 x 1024 -> 256 projection, the encoder bank) are bound by loads and MMAs: persistent CTAs,
+  // one per SM with three 64 KB stages, overlap the epilogue of tile i with the main loop of tile i+1 (171 -> 140 us).
+  // Short-K launches are bound by the epilogue (four warps per CTA drain TMEM and write 64 KB per tile): there one tile
+  // per CTA with a shallow ring lets two or three CTAs share an SM, i.e. 8-12 epilogue warps (persistent: 158 -> 221 us
+  // on the final dense, measured).
   const int nkb_max = c.taps * (c.Cp / BK);
-  p.stages = nkb_max >= 6 ? 3 : (nkb_max >= 3 ? 2 : 1);
-  // many more CTAs than SMs: a one-stage CTA (82 KB) lets two or three CTAs share an SM, so one CTA's epilogue
-  // overlaps its neighbours' loads and MMAs -- measured 2.08 -> 1.87 ms on the post-net of config 3
-  if ((long long)grid.x * grid.y * grid.z >= 1024) p.stages = 1;
-  {   // developer switch: TACO_UMMA_STAGES_MAX caps the ring depth (more CTAs per SM, less pipelining per CTA)
+  static const int force = [] { const char* e = getenv("TACO_UMMA_PERSISTENT"); return e ? atoi(e) : -1; }();
+  const bool persistent = force >= 0 ? force != 0 : nkb_max >= 24;
+  if (persistent) {
+    p.stages = MAX_STAGES;
+  } else {
+    p.stages = nkb_max >= 6 ? 3 : (nkb_max >= 3 ? 2 : 1);
+    if (ntiles >= 1024) p.stages = 1;
+  }
+  {   // developer switch: TACO_UMMA_STAGES_MAX caps the ring depth
     static const int cap = [] { const char* e = getenv("TACO_UMMA_STAGES_MAX"); return e ? atoi(e) : 0; }();
     if (cap >= 1 && p.stages > cap) p.stages = cap;
   }
+  static int n_sm[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (n_sm[dev & 63] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n_sm[dev & 63] = v;
+  }
+  static const int cta_cap = [] { const char* e = getenv("TACO_UMMA_CTAS"); return e ? atoi(e) : 0; }();
+  int nctas = persistent ? (cta_cap > 0 ? cta_cap : n_sm[dev & 63]) : p.ntiles;
+  if (nctas > p.ntiles) nctas = p.ntiles;
+  p.acc_cols = nctas < p.ntiles ? 256 : 128;
+  dim3 grid(nctas, 1, 1);
   const int chn = c.epi == EPI_HIGHWAY ? 2 : 1;
   auto al4 = [](long long v) { return (v & 3) == 0; };
   p.vec_epi = (al4(c.ldo) && al4(c.col_off) && al4(c.out_bs) && al4(c.Cout / chn) && (c.Cout % (4 * chn) == 0) &&
@@ -476,8 +541,6 @@ cudaError_t launch_conv_umma(const ConvUmma& c, cudaStream_t st) {
   if (c.epi == EPI_HIGHWAY && (c.bias == nullptr || c.res == nullptr)) return cudaErrorInvalidValue;
   const uint32_t smem = smem_bytes(p.stages, !p.vec_epi);
   static bool attr_done[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
   bool& attr_set = attr_done[dev & 63];
   if (!attr_set) {
     cudaError_t e1 = cudaFuncSetAttribute(conv_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_STAGES, true));
