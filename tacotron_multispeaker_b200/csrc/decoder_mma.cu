@@ -1,4 +1,4 @@
-// K7 (v4): the attention decoder loop as one persistent cluster kernel whose mat-vecs run on
+// K7 (v5): the attention decoder loop as one persistent cluster kernel whose mat-vecs run on
 // the warp-level tensor-core path (mma.sync m16n8k16, bf16 hi/lo split = fp32-class accuracy).
 //
 // Operator: tf.contrib.seq2seq.dynamic_decode(BasicDecoder(output_cell, helper, zero_state),
@@ -7,52 +7,44 @@
 // AttentionWrapper, two ResidualWrapper(GRUCell(256)), the 80*r output
 // projection and TacoTestHelper / TacoTrainingHelper (models/helpers.py:26-38,68-77).
 //
-// What the measurements of round 1 said about the previous kernels (decoder.cu, decoder_v3.cu):
-// they are bound by instruction issue (~5800 SASS instructions per thread and step, 16 warps)
-// and by the cluster exchange (~500-700 clk per all-gather, ~2.5 clk per DSMEM transaction),
-// not by bytes.  This kernel is built around those two numbers:
+// The earlier kernels (decoder.cu, decoder_v3.cu) are bound by instruction issue and by the cluster
+// exchange (~500-700 clk per all-gather), not by bytes.  This one is built around the measurements
+// listed in DESIGN.md section 4 (K7):
 //
 //  * a cluster of 16 CTAs owns S <= 8 utterances (S is a RUNTIME value per cluster, so a batch
 //    of 32 is cut 5,5,5,5,4,4,4 over the 7 clusters of 16 that fit on a B200 at once);
 //  * every weight matrix is cut by output columns into 16-column tiles, one (or two/three) per
 //    CTA and phase.  A tile times the S activations is a chain of m16n8k16 MMAs over 16-row
 //    chunks of K: A = W^T tile (bf16 hi and lo, pre-packed on the host in register-fragment
-//    order, streamed from L2 straight into registers one phase ahead), B = 16 inputs x 8
-//    samples (bf16 hi and lo, one LDS.128 per chunk), D = hi*hi + lo*hi + hi*lo in fp32.
-//    K is reduced inside the tensor core: no shuffle trees, ~10 instructions per chunk;
-//  * warps split the chunks of a phase; their partial tiles meet in shared memory after one
-//    block barrier and a group of four warps finishes the phase, one thread per (sample, column):
-//    sum, bias, gate math on the fp32 recurrent state, hi/lo split, pack.  After a second barrier
-//    warp p sends that S*64-byte block to peer p with one st.async instruction (the block is
-//    contiguous in the receiver's buffer: 16 DSMEM transactions per push instead of 256, and
-//    the 16 sends leave from 16 warps at once);
-//  * nothing on the step path touches local memory or indexed constants: the per-warp work
-//    table and the reducer's state sit in shared memory, the weight stream bypasses L1
-//    (L1::no_allocate), so the ~150-250 clk L1-miss stalls of the first version are gone;
+//    order: a 1 KB "chunk-tile"), B = 16 inputs x 8 samples (bf16 hi and lo, one LDS.128 per
+//    chunk, requested one chunk ahead), D = hi*hi + lo*hi + hi*lo in fp32;
+//  * the chunk-tiles of both decoder GRUs live in TENSOR MEMORY (written once with tcgen05.st,
+//    fetched with tcgen05.ld.32x32b.x8 into the A registers 40-50 clk before use); the rest is
+//    re-read from L2 by cp.async into a per-warp ring in shared memory whose groups are counted
+//    explicitly (loads straight into registers are tied to the register scoreboards and cannot
+//    run more than one exchange window ahead);
+//  * operands that are complete before a phase's exchange (recurrent states, the context of the
+//    previous step, y0 / h1' for the sums y1, y2) are multiplied in an EARLIER exchange window
+//    (mma_split<0>); the late part after the wait adds only what has just arrived.  Operand
+//    passes are skipped with real branches: a predicated-off HMMA still occupies the tensor pipe;
+//  * warps split the chunks of a phase (host-side work table); their partial tiles meet in shared
+//    memory after ONE block barrier, reducer groups on the least loaded warps (12-15 / 8-11 / 4-7)
+//    finish the phase -- sum, bias, gate math on the fp32 recurrent state, hi/lo split -- and each
+//    reducer warp pushes the rows it staged itself to all 16 peers (st.async + mbarrier tx bytes);
+//  * the warp index comes from a shuffle (ptxas then proves it uniform: no WARPSYNC / BSSY around
+//    per-warp decisions), every shared-memory region starts on a 128-byte line, the clock-stamp
+//    tracing is a separate template instantiation;
 //  * activations live in shared memory in MMA-fragment order X[chunk][sample][16 words]
 //    (words t*4+{0,1} = hi pairs k=2t,2t+1 / 2t+8,2t+9, words t*4+{2,3} = lo pairs), which is
 //    exactly what the producing lane holds, so nothing is ever transposed;
-//  * attention: exp(score - B) with B = min(||v||_1, 40) >= score is pushed instead of the raw
-//    score, so the softmax needs no max pass and its normaliser is summed with the context.
+//  * attention: v.tanh(k+p) through e^{2k} e^{2p} with one MUFU.RCP per four elements; exp(score - B)
+//    with B = min(||v||_1, 40) >= score is pushed instead of the raw score (16-byte words), so the
+//    softmax needs no max pass and its normaliser is summed with the context.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.cuh"
-
-// A/B switches (same-box comparisons with tools/ab): all on by default
-#ifndef TACO_DEC_REBAL
-#define TACO_DEC_REBAL 1   // early parts of P11 / P13 spread over the windows with slack
-#endif
-#ifndef TACO_DEC_QUADS
-#define TACO_DEC_QUADS 1   // exp(score) blocks cut at multiples of four pairs, sent as 16-byte words
-#endif
-#ifndef TACO_DEC_P13W12
-#define TACO_DEC_P13W12 1  // the early part of P13 runs in the window of P12 (1) or P11 (0)
-#endif
-#ifndef TACO_DEC_P8W6
-#define TACO_DEC_P8W6 1    // P8's streamed chunk-tiles are taken from the ring in the window of P6
-#endif
 
 namespace taco {
 
@@ -157,10 +149,6 @@ __device__ __forceinline__ void st_async_v4(uint32_t raddr, uint4 v, uint32_t rm
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
                ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rmbar) : "memory");
 }
-__device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t a, uint32_t rmbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
-               ::"r"(raddr), "r"(a), "r"(rmbar) : "memory");
-}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -249,10 +237,6 @@ __device__ __forceinline__ void ring_refill(Ring& r, const uint4* __restrict__ w
 // the four heaviest phases (both decoder GRUs: 16 chunk-tiles of 1 KB per warp).  A warp reads and writes its own lane
 // quarter (warp % 4) with the 32x32b shape: x8 = the eight 32-bit words (hi uint4, lo uint4) of one chunk-tile per lane.
 // Measured (tools/ubench/tmem_ld.cu): 40-50 clk load+wait, ~800 B/clk/SM with 16 warps, and no LSU / L2 traffic.
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint4& hi, uint4& lo) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w), "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(taddr));
-}
 __device__ __forceinline__ void tmem_ld8_if(bool on, uint32_t taddr, uint4& hi, uint4& lo) {   // `on` is warp-uniform
   asm volatile(
       "{\n"
@@ -280,29 +264,6 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint4& a, uint32_t
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
-}
-// One chunk of a work item: B fragment from shared memory, then hh += W_hi x_hi, lh += W_lo x_hi, hl += W_hi x_lo.
-// `on` is warp-uniform.  The block is skipped with a REAL branch (bra.uni): ptxas otherwise predicates the three HMMAs,
-// and a predicated-off HMMA still occupies the tensor pipe for its 8 cycles -- measured: a warp with no work in a phase
-// took as long as one with six chunks, and slowed the three warps it shares the pipe with.
-__device__ __forceinline__ void mma3_if(bool on, float (&hh)[4], float (&hl)[4], float (&lh)[4], const uint4& a, const uint4& b,
-                                        uint32_t xaddr) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      ".reg .b32 x0, x1, x2, x3;\n"
-      "setp.ne.u32 p, %21, 0;\n"
-      "@!p bra.uni MMA3_SKIP;\n"
-      "ld.shared.v4.b32 {x0, x1, x2, x3}, [%20];\n"
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%12,%13,%14,%15}, {x0,x1}, {%0,%1,%2,%3};\n"
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%8,%9,%10,%11}, {%16,%17,%18,%19}, {x0,x1}, {%8,%9,%10,%11};\n"
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%4,%5,%6,%7}, {%12,%13,%14,%15}, {x2,x3}, {%4,%5,%6,%7};\n"
-      "MMA3_SKIP:\n"
-      "}\n"
-      : "+f"(hh[0]), "+f"(hh[1]), "+f"(hh[2]), "+f"(hh[3]), "+f"(hl[0]), "+f"(hl[1]), "+f"(hl[2]), "+f"(hl[3]),
-        "+f"(lh[0]), "+f"(lh[1]), "+f"(lh[2]), "+f"(lh[3])
-      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "r"(xaddr), "r"((uint32_t)on)
-      : "memory");
 }
 // One operand pass of a work item: chunks 0..cnt-1 of the activation buffer at xaddr against the weight slots SL.
 // The B fragment of chunk i+1 is requested before the MMAs of chunk i (two register sets), so that the three
@@ -344,10 +305,6 @@ __device__ __forceinline__ uint4 pack_x(float4 v) {
   split2(v.z, v.w, r.y, r.w);
   return r;
 }
-
-// position of column c (0..15) of a tile inside a 16-float row: the four columns
-// {2t, 2t+1, 2t+8, 2t+9} that lane (n, t) finishes sit at floats t*4 .. t*4+3
-__host__ __device__ __forceinline__ int pos16(int c) { return ((c & 7) >> 1) * 4 + (c >> 3) * 2 + (c & 1); }
 
 // The weight registers are six slots of one chunk-tile (hi, lo uint4) each.  Every phase names the slots its chunks
 // use, chosen so that consecutive phases use disjoint slots wherever they fit: the stream of phase p+1 (or p+2) is
@@ -408,7 +365,6 @@ __device__ __forceinline__ void wait_t(uint4 (&wb)[NWB], Slots<SL...>) {
 template <int NX, int... SL>
 __device__ __forceinline__ void mma_chunks(const uint4 (&wb)[NWB], uint32_t xaddr, uint32_t csb, int cnt, uint32_t slot,
                                            int g, int t, Slots<SL...>, int nx = 0, uint32_t d1 = 0, uint32_t d2 = 0) {
-  constexpr int sl[] = {SL...};
   constexpr int I0 = 0, I1 = 8;
   float hh[4] = {0.f, 0.f, 0.f, 0.f}, hl[4] = {0.f, 0.f, 0.f, 0.f}, lh[4] = {0.f, 0.f, 0.f, 0.f};
   // one branch per operand pass (a block of this size is not if-converted), per-chunk predicates inside
@@ -439,7 +395,6 @@ __device__ __forceinline__ void mma_chunks(const uint4 (&wb)[NWB], uint32_t xadd
 template <int PART, int NX, int I0, int I1, bool ACC, int... SL>
 __device__ __forceinline__ void mma_split(float (&pre)[4], const uint4 (&wb)[NWB], uint32_t xl, uint32_t csb, uint32_t e,
                                           uint32_t slot, int g, int t, Slots<SL...>, uint32_t d1 = 0, uint32_t d2 = 0) {
-  constexpr int sl[] = {SL...};
   const int cnt = (int)(e & 7u), nx = (int)((e >> 28) & 3u);
   const bool early = ((e >> 30) & 1u) != 0;
   const uint32_t xaddr = xl + ((e & 0x0fffffffu) >> 3);
@@ -531,11 +486,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
   // attention scores are cut by flattened (position j, sample n) pair index p = j*S + n: 16 balanced ranges
   // (cut at multiples of four pairs: a CTA's exp(score) block goes out as 16-byte words)
   const int NP = T_in * S, NQ = (NP + 3) >> 2;
-#if TACO_DEC_QUADS
   const int p0 = 4 * ((q * NQ) / CS), npq = min(NP, 4 * (((q + 1) * NQ) / CS)) - p0;
-#else
-  const int p0 = (q * NP) / CS, npq = ((q + 1) * NP) / CS - p0;
-#endif
   if (S == 0) {   // cannot happen (nclusters <= N); keeps every CTA of a cluster on the same path
     cluster_sync_all();
     cluster_sync_all();
@@ -706,24 +657,12 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
 #define MMA_PRE(NX, SL, TP) mma_split<0, NX, 0, 8, false>(pre, wb, xl, csb, WCNT(TP), myslot, g, t, SL(), dH1, dH2);
 #define MMA_PRE_R(NX, SL, TP, I0, I1, ACC) mma_split<0, NX, I0, I1, ACC>(pre, wb, xl, csb, WCNT(TP), myslot, g, t, SL(), dH1, dH2);
 #define MMA_POST(NX, SL, TP) mma_split<1, NX, 0, 8, false>(pre, wb, xl, csb, WCNT(TP), myslot, g, t, SL(), dH1, dH2);
-// where the early parts of the two decoder GRUs' successors run (TACO_DEC_REBAL: spread over the windows with slack)
-
-#if TACO_DEC_REBAL
+// Window work of the decoder GRUs: the early part of P11 is spread over the windows of P9 (chunks 0-3) and P10 (4-5),
+// the early part of P13 runs in the window of P12 (same-box A/B, tools/ab: each placement was worth 0.5-1 %).
 #define W9_WORK TLOADP(T_P10, TC10, 0, 0, 1) TLOADP(T_P11, TC11, 0, 2, 3, 4, 5) TWAIT(SL11) MMA_PRE_R(1, SL11, T_P11, 0, 4, false)
 #define W10_WORK TLOADP(T_P11, TC11, 4, 0, 1) TWAIT(SL11) MMA_PRE_R(1, SL11, T_P11, 4, 6, true)
-#if TACO_DEC_P13W12
 #define W11_WORK TLOADP(T_P12, TC12, 0, 0, 1)
 #define W12_WORK RTAKE(T_P13, SL13) MMA_PRE(2, SL13, T_P13)
-#else
-#define W11_WORK TLOADP(T_P12, TC12, 0, 0, 1) RTAKE(T_P13, SL13) MMA_PRE(2, SL13, T_P13)
-#define W12_WORK
-#endif
-#else
-#define W9_WORK TLOADP(T_P10, TC10, 0, 0, 1)
-#define W10_WORK TLOADP(T_P11, TC11, 0, 2, 3, 4, 5, 0, 1) TWAIT(SL11) MMA_PRE(1, SL11, T_P11)
-#define W11_WORK TLOADP(T_P12, TC12, 0, 0, 1)
-#define W12_WORK RTAKE(T_P13, SL13) MMA_PRE(2, SL13, T_P13)
-#endif
 #define ST(slot) (st_nc + (slot) * 512)
 #define BIAS(tab) lds_f(bias_c + (tab) * 4)
   float pre[4] = {0.f, 0.f, 0.f, 0.f};   // early part of the next phase's partial tile (step 0, P1: the context is zero)
@@ -737,7 +676,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
       mbar_expect_tx(mb0 + B_P3 * 8, BLK);
       mbar_expect_tx(mb0 + B_P4 * 8, BLK);
       mbar_expect_tx(mb0 + B_P5 * 8, BLK);
-      mbar_expect_tx(mb0 + B_P6 * 8, TACO_DEC_QUADS ? (uint32_t)NQ * 16u : (uint32_t)NP * 4u);
+      mbar_expect_tx(mb0 + B_P6 * 8, (uint32_t)NQ * 16u);
       mbar_expect_tx(mb0 + B_P7 * 8, BLK);
       mbar_expect_tx(mb0 + B_P8 * 8, BLK);
       mbar_expect_tx(mb0 + B_P9 * 8, BLK);
@@ -910,15 +849,8 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     __syncthreads();
     TRM(16);
     // warp p -> peer p: this CTA's pairs into sc[p0 ..], four per DSMEM transaction (the tail of the last quad is padding)
-#if TACO_DEC_QUADS
     if (lane < ((npq + 3) >> 2)) st_async_v4(rx + L.sc + (uint32_t)p0 * 4u, lds128(sbase + L.stage + lane * 16), rmb0 + B_P6 * 8);
-#else
-    for (int i = lane; i < npq; i += 32)
-      st_async_b32(rx - lane * 16 + L.sc + (uint32_t)(p0 + i) * 4u, lds32(sbase + L.stage + i * 4), rmb0 + B_P6 * 8);
-#endif
-#if TACO_DEC_P8W6
     RTAKE(T_P8, SL8)                      // window of P6: P8's chunks into registers
-#endif
     TRM(17);
     mbar_wait(mb0 + B_P6 * 8, par);
     TRM(18);
@@ -985,9 +917,6 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
       if (rc == 0) reinterpret_cast<float*>(smem_raw + OFF_INV)[rn] = inv;
       send_rows(0, XBUF(DM_BC) + q * csb, B_P7, false);
     }
-#if !TACO_DEC_P8W6
-    RTAKE(T_P8, SL8)                      // window of P7: P8's chunks into registers
-#endif
     TRM(20);
     mbar_wait(mb0 + B_P7 * 8, par);
     TRM(21);

@@ -573,7 +573,6 @@ inline uint16_t bf16_rn(float f) {
   return (uint16_t)(u >> 16);
 }
 inline float bf16_f(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
-inline int dm_pos16(int c) { return ((c & 7) >> 1) * 4 + (c >> 3) * 2 + (c & 1); }
 
 struct DmOff { size_t stream, bias, att_v; };
 

@@ -98,7 +98,7 @@ def timings(N=32, T_in=100, iters=200):
     eng = Engine(hp, 60)
     eng.load_weights(w)
     eng.set_profiling(True)
-    ids, lengths, spk = make_inputs(N, T_in, 60, 1, min_len=60, vocab=(7108, 7325))
+    ids, lengths, spk = make_inputs(N, T_in, 60, 1, min_len=max(1, int(T_in * 0.6)), vocab=(7108, 7325))
     print("decoder geometry:", eng.decoder_geometry(N), flush=True)
     for i in range(4):
         torch.cuda.synchronize()
