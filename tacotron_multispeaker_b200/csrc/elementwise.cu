@@ -1,5 +1,7 @@
 // HBM-bound helpers around the GEMMs: batch-norm batch statistics, the
 // (affine +) max-pool of the conv bank, in-place affine, decode step count.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -49,9 +51,13 @@ __global__ void bn_finalize_kernel(const double* __restrict__ acc, int C, double
   shift[c] = (float)((double)beta[c] - mean * sc);
 }
 
+// SPLIT: the pooled tensor only feeds the next tcgen05 GEMM, so it is written directly as bf16 hi + lo
+// (x ~= hi + lo, the GEMM's operand format, dense [N*T][C]) instead of fp32 followed by a separate split pass.
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 affine_maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int T, int C4,
-                      const float* __restrict__ scale, const float* __restrict__ shift) {
+                      const float* __restrict__ scale, const float* __restrict__ shift,
+                      uint2* __restrict__ hi, uint2* __restrict__ lo) {
   const int64_t total = (int64_t)N * T * C4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -65,8 +71,17 @@ affine_maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, int N,
       a.x = fmaf(a.x, s.x, h.x); a.y = fmaf(a.y, s.y, h.y); a.z = fmaf(a.z, s.z, h.z); a.w = fmaf(a.w, s.w, h.w);
       b.x = fmaf(b.x, s.x, h.x); b.y = fmaf(b.y, s.y, h.y); b.z = fmaf(b.z, s.z, h.z); b.w = fmaf(b.w, s.w, h.w);
     }
-    reinterpret_cast<float4*>(y)[i] =
-        make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+    const float4 v = make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+    if (!SPLIT) {
+      reinterpret_cast<float4*>(y)[i] = v;
+    } else {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
+      const __nv_bfloat16 l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
+      auto pk = [](__nv_bfloat16 p, __nv_bfloat16 q2) { return (uint32_t)__bfloat16_as_ushort(p) | ((uint32_t)__bfloat16_as_ushort(q2) << 16); };
+      hi[i] = make_uint2(pk(h0, h1), pk(h2, h3));
+      lo[i] = make_uint2(pk(l0, l1), pk(l2, l3));
+    }
   }
 }
 
@@ -138,7 +153,17 @@ void launch_affine_maxpool(const float* x, float* y, int N, int T, int C, const 
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  affine_maxpool_kernel<<<blocks, 256, 0, st>>>(x, y, N, T, C / 4, scale, shift);
+  affine_maxpool_kernel<false><<<blocks, 256, 0, st>>>(x, y, N, T, C / 4, scale, shift, nullptr, nullptr);
+}
+
+void launch_affine_maxpool_split(const float* x, void* hi, void* lo, int N, int T, int C, const float* scale,
+                                 const float* shift, cudaStream_t st) {
+  const int64_t total = (int64_t)N * T * (C / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  affine_maxpool_kernel<true><<<blocks, 256, 0, st>>>(x, nullptr, N, T, C / 4, scale, shift,
+                                                      reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo));
 }
 
 void launch_affine_inplace(float* x, int64_t x_bs, int ldx, int N, int T, int C, const float* scale,

@@ -63,6 +63,8 @@ void launch_bn_batch_stats(const float* x, int64_t x_bs, int ldx, int col_off, i
                            float* scale_out, float* shift_out, cudaStream_t st);
 // y[n,t,c] = max(a(x[n,t,c]), a(x[n,t+1,c])) with a = per-channel affine (or identity when
 // scale == nullptr); last row passes through (max_pooling1d(2,1,'same')).
+void launch_affine_maxpool_split(const float* x, void* hi, void* lo, int N, int T, int C, const float* scale,
+                                 const float* shift, cudaStream_t st);
 void launch_affine_maxpool(const float* x, float* y, int N, int T, int C, const float* scale,
                            const float* shift, cudaStream_t st);
 // x[n,t,c] = x*scale[c] + shift[c] (+ res[n,t,c]) in place.

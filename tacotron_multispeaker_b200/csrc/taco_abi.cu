@@ -755,14 +755,15 @@ BfScratch take_bf(Bump& ws, int64_t rows, int maxCp) {
 // One conv1d/dense site: tensor cores (default) or the fp32 FFMA kernel (gemm_mode 0).
 void gemm(Ctx& c, const GemmW& g, const BfScratch& sc, const float* x, int64_t x_bs, int ldx, int N, int T,
           const float* bias, const float* scale, const float* shift, const float* res, int64_t res_bs, int ldres,
-          float* out, int64_t out_bs, int ldo, int col_off, int act, int epi = EPI_PLAIN) {
+          float* out, int64_t out_bs, int ldo, int col_off, int act, int epi = EPI_PLAIN, bool presplit = false) {
+  // presplit: sc already holds the bf16 hi/lo operand (written by the producer), x is not read
   taco_handle* h = c.h;
   if (h->gemm_mode == 0) {
     conv(c, x, x_bs, ldx, N, T, g.Cin, g.taps, c.W(g.w), g.ldw, bias, scale, shift, res, res_bs, ldres, out, out_bs, ldo,
          col_off, g.Cout, act, epi);
     return;
   }
-  launch_split_bf16(x, x_bs, ldx, N, T, g.Cin, g.Cp, sc.hi, sc.lo, c.st);
+  if (!presplit) launch_split_bf16(x, x_bs, ldx, N, T, g.Cin, g.Cp, sc.hi, sc.lo, c.st);
   ConvUmma u;
   u.a_hi = sc.hi; u.a_lo = sc.lo; u.N = N; u.T = T; u.Cp = g.Cp;
   u.b_hi = h->dB + g.bt; u.b_lo = h->dB + g.bt + (size_t)g.b_rows * g.Kld; u.b_rows = g.b_rows; u.Kld = g.Kld;
@@ -771,7 +772,7 @@ void gemm(Ctx& c, const GemmW& g, const BfScratch& sc, const float* x, int64_t x
   u.out = out; u.out_bs = out_bs; u.ldo = ldo; u.col_off = col_off; u.act = act; u.epi = epi;
   cudaError_t e = launch_conv_umma(u, c.st);
   if (e != cudaSuccess && h->err.empty()) h->err = std::string("conv_umma launch: ") + cudaGetErrorString(e);
-  h->launches += 2;
+  h->launches += presplit ? 1 : 2;
 }
 
 // reference cbhg() (models/modules.py:35-74).  x: [N,T,Cin] with batch stride x_bs; out [N,T,256] dense.
@@ -804,18 +805,20 @@ void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, 
            (int64_t)T * BC, BC, o, 128, TACO_ACT_RELU);
     }
   }
+  // max-pool (+ batch-mode BN affine); on the tcgen05 path its output goes straight into the GEMM operand format
+  const bool fuse_split = c.h->gemm_mode != 0 && D.g_p1.Cp == BC;
   if (batch) {
     launch_bn_batch_stats(bank, (int64_t)T * BC, BC, 0, N, T, BC, c.W(D.bank_gamma), c.W(D.bank_beta), kBnEps,
                           bnacc, bnv, bnv + 2048, c.st);
-    launch_affine_maxpool(bank, pooled, N, T, BC, bnv, bnv + 2048, c.st);
-    c.h->launches += 3;
-  } else {
-    launch_affine_maxpool(bank, pooled, N, T, BC, nullptr, nullptr, c.st);
-    c.h->launches += 1;
+    c.h->launches += 2;
   }
+  if (fuse_split) launch_affine_maxpool_split(bank, sc.hi, sc.lo, N, T, BC, batch ? bnv : nullptr, batch ? bnv + 2048 : nullptr, c.st);
+  else launch_affine_maxpool(bank, pooled, N, T, BC, batch ? bnv : nullptr, batch ? bnv + 2048 : nullptr, c.st);
+  c.h->launches += 1;
   // proj_1: conv k=3 + ReLU + BN
   gemm(c, D.g_p1, sc, pooled, (int64_t)T * BC, BC, N, T, c.W(D.p1_b), batch ? nullptr : c.W(D.p1_scale),
-       batch ? nullptr : c.W(D.p1_shift), nullptr, 0, 0, p1, (int64_t)T * D.P1, D.P1, 0, TACO_ACT_RELU);
+       batch ? nullptr : c.W(D.p1_shift), nullptr, 0, 0, p1, (int64_t)T * D.P1, D.P1, 0, TACO_ACT_RELU, EPI_PLAIN,
+       fuse_split);
   if (batch) {
     launch_bn_batch_stats(p1, (int64_t)T * D.P1, D.P1, 0, N, T, D.P1, c.W(D.p1_gamma), c.W(D.p1_beta), kBnEps,
                           bnacc, bnv, bnv + 2048, c.st);
