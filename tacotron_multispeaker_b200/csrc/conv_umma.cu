@@ -35,7 +35,8 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 64, MAX_STAGES = 3, NTHREADS = 192;
 constexpr uint32_t TILE_BYTES = BM * BK * 2;            // 16 KB: one bf16 operand tile (A or B)
 constexpr uint32_t STAGE_BYTES = 4 * TILE_BYTES;        // A_hi | A_lo | B_hi | B_lo
-constexpr uint32_t EPI_BYTES = 4 * 32 * 33 * 4;         // per-warp 32x33 fp32 transpose staging
+constexpr int EPI_LD = 36;                              // floats per staged row: 32 + 4 keeps 128-bit rows conflict free
+constexpr uint32_t EPI_BYTES = 4 * 32 * EPI_LD * 4;     // per-warp 32 x 36 fp32 transpose staging (both epilogue paths)
 // dynamic smem: 1024 (alignment slack) + stages * 64 KB + [transpose staging] + barriers
 __host__ __device__ constexpr uint32_t smem_bytes(int stages, bool transpose_epi) {
   return 1024u + (uint32_t)stages * STAGE_BYTES + (transpose_epi ? EPI_BYTES : 0u) + 256u;
@@ -122,13 +123,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 template <int NSPLIT>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, 3)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                  const UmmaArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const int STAGES = p.stages;
-  const uint32_t epi_bytes = p.vec_epi ? 0u : EPI_BYTES;
+  const uint32_t epi_bytes = EPI_BYTES;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   float* epi = reinterpret_cast<float*>(smem_al + STAGES * STAGE_BYTES);
@@ -250,11 +251,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const float* shift = p.shift ? p.shift + ci * p.Cout : nullptr;
     const int col_off = p.col_off + ci * p.Cout;
     if (p.vec_epi) {
-      // ---- direct path: thread = row, 32 consecutive columns per TMEM load, 128-bit global accesses ----
-      const int t = t0 + quarter * 32 + lane;
-      const bool rowok = t < p.T;
-      float* orow = p.out + (long long)n * p.out_bs + (long long)(rowok ? t : 0) * p.ldo + col_off;
-      const float* rrow = p.res ? p.res + (long long)n * p.res_bs + (long long)(rowok ? t : 0) * p.ldres : nullptr;
+      // ---- vector path: a thread reads ONE ROW of the accumulator from TMEM (32 columns per load).  Storing from there
+      // would touch 32 different rows per instruction (32 half-used sectors); the chunk is transposed through a
+      // 32 x 36 shared-memory tile instead, so that a store instruction covers 4 rows x 128 contiguous bytes and the
+      // residual is read the same way.  Bias / activation / BN affine / residual / highway gate run after the transpose.
+      float* stg = epi + (warp - 2) * 32 * EPI_LD;
+      const int tq = t0 + quarter * 32;
+      const int rsub = lane >> 3, c4 = lane & 7;                          // after the transpose: row 4 i + rsub, columns 4 c4 .. 4 c4 + 3
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         const int cbase = o0 + ch * 32;
@@ -263,55 +266,72 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         tmem_ld32(acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), v);
         if (p.epi == EPI_PLAIN) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const int col = cbase + 4 * g;
-            if (col >= p.Cout) break;                                     // Cout % 4 == 0 on this path
-            float4 x = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
-                                   __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
-            if (bias) { const float4 b = ldg_f4(bias + col); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
-            x.x = apply_act(x.x, p.act); x.y = apply_act(x.y, p.act); x.z = apply_act(x.z, p.act); x.w = apply_act(x.w, p.act);
-            if (scale) {
-              const float4 sc = ldg_f4(scale + col), sh = ldg_f4(shift + col);
-              x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y); x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
-            }
-            if (rowok) {
-              if (rrow) { const float4 r4 = ldg_f4(rrow + col); x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w; }
-              *reinterpret_cast<float4*>(orow + col) = x;
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * g) =
+                make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+          __syncwarp();
+          const int col = cbase + 4 * c4;
+          const bool cok = col < p.Cout;                                  // Cout % 4 == 0 on this path
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cok) {
+            if (bias) b4 = ldg_f4(bias + col);
+            if (scale) { sc4 = ldg_f4(scale + col); sh4 = ldg_f4(shift + col); }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + rsub, t = tq + r;
+            float4 x = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 4 * c4);
+            x.x = apply_act(x.x + b4.x, p.act); x.y = apply_act(x.y + b4.y, p.act);
+            x.z = apply_act(x.z + b4.z, p.act); x.w = apply_act(x.w + b4.w, p.act);
+            if (scale) { x.x = fmaf(x.x, sc4.x, sh4.x); x.y = fmaf(x.y, sc4.y, sh4.y); x.z = fmaf(x.z, sc4.z, sh4.z); x.w = fmaf(x.w, sc4.w, sh4.w); }
+            if (cok && t < p.T) {
+              if (p.res) {
+                const float4 r4 = ldg_f4(p.res + (long long)n * p.res_bs + (long long)t * p.ldres + col);
+                x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
+              }
+              *reinterpret_cast<float4*>(p.out + (long long)n * p.out_bs + (long long)t * p.ldo + col_off + col) = x;
             }
           }
         } else {   // EPI_HIGHWAY: columns (2c, 2c+1) = (H_c, T_c); 16 channels per 32-column load
-          const int chn0 = cbase >> 1;
+          // staged per row: a_c = relu(H_c) * sigmoid(T_c) at floats 0..15, b_c = 1 - sigmoid(T_c) at floats 16..31
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const int col = cbase + 8 * g;
-            if (col >= p.Cout) break;
-            const float4 b0 = ldg_f4(bias + col), b1 = ldg_f4(bias + col + 4);
-            float4 xin = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rowok) xin = ldg_f4(rrow + chn0 + 4 * g);
-            float4 o;
-            {
-              const float H = fmaxf(__uint_as_float(v[8 * g + 0]) + b0.x, 0.f), Tg = sigmoid_f(__uint_as_float(v[8 * g + 1]) + b0.y);
-              o.x = H * Tg + xin.x * (1.0f - Tg);
+            const int colb = cbase + 8 * g;
+            const bool bok = colb < p.Cout;                               // Cout % 8 == 0 on this path
+            const float4 b0 = bok ? ldg_f4(bias + colb) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b1 = bok ? ldg_f4(bias + colb + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float a4[4], g4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int c2 = 8 * g + 2 * k;
+              const float H = fmaxf(__uint_as_float(v[c2]) + bb[2 * k], 0.f), Tg = sigmoid_f(__uint_as_float(v[c2 + 1]) + bb[2 * k + 1]);
+              a4[k] = H * Tg; g4[k] = 1.0f - Tg;
             }
-            {
-              const float H = fmaxf(__uint_as_float(v[8 * g + 2]) + b0.z, 0.f), Tg = sigmoid_f(__uint_as_float(v[8 * g + 3]) + b0.w);
-              o.y = H * Tg + xin.y * (1.0f - Tg);
+            *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * g) = make_float4(a4[0], a4[1], a4[2], a4[3]);
+            *reinterpret_cast<float4*>(stg + lane * EPI_LD + 16 + 4 * g) = make_float4(g4[0], g4[1], g4[2], g4[3]);
+          }
+          __syncwarp();
+          const int chn0 = cbase >> 1;                                    // first of the 16 output channels of this chunk
+          const int rs2 = lane >> 2, q4 = lane & 3;                       // row 8 i + rs2, channels chn0 + 4 q4 ..
+          const bool cok = cbase + 8 * q4 < p.Cout;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = 8 * i + rs2, t = tq + r;
+            const float4 av = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 4 * q4);
+            const float4 gv = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 16 + 4 * q4);
+            if (cok && t < p.T) {
+              const float4 xin = ldg_f4(p.res + (long long)n * p.res_bs + (long long)t * p.ldres + chn0 + 4 * q4);
+              *reinterpret_cast<float4*>(p.out + (long long)n * p.out_bs + (long long)t * p.ldo + col_off + chn0 + 4 * q4) =
+                  make_float4(fmaf(xin.x, gv.x, av.x), fmaf(xin.y, gv.y, av.y), fmaf(xin.z, gv.z, av.z), fmaf(xin.w, gv.w, av.w));
             }
-            {
-              const float H = fmaxf(__uint_as_float(v[8 * g + 4]) + b1.x, 0.f), Tg = sigmoid_f(__uint_as_float(v[8 * g + 5]) + b1.y);
-              o.z = H * Tg + xin.z * (1.0f - Tg);
-            }
-            {
-              const float H = fmaxf(__uint_as_float(v[8 * g + 6]) + b1.z, 0.f), Tg = sigmoid_f(__uint_as_float(v[8 * g + 7]) + b1.w);
-              o.w = H * Tg + xin.w * (1.0f - Tg);
-            }
-            if (rowok) *reinterpret_cast<float4*>(orow + chn0 + 4 * g) = o;
           }
         }
+        __syncwarp();
       }
     } else {
       // ---- transpose path (rows not 16 B aligned, e.g. ldo = 1025): smem transpose -> coalesced scalar stores ----
-      float* stg = epi + (warp - 2) * 32 * 33;
+      float* stg = epi + (warp - 2) * 32 * EPI_LD;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         const int cbase = o0 + ch * 32;
@@ -319,7 +339,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         uint32_t v[32];
         tmem_ld32(acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), v);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = __uint_as_float(v[c]);
+        for (int c = 0; c < 32; ++c) stg[lane * EPI_LD + c] = __uint_as_float(v[c]);
         __syncwarp();
         const int col = cbase + lane;
         const bool cok = col < p.Cout;
@@ -337,7 +357,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           const bool has_scale = scale != nullptr;
 #pragma unroll 8
           for (int r = 0; r < rmax; ++r) {
-            float x = apply_act(stg[r * 33 + lane] + b, p.act);
+            float x = apply_act(stg[r * EPI_LD + lane] + b, p.act);
             if (has_scale) x = fmaf(x, sc, sh);
             if (cok) {
               if (rptr) x += __ldg(rptr);
@@ -352,7 +372,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           const float* rptr = p.res + (long long)n * p.res_bs + (long long)tq * p.ldres + chn;
 #pragma unroll 4
           for (int r = 0; r < rmax; ++r) {
-            const float x = stg[r * 33 + lane] + b;
+            const float x = stg[r * EPI_LD + lane] + b;
             const float tg = __shfl_down_sync(0xffffffffu, x, 1);
             if (cok && !(lane & 1)) {
               const float H = fmaxf(x, 0.f), Tg = sigmoid_f(tg);
@@ -539,7 +559,7 @@ cudaError_t launch_conv_umma(const ConvUmma& c, cudaStream_t st) {
                (c.scale == nullptr || ((reinterpret_cast<uintptr_t>(c.scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.shift) & 15) == 0)))
                   ? 1 : 0;
   if (c.epi == EPI_HIGHWAY && (c.bias == nullptr || c.res == nullptr)) return cudaErrorInvalidValue;
-  const uint32_t smem = smem_bytes(p.stages, !p.vec_epi);
+  const uint32_t smem = smem_bytes(p.stages, true);   // both epilogue paths stage through shared memory
   static bool attr_done[64] = {false};
   bool& attr_set = attr_done[dev & 63];
   if (!attr_set) {
