@@ -78,6 +78,12 @@ void launch_find_steps(const float* dec_out, int N, int max_steps, int D, int* f
 // ---- K6b: bidirectional GRU recurrence (bigru.cu) ---------------------------
 // xproj [N,T,768] = x*[Wg_fw|Wc_fw|Wg_bw|Wc_bw] + biases (hoisted input projection);
 // ug [2][128][256], uc [2][128][128] recurrent kernels; lengths nullable; out [N,T,256] (+bs).
+// Tensor-core variant (bigru_mma.cu): eight utterances per CTA, recurrent weights in tensor memory.  `frag` is the
+// fragment stream built by bigru_mma_pack (bigru_mma_frag_words() 32-bit words per CBHG).
+size_t bigru_mma_frag_words();
+void bigru_mma_pack(const float* ug, const float* uc, uint32_t* dst);
+cudaError_t launch_bigru_mma(const float* xproj, const void* frag, const int32_t* lengths, int N, int T, float* out,
+                             int64_t out_bs, cudaStream_t st);
 void launch_bigru(const float* xproj, const float* ug, const float* uc, const int32_t* lengths,
                   int N, int T, float* out, int64_t out_bs, cudaStream_t st);
 

@@ -130,6 +130,22 @@ def test_bigru(eng, ow, which, N, T, masked):
             assert np.all(g[i, lengths[i]:] == 0.0)
 
 
+@pytest.mark.parametrize("which,N,T,masked", [(0, 5, 23, True), (1, 2, 60, False), (0, 19, 9, True)])
+def test_bigru_tensor_core_variant(eng, ow, which, N, T, masked, monkeypatch):
+    """TACO_BIGRU=mma: the same recurrence on mma.sync with the recurrent weights in tensor memory, 8 utterances per
+    CTA (bf16 hi/lo operands: fp32-class; ragged lengths, a last CTA with fewer than 8 utterances)."""
+    monkeypatch.setenv("TACO_BIGRU", "mma")
+    rng = np.random.default_rng(N * 100 + T)
+    x = rng.standard_normal((N, T, 128)).astype(np.float32)
+    lengths = None
+    if masked:
+        lengths = rng.integers(1, T + 1, (N,)).astype(np.int32)
+        lengths[0] = T
+    got = eng.bigru(which, x, lengths)
+    ref = O.bigru(torch.from_numpy(x), lengths, ow, "encoder_cbhg" if which == 0 else "post_cbhg")
+    assert maxabs(got, ref) < 2e-4
+
+
 @pytest.mark.parametrize("which,bn", [(0, "moving"), (0, "batch"), (1, "moving"), (1, "batch")])
 def test_cbhg(eng, ow, which, bn):
     rng = np.random.default_rng(which * 10 + len(bn))
