@@ -383,6 +383,24 @@ def run_ours(args):
            "api": "taco_forward_host_begin/_wait/_end (C ABI, pinned host buffers; H2D + forward + D2H per step; %d lanes, "
                   "at most %d of them between _begin and the end of their decoder loop)" % (n_lanes, n_slots)}
 
+    # ---- the same two legs in the decoder's throughput geometry (informational) ----
+    # taco_set_decoder_clusters(4): 4 clusters of 8 utterances (64 SMs for 2.9 ms) instead of 7 clusters of 5/4 (112 SMs
+    # for 2.2 ms).  The headline legs above and the roofline use the default (latency) geometry.
+    thr = None
+    if not args.no_throughput_mode:
+        for l in lanes:
+            l["eng"].set_decoder_clusters(4)
+        timed(dev_lanes, 2 * n_dev)
+        ms_t, st_t = timed(dev_lanes, max(n_dev, args.steps // 2))
+        ms_t /= max(n_dev, args.steps // 2)
+        e2e_timed(lanes, 2 * n_lanes)
+        e2e_t = e2e_timed(lanes, k_e2e)
+        thr = {"decoder_geometry": "4 clusters x 16 CTAs, <= 8 utterances each",
+               "value": frames_per_step / (ms_t / 1e3), "ms_per_step": ms_t, "unit": UNIT,
+               "e2e": {"value": frames_per_step / e2e_t, "ms_per_step": 1e3 * e2e_t, "unit": UNIT}}
+        for l in lanes:
+            l["eng"].set_decoder_clusters(0)
+
     # ---- CPU restatement on the host cores (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -399,7 +417,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(world), inflight="%d batches in flight per GPU (one handle + CUDA stream "
                                                             "each); single_stream = one at a time" % n_dev),
-            "single_stream": single, "e2e": e2e, "gpu_launches": int(launches),
+            "single_stream": single, "e2e": e2e, "throughput_mode": thr, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "decoder_geometry": geo,
         }
@@ -420,6 +438,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU restatement leg")
     ap.add_argument("--inflight", type=int, default=4, help="batches in flight per GPU (handles/streams), device-resident leg")
     ap.add_argument("--e2e-lanes", type=int, default=6, help="batches in flight per GPU in the end-to-end leg")
+    ap.add_argument("--no-throughput-mode", action="store_true", help="skip the informational 4-cluster decoder legs")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on stdout when
     # NCCL_DEBUG is set): file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved one.

@@ -189,6 +189,11 @@ int taco_decoder_geometry(const taco_handle* h, int N, int* cluster_size, int* s
  * out[(phase*16 + warp)*5 + {0..4}] = {tile, buffer, first chunk, chunk count,
  * extra activation buffers multiplied by the same weights}; out_len >= 880. */
 int taco_decoder_work_table(int num_mels, int32_t* out, int out_len);
+/* Decoder geometry: 0 (default) picks the number of 16-CTA clusters for the shortest decode (batch 32: 7 clusters of
+ * 5/4 utterances, 112 SMs for 2.2 ms); n > 0 uses n clusters of up to 8 utterances each -- a throughput setting for
+ * callers that keep several batches in flight (batch 32, n = 4: 64 SMs for 2.9 ms; +10 % mel frames/s with four batches
+ * in flight, +16 % latency of a single one). */
+int taco_set_decoder_clusters(taco_handle* h, int n);
 /* Device time (ms, CUDA events on `stream`) of the stages of the last
  * taco_forward when profiling is on: [0]=encoder [1]=decoder stage (memory
  * layer + loop + step count) [2]=postnet [3]=the decoder loop kernel alone. */

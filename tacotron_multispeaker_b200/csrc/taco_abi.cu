@@ -106,6 +106,7 @@ struct taco_handle {
   int d_ints_n = 0;
   int* h_pinned = nullptr;    // [0]=oob, [1]=steps   (mapped pinned memory: kernels write it directly)
   int* d_pinned = nullptr;    // device address of h_pinned
+  int dec_clusters = 0;       // taco_set_decoder_clusters: 0 = pick for latency, n = use n clusters (throughput mode)
   int pending_steps = 0;      // step count of the forward started by taco_forward_host_begin
   // Free-running decodes almost always run max_iters steps (the stop condition is an exact-zero frame), so the forward
   // does not wait for the count in the middle: the post-net is enqueued for max_steps and the count is read from mapped
@@ -881,6 +882,7 @@ void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, 
 // Clusters for the mma.sync decoder: whole waves of co-resident clusters, <= 8 samples each; the
 // per-wave time grows with the samples per cluster (exchange bytes), roughly 1 + 0.1 S.
 int pick_mma_clusters(const taco_handle* h, int N) {
+  if (h->dec_clusters > 0) return std::min(N, std::max(h->dec_clusters, (N + 7) / 8));
   const char* en = getenv("TACO_DEC_NCL");
   if (en && atoi(en) > 0) return std::min(N, std::max(atoi(en), (N + 7) / 8));
   const char* es = getenv("TACO_DEC_S");   // samples per cluster (tests sweep it)
@@ -1629,6 +1631,12 @@ int taco_decoder_geometry(const taco_handle* h, int N, int* cluster_size, int* s
 int taco_set_gemm_mode(taco_handle* h, int mode) {
   if (!h || mode < 0 || mode > 2) return TACO_ERR_INVALID;
   h->gemm_mode = mode;
+  return TACO_OK;
+}
+
+int taco_set_decoder_clusters(taco_handle* h, int n) {
+  if (!h || n < 0) return TACO_ERR_INVALID;
+  h->dec_clusters = n;
   return TACO_OK;
 }
 

@@ -107,6 +107,10 @@ class Engine:
         """0 = fp32 FFMA, 1 = bf16x3 tcgen05 (default, fp32-class), 2 = plain bf16 tcgen05."""
         self._ck(self.lib.taco_set_gemm_mode(self._h, int(mode)))
 
+    def set_decoder_clusters(self, n: int):
+        """0 = geometry for the shortest decode (default); n > 0 = n clusters of <= 8 utterances (throughput setting)."""
+        self._ck(self.lib.taco_set_decoder_clusters(self._h, int(n)))
+
     def set_profiling(self, on: bool):
         self._ck(self.lib.taco_set_profiling(self._h, int(on)))
 
