@@ -106,9 +106,13 @@ constexpr uint32_t OFF_X = (OFF_SEQ + NW * 16 * 4 + 127u) & ~127u;
 static_assert(OFF_X % 16 == 0 && OFF_RED % 16 == 0 && OFF_STATE % 16 == 0 && OFF_BIAS % 16 == 0, "alignment");
 
 // chunks in front of buffer b (order DM_BF, DM_BC, DM_BP1, DM_BP2(8 chunks), DM_BHA, ...)
-__host__ __device__ __forceinline__ int cum_chunks(int b, int FC) { return b == 0 ? 0 : FC + 16 * (b - 1) - (b > DM_BP2 ? 8 : 0); }
+// (DM_BY1 and DM_BY2 take no space: y1 = y0 + h1' and y2 = y1 + h2' are never formed, their terms are multiplied)
+__host__ __device__ __forceinline__ int cum_chunks(int b, int FC) {
+  return b == 0 ? 0 : FC + 16 * (b - 1) - (b > DM_BP2 ? 8 : 0) - (b > DM_BY1 ? 16 : 0) - (b > DM_BY2 ? 16 : 0);
+}
 struct Dyn { uint32_t pq, sc, stage, pn, ksl, msl, ring, total; };
-__host__ __device__ inline Dyn make_dyn(int S, int T_in, int FC, bool att_res, int d0, int d1) {
+// att_res: bit 0 = e^{2 keys} of this CTA's pairs resident, bit 1 = this CTA's memory columns resident
+__host__ __device__ inline Dyn make_dyn(int S, int T_in, int FC, int att_res, int d0, int d1) {
   Dyn d;
   const uint32_t csb = (uint32_t)S * 64u;
   const uint32_t npq = (uint32_t)(T_in * S) / CS + 4;              // (position, sample) pairs per CTA, upper bound
@@ -120,8 +124,8 @@ __host__ __device__ inline Dyn make_dyn(int S, int T_in, int FC, bool att_res, i
   d.stage = up(d.sc + (uint32_t)T_in * S * 4 + 16u);               // this CTA's pairs
   d.pn = d.stage + ((npq * 4 + 15u) & ~15u);                       // sample index of this CTA's pairs (bytes)
   d.ksl = up(d.pn + npq);                                          // exp(2 * keys) rows of this CTA's pairs
-  d.msl = up(d.ksl + (att_res ? npq * DH * 4 : 0u));               // memory columns of this CTA, tile order
-  d.ring = up(d.msl + (att_res ? (uint32_t)S * T_in * 64u : 0u));  // weight ring: d0 KB for each of warps 0-7, d1 KB for 8-15
+  d.msl = up(d.ksl + ((att_res & 1) ? npq * DH * 4 : 0u));         // memory columns of this CTA, tile order
+  d.ring = up(d.msl + ((att_res & 2) ? (uint32_t)S * T_in * 64u : 0u));   // weight ring: d0 KB for each of warps 0-7, d1 KB for 8-15
   d.total = d.ring + (uint32_t)(8 * d0 + 8 * d1) * 1024u;
   return d;
 }
@@ -478,8 +482,8 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
   const int S = base + (cid < rem ? 1 : 0);
   const int n0 = cid * base + min(cid, rem);
   const int M = w.M, Dout = w.Dout, FC = M >> 4, T_in = a.T_in;
-  const bool att_res = a.att_res != 0;
-  const Dyn L = make_dyn(S, T_in, FC, att_res, a.ring_d0, a.ring_d1);
+  const bool res_k = (a.att_res & 1) != 0, res_m = (a.att_res & 2) != 0;
+  const Dyn L = make_dyn(S, T_in, FC, a.att_res, a.ring_d0, a.ring_d1);
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t csb = (uint32_t)S * 64u;
   const uint32_t mb0 = sbase + OFF_MBAR;
@@ -505,9 +509,8 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
   }
   if (tid < DM_NBIAS) reinterpret_cast<float*>(smem_raw + OFF_BIAS)[tid] = __ldg(w.bias + q * DM_NBIAS + tid);
   if (tid < DH) reinterpret_cast<float*>(smem_raw + OFF_VATT)[tid] = __ldg(w.att_v + tid);
-  if (att_res) {
+  if (res_k) {
     float* ksl = reinterpret_cast<float*>(smem_raw + L.ksl);
-    float* msl = reinterpret_cast<float*>(smem_raw + L.msl);
     for (int i = tid; i < npq * (DH / 4); i += NT) {   // exp(2 key): tanh(k + p) = 1 - 2 / (1 + e^{2k} e^{2p})
       const int c4 = i % (DH / 4), pp = i / (DH / 4), p = p0 + pp, j = p / S, n = p - j * S;   // (prologue only)
       float4 k4 = ldg_f4(a.keys + ((size_t)(n0 + n) * T_in + j) * DH + c4 * 4);
@@ -515,6 +518,9 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
       k4.z = __expf(2.0f * fminf(fmaxf(k4.z, -30.f), 30.f)); k4.w = __expf(2.0f * fminf(fmaxf(k4.w, -30.f), 30.f));
       *reinterpret_cast<float4*>(ksl + (size_t)pp * DH + c4 * 4) = k4;
     }
+  }
+  if (res_m) {
+    float* msl = reinterpret_cast<float*>(smem_raw + L.msl);
     for (int i = tid; i < S * T_in * 4; i += NT) {   // 16 columns = four float4 per (sample, position)
       const int c4 = i & 3, r = i >> 2, s = r / T_in, j = r - s * T_in;
       *reinterpret_cast<float4*>(msl + ((size_t)j * S + s) * 16 + c4 * 4) =
@@ -820,7 +826,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
         const int n = smem_raw[L.pn + pl];
         const float4 e0 = lds_f4(pq_l + (uint32_t)n * 64u), e1 = lds_f4(pq_l + (uint32_t)n * 64u + 8 * csb);   // e^{2 pq}
         float4 k0, k1;                                                                                     // e^{2 key}
-        if (att_res) {
+        if (res_k) {
           k0 = lds_f4(sbase + L.ksl + (uint32_t)pl * (DH * 4) + lane * 16);
           k1 = lds_f4(sbase + L.ksl + (uint32_t)pl * (DH * 4) + 512 + lane * 16);
         } else {
@@ -861,7 +867,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
       float ssum = 0.f, ssum2 = 0.f;
       if (g < S) {
         const int niter = (T_in - warp + NW - 1) / NW;
-        if (att_res) {
+        if (res_m) {
           uint32_t pa = sbase + L.sc + (uint32_t)(warp * S + g) * 4u;
           uint32_t ma = sbase + L.msl + (uint32_t)((warp * S + g) * 16 + t * 4) * 4u;
           const uint32_t dp = (uint32_t)NW * S * 4u, dm = (uint32_t)NW * S * 64u;
@@ -1005,7 +1011,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
 
 }  // namespace
 
-size_t decoder_mma_smem_bytes(int s_max, int T_in, int M, bool att_res, int ring_d0, int ring_d1) {
+size_t decoder_mma_smem_bytes(int s_max, int T_in, int M, int att_res, int ring_d0, int ring_d1) {
   return make_dyn(s_max, T_in, M >> 4, att_res, ring_d0, ring_d1).total;
 }
 
@@ -1042,16 +1048,21 @@ cudaError_t launch_decoder_mma(const DecoderMmaWeights& w, const DecoderArgs& a_
   if (a.s_max > 8 || (w.M & 15) || (w.Dout & 15) || w.M > 128) return cudaErrorInvalidValue;
   // shared memory: the attention operands resident if they fit, then the deepest weight ring that fits
   // (warps 0-7 consume up to 14 streamed chunk-tiles per step, 4 of them in one phase; warps 8-15 at most 6, 2 at a time)
+  // residency mask: both, e^{2 keys} only (also saves the per-step exponentials), memory columns only, none
   const char* env = getenv("TACO_DEC_ATT_RES");
-  const bool want_res = !env || atoi(env) != 0;
+  const int allow = env ? (atoi(env) & 3) : 3;
+  static const int masks[4] = {3, 1, 2, 0};
   static const int rings[3][2] = {{6, 3}, {5, 3}, {4, 2}};
   size_t smem = 0;
   bool ok = false;
-  for (int res = want_res ? 1 : 0; res >= 0 && !ok; --res)
+  for (int m = 0; m < 4 && !ok; ++m) {
+    const int res = masks[m];
+    if ((res & allow) != res) continue;
     for (int k = 0; k < 3 && !ok; ++k) {
-      smem = decoder_mma_smem_bytes(a.s_max, a.T_in, w.M, res != 0, rings[k][0], rings[k][1]);
+      smem = decoder_mma_smem_bytes(a.s_max, a.T_in, w.M, res, rings[k][0], rings[k][1]);
       if (smem <= 227 * 1024) { a.att_res = res; a.ring_d0 = rings[k][0]; a.ring_d1 = rings[k][1]; ok = true; }
     }
+  }
   if (!ok) return cudaErrorInvalidValue;
   auto kern = a.trace != nullptr ? decoder_mma_kernel<true> : decoder_mma_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

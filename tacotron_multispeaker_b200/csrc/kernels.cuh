@@ -147,7 +147,7 @@ struct DecoderMmaWeights {
   uint32_t tab[DM_NPHASE][16];
 };
 cudaError_t launch_decoder_mma(const DecoderMmaWeights& w, const DecoderArgs& a, int nclusters, cudaStream_t st);
-size_t decoder_mma_smem_bytes(int s_max, int T_in, int M, bool att_res, int ring_d0, int ring_d1);
+size_t decoder_mma_smem_bytes(int s_max, int T_in, int M, int att_res, int ring_d0, int ring_d1);
 int decoder_mma_max_clusters();
 
 // S = samples per cluster (1,2,4,8).  Returns cudaError of the launch.
