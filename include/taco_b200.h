@@ -168,6 +168,29 @@ int taco_bigru(taco_handle* h, int which, const float* x, const int32_t* lengths
 int taco_conv1d(taco_handle* h, const float* x, int N, int T, int Cin, const float* kernel,
                 const float* bias, int k, int Cout, int act, float* out, void* stream);
 
+/* ---- vocoder: the step right after the path ----------- */
+/* Fields of reference hparams.py:13-18,35-36 that util/audio.py reads. */
+typedef struct taco_audio_params {
+  int32_t sample_rate;        /* hparams.py:13 (20000) */
+  int32_t griffin_lim_iters;  /* hparams.py:35 (100)   */
+  double frame_length_ms;     /* hparams.py:14 (50)    */
+  double frame_shift_ms;      /* hparams.py:15 (12.5)  */
+  double preemphasis;         /* hparams.py:16 (0.97); 0 skips the inverse pre-emphasis */
+  double min_level_db;        /* hparams.py:17 (-100)  */
+  double ref_level_db;        /* hparams.py:18 (20)    */
+  double power;               /* hparams.py:36 (1.5)   */
+} taco_audio_params;
+/* Samples per utterance that taco_griffin_lim writes for T frames: (T-1)*hop + win with
+ * hop = int(frame_shift_ms/1000*sample_rate), win = int(frame_length_ms/1000*sample_rate)
+ * (util/audio.py:114-118; tf.contrib.signal.inverse_stft's overlap_and_add). < 0 on bad arguments. */
+int64_t taco_wav_length(const taco_audio_params* ap, int T);
+/* audio.inv_spectrogram_tensorflow(linear_outputs) followed by audio.inv_preemphasis
+ * (synthesizer.py:27,50; util/audio.py:23-24,39-46,78-91,105-112) for a batch: linear [N,T,num_freq]
+ * (batch stride linear_batch_stride floats, 0 = dense) -> wav_out [N, taco_wav_length(ap,T)] float32.
+ * Needs num_freq == 1025 (n_fft 2048) and win <= 2048; TACO_ERR_UNSUPPORTED otherwise.  Does not need weights. */
+int taco_griffin_lim(taco_handle* h, const taco_audio_params* ap, const float* linear, int N, int T,
+                     int64_t linear_batch_stride, float* wav_out, void* stream);
+
 /* ---- arithmetic mode of the dense layers ----------------------------------- */
 /* The reference computes in fp32.  0 = fp32 FFMA kernels; 1 (default) = tcgen05 tensor
  * cores with every operand split into bf16 hi+lo and three products per k-step

@@ -34,6 +34,7 @@ SYMBOLS = [
     "taco_embed", "taco_check_ids", "taco_encoder", "taco_decode", "taco_cbhg", "taco_postnet",
     "taco_bigru", "taco_conv1d",
     "taco_set_gemm_mode", "taco_launch_count", "taco_decoder_geometry", "taco_decoder_work_table", "taco_set_decoder_clusters", "taco_set_profiling", "taco_last_stage_ms",
+    "taco_wav_length", "taco_griffin_lim",
 ]
 
 
@@ -42,6 +43,14 @@ class TacoHParams(C.Structure):
         ("num_mels", C.c_int32), ("num_freq", C.c_int32), ("outputs_per_step", C.c_int32),
         ("max_iters", C.c_int32), ("embedding_text_channels", C.c_int32),
         ("embedding_id_channels", C.c_int32), ("num_symbols", C.c_int32), ("id_num", C.c_int32),
+    ]
+
+
+class TacoAudioParams(C.Structure):
+    _fields_ = [
+        ("sample_rate", C.c_int32), ("griffin_lim_iters", C.c_int32),
+        ("frame_length_ms", C.c_double), ("frame_shift_ms", C.c_double), ("preemphasis", C.c_double),
+        ("min_level_db", C.c_double), ("ref_level_db", C.c_double), ("power", C.c_double),
     ]
 
 
@@ -99,6 +108,9 @@ def load() -> C.CDLL:
     lib.taco_decoder_geometry.argtypes = [H, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     lib.taco_set_profiling.argtypes = [H, i]
     lib.taco_last_stage_ms.argtypes = [H, C.POINTER(C.c_float)]
+    lib.taco_wav_length.argtypes = [C.POINTER(TacoAudioParams), i]
+    lib.taco_wav_length.restype = i64
+    lib.taco_griffin_lim.argtypes = [H, C.POINTER(TacoAudioParams), fp, i, i, i64, fp, vp]
     for name in SYMBOLS:
         getattr(lib, name)  # AttributeError here = header and library out of sync
     _lib = lib

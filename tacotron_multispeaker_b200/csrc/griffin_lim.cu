@@ -1,0 +1,236 @@
+// Griffin-Lim vocoder of the reference's synthesis graph (util/audio.py:39-46 inv_spectrogram_tensorflow,
+// :78-91 _griffin_lim_tensorflow, :105-112 tf.contrib.signal.stft / inverse_stft, synthesizer.py:27,50) for a
+// whole batch of linear spectrograms on the device.
+//
+// One Griffin-Lim iteration is ONE launch: a CTA owns one frame of one utterance and does
+//   overlap-add of the previous iteration's windowed inverse frames (the signal is never materialised)
+//   -> analysis window -> 2048-point FFT in shared memory -> est / max(1e-8, |est|) * S
+//   -> inverse FFT in shared memory -> synthesis window -> its inverse frame for the next iteration.
+// The forward transform is decimation in frequency (natural order in, bit-reversed out), the phase step works on
+// the bit-reversed positions, and the inverse is decimation in time (bit-reversed in, natural out): no reordering
+// pass.  Three radix-2 stages are done in registers per shared-memory round trip (8 elements per thread), so a
+// transform is four round trips.  The upper half of the spectrum is not mirrored explicitly: for a real frame
+// X[N-k] = conj(X[k]) already sits in its bit-reversed position and takes the magnitude of bin N-k, and the real
+// part of the inverse is what irfft returns.
+//
+// TF conventions restated: frame(signal, win, hop, pad_end=False), periodic Hann of `win` points for analysis AND
+// synthesis (inverse_stft's default window_fn, no window-sum normalisation), rfft/irfft of n_fft = 2 (num_freq - 1)
+// points with the frame zero-padded at its end, irfft scaled by 1/n_fft and cut to `win` samples, overlap_and_add.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace taco {
+namespace {
+
+constexpr int GL_N = 2048, GL_BINS = GL_N / 2 + 1, GL_NT = 256;
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {   // a * conj(b)
+  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+
+// twiddles exp(-2 pi i k / 2048), k < 1024, and the periodic Hann window, evaluated in double
+__global__ void gl_tables_kernel(float2* tw, float* win, int win_len) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < GL_N / 2) {
+    double s, c;
+    sincospi(-2.0 * (double)i / (double)GL_N, &s, &c);
+    tw[i] = make_float2((float)c, (float)s);
+  }
+  if (i < win_len) win[i] = (float)(0.5 - 0.5 * cospi(2.0 * (double)i / (double)win_len));
+}
+
+// util/audio.py:42-43: S = db_to_amp(denormalize(x) + ref_level_db) ** power, as one exp2
+__global__ void gl_mags_kernel(const float* __restrict__ lin, int64_t lin_bs, int T, int F, float scale_db,
+                               float off_db, float expo, float* __restrict__ mags, int64_t total) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = idx / F;
+    const int f = (int)(idx - row * F), n = (int)(row / T), t = (int)(row - (int64_t)n * T);
+    float x = __ldg(lin + (int64_t)n * lin_bs + (int64_t)t * F + f);
+    x = fminf(fmaxf(x, 0.0f), 1.0f);
+    mags[idx] = exp2f(fmaf(x, scale_db, off_db) * expo);
+  }
+}
+
+// LOGR radix-2 stages, decimation in frequency, half-spans (R/2) q, (R/4) q, ..., q  (R = 2^LOGR, q = 2^LOGQ)
+template <int LOGR, int LOGQ>
+__device__ __forceinline__ void dif_pass(float2* d, const float2* tw, int tid) {
+  constexpr int R = 1 << LOGR, Q = 1 << LOGQ;
+#pragma unroll 1
+  for (int g = tid; g < GL_N / R; g += GL_NT) {
+    const int lo = g & (Q - 1), base = ((g >> LOGQ) << (LOGR + LOGQ)) + lo;
+    float2 v[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) v[m] = d[base + m * Q];
+#pragma unroll
+    for (int s = 0; s < LOGR; ++s) {
+      const int hs = R >> (s + 1);
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        if (m & hs) continue;
+        const float2 a = v[m], b = v[m + hs];
+        const int idx = (lo + (m & (hs - 1)) * Q) * (GL_N / (2 * hs * Q));
+        v[m] = make_float2(a.x + b.x, a.y + b.y);
+        v[m + hs] = cmul(make_float2(a.x - b.x, a.y - b.y), tw[idx]);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) d[base + m * Q] = v[m];
+  }
+}
+
+// LOGR radix-2 stages of the inverse, decimation in time, half-spans q, 2q, ..., (R/2) q
+template <int LOGR, int LOGQ>
+__device__ __forceinline__ void dit_pass(float2* d, const float2* tw, int tid) {
+  constexpr int R = 1 << LOGR, Q = 1 << LOGQ;
+#pragma unroll 1
+  for (int g = tid; g < GL_N / R; g += GL_NT) {
+    const int lo = g & (Q - 1), base = ((g >> LOGQ) << (LOGR + LOGQ)) + lo;
+    float2 v[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) v[m] = d[base + m * Q];
+#pragma unroll
+    for (int s = 0; s < LOGR; ++s) {
+      const int hs = 1 << s;
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        if (m & hs) continue;
+        const int idx = (lo + (m & (hs - 1)) * Q) * (GL_N / (2 * hs * Q));
+        const float2 a = v[m], b = cmul_conj(v[m + hs], tw[idx]);
+        v[m] = make_float2(a.x + b.x, a.y + b.y);
+        v[m + hs] = make_float2(a.x - b.x, a.y - b.y);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) d[base + m * Q] = v[m];
+  }
+}
+
+// sum over the frames that cover sample m of utterance rows r[t][0..win)
+__device__ __forceinline__ float ola_at(const float* __restrict__ r, int m, int T, int win, int hop) {
+  const int num = m - win + hop;
+  const int t_lo = num > 0 ? num / hop : 0;
+  const int t_hi = min(T - 1, m / hop);
+  float acc = 0.0f;
+  for (int tp = t_lo; tp <= t_hi; ++tp) acc += __ldg(r + (size_t)tp * win + (m - tp * hop));
+  return acc;
+}
+
+// One Griffin-Lim iteration for frame blockIdx.x (first != 0: the zero-phase start, util/audio.py:84-85).
+__global__ void __launch_bounds__(GL_NT)
+gl_iter_kernel(const float* __restrict__ mags, const float* __restrict__ r_prev, float* __restrict__ r_next,
+               const float2* __restrict__ tw_g, const float* __restrict__ win_g, int T, int win, int hop, int first) {
+  __shared__ float2 d[GL_N];
+  __shared__ float2 tw[GL_N / 2];
+  __shared__ float mg[GL_BINS];
+  const int tid = threadIdx.x;
+  const int frame = blockIdx.x, n = frame / T, t = frame - n * T;
+  for (int i = tid; i < GL_N / 2; i += GL_NT) tw[i] = tw_g[i];
+  for (int i = tid; i < GL_BINS; i += GL_NT) mg[i] = __ldg(mags + (size_t)frame * GL_BINS + i);
+  __syncthreads();
+  if (!first) {
+    const float* r = r_prev + (size_t)n * T * win;
+    for (int i = tid; i < GL_N; i += GL_NT) {
+      float x = 0.0f;
+      if (i < win) x = ola_at(r, t * hop + i, T, win, hop) * __ldg(win_g + i);
+      d[i] = make_float2(x, 0.0f);
+    }
+    __syncthreads();
+    dif_pass<3, 8>(d, tw, tid); __syncthreads();
+    dif_pass<3, 5>(d, tw, tid); __syncthreads();
+    dif_pass<3, 2>(d, tw, tid); __syncthreads();
+    dif_pass<2, 0>(d, tw, tid); __syncthreads();
+    for (int p = tid; p < GL_N; p += GL_NT) {   // util/audio.py:87-89
+      const int k = (int)(__brev((unsigned)p) >> 21), kk = min(k, GL_N - k);
+      const float2 x = d[p];
+      const float s = mg[kk] / fmaxf(1e-8f, sqrtf(fmaf(x.x, x.x, x.y * x.y)));
+      d[p] = make_float2(x.x * s, x.y * s);
+    }
+  } else {
+    for (int p = tid; p < GL_N; p += GL_NT) {
+      const int k = (int)(__brev((unsigned)p) >> 21), kk = min(k, GL_N - k);
+      d[p] = make_float2(mg[kk], 0.0f);
+    }
+  }
+  __syncthreads();
+  dit_pass<3, 0>(d, tw, tid); __syncthreads();
+  dit_pass<3, 3>(d, tw, tid); __syncthreads();
+  dit_pass<3, 6>(d, tw, tid); __syncthreads();
+  dit_pass<2, 9>(d, tw, tid); __syncthreads();
+  float* o = r_next + (size_t)frame * win;
+  for (int i = tid; i < win; i += GL_NT) o[i] = d[i].x * (__ldg(win_g + i) * (1.0f / GL_N));
+}
+
+// overlap_and_add of the last inverse frames: y [N, L]
+__global__ void gl_ola_kernel(const float* __restrict__ r, float* __restrict__ y, int T, int win, int hop, int L) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
+  if (m < L) y[(size_t)n * L + m] = ola_at(r + (size_t)n * T * win, m, T, win, hop);
+}
+
+// util/audio.py:23-24 inv_preemphasis = lfilter([1], [1, -a]): y[i] = x[i] + a y[i-1], in place.  One CTA per
+// utterance: every thread filters its own chunk from a zero state, thread 0 chains the chunk ends, second pass.
+__global__ void __launch_bounds__(1024) gl_deemph_kernel(float* __restrict__ y, int L, float a) {
+  __shared__ float zend[1024];
+  __shared__ float carry[1024];
+  const int tid = threadIdx.x;
+  float* p = y + (size_t)blockIdx.x * L;
+  const int chunk = (L + 1023) / 1024;
+  const int s = min(L, tid * chunk), e = min(L, s + chunk);
+  float z = 0.0f;
+  for (int i = s; i < e; ++i) z = fmaf(a, z, p[i]);
+  zend[tid] = z;
+  __syncthreads();
+  if (tid == 0) {
+    float ap = 1.0f;
+    for (int i = 0; i < chunk; ++i) ap *= a;
+    float c = 0.0f;
+    for (int k = 0; k < 1024; ++k) { carry[k] = c; c = fmaf(ap, c, zend[k]); }
+  }
+  __syncthreads();
+  z = carry[tid];
+  for (int i = s; i < e; ++i) { z = fmaf(a, z, p[i]); p[i] = z; }
+}
+
+}  // namespace
+
+size_t griffin_lim_ws_bytes(int N, int T, int win) {
+  const size_t frames = (size_t)N * T;
+  return frames * GL_BINS * sizeof(float) + 2 * frames * win * sizeof(float) + GL_N / 2 * sizeof(float2) +
+         (size_t)win * sizeof(float) + 4096;
+}
+
+cudaError_t launch_griffin_lim(const GriffinLimArgs& a, void* ws, cudaStream_t st, int* launches) {
+  if (a.n_fft != GL_N || a.win < 1 || a.win > GL_N || a.hop < 1 || a.N < 1 || a.T < 1 || a.iters < 0)
+    return cudaErrorInvalidValue;
+  const size_t frames = (size_t)a.N * a.T;
+  char* p = static_cast<char*>(ws);
+  auto take = [&](size_t bytes) { char* q = p; p += (bytes + 255) & ~size_t(255); return q; };
+  float* mags = reinterpret_cast<float*>(take(frames * GL_BINS * sizeof(float)));
+  float* r0 = reinterpret_cast<float*>(take(frames * a.win * sizeof(float)));
+  float* r1 = reinterpret_cast<float*>(take(frames * a.win * sizeof(float)));
+  float2* tw = reinterpret_cast<float2*>(take(GL_N / 2 * sizeof(float2)));
+  float* win = reinterpret_cast<float*>(take((size_t)a.win * sizeof(float)));
+  gl_tables_kernel<<<(GL_N + 255) / 256, 256, 0, st>>>(tw, win, a.win);
+  const int64_t total = (int64_t)frames * GL_BINS;
+  // dB = clip(x, 0, 1) * (-min_level_db) + min_level_db + ref_level_db;  S^power = 10^(0.05 * power * dB)
+  gl_mags_kernel<<<(unsigned)((total + 1023) / 1024 < 148 * 16 ? (total + 1023) / 1024 : 148 * 16), 256, 0, st>>>(
+      a.linear, a.linear_bs, a.T, GL_BINS, -a.min_level_db, a.min_level_db + a.ref_level_db,
+      0.05f * a.power * 3.3219280948873623f, mags, total);
+  float *cur = r0, *nxt = r1;
+  gl_iter_kernel<<<(unsigned)frames, GL_NT, 0, st>>>(mags, nullptr, cur, tw, win, a.T, a.win, a.hop, 1);
+  for (int it = 0; it < a.iters; ++it) {
+    gl_iter_kernel<<<(unsigned)frames, GL_NT, 0, st>>>(mags, cur, nxt, tw, win, a.T, a.win, a.hop, 0);
+    float* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  const int L = (a.T - 1) * a.hop + a.win;
+  gl_ola_kernel<<<dim3((L + 255) / 256, a.N), 256, 0, st>>>(cur, a.wav, a.T, a.win, a.hop, L);
+  if (a.preemphasis != 0.0f) gl_deemph_kernel<<<a.N, 1024, 0, st>>>(a.wav, L, a.preemphasis);
+  if (launches) *launches = 4 + a.iters + (a.preemphasis != 0.0f ? 1 : 0);
+  return cudaGetLastError();
+}
+
+}  // namespace taco

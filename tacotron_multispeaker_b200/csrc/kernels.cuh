@@ -157,4 +157,15 @@ int decoder_pick_cluster_size();
 size_t decoder_smem_bytes(int S, int T_in, int M, int CS, bool att_res);
 int decoder_max_clusters(int CS);
 
+// Griffin-Lim vocoder (griffin_lim.cu): util/audio.py:39-46,78-91,105-112 + inv_preemphasis (:23-24) on the device.
+struct GriffinLimArgs {
+  const float* linear;   // [N][T][n_fft/2+1] normalised spectrogram (the post-net output), batch stride linear_bs floats
+  int64_t linear_bs;
+  int N, T, n_fft, win, hop, iters;
+  float min_level_db, ref_level_db, power, preemphasis;
+  float* wav;            // [N][(T-1)*hop + win]
+};
+size_t griffin_lim_ws_bytes(int N, int T, int win);
+cudaError_t launch_griffin_lim(const GriffinLimArgs& a, void* ws, cudaStream_t st, int* launches);
+
 }  // namespace taco

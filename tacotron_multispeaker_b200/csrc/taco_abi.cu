@@ -1596,6 +1596,44 @@ int taco_forward_host(taco_handle* h, const int32_t* ids_host, const int32_t* le
   return taco_forward_host_end(h, steps_out_host, stream);
 }
 
+static bool audio_geometry(const taco_audio_params* ap, int* hop, int* win) {
+  if (!ap || ap->sample_rate <= 0) return false;
+  *hop = (int)(ap->frame_shift_ms / 1000.0 * ap->sample_rate);    // util/audio.py:116
+  *win = (int)(ap->frame_length_ms / 1000.0 * ap->sample_rate);   // util/audio.py:117
+  return *hop >= 1 && *win >= 1;
+}
+
+int64_t taco_wav_length(const taco_audio_params* ap, int T) {
+  int hop = 0, win = 0;
+  if (T < 1 || !audio_geometry(ap, &hop, &win)) return -1;
+  return (int64_t)(T - 1) * hop + win;
+}
+
+int taco_griffin_lim(taco_handle* h, const taco_audio_params* ap, const float* linear, int N, int T,
+                     int64_t linear_batch_stride, float* wav_out, void* stream) {
+  if (!h) return TACO_ERR_INVALID;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  int hop = 0, win = 0;
+  if (!linear || !wav_out || N <= 0 || T <= 0 || !audio_geometry(ap, &hop, &win) || ap->griffin_lim_iters < 0)
+    return fail(h, TACO_ERR_INVALID, "bad argument");
+  const int n_fft = (h->hp.num_freq - 1) * 2;                     // util/audio.py:115
+  if (n_fft != 2048 || win > n_fft) return fail(h, TACO_ERR_UNSUPPORTED, "griffin_lim: n_fft must be 2048 and win <= n_fft");
+  if ((int64_t)N * T > 0x7fffffff / 1025) return fail(h, TACO_ERR_UNSUPPORTED, "griffin_lim: too many frames for one call");
+  int rc = ensure_ws(h, griffin_lim_ws_bytes(N, T, win));
+  if (rc) return rc;
+  GriffinLimArgs a;
+  a.linear = linear;
+  a.linear_bs = linear_batch_stride ? linear_batch_stride : (int64_t)T * h->hp.num_freq;
+  a.N = N; a.T = T; a.n_fft = n_fft; a.win = win; a.hop = hop; a.iters = ap->griffin_lim_iters;
+  a.min_level_db = (float)ap->min_level_db; a.ref_level_db = (float)ap->ref_level_db;
+  a.power = (float)ap->power; a.preemphasis = (float)ap->preemphasis;
+  a.wav = wav_out;
+  int launches = 0;
+  CUDA_OK(h, launch_griffin_lim(a, h->ws, (cudaStream_t)stream, &launches));
+  h->launches += launches;
+  return check_launch(h, "griffin_lim");
+}
+
 int64_t taco_launch_count(const taco_handle* h) { return h ? h->launches : 0; }
 
 // Host-only: the decoder's work table for a given num_mels (no GPU, no handle).  out[phase][warp][5] =

@@ -189,6 +189,34 @@ class Engine:
                                       _ptr(out), self.stream))
         return out
 
+    # ---- vocoder (the step after the path) ----
+    def audio_params(self, griffin_lim_iters: Optional[int] = None) -> "_abi.TacoAudioParams":
+        hp = self.hp
+        return _abi.TacoAudioParams(
+            int(hp.sample_rate), int(hp.griffin_lim_iters if griffin_lim_iters is None else griffin_lim_iters),
+            float(hp.frame_length_ms), float(hp.frame_shift_ms), float(hp.preemphasis),
+            float(hp.min_level_db), float(hp.ref_level_db), float(hp.power))
+
+    def griffin_lim(self, linear, griffin_lim_iters: Optional[int] = None, inv_preemphasis: bool = True):
+        """``audio.inv_spectrogram_tensorflow`` + ``audio.inv_preemphasis`` (reference synthesizer.py:27,50) for a
+        batch ``linear [N,T,num_freq]`` (or one ``[T,num_freq]``): returns wav ``[N,(T-1)*hop+win]`` on the device."""
+        linear = self._f32(linear)
+        single = linear.dim() == 2
+        if single:
+            linear = linear[None]
+        N, T, F = linear.shape
+        if F != self.hp.num_freq:
+            raise ValueError("linear spectrogram has %d bins, hparams.num_freq is %d" % (F, self.hp.num_freq))
+        ap = self.audio_params(griffin_lim_iters)
+        if not inv_preemphasis:
+            ap.preemphasis = 0.0
+        L = self.lib.taco_wav_length(C.byref(ap), T)
+        if L < 0:
+            raise ValueError("bad audio hparams")
+        wav = torch.empty(N, L, device=self.device, dtype=torch.float32)
+        self._ck(self.lib.taco_griffin_lim(self._h, C.byref(ap), _ptr(linear), N, T, 0, _ptr(wav), self.stream))
+        return wav[0] if single else wav
+
     # ---- whole path ----
     def forward(self, ids, lengths, spk=None, mel_targets=None, teacher_force=False,
                 bn_mode=_abi.BN_MOVING, want_linear=True, want_alignments=True, out=None):

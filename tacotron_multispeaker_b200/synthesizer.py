@@ -9,9 +9,12 @@ exactly like the reference); ``synthesize(text, identity, path, path_align)``
 converts text with ``text_to_sequence2(...)[:-1]`` (``synthesizer.py:39``) and
 runs the forward path.
 
-Scope: the path ends at the post-net linear spectrogram, so
-``synthesize`` returns / saves the spectrogram and alignment instead of a
-Griffin-Lim waveform (``util/audio.py:39-46`` is the next row, not built yet).
+``synthesize`` then runs the reference's Griffin-Lim graph (``synthesizer.py:27``,
+``util/audio.py:39-46``) and ``inv_preemphasis`` (``synthesizer.py:50``) on the GPU
+(``taco_griffin_lim``), writes the waveform with ``save_wav`` to ``path`` (``./1.wav``
+when ``path`` is None, as the reference does) and the alignment image to
+``path_align``.  It returns the bytes of the WAV file (the reference returns an
+empty ``BytesIO`` it never writes to -- ``synthesizer.py:52-58``).
 Checkpoints are TensorFlow V2 bundles (``model.ckpt-N.index`` + ``.data-*``, read by
 ``tf_checkpoint.py`` without TensorFlow) or ``.npz`` archives keyed by TF variable
 names; without one, ``load(None, id_num=...)`` uses random-init weights.
@@ -23,6 +26,7 @@ from typing import Optional
 
 import numpy as np
 
+from . import audio, plot
 from .hparams import HParams, hparams as default_hparams
 from .tacotron import create_model
 from .text import sequence_to_text2, text_to_sequence2
@@ -66,15 +70,24 @@ class Synthesizer:
         self.model.initialize(seq, lengths, identities=ident, id_num=self.id_num)
         return (self.model.linear_outputs[0].cpu().numpy(), self.model.alignments[0].cpu().numpy())
 
+    def synthesize_sequence_wav(self, seq, identity: int):
+        """Batch-1 forward + vocoder on an id sequence.  Returns (wav float32 [L], alignment [T_in,steps])."""
+        seq = np.asarray(seq, dtype=np.int32)[None, :]
+        lengths = np.asarray([seq.shape[1]], dtype=np.int32)
+        ident = np.asarray([identity], dtype=np.int32)
+        self.model.initialize(seq, lengths, identities=ident, id_num=self.id_num)
+        wav = audio.synthesize_wav(self.model.engine, self.model.linear_outputs[0])
+        return wav.cpu().numpy(), self.model.alignments[0].cpu().numpy()
+
     def synthesize(self, text, identity, path=None, path_align=None):
         seq = text_to_sequence2(text, [x.strip() for x in self.hparams.cleaners.split(",")])[:-1]
         print(seq)
         print(sequence_to_text2(seq))
-        linear, alignment = self.synthesize_sequence(seq, identity)
-        out = io.BytesIO()
-        np.save(out, linear)
-        if path is not None:
-            np.save(path, linear)
+        wav, alignment = self.synthesize_sequence_wav(seq, identity)
         if path_align is not None:
-            np.save(path_align, alignment)
+            plot.plot_alignment(alignment, path_align)
+        # wav = wav[:audio.find_endpoint(wav, self.hparams.sample_rate)]   (disabled in the reference too)
+        out = io.BytesIO()
+        audio.save_wav(wav, out, self.hparams.sample_rate)
+        audio.save_wav(wav, path if path is not None else "./1.wav", self.hparams.sample_rate)
         return out.getvalue()

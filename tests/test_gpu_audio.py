@@ -1,0 +1,143 @@
+"""Parity of the GPU Griffin-Lim vocoder (taco_griffin_lim, through the C ABI) against the float64 numpy
+restatement of the reference's TF graph (oracle/audio_oracle.py; reference util/audio.py:39-46,78-91).
+
+Tolerances, relative to the waveform's peak: 2e-5 for the zero-phase start and the first iterations (fp32 FFTs
+against float64); Griffin-Lim renormalises every bin's phase each iteration, so bins with |est| near zero amplify
+rounding differences -- after many iterations the comparison is on the spectral inconsistency the algorithm
+minimises, which must match the oracle's within 5 %."""
+import io
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import audio_oracle as A  # noqa: E402  (tests may use the oracle)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from tacotron_multispeaker_b200.engine import Engine
+    from tacotron_multispeaker_b200.hparams import HParams
+    e = Engine(HParams(), id_num=0)       # the vocoder needs no weights
+    yield e
+    e.close()
+
+
+def spectrogram(T, seed, lo=-0.1, hi=1.05):
+    rng = np.random.default_rng(seed)
+    # smooth-ish in time and frequency, leaving [0, 1] at both ends so that the clip is exercised
+    x = rng.uniform(lo, hi, (T, 1025)).astype(np.float32)
+    x[:, 1:] = 0.5 * (x[:, 1:] + x[:, :-1])
+    return x
+
+
+def rel_err(got, want):
+    want = np.asarray(want, np.float64)
+    got = got.detach().cpu().numpy().astype(np.float64) if isinstance(got, torch.Tensor) else np.asarray(got, np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    return float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
+
+
+@pytest.mark.parametrize("T", [1, 2, 7, 33])
+def test_zero_phase_start_matches_oracle(eng, T):
+    x = spectrogram(T, T)
+    got = eng.griffin_lim(x, griffin_lim_iters=0, inv_preemphasis=False)
+    assert got.shape == ((T - 1) * 250 + 1000,)
+    assert rel_err(got, A.inv_spectrogram_tensorflow(x, eng.hp, iters=0)) < 2e-5
+
+
+@pytest.mark.parametrize("iters", [1, 2, 4])
+def test_first_iterations_match_oracle(eng, iters):
+    x = spectrogram(24, 100 + iters)
+    got = eng.griffin_lim(x, griffin_lim_iters=iters, inv_preemphasis=False)
+    assert rel_err(got, A.inv_spectrogram_tensorflow(x, eng.hp, iters=iters)) < 2e-4
+
+
+def test_inverse_preemphasis_on_device(eng):
+    x = spectrogram(50, 7)
+    got = eng.griffin_lim(x, griffin_lim_iters=0, inv_preemphasis=True)
+    assert rel_err(got, A.synthesize_wav(x, eng.hp, iters=0)) < 2e-5
+
+
+def test_batch_with_stride_equals_single_calls(eng):
+    xs = np.stack([spectrogram(12, 20 + i) for i in range(3)])
+    big = torch.zeros(3, 20, 1025, device=eng.device)
+    big[:, :12] = torch.as_tensor(xs, device=eng.device)
+    got = eng.griffin_lim(big[:, :12].contiguous(), griffin_lim_iters=3)
+    assert got.shape == (3, 11 * 250 + 1000)
+    for i in range(3):
+        one = eng.griffin_lim(xs[i], griffin_lim_iters=3)
+        assert torch.equal(got[i], one)                       # bit-identical: no cross-utterance arithmetic
+        assert rel_err(one, A.synthesize_wav(xs[i], eng.hp, iters=3)) < 2e-4
+    # batch stride through the C ABI directly (the post-net writes [N, max_steps*r, F] with only steps*r rows valid)
+    import ctypes as C
+    ap = eng.audio_params(3)
+    out = torch.empty(3, 11 * 250 + 1000, device=eng.device)
+    eng._ck(eng.lib.taco_griffin_lim(eng._h, C.byref(ap), C.c_void_p(big.data_ptr()), 3, 12, 20 * 1025,
+                                     C.c_void_p(out.data_ptr()), eng.stream))
+    assert torch.equal(out, got)
+
+
+def test_hundred_iterations_reach_the_oracles_consistency(eng):
+    hp = eng.hp
+    n_fft, hop, win = A.stft_parameters(hp)
+    x = spectrogram(40, 11, lo=0.2, hi=0.9)
+    S = np.power(A.db_to_amp(A.denormalize(x.astype(np.float64), hp) + hp.ref_level_db), hp.power)
+
+    def inconsistency(y):
+        return np.linalg.norm(np.abs(A.stft_tf(y, win, hop, n_fft)) - S) / np.linalg.norm(S)
+    got = eng.griffin_lim(x, inv_preemphasis=False).cpu().numpy().astype(np.float64)     # hparams: 100 iterations
+    want = A.inv_spectrogram_tensorflow(x, hp)
+    start = A.inv_spectrogram_tensorflow(x, hp, iters=0)
+    e_got, e_want, e_start = inconsistency(got), inconsistency(want), inconsistency(start)
+    assert np.isfinite(got).all()
+    assert e_want < e_start
+    assert abs(e_got - e_want) < 0.05 * e_want, (e_got, e_want, e_start)
+
+
+def test_full_size_utterances(eng):
+    # config-3 sized utterances (1000 frames): two iterations against the oracle
+    xs = np.stack([spectrogram(1000, 50 + i) for i in range(2)])
+    got = eng.griffin_lim(xs, griffin_lim_iters=2)
+    assert got.shape == (2, 999 * 250 + 1000)
+    for i in range(2):
+        assert rel_err(got[i], A.synthesize_wav(xs[i], eng.hp, iters=2)) < 2e-4
+
+
+def test_bad_arguments(eng):
+    from tacotron_multispeaker_b200 import _abi
+    with pytest.raises(ValueError):
+        eng.griffin_lim(np.zeros((4, 513), np.float32))
+    import ctypes as C
+    ap = eng.audio_params(1)
+    ap.frame_length_ms = 200.0                                   # win 4000 > n_fft
+    x = torch.zeros(1, 2, 1025, device=eng.device)
+    out = torch.zeros(1, 8000, device=eng.device)
+    rc = eng.lib.taco_griffin_lim(eng._h, C.byref(ap), C.c_void_p(x.data_ptr()), 1, 2, 0, C.c_void_p(out.data_ptr()), eng.stream)
+    assert rc == _abi.TACO_ERR_UNSUPPORTED
+
+
+def test_synthesizer_writes_wav_and_alignment(tmp_path):
+    from tacotron_multispeaker_b200 import text
+    from tacotron_multispeaker_b200.hparams import HParams
+    from tacotron_multispeaker_b200.synthesizer import Synthesizer
+    text.load_symbols([chr(0x4E00 + i) for i in range(7350)])
+    hp = HParams(griffin_lim_iters=5)
+    syn = Synthesizer(hp).load(None, id_num=4)
+    syn.hparams.max_iters = 12
+    sentence = "".join(chr(0x4E00 + i) for i in (5, 17, 300, 4000, 22))
+    wav_path, png_path = tmp_path / "o.wav", tmp_path / "o.png"
+    data = syn.synthesize(sentence, 2, str(wav_path), str(png_path))
+    assert data == wav_path.read_bytes() and png_path.read_bytes()[:4] == b"\x89PNG"
+    with wave.open(io.BytesIO(data), "rb") as f:
+        steps = syn.model.steps
+        assert f.getframerate() == 20000 and f.getnframes() == (steps * hp.outputs_per_step - 1) * 250 + 1000
+        pcm = np.frombuffer(f.readframes(f.getnframes()), "<i2")
+    # (random-init weights give a near-silent spectrogram: save_wav's 0.01 peak floor applies, not 32767)
+    # the same waveform from the oracle on the model's own linear output
+    lin = syn.model.linear_outputs[0].cpu().numpy()
+    want = A.save_wav_int16(A.synthesize_wav(lin, hp, iters=5))
+    assert np.max(np.abs(pcm.astype(np.int32) - want.astype(np.int32))) <= 8
