@@ -8,10 +8,9 @@
 //   -> inverse FFT in shared memory -> synthesis window -> its inverse frame for the next iteration.
 // The forward transform is decimation in frequency (natural order in, bit-reversed out), the phase step works on
 // the bit-reversed positions, and the inverse is decimation in time (bit-reversed in, natural out): no reordering
-// pass.  Three radix-2 stages are done in registers per shared-memory round trip (8 elements per thread), so a
-// transform is four round trips.  The upper half of the spectrum is not mirrored explicitly: for a real frame
-// X[N-k] = conj(X[k]) already sits in its bit-reversed position and takes the magnitude of bin N-k, and the real
-// part of the inverse is what irfft returns.
+// pass.  The real 2048-point transforms are 1024-point complex ones on even/odd packed samples; three or four
+// radix-2 stages are done in registers per shared-memory round trip (8 or 16 elements per thread, passes of
+// 3 + 3 + 4 stages), so a transform is three round trips, all of them bank-conflict free (one pad per 16 elements).
 //
 // TF conventions restated: frame(signal, win, hop, pad_end=False), periodic Hann of `win` points for analysis AND
 // synthesis (inverse_stft's default window_fn, no window-sum normalisation), rfft/irfft of n_fft = 2 (num_freq - 1)
@@ -24,7 +23,8 @@
 namespace taco {
 namespace {
 
-constexpr int GL_N = 2048, GL_BINS = GL_N / 2 + 1, GL_NT = 256;
+constexpr int GL_N = 2048, GL_M = GL_N / 2, GL_BINS = GL_N / 2 + 1, GL_NT = 128;
+constexpr int GL_TW = GL_N / 4 + 1;   // twiddles W_N^k the kernel touches: k <= N/4
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
@@ -32,11 +32,31 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {   // a * conj(b)
   return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
 }
+__device__ __forceinline__ int PD(int i) { return i + (i >> 4); }   // one pad word pair per 16: every pass conflict free
 
-// twiddles exp(-2 pi i k / 2048), k < 1024, and the periodic Hann window, evaluated in double
+// a * exp(-i pi j / 8) (CONJ: a * exp(+i pi j / 8)), j a compile-time constant after unrolling
+template <bool CONJ>
+__device__ __forceinline__ float2 mul_w16(float2 a, int j) {
+  constexpr float C1 = 0.9238795325112867f, S1 = 0.3826834323650898f, H = 0.7071067811865476f;
+  float c, s;
+  switch (j) {
+    case 0: return a;
+    case 4: return CONJ ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+    case 1: c = C1; s = S1; break;
+    case 2: c = H; s = H; break;
+    case 3: c = S1; s = C1; break;
+    case 5: c = -S1; s = C1; break;
+    case 6: c = -H; s = H; break;
+    default: c = -C1; s = S1; break;
+  }
+  const float2 w = make_float2(c, -s);
+  return CONJ ? cmul_conj(a, w) : cmul(a, w);
+}
+
+// twiddles exp(-2 pi i k / 2048), k <= 512, and the periodic Hann window, evaluated in double
 __global__ void gl_tables_kernel(float2* tw, float* win, int win_len) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < GL_N / 2) {
+  if (i < GL_TW) {
     double s, c;
     sincospi(-2.0 * (double)i / (double)GL_N, &s, &c);
     tw[i] = make_float2((float)c, (float)s);
@@ -56,16 +76,21 @@ __global__ void gl_mags_kernel(const float* __restrict__ lin, int64_t lin_bs, in
   }
 }
 
-// LOGR radix-2 stages, decimation in frequency, half-spans (R/2) q, (R/4) q, ..., q  (R = 2^LOGR, q = 2^LOGQ)
+// LOGR radix-2 stages of the 1024-point transform, decimation in frequency, half-spans (R/2) q, ..., q (R = 2^LOGR,
+// q = 2^LOGQ), in registers.  The twiddle of stage s for element lo + j q is W_{2 hs q}^{lo} * W_{2 hs}^{j}: one table
+// read per group (squared from stage to stage) times a constant.
 template <int LOGR, int LOGQ>
 __device__ __forceinline__ void dif_pass(float2* d, const float2* tw, int tid) {
   constexpr int R = 1 << LOGR, Q = 1 << LOGQ;
+  static_assert(R <= 16, "constant twiddles go up to W_16");
 #pragma unroll 1
-  for (int g = tid; g < GL_N / R; g += GL_NT) {
+  for (int g = tid; g < GL_M / R; g += GL_NT) {
     const int lo = g & (Q - 1), base = ((g >> LOGQ) << (LOGR + LOGQ)) + lo;
     float2 v[R];
 #pragma unroll
-    for (int m = 0; m < R; ++m) v[m] = d[base + m * Q];
+    for (int m = 0; m < R; ++m) v[m] = d[PD(base + m * Q)];
+    float2 wb = make_float2(1.0f, 0.0f);
+    if (LOGQ > 0) wb = tw[lo * (GL_N / (R * Q))];
 #pragma unroll
     for (int s = 0; s < LOGR; ++s) {
       const int hs = R >> (s + 1);
@@ -73,40 +98,51 @@ __device__ __forceinline__ void dif_pass(float2* d, const float2* tw, int tid) {
       for (int m = 0; m < R; ++m) {
         if (m & hs) continue;
         const float2 a = v[m], b = v[m + hs];
-        const int idx = (lo + (m & (hs - 1)) * Q) * (GL_N / (2 * hs * Q));
         v[m] = make_float2(a.x + b.x, a.y + b.y);
-        v[m + hs] = cmul(make_float2(a.x - b.x, a.y - b.y), tw[idx]);
+        float2 t = mul_w16<false>(make_float2(a.x - b.x, a.y - b.y), (m & (hs - 1)) * (8 / hs));
+        if (LOGQ > 0) t = cmul(t, wb);
+        v[m + hs] = t;
       }
+      if (LOGQ > 0) wb = cmul(wb, wb);
     }
 #pragma unroll
-    for (int m = 0; m < R; ++m) d[base + m * Q] = v[m];
+    for (int m = 0; m < R; ++m) d[PD(base + m * Q)] = v[m];
   }
 }
 
-// LOGR radix-2 stages of the inverse, decimation in time, half-spans q, 2q, ..., (R/2) q
+// the inverse: decimation in time, half-spans q, 2q, ..., (R/2) q, conjugate twiddles
 template <int LOGR, int LOGQ>
 __device__ __forceinline__ void dit_pass(float2* d, const float2* tw, int tid) {
   constexpr int R = 1 << LOGR, Q = 1 << LOGQ;
+  static_assert(R <= 16, "constant twiddles go up to W_16");
 #pragma unroll 1
-  for (int g = tid; g < GL_N / R; g += GL_NT) {
+  for (int g = tid; g < GL_M / R; g += GL_NT) {
     const int lo = g & (Q - 1), base = ((g >> LOGQ) << (LOGR + LOGQ)) + lo;
     float2 v[R];
 #pragma unroll
-    for (int m = 0; m < R; ++m) v[m] = d[base + m * Q];
+    for (int m = 0; m < R; ++m) v[m] = d[PD(base + m * Q)];
+    float2 wbs[LOGR];
+    wbs[LOGR - 1] = make_float2(1.0f, 0.0f);
+    if (LOGQ > 0) {
+      wbs[LOGR - 1] = tw[lo * (GL_N / (R * Q))];
+#pragma unroll
+      for (int s = LOGR - 2; s >= 0; --s) wbs[s] = cmul(wbs[s + 1], wbs[s + 1]);
+    }
 #pragma unroll
     for (int s = 0; s < LOGR; ++s) {
       const int hs = 1 << s;
 #pragma unroll
       for (int m = 0; m < R; ++m) {
         if (m & hs) continue;
-        const int idx = (lo + (m & (hs - 1)) * Q) * (GL_N / (2 * hs * Q));
-        const float2 a = v[m], b = cmul_conj(v[m + hs], tw[idx]);
+        float2 b = mul_w16<true>(v[m + hs], (m & (hs - 1)) * (8 / hs));
+        if (LOGQ > 0) b = cmul_conj(b, wbs[s]);
+        const float2 a = v[m];
         v[m] = make_float2(a.x + b.x, a.y + b.y);
         v[m + hs] = make_float2(a.x - b.x, a.y - b.y);
       }
     }
 #pragma unroll
-    for (int m = 0; m < R; ++m) d[base + m * Q] = v[m];
+    for (int m = 0; m < R; ++m) d[PD(base + m * Q)] = v[m];
   }
 }
 
@@ -119,50 +155,102 @@ __device__ __forceinline__ float ola_at(const float* __restrict__ r, int m, int 
   for (int tp = t_lo; tp <= t_hi; ++tp) acc += __ldg(r + (size_t)tp * win + (m - tp * hop));
   return acc;
 }
+// samples m, m + 1 (m, win and hop even: both are covered by the same frames and every address is 8-byte aligned)
+__device__ __forceinline__ float2 ola2_at(const float* __restrict__ r, int m, int T, int win, int hop) {
+  const int num = m - win + hop;
+  const int t_lo = num > 0 ? num / hop : 0;
+  const int t_hi = min(T - 1, m / hop);
+  float2 acc = make_float2(0.0f, 0.0f);
+  for (int tp = t_lo; tp <= t_hi; ++tp) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(r + (size_t)tp * win + (m - tp * hop)));
+    acc.x += v.x; acc.y += v.y;
+  }
+  return acc;
+}
+
+__device__ __forceinline__ float2 to_magnitude(float2 x, float mag) {   // util/audio.py:88-89
+  const float s = mag / fmaxf(1e-8f, sqrtf(fmaf(x.x, x.x, x.y * x.y)));
+  return make_float2(x.x * s, x.y * s);
+}
 
 // One Griffin-Lim iteration for frame blockIdx.x (first != 0: the zero-phase start, util/audio.py:84-85).
+// The real 2048-point transforms run as 1024-point complex ones on z[m] = x[2m] + i x[2m+1]; the phase step
+// un-mixes the bin pair (k, 1024 - k), rescales both and mixes them again for the inverse.
 __global__ void __launch_bounds__(GL_NT)
 gl_iter_kernel(const float* __restrict__ mags, const float* __restrict__ r_prev, float* __restrict__ r_next,
                const float2* __restrict__ tw_g, const float* __restrict__ win_g, int T, int win, int hop, int first) {
-  __shared__ float2 d[GL_N];
-  __shared__ float2 tw[GL_N / 2];
+  __shared__ float2 d[GL_M + GL_M / 16];
+  __shared__ float2 tw[GL_TW];
   __shared__ float mg[GL_BINS];
   const int tid = threadIdx.x;
   const int frame = blockIdx.x, n = frame / T, t = frame - n * T;
-  for (int i = tid; i < GL_N / 2; i += GL_NT) tw[i] = tw_g[i];
+  const bool even = ((win | hop) & 1) == 0;
+  for (int i = tid; i < GL_TW; i += GL_NT) tw[i] = tw_g[i];
   for (int i = tid; i < GL_BINS; i += GL_NT) mg[i] = __ldg(mags + (size_t)frame * GL_BINS + i);
-  __syncthreads();
   if (!first) {
     const float* r = r_prev + (size_t)n * T * win;
-    for (int i = tid; i < GL_N; i += GL_NT) {
-      float x = 0.0f;
-      if (i < win) x = ola_at(r, t * hop + i, T, win, hop) * __ldg(win_g + i);
-      d[i] = make_float2(x, 0.0f);
+    for (int m = tid; m < GL_M; m += GL_NT) {
+      float2 x = make_float2(0.0f, 0.0f);
+      const int i = 2 * m;
+      if (even) {
+        if (i < win) {
+          const float2 w = __ldg(reinterpret_cast<const float2*>(win_g + i));
+          x = ola2_at(r, t * hop + i, T, win, hop);
+          x.x *= w.x; x.y *= w.y;
+        }
+      } else {
+        if (i < win) x.x = ola_at(r, t * hop + i, T, win, hop) * __ldg(win_g + i);
+        if (i + 1 < win) x.y = ola_at(r, t * hop + i + 1, T, win, hop) * __ldg(win_g + i + 1);
+      }
+      d[PD(m)] = x;
     }
     __syncthreads();
-    dif_pass<3, 8>(d, tw, tid); __syncthreads();
-    dif_pass<3, 5>(d, tw, tid); __syncthreads();
-    dif_pass<3, 2>(d, tw, tid); __syncthreads();
-    dif_pass<2, 0>(d, tw, tid); __syncthreads();
-    for (int p = tid; p < GL_N; p += GL_NT) {   // util/audio.py:87-89
-      const int k = (int)(__brev((unsigned)p) >> 21), kk = min(k, GL_N - k);
-      const float2 x = d[p];
-      const float s = mg[kk] / fmaxf(1e-8f, sqrtf(fmaf(x.x, x.x, x.y * x.y)));
-      d[p] = make_float2(x.x * s, x.y * s);
-    }
-  } else {
-    for (int p = tid; p < GL_N; p += GL_NT) {
-      const int k = (int)(__brev((unsigned)p) >> 21), kk = min(k, GL_N - k);
-      d[p] = make_float2(mg[kk], 0.0f);
-    }
+    dif_pass<3, 7>(d, tw, tid); __syncthreads();
+    dif_pass<3, 4>(d, tw, tid); __syncthreads();
+    dif_pass<4, 0>(d, tw, tid);
   }
   __syncthreads();
-  dit_pass<3, 0>(d, tw, tid); __syncthreads();
-  dit_pass<3, 3>(d, tw, tid); __syncthreads();
-  dit_pass<3, 6>(d, tw, tid); __syncthreads();
-  dit_pass<2, 9>(d, tw, tid); __syncthreads();
+  for (int k = tid; k <= GL_M / 2; k += GL_NT) {
+    const int km = GL_M - k;
+    const int pk = PD((int)(__brev((unsigned)k) >> 22)), pm = PD((int)(__brev((unsigned)(km & (GL_M - 1))) >> 22));
+    const float2 w = tw[k];
+    float2 yk, ym;
+    if (first) {
+      yk = make_float2(mg[k], 0.0f);
+      ym = make_float2(mg[km], 0.0f);
+    } else {
+      const float2 zk = d[pk], zm = d[pm];
+      // E = (Z[k] + conj Z[M-k]) / 2, O = (Z[k] - conj Z[M-k]) / 2i;  X[k] = E + W^k O,  X[M-k] = conj(E - W^k O)
+      const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+      const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+      const float2 tt = cmul(w, o);
+      yk = to_magnitude(make_float2(e.x + tt.x, e.y + tt.y), mg[k]);
+      ym = to_magnitude(make_float2(e.x - tt.x, -(e.y - tt.y)), mg[km]);
+    }
+    // Z'[k] = E' + i O' with E' = Y[k] + conj Y[M-k], O' = (Y[k] - conj Y[M-k]) conj(W^k)   (the 1/2 is in the final scale)
+    const float2 ep = make_float2(yk.x + ym.x, yk.y - ym.y);
+    const float2 op = cmul_conj(make_float2(yk.x - ym.x, yk.y + ym.y), w);
+    d[pk] = make_float2(ep.x - op.y, ep.y + op.x);
+    if (k != 0 && k != GL_M / 2) d[pm] = make_float2(ep.x + op.y, op.x - ep.y);
+  }
+  __syncthreads();
+  dit_pass<4, 0>(d, tw, tid); __syncthreads();
+  dit_pass<3, 4>(d, tw, tid); __syncthreads();
+  dit_pass<3, 7>(d, tw, tid); __syncthreads();
   float* o = r_next + (size_t)frame * win;
-  for (int i = tid; i < win; i += GL_NT) o[i] = d[i].x * (__ldg(win_g + i) * (1.0f / GL_N));
+  for (int m = tid; m < GL_M; m += GL_NT) {
+    const int i = 2 * m;
+    const float2 z = d[PD(m)];
+    if (even) {
+      if (i < win) {
+        const float2 w = __ldg(reinterpret_cast<const float2*>(win_g + i));
+        *reinterpret_cast<float2*>(o + i) = make_float2(z.x * (w.x * (1.0f / GL_N)), z.y * (w.y * (1.0f / GL_N)));
+      }
+    } else {
+      if (i < win) o[i] = z.x * (__ldg(win_g + i) * (1.0f / GL_N));
+      if (i + 1 < win) o[i + 1] = z.y * (__ldg(win_g + i + 1) * (1.0f / GL_N));
+    }
+  }
 }
 
 // overlap_and_add of the last inverse frames: y [N, L]
@@ -199,7 +287,7 @@ __global__ void __launch_bounds__(1024) gl_deemph_kernel(float* __restrict__ y, 
 
 size_t griffin_lim_ws_bytes(int N, int T, int win) {
   const size_t frames = (size_t)N * T;
-  return frames * GL_BINS * sizeof(float) + 2 * frames * win * sizeof(float) + GL_N / 2 * sizeof(float2) +
+  return frames * GL_BINS * sizeof(float) + 2 * frames * win * sizeof(float) + GL_TW * sizeof(float2) +
          (size_t)win * sizeof(float) + 4096;
 }
 
@@ -212,7 +300,7 @@ cudaError_t launch_griffin_lim(const GriffinLimArgs& a, void* ws, cudaStream_t s
   float* mags = reinterpret_cast<float*>(take(frames * GL_BINS * sizeof(float)));
   float* r0 = reinterpret_cast<float*>(take(frames * a.win * sizeof(float)));
   float* r1 = reinterpret_cast<float*>(take(frames * a.win * sizeof(float)));
-  float2* tw = reinterpret_cast<float2*>(take(GL_N / 2 * sizeof(float2)));
+  float2* tw = reinterpret_cast<float2*>(take(GL_TW * sizeof(float2)));
   float* win = reinterpret_cast<float*>(take((size_t)a.win * sizeof(float)));
   gl_tables_kernel<<<(GL_N + 255) / 256, 256, 0, st>>>(tw, win, a.win);
   const int64_t total = (int64_t)frames * GL_BINS;
