@@ -83,8 +83,9 @@ template <int LOGR, int LOGQ>
 __device__ __forceinline__ void dif_pass(float2* d, const float2* tw, int tid) {
   constexpr int R = 1 << LOGR, Q = 1 << LOGQ;
   static_assert(R <= 16, "constant twiddles go up to W_16");
-#pragma unroll 1
-  for (int g = tid; g < GL_M / R; g += GL_NT) {
+  static_assert(GL_M / R <= GL_NT, "one group per thread");
+  if (tid < GL_M / R) {   // GL_M / R <= GL_NT: at most one group per thread
+    const int g = tid;
     const int lo = g & (Q - 1), base = ((g >> LOGQ) << (LOGR + LOGQ)) + lo;
     float2 v[R];
 #pragma unroll
@@ -115,8 +116,9 @@ template <int LOGR, int LOGQ>
 __device__ __forceinline__ void dit_pass(float2* d, const float2* tw, int tid) {
   constexpr int R = 1 << LOGR, Q = 1 << LOGQ;
   static_assert(R <= 16, "constant twiddles go up to W_16");
-#pragma unroll 1
-  for (int g = tid; g < GL_M / R; g += GL_NT) {
+  static_assert(GL_M / R <= GL_NT, "one group per thread");
+  if (tid < GL_M / R) {   // GL_M / R <= GL_NT: at most one group per thread
+    const int g = tid;
     const int lo = g & (Q - 1), base = ((g >> LOGQ) << (LOGR + LOGQ)) + lo;
     float2 v[R];
 #pragma unroll
@@ -155,15 +157,32 @@ __device__ __forceinline__ float ola_at(const float* __restrict__ r, int m, int 
   for (int tp = t_lo; tp <= t_hi; ++tp) acc += __ldg(r + (size_t)tp * win + (m - tp * hop));
   return acc;
 }
-// samples m, m + 1 (m, win and hop even: both are covered by the same frames and every address is 8-byte aligned)
-__device__ __forceinline__ float2 ola2_at(const float* __restrict__ r, int m, int T, int win, int hop) {
-  const int num = m - win + hop;
-  const int t_lo = num > 0 ? num / hop : 0;
-  const int t_hi = min(T - 1, m / hop);
+// samples i, i + 1 of frame t before the analysis window (i, win and hop even: both samples are covered by the same
+// frames and every address is 8-byte aligned).  Frame t + dd holds them at offset i - dd hop; K = (win - 1) / hop
+// frames overlap on each side.  KT >= 0: K known at compile time (all loads issued back to back).
+template <int KT>
+__device__ __forceinline__ float2 ola2_frame(const float* __restrict__ r, int t, int i, int T, int win, int hop, int K) {
+  const float* p = r + (size_t)t * win + i;
+  const int step = win - hop;
   float2 acc = make_float2(0.0f, 0.0f);
-  for (int tp = t_lo; tp <= t_hi; ++tp) {
-    const float2 v = __ldg(reinterpret_cast<const float2*>(r + (size_t)tp * win + (m - tp * hop)));
-    acc.x += v.x; acc.y += v.y;
+  if (KT >= 0) {
+    float2 v[2 * (KT >= 0 ? KT : 0) + 1];
+#pragma unroll
+    for (int dd = -KT; dd <= KT; ++dd) {
+      const bool ok = (unsigned)(i - dd * hop) < (unsigned)win && (unsigned)(t + dd) < (unsigned)T;
+      v[dd + KT] = ok ? __ldg(reinterpret_cast<const float2*>(p + dd * step)) : make_float2(0.0f, 0.0f);
+    }
+#pragma unroll
+    for (int dd = -KT; dd <= KT; ++dd) {
+      const bool ok = (unsigned)(i - dd * hop) < (unsigned)win && (unsigned)(t + dd) < (unsigned)T;
+      if (ok) { acc.x += v[dd + KT].x; acc.y += v[dd + KT].y; }
+    }
+  } else {
+    for (int dd = -K; dd <= K; ++dd)
+      if ((unsigned)(i - dd * hop) < (unsigned)win && (unsigned)(t + dd) < (unsigned)T) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(p + dd * step));
+        acc.x += v.x; acc.y += v.y;
+      }
   }
   return acc;
 }
@@ -176,6 +195,7 @@ __device__ __forceinline__ float2 to_magnitude(float2 x, float mag) {   // util/
 // One Griffin-Lim iteration for frame blockIdx.x (first != 0: the zero-phase start, util/audio.py:84-85).
 // The real 2048-point transforms run as 1024-point complex ones on z[m] = x[2m] + i x[2m+1]; the phase step
 // un-mixes the bin pair (k, 1024 - k), rescales both and mixes them again for the inverse.
+template <int KT>
 __global__ void __launch_bounds__(GL_NT)
 gl_iter_kernel(const float* __restrict__ mags, const float* __restrict__ r_prev, float* __restrict__ r_next,
                const float2* __restrict__ tw_g, const float* __restrict__ win_g, int T, int win, int hop, int first) {
@@ -195,7 +215,7 @@ gl_iter_kernel(const float* __restrict__ mags, const float* __restrict__ r_prev,
       if (even) {
         if (i < win) {
           const float2 w = __ldg(reinterpret_cast<const float2*>(win_g + i));
-          x = ola2_at(r, t * hop + i, T, win, hop);
+          x = ola2_frame<KT>(r, t, i, T, win, hop, (win - 1) / hop);
           x.x *= w.x; x.y *= w.y;
         }
       } else {
@@ -309,9 +329,11 @@ cudaError_t launch_griffin_lim(const GriffinLimArgs& a, void* ws, cudaStream_t s
       a.linear, a.linear_bs, a.T, GL_BINS, -a.min_level_db, a.min_level_db + a.ref_level_db,
       0.05f * a.power * 3.3219280948873623f, mags, total);
   float *cur = r0, *nxt = r1;
-  gl_iter_kernel<<<(unsigned)frames, GL_NT, 0, st>>>(mags, nullptr, cur, tw, win, a.T, a.win, a.hop, 1);
+  // the reference geometry (win 1000, hop 250: three overlapping frames on each side) gets the unrolled overlap-add
+  auto kern = (a.win - 1) / a.hop == 3 ? gl_iter_kernel<3> : gl_iter_kernel<-1>;
+  kern<<<(unsigned)frames, GL_NT, 0, st>>>(mags, nullptr, cur, tw, win, a.T, a.win, a.hop, 1);
   for (int it = 0; it < a.iters; ++it) {
-    gl_iter_kernel<<<(unsigned)frames, GL_NT, 0, st>>>(mags, cur, nxt, tw, win, a.T, a.win, a.hop, 0);
+    kern<<<(unsigned)frames, GL_NT, 0, st>>>(mags, cur, nxt, tw, win, a.T, a.win, a.hop, 0);
     float* tmp = cur; cur = nxt; nxt = tmp;
   }
   const int L = (a.T - 1) * a.hop + a.win;

@@ -56,6 +56,23 @@ def test_first_iterations_match_oracle(eng, iters):
     assert rel_err(got, A.inv_spectrogram_tensorflow(x, eng.hp, iters=iters)) < 2e-4
 
 
+@pytest.mark.parametrize("frame_length_ms,frame_shift_ms", [(50.0, 10.0), (49.95, 12.5), (30.0, 12.5), (102.4, 6.25)])
+def test_other_frame_geometries(frame_length_ms, frame_shift_ms):
+    # generic overlap counts (win 1000 / hop 200), odd window length (999: scalar loads), short and full-length windows
+    from tacotron_multispeaker_b200.engine import Engine
+    from tacotron_multispeaker_b200.hparams import HParams
+    hp = HParams(frame_length_ms=frame_length_ms, frame_shift_ms=frame_shift_ms)
+    e = Engine(hp, id_num=0)
+    try:
+        x = spectrogram(19, 77)
+        n_fft, hop, win = A.stft_parameters(hp)
+        got = e.griffin_lim(x, griffin_lim_iters=3)
+        assert got.shape == (18 * hop + win,)
+        assert rel_err(got, A.synthesize_wav(x, hp, iters=3)) < 2e-4
+    finally:
+        e.close()
+
+
 def test_inverse_preemphasis_on_device(eng):
     x = spectrogram(50, 7)
     got = eng.griffin_lim(x, griffin_lim_iters=0, inv_preemphasis=True)
