@@ -87,11 +87,15 @@ __device__ __forceinline__ void dif_pass(float2* d, const float2* tw, int tid) {
   if (tid < GL_M / R) {   // GL_M / R <= GL_NT: at most one group per thread
     const int g = tid;
     const int lo = g & (Q - 1), base = ((g >> LOGQ) << (LOGR + LOGQ)) + lo;
+    // element m sits at PD(base + m q) = PD(base) + m PS: q is a multiple of 16, or base is and the group fits in 16
+    static_assert(Q >= 16 || R * Q <= 16, "padded stride");
+    constexpr int PS = Q >= 16 ? Q + Q / 16 : Q;
+    float2* dp = d + PD(base);
     float2 v[R];
 #pragma unroll
-    for (int m = 0; m < R; ++m) v[m] = d[PD(base + m * Q)];
+    for (int m = 0; m < R; ++m) v[m] = dp[m * PS];
     float2 wb = make_float2(1.0f, 0.0f);
-    if (LOGQ > 0) wb = tw[lo * (GL_N / (R * Q))];
+    if (LOGQ > 0) wb = __ldg(tw + lo * (GL_N / (R * Q)));
 #pragma unroll
     for (int s = 0; s < LOGR; ++s) {
       const int hs = R >> (s + 1);
@@ -107,7 +111,7 @@ __device__ __forceinline__ void dif_pass(float2* d, const float2* tw, int tid) {
       if (LOGQ > 0) wb = cmul(wb, wb);
     }
 #pragma unroll
-    for (int m = 0; m < R; ++m) d[PD(base + m * Q)] = v[m];
+    for (int m = 0; m < R; ++m) dp[m * PS] = v[m];
   }
 }
 
@@ -120,13 +124,16 @@ __device__ __forceinline__ void dit_pass(float2* d, const float2* tw, int tid) {
   if (tid < GL_M / R) {   // GL_M / R <= GL_NT: at most one group per thread
     const int g = tid;
     const int lo = g & (Q - 1), base = ((g >> LOGQ) << (LOGR + LOGQ)) + lo;
+    static_assert(Q >= 16 || R * Q <= 16, "padded stride");
+    constexpr int PS = Q >= 16 ? Q + Q / 16 : Q;
+    float2* dp = d + PD(base);
     float2 v[R];
 #pragma unroll
-    for (int m = 0; m < R; ++m) v[m] = d[PD(base + m * Q)];
+    for (int m = 0; m < R; ++m) v[m] = dp[m * PS];
     float2 wbs[LOGR];
     wbs[LOGR - 1] = make_float2(1.0f, 0.0f);
     if (LOGQ > 0) {
-      wbs[LOGR - 1] = tw[lo * (GL_N / (R * Q))];
+      wbs[LOGR - 1] = __ldg(tw + lo * (GL_N / (R * Q)));
 #pragma unroll
       for (int s = LOGR - 2; s >= 0; --s) wbs[s] = cmul(wbs[s + 1], wbs[s + 1]);
     }
@@ -144,7 +151,7 @@ __device__ __forceinline__ void dit_pass(float2* d, const float2* tw, int tid) {
       }
     }
 #pragma unroll
-    for (int m = 0; m < R; ++m) d[PD(base + m * Q)] = v[m];
+    for (int m = 0; m < R; ++m) dp[m * PS] = v[m];
   }
 }
 
@@ -192,75 +199,116 @@ __device__ __forceinline__ float2 to_magnitude(float2 x, float mag) {   // util/
   return make_float2(x.x * s, x.y * s);
 }
 
-// One Griffin-Lim iteration for frame blockIdx.x (first != 0: the zero-phase start, util/audio.py:84-85).
+// One Griffin-Lim iteration for frame blockIdx.x (FIRST: the zero-phase start, util/audio.py:84-85).
 // The real 2048-point transforms run as 1024-point complex ones on z[m] = x[2m] + i x[2m+1]; the phase step
 // un-mixes the bin pair (k, 1024 - k), rescales both and mixes them again for the inverse.
-template <int KT>
+// REF: win == 4 hop, both even (the reference's 1000 / 250): sample i of an interior frame is the sum of exactly
+// four rows at constant distances; other geometries and the three frames at each end take the predicated loop.
+// Twiddles (4 KB, L1 resident) and the frame's magnitudes are read straight from global memory: a thread needs two
+// twiddles per transform and the magnitudes of its own five bin pairs, requested before the forward transform.
+template <bool FIRST, bool REF>
 __global__ void __launch_bounds__(GL_NT)
 gl_iter_kernel(const float* __restrict__ mags, const float* __restrict__ r_prev, float* __restrict__ r_next,
-               const float2* __restrict__ tw_g, const float* __restrict__ win_g, int T, int win, int hop, int first) {
+               const float2* __restrict__ tw, const float* __restrict__ win_g, int T, int win, int hop) {
   __shared__ float2 d[GL_M + GL_M / 16];
-  __shared__ float2 tw[GL_TW];
-  __shared__ float mg[GL_BINS];
+  constexpr int PJ = GL_NT + GL_NT / 16;          // m = tid + 128 j sits at PD(tid) + 136 j
+  constexpr int NPAIR = (GL_M / 2 + GL_NT) / GL_NT;   // bin pairs (k, M - k), k = tid + 128 j <= 512
   const int tid = threadIdx.x;
   const int frame = blockIdx.x, n = frame / T, t = frame - n * T;
-  const bool even = ((win | hop) & 1) == 0;
-  for (int i = tid; i < GL_TW; i += GL_NT) tw[i] = tw_g[i];
-  for (int i = tid; i < GL_BINS; i += GL_NT) mg[i] = __ldg(mags + (size_t)frame * GL_BINS + i);
-  if (!first) {
+  const bool even = REF || ((win | hop) & 1) == 0;
+  float mk[NPAIR], mkm[NPAIR];
+  {
+    const float* mrow = mags + (size_t)frame * GL_BINS;
+#pragma unroll
+    for (int j = 0; j < NPAIR; ++j) {
+      const int k = tid + GL_NT * j;
+      mk[j] = k <= GL_M / 2 ? __ldg(mrow + k) : 0.0f;
+      mkm[j] = k <= GL_M / 2 ? __ldg(mrow + GL_M - k) : 0.0f;
+    }
+  }
+  if (!FIRST) {
     const float* r = r_prev + (size_t)n * T * win;
-    for (int m = tid; m < GL_M; m += GL_NT) {
-      float2 x = make_float2(0.0f, 0.0f);
-      const int i = 2 * m;
-      if (even) {
+    if (REF && t >= 3 && t + 3 < T) {
+      const float* pt = r + (size_t)t * win;
+      const int step = win - hop;   // frame t + dd holds sample i at pt[i + dd step]
+#pragma unroll
+      for (int j = 0; j < GL_M / GL_NT; ++j) {
+        const int i = 2 * (tid + GL_NT * j);
+        float2 x = make_float2(0.0f, 0.0f);
         if (i < win) {
+          const int a = (i >= hop) + (i >= 2 * hop) + (i >= 3 * hop);   // frames t + a - 3 .. t + a cover sample i
+          const float* q = pt + i + (a - 3) * step;
+          const float2 v0 = __ldg(reinterpret_cast<const float2*>(q));
+          const float2 v1 = __ldg(reinterpret_cast<const float2*>(q + step));
+          const float2 v2 = __ldg(reinterpret_cast<const float2*>(q + 2 * step));
+          const float2 v3 = __ldg(reinterpret_cast<const float2*>(q + 3 * step));
           const float2 w = __ldg(reinterpret_cast<const float2*>(win_g + i));
-          x = ola2_frame<KT>(r, t, i, T, win, hop, (win - 1) / hop);
-          x.x *= w.x; x.y *= w.y;
+          x.x = (((v0.x + v1.x) + v2.x) + v3.x) * w.x;
+          x.y = (((v0.y + v1.y) + v2.y) + v3.y) * w.y;
         }
-      } else {
-        if (i < win) x.x = ola_at(r, t * hop + i, T, win, hop) * __ldg(win_g + i);
-        if (i + 1 < win) x.y = ola_at(r, t * hop + i + 1, T, win, hop) * __ldg(win_g + i + 1);
+        d[PD(tid) + PJ * j] = x;
       }
-      d[PD(m)] = x;
+    } else {
+      const int K = (win - 1) / hop;
+#pragma unroll 1
+      for (int j = 0; j < GL_M / GL_NT; ++j) {
+        const int i = 2 * (tid + GL_NT * j);
+        float2 x = make_float2(0.0f, 0.0f);
+        if (even) {
+          if (i < win) {
+            const float2 w = __ldg(reinterpret_cast<const float2*>(win_g + i));
+            x = ola2_frame<-1>(r, t, i, T, win, hop, K);
+            x.x *= w.x; x.y *= w.y;
+          }
+        } else {
+          if (i < win) x.x = ola_at(r, t * hop + i, T, win, hop) * __ldg(win_g + i);
+          if (i + 1 < win) x.y = ola_at(r, t * hop + i + 1, T, win, hop) * __ldg(win_g + i + 1);
+        }
+        d[PD(tid) + PJ * j] = x;
+      }
     }
     __syncthreads();
     dif_pass<3, 7>(d, tw, tid); __syncthreads();
     dif_pass<3, 4>(d, tw, tid); __syncthreads();
     dif_pass<4, 0>(d, tw, tid);
+    __syncthreads();
   }
-  __syncthreads();
-  for (int k = tid; k <= GL_M / 2; k += GL_NT) {
-    const int km = GL_M - k;
-    const int pk = PD((int)(__brev((unsigned)k) >> 22)), pm = PD((int)(__brev((unsigned)(km & (GL_M - 1))) >> 22));
-    const float2 w = tw[k];
-    float2 yk, ym;
-    if (first) {
-      yk = make_float2(mg[k], 0.0f);
-      ym = make_float2(mg[km], 0.0f);
-    } else {
-      const float2 zk = d[pk], zm = d[pm];
-      // E = (Z[k] + conj Z[M-k]) / 2, O = (Z[k] - conj Z[M-k]) / 2i;  X[k] = E + W^k O,  X[M-k] = conj(E - W^k O)
-      const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-      const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
-      const float2 tt = cmul(w, o);
-      yk = to_magnitude(make_float2(e.x + tt.x, e.y + tt.y), mg[k]);
-      ym = to_magnitude(make_float2(e.x - tt.x, -(e.y - tt.y)), mg[km]);
+#pragma unroll
+  for (int j = 0; j < NPAIR; ++j) {
+    const int k = tid + GL_NT * j;
+    if (k <= GL_M / 2) {
+      const int km = GL_M - k;
+      const int pk = PD((int)(__brev((unsigned)k) >> 22)), pm = PD((int)(__brev((unsigned)(km & (GL_M - 1))) >> 22));
+      const float2 w = __ldg(tw + k);
+      float2 yk, ym;
+      if (FIRST) {
+        yk = make_float2(mk[j], 0.0f);
+        ym = make_float2(mkm[j], 0.0f);
+      } else {
+        const float2 zk = d[pk], zm = d[pm];
+        // E = (Z[k] + conj Z[M-k]) / 2, O = (Z[k] - conj Z[M-k]) / 2i;  X[k] = E + W^k O,  X[M-k] = conj(E - W^k O)
+        const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+        const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+        const float2 tt = cmul(w, o);
+        yk = to_magnitude(make_float2(e.x + tt.x, e.y + tt.y), mk[j]);
+        ym = to_magnitude(make_float2(e.x - tt.x, -(e.y - tt.y)), mkm[j]);
+      }
+      // Z'[k] = E' + i O' with E' = Y[k] + conj Y[M-k], O' = (Y[k] - conj Y[M-k]) conj(W^k)   (the 1/2 is in the final scale)
+      const float2 ep = make_float2(yk.x + ym.x, yk.y - ym.y);
+      const float2 op = cmul_conj(make_float2(yk.x - ym.x, yk.y + ym.y), w);
+      d[pk] = make_float2(ep.x - op.y, ep.y + op.x);
+      if (k != 0 && k != GL_M / 2) d[pm] = make_float2(ep.x + op.y, op.x - ep.y);
     }
-    // Z'[k] = E' + i O' with E' = Y[k] + conj Y[M-k], O' = (Y[k] - conj Y[M-k]) conj(W^k)   (the 1/2 is in the final scale)
-    const float2 ep = make_float2(yk.x + ym.x, yk.y - ym.y);
-    const float2 op = cmul_conj(make_float2(yk.x - ym.x, yk.y + ym.y), w);
-    d[pk] = make_float2(ep.x - op.y, ep.y + op.x);
-    if (k != 0 && k != GL_M / 2) d[pm] = make_float2(ep.x + op.y, op.x - ep.y);
   }
   __syncthreads();
   dit_pass<4, 0>(d, tw, tid); __syncthreads();
   dit_pass<3, 4>(d, tw, tid); __syncthreads();
   dit_pass<3, 7>(d, tw, tid); __syncthreads();
   float* o = r_next + (size_t)frame * win;
-  for (int m = tid; m < GL_M; m += GL_NT) {
-    const int i = 2 * m;
-    const float2 z = d[PD(m)];
+#pragma unroll
+  for (int j = 0; j < GL_M / GL_NT; ++j) {
+    const int i = 2 * (tid + GL_NT * j);
+    const float2 z = d[PD(tid) + PJ * j];
     if (even) {
       if (i < win) {
         const float2 w = __ldg(reinterpret_cast<const float2*>(win_g + i));
@@ -329,11 +377,12 @@ cudaError_t launch_griffin_lim(const GriffinLimArgs& a, void* ws, cudaStream_t s
       a.linear, a.linear_bs, a.T, GL_BINS, -a.min_level_db, a.min_level_db + a.ref_level_db,
       0.05f * a.power * 3.3219280948873623f, mags, total);
   float *cur = r0, *nxt = r1;
-  // the reference geometry (win 1000, hop 250: three overlapping frames on each side) gets the unrolled overlap-add
-  auto kern = (a.win - 1) / a.hop == 3 ? gl_iter_kernel<3> : gl_iter_kernel<-1>;
-  kern<<<(unsigned)frames, GL_NT, 0, st>>>(mags, nullptr, cur, tw, win, a.T, a.win, a.hop, 1);
+  const bool ref = a.win == 4 * a.hop && ((a.win | a.hop) & 1) == 0;   // the reference's 1000 / 250
+  if (ref) gl_iter_kernel<true, true><<<(unsigned)frames, GL_NT, 0, st>>>(mags, nullptr, cur, tw, win, a.T, a.win, a.hop);
+  else gl_iter_kernel<true, false><<<(unsigned)frames, GL_NT, 0, st>>>(mags, nullptr, cur, tw, win, a.T, a.win, a.hop);
   for (int it = 0; it < a.iters; ++it) {
-    kern<<<(unsigned)frames, GL_NT, 0, st>>>(mags, cur, nxt, tw, win, a.T, a.win, a.hop, 0);
+    if (ref) gl_iter_kernel<false, true><<<(unsigned)frames, GL_NT, 0, st>>>(mags, cur, nxt, tw, win, a.T, a.win, a.hop);
+    else gl_iter_kernel<false, false><<<(unsigned)frames, GL_NT, 0, st>>>(mags, cur, nxt, tw, win, a.T, a.win, a.hop);
     float* tmp = cur; cur = nxt; nxt = tmp;
   }
   const int L = (a.T - 1) * a.hop + a.win;
