@@ -401,6 +401,26 @@ def run_ours(args):
         for l in lanes:
             l["eng"].set_decoder_clusters(0)
 
+    # ---- the step after the path (informational): Griffin-Lim vocoder on the last linear output of lane 0 ----
+    voc = None
+    if not args.no_vocoder:
+        lin = lanes[0]["outs"][1]
+        eng.griffin_lim(lin)                                   # warm-up (workspace growth)
+        torch.cuda.synchronize()
+        voc_l0 = eng.launch_count()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        for _ in range(3):
+            wav = eng.griffin_lim(lin)
+        v1.record()
+        torch.cuda.synchronize()
+        v_ms = v0.elapsed_time(v1) / 3
+        voc = {"what": "taco_griffin_lim: %d iterations + inverse pre-emphasis on the batch's linear spectrograms "
+                       "(reference synthesizer.py:27,50); not part of `value`" % hp.griffin_lim_iters,
+               "ms_per_batch": v_ms, "us_per_iteration": 1e3 * v_ms / hp.griffin_lim_iters,
+               "frames_per_s": frames_per_step / (v_ms / 1e3), "launches_per_batch": (eng.launch_count() - voc_l0) // 3,
+               "audio_seconds_per_batch": BATCH * wav.shape[-1] / hp.sample_rate}
+
     # ---- CPU restatement on the host cores (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -417,7 +437,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(world), inflight="%d batches in flight per GPU (one handle + CUDA stream "
                                                             "each); single_stream = one at a time" % n_dev),
-            "single_stream": single, "e2e": e2e, "throughput_mode": thr, "gpu_launches": int(launches),
+            "single_stream": single, "e2e": e2e, "throughput_mode": thr, "vocoder": voc, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "decoder_geometry": geo,
         }
@@ -438,6 +458,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU restatement leg")
     ap.add_argument("--inflight", type=int, default=4, help="batches in flight per GPU (handles/streams), device-resident leg")
     ap.add_argument("--e2e-lanes", type=int, default=6, help="batches in flight per GPU in the end-to-end leg")
+    ap.add_argument("--no-vocoder", action="store_true", help="skip the informational Griffin-Lim leg")
     ap.add_argument("--no-throughput-mode", action="store_true", help="skip the informational 4-cluster decoder legs")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on stdout when
