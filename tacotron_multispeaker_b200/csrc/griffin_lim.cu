@@ -194,8 +194,10 @@ __device__ __forceinline__ float2 ola2_frame(const float* __restrict__ r, int t,
   return acc;
 }
 
-__device__ __forceinline__ float2 to_magnitude(float2 x, float mag) {   // util/audio.py:88-89
-  const float s = mag / fmaxf(1e-8f, sqrtf(fmaf(x.x, x.x, x.y * x.y)));
+// util/audio.py:88-89: mag * x / max(1e-8, |x|) = mag * x * rsqrt(max(1e-16, |x|^2)); MUFU.RSQ has no slow path for
+// the tiny values of silent frames (sqrtf and the division do)
+__device__ __forceinline__ float2 to_magnitude(float2 x, float mag) {
+  const float s = mag * rsqrtf(fmaxf(1e-16f, fmaf(x.x, x.x, x.y * x.y)));
   return make_float2(x.x * s, x.y * s);
 }
 
