@@ -32,7 +32,10 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {   // a * conj(b)
   return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
 }
-__device__ __forceinline__ int PD(int i) { return i + (i >> 4); }   // one pad word pair per 16: every pass conflict free
+// element i of the transform sits at PD(i): one pad per 16 elements makes every FFT pass bank-conflict free, one more
+// per 256 spreads the bit-reversed positions of the phase step (stride 64) over the banks (3.9 -> 1.5 wavefronts)
+__device__ __forceinline__ int PD(int i) { return i + (i >> 4) + (i >> 8); }
+constexpr int GL_DSIZE = GL_M + GL_M / 16 + GL_M / 256;
 
 // a * exp(-i pi j / 8) (CONJ: a * exp(+i pi j / 8)), j a compile-time constant after unrolling
 template <bool CONJ>
@@ -87,13 +90,15 @@ __device__ __forceinline__ void dif_pass(float2* d, const float2* tw, int tid) {
   if (tid < GL_M / R) {   // GL_M / R <= GL_NT: at most one group per thread
     const int g = tid;
     const int lo = g & (Q - 1), base = ((g >> LOGQ) << (LOGR + LOGQ)) + lo;
-    // element m sits at PD(base + m q) = PD(base) + m PS: q is a multiple of 16, or base is and the group fits in 16
+    // element m sits at PD(base + m q) = PD(base) + m PS + (m q >> 8): q is a multiple of 16, or base is and the group
+    // fits in 16; the per-256 pad moves only for q = 128 (base < 128), otherwise a group stays inside one 256 block
     static_assert(Q >= 16 || R * Q <= 16, "padded stride");
+    static_assert(Q == 128 || R * Q <= 128, "per-256 pad");
     constexpr int PS = Q >= 16 ? Q + Q / 16 : Q;
     float2* dp = d + PD(base);
     float2 v[R];
 #pragma unroll
-    for (int m = 0; m < R; ++m) v[m] = dp[m * PS];
+    for (int m = 0; m < R; ++m) v[m] = dp[m * PS + (Q == 128 ? (m >> 1) : 0)];
     float2 wb = make_float2(1.0f, 0.0f);
     if (LOGQ > 0) wb = __ldg(tw + lo * (GL_N / (R * Q)));
 #pragma unroll
@@ -111,7 +116,7 @@ __device__ __forceinline__ void dif_pass(float2* d, const float2* tw, int tid) {
       if (LOGQ > 0) wb = cmul(wb, wb);
     }
 #pragma unroll
-    for (int m = 0; m < R; ++m) dp[m * PS] = v[m];
+    for (int m = 0; m < R; ++m) dp[m * PS + (Q == 128 ? (m >> 1) : 0)] = v[m];
   }
 }
 
@@ -125,11 +130,12 @@ __device__ __forceinline__ void dit_pass(float2* d, const float2* tw, int tid) {
     const int g = tid;
     const int lo = g & (Q - 1), base = ((g >> LOGQ) << (LOGR + LOGQ)) + lo;
     static_assert(Q >= 16 || R * Q <= 16, "padded stride");
+    static_assert(Q == 128 || R * Q <= 128, "per-256 pad");
     constexpr int PS = Q >= 16 ? Q + Q / 16 : Q;
     float2* dp = d + PD(base);
     float2 v[R];
 #pragma unroll
-    for (int m = 0; m < R; ++m) v[m] = dp[m * PS];
+    for (int m = 0; m < R; ++m) v[m] = dp[m * PS + (Q == 128 ? (m >> 1) : 0)];
     float2 wbs[LOGR];
     wbs[LOGR - 1] = make_float2(1.0f, 0.0f);
     if (LOGQ > 0) {
@@ -151,7 +157,7 @@ __device__ __forceinline__ void dit_pass(float2* d, const float2* tw, int tid) {
       }
     }
 #pragma unroll
-    for (int m = 0; m < R; ++m) dp[m * PS] = v[m];
+    for (int m = 0; m < R; ++m) dp[m * PS + (Q == 128 ? (m >> 1) : 0)] = v[m];
   }
 }
 
@@ -212,8 +218,8 @@ template <bool FIRST, bool REF>
 __global__ void __launch_bounds__(GL_NT)
 gl_iter_kernel(const float* __restrict__ mags, const float* __restrict__ r_prev, float* __restrict__ r_next,
                const float2* __restrict__ tw, const float* __restrict__ win_g, int T, int win, int hop) {
-  __shared__ float2 d[GL_M + GL_M / 16];
-  constexpr int PJ = GL_NT + GL_NT / 16;          // m = tid + 128 j sits at PD(tid) + 136 j
+  __shared__ float2 d[GL_DSIZE];
+  constexpr int PJ = GL_NT + GL_NT / 16;          // m = tid + 128 j sits at PD(tid) + 136 j + (j >> 1)
   constexpr int NPAIR = (GL_M / 2 + GL_NT) / GL_NT;   // bin pairs (k, M - k), k = tid + 128 j <= 512
   const int tid = threadIdx.x;
   const int frame = blockIdx.x, n = frame / T, t = frame - n * T;
@@ -248,7 +254,7 @@ gl_iter_kernel(const float* __restrict__ mags, const float* __restrict__ r_prev,
           x.x = (((v0.x + v1.x) + v2.x) + v3.x) * w.x;
           x.y = (((v0.y + v1.y) + v2.y) + v3.y) * w.y;
         }
-        d[PD(tid) + PJ * j] = x;
+        d[PD(tid) + PJ * j + (j >> 1)] = x;
       }
     } else {
       const int K = (win - 1) / hop;
@@ -266,7 +272,7 @@ gl_iter_kernel(const float* __restrict__ mags, const float* __restrict__ r_prev,
           if (i < win) x.x = ola_at(r, t * hop + i, T, win, hop) * __ldg(win_g + i);
           if (i + 1 < win) x.y = ola_at(r, t * hop + i + 1, T, win, hop) * __ldg(win_g + i + 1);
         }
-        d[PD(tid) + PJ * j] = x;
+        d[PD(tid) + PJ * j + (j >> 1)] = x;
       }
     }
     __syncthreads();
@@ -310,7 +316,7 @@ gl_iter_kernel(const float* __restrict__ mags, const float* __restrict__ r_prev,
 #pragma unroll
   for (int j = 0; j < GL_M / GL_NT; ++j) {
     const int i = 2 * (tid + GL_NT * j);
-    const float2 z = d[PD(tid) + PJ * j];
+    const float2 z = d[PD(tid) + PJ * j + (j >> 1)];
     if (even) {
       if (i < win) {
         const float2 w = __ldg(reinterpret_cast<const float2*>(win_g + i));
