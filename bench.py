@@ -401,9 +401,45 @@ def run_ours(args):
         for l in lanes:
             l["eng"].set_decoder_clusters(0)
 
+    # ---- the second half of BASELINE.json's metric: p50 batch-1 utterance latency (config 5 shapes, r=5, 200 steps) ----
+    lat = None
+    if not args.no_latency and world == 1:
+        import statistics
+        lat = {"what": "one utterance, device resident, one stream; CUDA events around taco_forward (gather -> linear "
+                       "output, step count read back), p50 over 30 runs per input length", "unit": "ms", "p50": {}}
+        out1 = (torch.zeros(1, T_out, hp.num_mels, device=dev), torch.zeros(1, T_out, hp.num_freq, device=dev), None)
+        for t_in in (20, 60, 100, 200):
+            rng1 = np.random.default_rng(500 + t_in)
+            ids1 = torch.from_numpy(rng1.integers(7108, 7325, (1, t_in)).astype(np.int32)).to(dev)
+            len1 = torch.tensor([t_in], dtype=torch.int32, device=dev)
+            spk1 = torch.tensor([3], dtype=torch.int32, device=dev)
+            al1 = torch.zeros(1, t_in, MAX_ITERS, device=dev)
+            ts = []
+            for i in range(33):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                eng.forward(ids1, len1, spk1, out=(out1[0], out1[1], al1))
+                a1.record()
+                a1.synchronize()
+                if i >= 3:
+                    ts.append(a0.elapsed_time(a1))
+            lat["p50"]["T_in=%d" % t_in] = statistics.median(ts)
+        # the same utterance down to the waveform (reference Synthesizer.synthesize: + Griffin-Lim, 100 iterations)
+        ts = []
+        for i in range(13):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            _, lin1, _, _ = eng.forward(ids1, len1, spk1, out=(out1[0], out1[1], al1))
+            eng.griffin_lim(lin1)
+            a1.record()
+            a1.synchronize()
+            if i >= 3:
+                ts.append(a0.elapsed_time(a1))
+        lat["p50_with_griffin_lim_T_in=200"] = statistics.median(ts)
+
     # ---- the step after the path (informational): Griffin-Lim vocoder on the last linear output of lane 0 ----
     voc = None
-    if not args.no_vocoder:
+    if not args.no_vocoder and world == 1:
         lin = lanes[0]["outs"][1]
         eng.griffin_lim(lin)                                   # warm-up (workspace growth)
         torch.cuda.synchronize()
@@ -437,7 +473,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(world), inflight="%d batches in flight per GPU (one handle + CUDA stream "
                                                             "each); single_stream = one at a time" % n_dev),
-            "single_stream": single, "e2e": e2e, "throughput_mode": thr, "vocoder": voc, "gpu_launches": int(launches),
+            "single_stream": single, "e2e": e2e, "throughput_mode": thr, "latency_batch1": lat, "vocoder": voc, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "decoder_geometry": geo,
         }
@@ -458,6 +494,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU restatement leg")
     ap.add_argument("--inflight", type=int, default=4, help="batches in flight per GPU (handles/streams), device-resident leg")
     ap.add_argument("--e2e-lanes", type=int, default=6, help="batches in flight per GPU in the end-to-end leg")
+    ap.add_argument("--no-latency", action="store_true", help="skip the batch-1 latency leg")
     ap.add_argument("--no-vocoder", action="store_true", help="skip the informational Griffin-Lim leg")
     ap.add_argument("--no-throughput-mode", action="store_true", help="skip the informational 4-cluster decoder legs")
     args = ap.parse_args()
