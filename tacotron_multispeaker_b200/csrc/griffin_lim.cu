@@ -83,9 +83,29 @@ __global__ void gl_mags_kernel(const float* __restrict__ lin, int64_t lin_bs, in
 // q = 2^LOGQ), in registers.  The twiddle of stage s for element lo + j q is W_{2 hs q}^{lo} * W_{2 hs}^{j}: one table
 // read per group (squared from stage to stage) times a constant.
 template <int LOGR, int LOGQ>
-__device__ __forceinline__ void dif_pass(float2* d, const float2* tw, int tid) {
+__device__ __forceinline__ void dif_core(float2 (&v)[1 << LOGR], int lo, const float2* tw) {
   constexpr int R = 1 << LOGR, Q = 1 << LOGQ;
   static_assert(R <= 16, "constant twiddles go up to W_16");
+  float2 wb = make_float2(1.0f, 0.0f);
+  if (LOGQ > 0) wb = __ldg(tw + lo * (GL_N / (R * Q)));
+#pragma unroll
+  for (int s = 0; s < LOGR; ++s) {
+    const int hs = R >> (s + 1);
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      if (m & hs) continue;
+      const float2 a = v[m], b = v[m + hs];
+      v[m] = make_float2(a.x + b.x, a.y + b.y);
+      float2 t = mul_w16<false>(make_float2(a.x - b.x, a.y - b.y), (m & (hs - 1)) * (8 / hs));
+      if (LOGQ > 0) t = cmul(t, wb);
+      v[m + hs] = t;
+    }
+    if (LOGQ > 0) wb = cmul(wb, wb);
+  }
+}
+template <int LOGR, int LOGQ, bool LOAD = true>
+__device__ __forceinline__ void dif_pass(float2* d, const float2* tw, int tid, float2* vin = nullptr) {
+  constexpr int R = 1 << LOGR, Q = 1 << LOGQ;
   static_assert(GL_M / R <= GL_NT, "one group per thread");
   if (tid < GL_M / R) {   // GL_M / R <= GL_NT: at most one group per thread
     const int g = tid;
@@ -98,23 +118,8 @@ __device__ __forceinline__ void dif_pass(float2* d, const float2* tw, int tid) {
     float2* dp = d + PD(base);
     float2 v[R];
 #pragma unroll
-    for (int m = 0; m < R; ++m) v[m] = dp[m * PS + (Q == 128 ? (m >> 1) : 0)];
-    float2 wb = make_float2(1.0f, 0.0f);
-    if (LOGQ > 0) wb = __ldg(tw + lo * (GL_N / (R * Q)));
-#pragma unroll
-    for (int s = 0; s < LOGR; ++s) {
-      const int hs = R >> (s + 1);
-#pragma unroll
-      for (int m = 0; m < R; ++m) {
-        if (m & hs) continue;
-        const float2 a = v[m], b = v[m + hs];
-        v[m] = make_float2(a.x + b.x, a.y + b.y);
-        float2 t = mul_w16<false>(make_float2(a.x - b.x, a.y - b.y), (m & (hs - 1)) * (8 / hs));
-        if (LOGQ > 0) t = cmul(t, wb);
-        v[m + hs] = t;
-      }
-      if (LOGQ > 0) wb = cmul(wb, wb);
-    }
+    for (int m = 0; m < R; ++m) v[m] = LOAD ? dp[m * PS + (Q == 128 ? (m >> 1) : 0)] : vin[m];
+    dif_core<LOGR, LOGQ>(v, lo, tw);
 #pragma unroll
     for (int m = 0; m < R; ++m) dp[m * PS + (Q == 128 ? (m >> 1) : 0)] = v[m];
   }
@@ -122,9 +127,33 @@ __device__ __forceinline__ void dif_pass(float2* d, const float2* tw, int tid) {
 
 // the inverse: decimation in time, half-spans q, 2q, ..., (R/2) q, conjugate twiddles
 template <int LOGR, int LOGQ>
-__device__ __forceinline__ void dit_pass(float2* d, const float2* tw, int tid) {
+__device__ __forceinline__ void dit_core(float2 (&v)[1 << LOGR], int lo, const float2* tw) {
   constexpr int R = 1 << LOGR, Q = 1 << LOGQ;
   static_assert(R <= 16, "constant twiddles go up to W_16");
+  float2 wbs[LOGR];
+  wbs[LOGR - 1] = make_float2(1.0f, 0.0f);
+  if (LOGQ > 0) {
+    wbs[LOGR - 1] = __ldg(tw + lo * (GL_N / (R * Q)));
+#pragma unroll
+    for (int s = LOGR - 2; s >= 0; --s) wbs[s] = cmul(wbs[s + 1], wbs[s + 1]);
+  }
+#pragma unroll
+  for (int s = 0; s < LOGR; ++s) {
+    const int hs = 1 << s;
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      if (m & hs) continue;
+      float2 b = mul_w16<true>(v[m + hs], (m & (hs - 1)) * (8 / hs));
+      if (LOGQ > 0) b = cmul_conj(b, wbs[s]);
+      const float2 a = v[m];
+      v[m] = make_float2(a.x + b.x, a.y + b.y);
+      v[m + hs] = make_float2(a.x - b.x, a.y - b.y);
+    }
+  }
+}
+template <int LOGR, int LOGQ, bool STORE = true>
+__device__ __forceinline__ void dit_pass(float2* d, const float2* tw, int tid, float2* vout = nullptr) {
+  constexpr int R = 1 << LOGR, Q = 1 << LOGQ;
   static_assert(GL_M / R <= GL_NT, "one group per thread");
   if (tid < GL_M / R) {   // GL_M / R <= GL_NT: at most one group per thread
     const int g = tid;
@@ -136,28 +165,12 @@ __device__ __forceinline__ void dit_pass(float2* d, const float2* tw, int tid) {
     float2 v[R];
 #pragma unroll
     for (int m = 0; m < R; ++m) v[m] = dp[m * PS + (Q == 128 ? (m >> 1) : 0)];
-    float2 wbs[LOGR];
-    wbs[LOGR - 1] = make_float2(1.0f, 0.0f);
-    if (LOGQ > 0) {
-      wbs[LOGR - 1] = __ldg(tw + lo * (GL_N / (R * Q)));
+    dit_core<LOGR, LOGQ>(v, lo, tw);
 #pragma unroll
-      for (int s = LOGR - 2; s >= 0; --s) wbs[s] = cmul(wbs[s + 1], wbs[s + 1]);
+    for (int m = 0; m < R; ++m) {
+      if (STORE) dp[m * PS + (Q == 128 ? (m >> 1) : 0)] = v[m];
+      else vout[m] = v[m];
     }
-#pragma unroll
-    for (int s = 0; s < LOGR; ++s) {
-      const int hs = 1 << s;
-#pragma unroll
-      for (int m = 0; m < R; ++m) {
-        if (m & hs) continue;
-        float2 b = mul_w16<true>(v[m + hs], (m & (hs - 1)) * (8 / hs));
-        if (LOGQ > 0) b = cmul_conj(b, wbs[s]);
-        const float2 a = v[m];
-        v[m] = make_float2(a.x + b.x, a.y + b.y);
-        v[m + hs] = make_float2(a.x - b.x, a.y - b.y);
-      }
-    }
-#pragma unroll
-    for (int m = 0; m < R; ++m) dp[m * PS + (Q == 128 ? (m >> 1) : 0)] = v[m];
   }
 }
 
@@ -219,7 +232,6 @@ __global__ void __launch_bounds__(GL_NT)
 gl_iter_kernel(const float* __restrict__ mags, const float* __restrict__ r_prev, float* __restrict__ r_next,
                const float2* __restrict__ tw, const float* __restrict__ win_g, int T, int win, int hop) {
   __shared__ float2 d[GL_DSIZE];
-  constexpr int PJ = GL_NT + GL_NT / 16;          // m = tid + 128 j sits at PD(tid) + 136 j + (j >> 1)
   constexpr int NPAIR = (GL_M / 2 + GL_NT) / GL_NT;   // bin pairs (k, M - k), k = tid + 128 j <= 512
   const int tid = threadIdx.x;
   const int frame = blockIdx.x, n = frame / T, t = frame - n * T;
@@ -235,6 +247,7 @@ gl_iter_kernel(const float* __restrict__ mags, const float* __restrict__ r_prev,
     }
   }
   if (!FIRST) {
+    float2 xin[GL_M / GL_NT];
     const float* r = r_prev + (size_t)n * T * win;
     if (REF && t >= 3 && t + 3 < T) {
       const float* pt = r + (size_t)t * win;
@@ -254,11 +267,11 @@ gl_iter_kernel(const float* __restrict__ mags, const float* __restrict__ r_prev,
           x.x = (((v0.x + v1.x) + v2.x) + v3.x) * w.x;
           x.y = (((v0.y + v1.y) + v2.y) + v3.y) * w.y;
         }
-        d[PD(tid) + PJ * j + (j >> 1)] = x;
+        xin[j] = x;
       }
     } else {
       const int K = (win - 1) / hop;
-#pragma unroll 1
+#pragma unroll
       for (int j = 0; j < GL_M / GL_NT; ++j) {
         const int i = 2 * (tid + GL_NT * j);
         float2 x = make_float2(0.0f, 0.0f);
@@ -272,11 +285,11 @@ gl_iter_kernel(const float* __restrict__ mags, const float* __restrict__ r_prev,
           if (i < win) x.x = ola_at(r, t * hop + i, T, win, hop) * __ldg(win_g + i);
           if (i + 1 < win) x.y = ola_at(r, t * hop + i + 1, T, win, hop) * __ldg(win_g + i + 1);
         }
-        d[PD(tid) + PJ * j + (j >> 1)] = x;
+        xin[j] = x;
       }
     }
-    __syncthreads();
-    dif_pass<3, 7>(d, tw, tid); __syncthreads();
+    // element tid + 128 j is input j of thread tid's group in the first pass: no shared-memory trip for the frame
+    dif_pass<3, 7, false>(d, tw, tid, xin); __syncthreads();
     dif_pass<3, 4>(d, tw, tid); __syncthreads();
     dif_pass<4, 0>(d, tw, tid);
     __syncthreads();
@@ -311,12 +324,13 @@ gl_iter_kernel(const float* __restrict__ mags, const float* __restrict__ r_prev,
   __syncthreads();
   dit_pass<4, 0>(d, tw, tid); __syncthreads();
   dit_pass<3, 4>(d, tw, tid); __syncthreads();
-  dit_pass<3, 7>(d, tw, tid); __syncthreads();
+  float2 zout[GL_M / GL_NT];   // ... and the last pass leaves element tid + 128 j in register j
+  dit_pass<3, 7, false>(d, tw, tid, zout);
   float* o = r_next + (size_t)frame * win;
 #pragma unroll
   for (int j = 0; j < GL_M / GL_NT; ++j) {
     const int i = 2 * (tid + GL_NT * j);
-    const float2 z = d[PD(tid) + PJ * j + (j >> 1)];
+    const float2 z = zout[j];
     if (even) {
       if (i < win) {
         const float2 w = __ldg(reinterpret_cast<const float2*>(win_g + i));
