@@ -36,6 +36,27 @@ def test_stft_frame_count_and_zero_padding(hp):
     assert abs(S[2, 0] - np.sum(y[2 * hop:2 * hop + win] * A.hann_periodic(win))) < 1e-9
 
 
+def test_stft_matches_scipy(hp):
+    # independent implementation: scipy.signal.stft without boundary extension or padding, periodic Hann, divides by sum(w)
+    from scipy import signal
+    n_fft, hop, win = A.stft_parameters(hp)
+    y = np.random.default_rng(6).standard_normal(7 * hop + win)
+    _, _, Z = signal.stft(y, window=signal.get_window("hann", win, fftbins=True), nperseg=win, noverlap=win - hop,
+                          nfft=n_fft, boundary=None, padded=False)
+    S = A.stft_tf(y, win, hop, n_fft)
+    assert Z.T.shape == S.shape
+    assert np.max(np.abs(Z.T * A.hann_periodic(win).sum() - S)) < 1e-9
+
+
+def test_golden_audio_fixture_reproduces(hp):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "audio_gl.npz"))
+    x = g["spectrogram"]
+    for it in (0, 3):
+        assert np.max(np.abs(A.synthesize_wav(x, hp, iters=it) - g["wav_iters%d" % it])) < 1e-12
+        assert np.max(np.abs(A.inv_spectrogram_tensorflow(x, hp, iters=it) - g["wav_noemph_iters%d" % it])) < 1e-12
+
+
 def test_istft_of_stft_scales_by_window_square_sum(hp):
     # no window-sum normalisation in inverse_stft: Hann^2 at 75 % overlap sums to 1.5 in the interior
     n_fft, hop, win = A.stft_parameters(hp)

@@ -49,6 +49,15 @@ def test_zero_phase_start_matches_oracle(eng, T):
     assert rel_err(got, A.inv_spectrogram_tensorflow(x, eng.hp, iters=0)) < 2e-5
 
 
+def test_golden_audio_fixture(eng):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "audio_gl.npz"))
+    x = g["spectrogram"]
+    for it, tol in ((0, 2e-5), (3, 2e-4)):
+        assert rel_err(eng.griffin_lim(x, griffin_lim_iters=it), g["wav_iters%d" % it]) < tol
+        assert rel_err(eng.griffin_lim(x, griffin_lim_iters=it, inv_preemphasis=False), g["wav_noemph_iters%d" % it]) < tol
+
+
 @pytest.mark.parametrize("iters", [1, 2, 4])
 def test_first_iterations_match_oracle(eng, iters):
     x = spectrogram(24, 100 + iters)
