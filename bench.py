@@ -383,19 +383,34 @@ def run_ours(args):
            "api": "taco_forward_host_begin/_wait/_end (C ABI, pinned host buffers; H2D + forward + D2H per step; %d lanes, "
                   "at most %d of them between _begin and the end of their decoder loop)" % (n_lanes, n_slots)}
 
+    # what the link alone allows: one batch's outputs copied device -> pinned host with nothing else running
+    lin_pin = torch.from_numpy(pb["lin"])
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lin_pin.copy_(lanes[0]["outs"][1], non_blocking=True)
+    torch.cuda.synchronize()
+    c0.record()
+    for _ in range(4):
+        lin_pin.copy_(lanes[0]["outs"][1], non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    d2h_gbs = 4 * pb["lin"].nbytes / (c0.elapsed_time(c1) * 1e6)
+    e2e["d2h_link_gbs"] = d2h_gbs
+    e2e["d2h_floor_ms_per_step"] = e2e["d2h_bytes_per_step"] / (d2h_gbs * 1e6)
+
     # ---- the same two legs in the decoder's throughput geometry (informational) ----
     # taco_set_decoder_clusters(4): 4 clusters of 8 utterances (64 SMs for 2.9 ms) instead of 7 clusters of 5/4 (112 SMs
     # for 2.2 ms).  The headline legs above and the roofline use the default (latency) geometry.
     thr = None
+    thr_clusters = int(os.environ.get("TACO_BENCH_CLUSTERS", "4"))
     if not args.no_throughput_mode:
         for l in lanes:
-            l["eng"].set_decoder_clusters(4)
+            l["eng"].set_decoder_clusters(thr_clusters)
         timed(dev_lanes, 2 * n_dev)
         ms_t, st_t = timed(dev_lanes, max(n_dev, args.steps // 2))
         ms_t /= max(n_dev, args.steps // 2)
         e2e_timed(lanes, 2 * n_lanes)
         e2e_t = e2e_timed(lanes, k_e2e)
-        thr = {"decoder_geometry": "4 clusters x 16 CTAs, <= 8 utterances each",
+        thr = {"decoder_geometry": "%d clusters x 16 CTAs, <= %d utterances each" % (thr_clusters, -(-BATCH // thr_clusters)),
                "value": frames_per_step / (ms_t / 1e3), "ms_per_step": ms_t, "unit": UNIT,
                "e2e": {"value": frames_per_step / e2e_t, "ms_per_step": 1e3 * e2e_t, "unit": UNIT}}
         for l in lanes:
