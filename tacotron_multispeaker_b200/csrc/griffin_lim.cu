@@ -17,6 +17,7 @@
 // points with the frame zero-padded at its end, irfft scaled by 1/n_fft and cut to `win` samples, overlap_and_add.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 
@@ -236,6 +237,7 @@ gl_iter_kernel(const float* __restrict__ mags, const float* __restrict__ r_prev,
   const int tid = threadIdx.x;
   const int frame = blockIdx.x, n = frame / T, t = frame - n * T;
   const bool even = REF || ((win | hop) & 1) == 0;
+  if (!FIRST) asm volatile("griddepcontrol.launch_dependents;");   // the next iteration may start to launch
   float mk[NPAIR], mkm[NPAIR];
   {
     const float* mrow = mags + (size_t)frame * GL_BINS;
@@ -247,6 +249,10 @@ gl_iter_kernel(const float* __restrict__ mags, const float* __restrict__ r_prev,
     }
   }
   if (!FIRST) {
+    // Iterations are launched with programmatic stream serialisation: this grid may become resident while the previous
+    // iteration drains (its magnitudes are already requested above); nothing of the previous iteration is touched
+    // before this point, and the previous grid's rows are complete and visible after it.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     float2 xin[GL_M / GL_NT];
     const float* r = r_prev + (size_t)n * T * win;
     if (REF && t >= 3 && t + 3 < T) {
@@ -402,9 +408,23 @@ cudaError_t launch_griffin_lim(const GriffinLimArgs& a, void* ws, cudaStream_t s
   const bool ref = a.win == 4 * a.hop && ((a.win | a.hop) & 1) == 0;   // the reference's 1000 / 250
   if (ref) gl_iter_kernel<true, true><<<(unsigned)frames, GL_NT, 0, st>>>(mags, nullptr, cur, tw, win, a.T, a.win, a.hop);
   else gl_iter_kernel<true, false><<<(unsigned)frames, GL_NT, 0, st>>>(mags, nullptr, cur, tw, win, a.T, a.win, a.hop);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)frames);
+  cfg.blockDim = dim3(GL_NT);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  const char* pdl = getenv("TACO_GL_PDL");      // programmatic dependent launch of the iterations (opt-in until measured)
+  cfg.numAttrs = (pdl && atoi(pdl) != 0) ? 1 : 0;
   for (int it = 0; it < a.iters; ++it) {
-    if (ref) gl_iter_kernel<false, true><<<(unsigned)frames, GL_NT, 0, st>>>(mags, cur, nxt, tw, win, a.T, a.win, a.hop);
-    else gl_iter_kernel<false, false><<<(unsigned)frames, GL_NT, 0, st>>>(mags, cur, nxt, tw, win, a.T, a.win, a.hop);
+    const float* rp = cur;
+    cudaError_t e = ref ? cudaLaunchKernelEx(&cfg, gl_iter_kernel<false, true>, (const float*)mags, rp, nxt, (const float2*)tw,
+                                             (const float*)win, a.T, a.win, a.hop)
+                        : cudaLaunchKernelEx(&cfg, gl_iter_kernel<false, false>, (const float*)mags, rp, nxt, (const float2*)tw,
+                                             (const float*)win, a.T, a.win, a.hop);
+    if (e != cudaSuccess) return e;
     float* tmp = cur; cur = nxt; nxt = tmp;
   }
   const int L = (a.T - 1) * a.hop + a.win;

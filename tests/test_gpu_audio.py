@@ -167,3 +167,26 @@ def test_synthesizer_writes_wav_and_alignment(tmp_path):
     lin = syn.model.linear_outputs[0].cpu().numpy()
     want = A.save_wav_int16(A.synthesize_wav(lin, hp, iters=5))
     assert np.max(np.abs(pcm.astype(np.int32) - want.astype(np.int32))) <= 8
+
+
+def test_eval_loop_writes_the_reference_file_names(tmp_path):
+    # eval.py:55-65: <i>-identity-<id>-<text>.wav and <i>-identity-<id>.png under <base>/eval/eval[-step]/
+    from tacotron_multispeaker_b200 import eval as ev, text
+    from tacotron_multispeaker_b200.hparams import hparams
+    text.load_symbols([chr(0x4E00 + i) for i in range(7350)])
+    saved = hparams.copy()
+    sentences = tmp_path / "s.txt"
+    a, b = "".join(chr(0x4E00 + i) for i in (1, 2, 3)), "".join(chr(0x4E00 + i) for i in (40, 50, 60, 70))
+    sentences.write_text(a + "，abc\n" + b + "\n", encoding="utf-8")
+    try:
+        written = ev.main(["--id_num", "3", "--identity", "1", "--base_dir", str(tmp_path), "--sentences_file", str(sentences),
+                           "--hparams", "griffin_lim_iters=2"])
+    finally:
+        for f in vars(saved):
+            setattr(hparams, f, getattr(saved, f))
+    base = tmp_path / "eval" / "eval"
+    assert [str(p) for p in (base / ("0-identity-1-%s.wav" % a), base / ("1-identity-1-%s.wav" % b))] == written
+    for i in range(2):
+        assert (base / ("%d-identity-1.png" % i)).read_bytes()[:4] == b"\x89PNG"
+    with wave.open(written[0], "rb") as f:
+        assert f.getframerate() == 20000 and f.getnframes() == 399 * 250 + 1000      # Synthesizer: max_iters 400, r = 1
