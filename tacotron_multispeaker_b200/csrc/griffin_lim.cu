@@ -416,8 +416,8 @@ cudaError_t launch_griffin_lim(const GriffinLimArgs& a, void* ws, cudaStream_t s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  const char* pdl = getenv("TACO_GL_PDL");      // programmatic dependent launch of the iterations (opt-in until measured)
-  cfg.numAttrs = (pdl && atoi(pdl) != 0) ? 1 : 0;
+  const char* pdl = getenv("TACO_GL_PDL");      // programmatic dependent launch of the iterations (TACO_GL_PDL=0: off)
+  cfg.numAttrs = (pdl && atoi(pdl) == 0) ? 0 : 1;   // batch 1 x 1000 frames: 1.43 -> 1.20 ms; batch 32: 19.8 -> 19.6 ms
   for (int it = 0; it < a.iters; ++it) {
     const float* rp = cur;
     cudaError_t e = ref ? cudaLaunchKernelEx(&cfg, gl_iter_kernel<false, true>, (const float*)mags, rp, nxt, (const float2*)tw,
