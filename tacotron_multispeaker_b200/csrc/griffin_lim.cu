@@ -356,27 +356,54 @@ __global__ void gl_ola_kernel(const float* __restrict__ r, float* __restrict__ y
 }
 
 // util/audio.py:23-24 inv_preemphasis = lfilter([1], [1, -a]): y[i] = x[i] + a y[i-1], in place.  One CTA per
-// utterance: every thread filters its own chunk from a zero state, thread 0 chains the chunk ends, second pass.
+// utterance; warp w owns a contiguous segment and walks it 32 samples at a time (coalesced): a shuffle scan with the
+// powers a, a^2, ..., a^16 gives the 32 outputs of a step, the last one carries into the next step.  The state at
+// the end of each segment is chained over the 32 warps, and a second pass adds carry * a^(k+1) to the head of each
+// segment until the factor has decayed by 1e-12 (a = 0.97: 900 samples; far below any rounding of the first pass).
 __global__ void __launch_bounds__(1024) gl_deemph_kernel(float* __restrict__ y, int L, float a) {
-  __shared__ float zend[1024];
-  __shared__ float carry[1024];
-  const int tid = threadIdx.x;
+  __shared__ float zend[32];
+  __shared__ float carry[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* p = y + (size_t)blockIdx.x * L;
-  const int chunk = (L + 1023) / 1024;
-  const int s = min(L, tid * chunk), e = min(L, s + chunk);
-  float z = 0.0f;
-  for (int i = s; i < e; ++i) z = fmaf(a, z, p[i]);
-  zend[tid] = z;
+  const int seg = (((L + 31) / 32) + 31) & ~31;
+  const int s = min(L, warp * seg), e = min(L, s + seg);
+  const float a2 = a * a, a4 = a2 * a2, a8 = a4 * a4, a16 = a8 * a8, a32 = a16 * a16;
+  float alp = a;                                   // a^(lane + 1)
+  if (lane & 1) alp *= a;
+  if (lane & 2) alp *= a2;
+  if (lane & 4) alp *= a4;
+  if (lane & 8) alp *= a8;
+  if (lane & 16) alp *= a16;
+  float c = 0.0f;
+  float x = s + lane < e ? p[s + lane] : 0.0f;
+  for (int i0 = s; i0 < e; i0 += 32) {
+    const int i = i0 + lane;
+    const float xn = i + 32 < e ? p[i + 32] : 0.0f;   // next step's sample, requested before the scan
+    float v = x, t;
+    t = __shfl_up_sync(0xffffffffu, v, 1);  if (lane >= 1) v = fmaf(a, t, v);
+    t = __shfl_up_sync(0xffffffffu, v, 2);  if (lane >= 2) v = fmaf(a2, t, v);
+    t = __shfl_up_sync(0xffffffffu, v, 4);  if (lane >= 4) v = fmaf(a4, t, v);
+    t = __shfl_up_sync(0xffffffffu, v, 8);  if (lane >= 8) v = fmaf(a8, t, v);
+    t = __shfl_up_sync(0xffffffffu, v, 16); if (lane >= 16) v = fmaf(a16, t, v);
+    v = fmaf(alp, c, v);
+    if (i < e) p[i] = v;
+    c = __shfl_sync(0xffffffffu, v, 31);
+    x = xn;
+  }
+  if (lane == 0) zend[warp] = c;
   __syncthreads();
-  if (tid == 0) {
-    float ap = 1.0f;
-    for (int i = 0; i < chunk; ++i) ap *= a;
-    float c = 0.0f;
-    for (int k = 0; k < 1024; ++k) { carry[k] = c; c = fmaf(ap, c, zend[k]); }
+  if (threadIdx.x == 0) {
+    const float aseg = powf(a, (float)seg);
+    float cc = 0.0f;
+    for (int w = 0; w < 32; ++w) { carry[w] = cc; cc = fmaf(aseg, cc, zend[w]); }
   }
   __syncthreads();
-  z = carry[tid];
-  for (int i = s; i < e; ++i) { z = fmaf(a, z, p[i]); p[i] = z; }
+  const float cw = carry[warp];
+  if (cw != 0.0f) {
+    float f = cw * alp;
+    const float tiny = fabsf(cw) * 1e-12f;
+    for (int i = s + lane; i < e && fabsf(f) >= tiny; i += 32) { p[i] += f; f *= a32; }
+  }
 }
 
 }  // namespace

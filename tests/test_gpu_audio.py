@@ -88,6 +88,22 @@ def test_inverse_preemphasis_on_device(eng):
     assert rel_err(got, A.synthesize_wav(x, eng.hp, iters=0)) < 2e-5
 
 
+@pytest.mark.parametrize("T,preemphasis", [(3, 0.97), (200, 0.97), (200, 0.999), (37, 0.5)])
+def test_inverse_preemphasis_lengths_and_coefficients(T, preemphasis):
+    # segment chaining across the 32 warps: short signals (segments of 32 samples, carries matter everywhere), long ones,
+    # and a coefficient close to 1 whose carry never becomes negligible inside a segment
+    from tacotron_multispeaker_b200.engine import Engine
+    from tacotron_multispeaker_b200.hparams import HParams
+    hp = HParams(preemphasis=preemphasis)
+    e = Engine(hp, id_num=0)
+    try:
+        x = spectrogram(T, 300 + T)
+        got = e.griffin_lim(x, griffin_lim_iters=1)
+        assert rel_err(got, A.synthesize_wav(x, hp, iters=1)) < 1e-4
+    finally:
+        e.close()
+
+
 def test_batch_with_stride_equals_single_calls(eng):
     xs = np.stack([spectrogram(12, 20 + i) for i in range(3)])
     big = torch.zeros(3, 20, 1025, device=eng.device)
