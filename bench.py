@@ -208,6 +208,9 @@ def run_ours(args):
     n_lanes = max(n_dev, args.e2e_lanes)     # lanes of the end-to-end measurement (their D2H traffic needs more of them)
     # One handle (own weights copy, workspace and CUDA stream) per batch in flight: the decoder loop
     # occupies 112 of the 148 SMs for 2.2 ms, another batch's encoder / post-net (GEMMs, 64-CTA BiGRU) fills the rest and the gaps.
+    # more waiting host threads than cores (8 ranks x 6 lanes on 16 cores): let the C ABI's waits sleep instead of spin
+    if "TACO_BLOCKING_SYNC" not in os.environ and world * (n_lanes + 1) > (os.cpu_count() or 1):
+        os.environ["TACO_BLOCKING_SYNC"] = "1"
     lanes = []
     for li in range(n_lanes):
         e = Engine(hp, ID_NUM, local)
@@ -381,7 +384,9 @@ def run_ours(args):
            "h2d_bytes_per_step": int(pb["ids"].nbytes + pb["lens"].nbytes + pb["spk"].nbytes),
            "d2h_bytes_per_step": int(pb["mel"].nbytes + pb["lin"].nbytes + pb["al"].nbytes),
            "api": "taco_forward_host_begin/_wait/_end (C ABI, pinned host buffers; H2D + forward + D2H per step; %d lanes, "
-                  "at most %d of them between _begin and the end of their decoder loop)" % (n_lanes, n_slots)}
+                  "at most %d of them between _begin and the end of their decoder loop)" % (n_lanes, n_slots),
+           "host_waits": "blocking" if os.environ.get("TACO_BLOCKING_SYNC", "0") not in ("", "0") else "spinning",
+           "host_cores": os.cpu_count()}
 
     # what the link alone allows: one batch's outputs copied device -> pinned host with nothing else running
     lin_pin = torch.from_numpy(pb["lin"])

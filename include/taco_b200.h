@@ -125,7 +125,9 @@ int taco_forward_host(taco_handle* h, const int32_t* ids_host, const int32_t* le
  * the next decoder leaves free and its 144 MB of D2H traffic drains; _end
  * waits for the copies and returns the step count.  The
  * host buffers must stay valid until _end returns.  taco_forward_host == _begin
- * followed by _end. */
+ * followed by _end.  _wait and _end spin by default; with TACO_BLOCKING_SYNC=1 in the
+ * environment at taco_create they sleep on blocking-sync events (for hosts with more
+ * waiting threads than cores). */
 int taco_forward_host_begin(taco_handle* h, const int32_t* ids_host, const int32_t* lengths_host,
                             const int32_t* spk_host, const float* mel_targets_host, int N,
                             int T_in, int T_tgt, int bn_mode, int teacher_force,

@@ -122,6 +122,8 @@ struct taco_handle {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [4],[5] bracket the decoder kernel
   cudaEvent_t ev_compute = nullptr;   // taco_forward_host_begin: last kernel enqueued, output copies not yet
   cudaEvent_t ev_decoder = nullptr;   // ... and the end of the decoder loop (the post-net follows)
+  cudaEvent_t ev_end = nullptr;       // blocking mode: end of the output copies
+  bool blocking = false;              // TACO_BLOCKING_SYNC=1: host waits sleep instead of spinning (many lanes per core)
   float stage_ms[4] = {0, 0, 0, 0};
 };
 
@@ -1085,8 +1087,17 @@ int taco_create(const taco_hparams* hp, int device, taco_handle** out) {
   if (cudaHostAlloc(&h->h_pinned, sizeof(int) * 4, cudaHostAllocMapped) != cudaSuccess ||
       cudaHostGetDevicePointer(&h->d_pinned, h->h_pinned, 0) != cudaSuccess) { delete h; return TACO_ERR_CUDA; }
   for (int i = 0; i < 6; ++i) cudaEventCreate(&h->ev[i]);
-  cudaEventCreateWithFlags(&h->ev_compute, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&h->ev_decoder, cudaEventDisableTiming);
+  {
+    // The pipelined host API has one waiting thread per batch in flight.  With more waiting threads than host cores
+    // (8 ranks x 6 lanes on a 16-core box) spinning waits starve the threads that enqueue work: TACO_BLOCKING_SYNC=1
+    // makes taco_forward_host_wait / _end sleep on blocking-sync events instead.
+    const char* bs = getenv("TACO_BLOCKING_SYNC");
+    h->blocking = bs && atoi(bs) != 0;
+    const unsigned flags = cudaEventDisableTiming | (h->blocking ? cudaEventBlockingSync : 0u);
+    cudaEventCreateWithFlags(&h->ev_compute, flags);
+    cudaEventCreateWithFlags(&h->ev_decoder, flags);
+    cudaEventCreateWithFlags(&h->ev_end, flags);
+  }
   if (ensure_ints(h, 2 + 1024) != TACO_OK) { taco_destroy(h); return TACO_ERR_CUDA; }
   *out = h;
   return TACO_OK;
@@ -1105,6 +1116,7 @@ int taco_destroy(taco_handle* h) {
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->ev_compute) cudaEventDestroy(h->ev_compute);
   if (h->ev_decoder) cudaEventDestroy(h->ev_decoder);
+  if (h->ev_end) cudaEventDestroy(h->ev_end);
   delete h;
   return TACO_OK;
 }
@@ -1560,7 +1572,13 @@ int taco_forward_host_wait(taco_handle* h, int stage) {
 
 int taco_forward_host_end(taco_handle* h, int32_t* steps_out_host, void* stream) {
   REQUIRE_READY(h);
-  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  cudaError_t e;
+  if (h->blocking) {
+    e = cudaEventRecord(h->ev_end, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(h->ev_end);
+  } else {
+    e = cudaStreamSynchronize((cudaStream_t)stream);
+  }
   if (e != cudaSuccess) return fail(h, TACO_ERR_CUDA, std::string("sync: ") + cudaGetErrorString(e));
   if (h->spec.active) {   // free-running forward enqueued with the optimistic step count
     h->spec.active = false;
