@@ -271,8 +271,12 @@ def run_ours(args):
                 step(l)
         l["eng"].check_ids()
     dev_lanes = lanes[:n_dev]
-    timed(dev_lanes, 2 * n_dev)                      # warm the concurrent schedule too
     sampler = ClockSampler(local) if rank == 0 else None
+    timed(dev_lanes, 2 * n_dev)                      # warm the concurrent schedule too
+    if sampler is not None and sampler.proc is not None:   # nvidia-smi needs a moment to start: wait for its first sample
+        t_dead = time.time() + 3.0
+        while not sampler.lines and time.time() < t_dead:
+            time.sleep(0.02)
     launches0 = sum(l["eng"].launch_count() for l in lanes)
     t_wall0 = time.time()
     ms_total, steps_taken = timed(dev_lanes, args.steps)
@@ -464,18 +468,25 @@ def run_ours(args):
         eng.griffin_lim(lin)                                   # warm-up (workspace growth)
         torch.cuda.synchronize()
         voc_l0 = eng.launch_count()
+        voc_sampler = ClockSampler(local)
+        t_dead = time.time() + 3.0
+        while voc_sampler.proc is not None and not voc_sampler.lines and time.time() < t_dead:
+            time.sleep(0.02)
         v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        vt0 = time.time()
         v0.record()
         for _ in range(3):
             wav = eng.griffin_lim(lin)
         v1.record()
         torch.cuda.synchronize()
+        vt1 = time.time()
+        voc_clocks = voc_sampler.stop(vt0, vt1)
         v_ms = v0.elapsed_time(v1) / 3
         voc = {"what": "taco_griffin_lim: %d iterations + inverse pre-emphasis on the batch's linear spectrograms "
                        "(reference synthesizer.py:27,50); not part of `value`" % hp.griffin_lim_iters,
                "ms_per_batch": v_ms, "us_per_iteration": 1e3 * v_ms / hp.griffin_lim_iters,
                "frames_per_s": frames_per_step / (v_ms / 1e3), "launches_per_batch": (eng.launch_count() - voc_l0) // 3,
-               "audio_seconds_per_batch": BATCH * wav.shape[-1] / hp.sample_rate}
+               "audio_seconds_per_batch": BATCH * wav.shape[-1] / hp.sample_rate, "clocks": voc_clocks}
 
     # ---- CPU restatement on the host cores (rank 0, N=1 only) ----
     cpu = None
