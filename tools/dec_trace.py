@@ -54,7 +54,7 @@ if __name__ == "__main__":
         ctas = [int(c) for c in os.environ.get("TRACE_CTAS", "0").split(",")]
         for cta in ctas:
             os.environ["TACO_DEC_TRACE_CTA"] = str(cta)
-            for (N, T_in, S) in ([(1, 50, 1), (32, 100, 5)] if cta == 0 else [(32, 100, 5)]):
+            for (N, T_in, S) in ([(1, 50, 1), (32, 100, 5), (32, 100, 8)] if cta == 0 else [(32, 100, 5)]):
                 run(N, T_in, 16, S, "mma_n%d_s%d_cta%d" % (N, S, cta), iters=200)
     else:
         run(1, 50, 16, 1, "n1_cs16_s1")
