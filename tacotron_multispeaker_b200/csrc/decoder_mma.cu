@@ -805,6 +805,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
     TRM(14);
     mbar_wait(mb0 + B_P5 * 8, par);
     TRM(15);
+    TRW(256);
     // ================= P6: Bahdanau scores of this CTA's (position, sample) pairs: exp(v . tanh(keys + pq) - B) ======
     // v.tanh(k + p) = sum v - 2 sum_k v_k / (1 + e^{2k} e^{2p}); e^{2k} is resident, e^{2p} was pushed by P5.
     // Warp w takes the local pairs 2w, 2w+1 (+32, ...): two per pass, one butterfly reduces both.
@@ -852,14 +853,17 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
         if (lane == 0 || (lane == 16 && two)) sts_f(sbase + L.stage + (uint32_t)(up ? pp + 1 : pp) * 4u, ex);
       }
     }
+    TRW(272);
     __syncthreads();
     TRM(16);
     // warp p -> peer p: this CTA's pairs into sc[p0 ..], four per DSMEM transaction (the tail of the last quad is padding)
     if (lane < ((npq + 3) >> 2)) st_async_v4(rx + L.sc + (uint32_t)p0 * 4u, lds128(sbase + L.stage + lane * 16), rmb0 + B_P6 * 8);
     RTAKE(T_P8, SL8)                      // window of P6: P8's chunks into registers
+    TRW(288);
     TRM(17);
     mbar_wait(mb0 + B_P6 * 8, par);
     TRM(18);
+    TRW(304);
     // ================= P7: context slice sum_j p_j memory[j][16q..16q+15] / sum_j p_j =================
     // lane (g, t): sample g, columns 4t..4t+3; warp w takes the positions j = w (mod 16)
     {
@@ -911,6 +915,7 @@ decoder_mma_kernel(const DecoderMmaWeights w, const DecoderArgs a, const int ncl
       sts_f4(myslot + (g * RS + t * 4) * 4, acc);   // partial context of sample g, columns 4t..4t+3
       if (t == 0) sts_f(sbase + OFF_REDS + (uint32_t)(warp * 8 + g) * 4u, ssum);
     }
+    TRW(320);
     __syncthreads();
     TRM(19);
     if (red_grp) {

@@ -993,8 +993,8 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
   const char* trace_path = getenv("TACO_DEC_TRACE");   // developer aid: per-phase clock stamps of CTA 0
   long long* d_trace = nullptr;
   if (trace_path) {
-    cudaMalloc(&d_trace, 256 * sizeof(long long));
-    cudaMemsetAsync(d_trace, 0, 256 * sizeof(long long), st);
+    cudaMalloc(&d_trace, 512 * sizeof(long long));
+    cudaMemsetAsync(d_trace, 0, 512 * sizeof(long long), st);
     a.trace = d_trace;
     if (const char* tc = getenv("TACO_DEC_TRACE_CTA")) a.trace_cta = atoi(tc);
   }
@@ -1012,13 +1012,13 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
   if (e != cudaSuccess) return fail(h, TACO_ERR_CUDA, std::string("decoder launch: ") + cudaGetErrorString(e));
   h->launches += 1;
   if (d_trace) {
-    long long ht[256];
+    long long ht[512];
     cudaStreamSynchronize(st);
     cudaMemcpy(ht, d_trace, sizeof(ht), cudaMemcpyDeviceToHost);
     cudaFree(d_trace);
     if (FILE* f = fopen(trace_path, "w")) {
       fprintf(f, "# N=%d T_in=%d CS=%d S=%d\n", N, T_in, CS, S);
-      for (int i = 0; i < 256; ++i) fprintf(f, "%d %lld\n", i, ht[i]);
+      for (int i = 0; i < 512; ++i) fprintf(f, "%d %lld\n", i, ht[i]);
       fclose(f);
     }
   }

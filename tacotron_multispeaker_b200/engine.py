@@ -17,6 +17,22 @@ from .hparams import HParams
 from .weights import canonicalize
 
 
+def pad_inputs(seqs, pad: int = 0) -> np.ndarray:
+    """Batch of id sequences padded with ``pad`` to the longest one: the layout the reference feeder hands to
+    ``Tacotron.initialize`` (reference ``datasets/datafeeder_npy.py:174-176,184-185``)."""
+    n = max(len(x) for x in seqs)
+    return np.stack([np.pad(np.asarray(x), (0, n - len(x)), mode="constant", constant_values=pad) for x in seqs])
+
+
+def pad_targets(targets, outputs_per_step: int, pad: float = 0.0) -> np.ndarray:
+    """Teacher-forcing targets ``[T_i, C]`` padded with ``pad`` to ``max(T_i) + 1`` rounded up to a multiple of
+    ``outputs_per_step`` (reference ``datasets/datafeeder_npy.py:179-181,188-195``)."""
+    n = max(len(t) for t in targets) + 1
+    n = -(-n // outputs_per_step) * outputs_per_step
+    return np.stack([np.pad(np.asarray(t), [(0, n - len(t)), (0, 0)], mode="constant", constant_values=pad)
+                     for t in targets])
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 

@@ -12,7 +12,7 @@ from tacotron_multispeaker_b200.hparams import HParams
 from tacotron_multispeaker_b200.weights import random_init
 
 GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-              if not os.path.basename(p).startswith("audio_"))   # audio_*.npz: tests/test_audio_oracle.py, test_gpu_audio.py
+              if not os.path.basename(p).startswith(("audio_", "ref_")))   # ref_*: tests/test_ref_pinned.py; audio_*.npz: tests/test_audio_oracle.py, test_gpu_audio.py
 
 
 def load(path):

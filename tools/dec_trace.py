@@ -39,10 +39,11 @@ def run(N, T_in, cs, S, tag, iters=40):
     if impl_mma():
         names = {160: "P8 sent, before TLOADP(P9)", 144: "TLOADP(P9) issued", 64: "TWAIT(P9) done", 80: "PRE(P9) done",
                  192: "P3 start (after wait P2)", 208: "P3 mma done", 224: "P3 reduce done",
-                 96: "P10 start (after wait P9)", 112: "P10 mma done", 128: "P10 reduce/loads done"}
+                 96: "P10 start (after wait P9)", 112: "P10 mma done", 128: "P10 reduce/loads done",
+                 256: "P6 start", 272: "P6 compute done", 288: "P6 sent + RTAKE(P8)", 304: "P7 start", 320: "P7 compute done"}
         stamps = [int(l.split()[1]) for l in open(path) if not l.startswith("#")]
-        for b0 in (160, 144, 64, 80, 192, 208, 224, 96, 112, 128):
-            ref = {160: 22, 144: 22, 64: 22, 80: 22, 192: 6, 208: 6, 224: 6, 96: 27, 112: 27, 128: 27}[b0]
+        for b0 in (160, 144, 64, 80, 192, 208, 224, 96, 112, 128, 256, 272, 288, 304, 320):
+            ref = {160: 22, 144: 22, 64: 22, 80: 22, 192: 6, 208: 6, 224: 6, 96: 27, 112: 27, 128: 27, 256: 15, 272: 15, 288: 15, 304: 18, 320: 18}[b0]
             print("   per-warp %-28s rel. stamp %d: %s" % (names[b0], ref, [stamps[b0 + w] - stamps[ref] if stamps[b0 + w] else None for w in range(16)]), flush=True)
     eng.close()
 
