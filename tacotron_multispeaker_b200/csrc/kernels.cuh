@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "decoder_cw.h"
+
 namespace taco {
 
 // ---- K1: embedding gather + speaker concat (gather.cu) --------------------
@@ -149,6 +151,11 @@ struct DecoderMmaWeights {
 cudaError_t launch_decoder_mma(const DecoderMmaWeights& w, const DecoderArgs& a, int nclusters, cudaStream_t st);
 size_t decoder_mma_smem_bytes(int s_max, int T_in, int M, int att_res, int ring_d0, int ring_d1);
 int decoder_mma_max_clusters();
+
+// v6 (decoder_cw.cu): cluster of 16, critical warp group + background groups, 11 exchanges per step (layout: decoder_cw.h).
+cudaError_t launch_decoder_cw(const cw::Weights& w, const DecoderArgs& a, int nclusters, cudaStream_t st);
+size_t decoder_cw_smem_bytes(int s_max, int T_in, int att_res, int ring_kb);
+int decoder_cw_max_clusters();
 
 // S = samples per cluster (1,2,4,8).  Returns cudaError of the launch.
 cudaError_t launch_decoder(const DecoderWeights& w, const DecoderArgs& a, int S, cudaStream_t st);

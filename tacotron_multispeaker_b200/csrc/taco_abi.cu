@@ -94,9 +94,11 @@ struct taco_handle {
   int force_cs = 0;
   DecoderWeightsV3 dec3;               // warp-owned-unit kernel (cluster of 16)
   int use_v3 = 1;
-  DecoderMmaWeights dec4;              // mma.sync kernel (decoder_mma.cu): the default decoder
+  DecoderMmaWeights dec4;              // mma.sync kernel, all warps in lock step (decoder_mma.cu)
   int use_mma = 0;
   int max_clusters_mma = 0;
+  cw::Weights decw;                    // critical-warp kernel (decoder_cw.cu): the default decoder
+  int use_cw = 0;
   // workspace
   char* ws = nullptr;
   size_t ws_bytes = 0;
@@ -695,6 +697,8 @@ bool pack_decoder_mma(taco_handle* h, Arena& A, DmOff& O, uint32_t (&tabw)[DM_NP
   return true;
 }
 
+#include "decoder_cw_pack.inc"
+
 // ---- workspace ---------------------------------------------------------------
 struct Bump {
   char* base; size_t cap, off = 0; bool overflow = false;
@@ -1002,10 +1006,12 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
   pick_geometry(h, N, &CS, &S);
   if (getenv("TACO_DEBUG"))
     fprintf(stderr, "[taco] decode N=%d T_in=%d steps=%d CS=%d S=%d kernel=%s max_clusters(8)=%d (16)=%d\n", N, T_in,
-            max_steps, CS, S, h->use_mma ? "mma" : ((h->use_v3 && CS == 16) ? "v3" : "v2"), h->max_clusters[0], h->max_clusters[1]);
+            max_steps, CS, S, h->use_cw ? "cw" : h->use_mma ? "mma" : ((h->use_v3 && CS == 16) ? "v3" : "v2"), h->max_clusters[0], h->max_clusters[1]);
   if (h->profiling) cudaEventRecord(h->ev[4], st);
-  const bool use_mma = h->use_mma && (N + pick_mma_clusters(h, N) - 1) / pick_mma_clusters(h, N) <= 8;
-  cudaError_t e = use_mma ? launch_decoder_mma(h->dec4, a, pick_mma_clusters(h, N), st)
+  const bool fits8 = (N + pick_mma_clusters(h, N) - 1) / pick_mma_clusters(h, N) <= 8;
+  const bool use_cw = h->use_cw && fits8, use_mma = h->use_mma && fits8;
+  cudaError_t e = use_cw ? launch_decoder_cw(h->decw, a, pick_mma_clusters(h, N), st)
+                  : use_mma ? launch_decoder_mma(h->dec4, a, pick_mma_clusters(h, N), st)
                   : (h->use_v3 && CS == 16) ? launch_decoder_v3(h->dec3, a, S, st)
                                             : launch_decoder(h->dec[CS == 16 ? 1 : 0], a, S, st);
   if (h->profiling) cudaEventRecord(h->ev[5], st);
@@ -1205,6 +1211,9 @@ int taco_finalize_weights(taco_handle* h) {
   const bool mma_ok = hp.num_mels % 16 == 0 && hp.num_mels <= 128;
   if (mma_ok && !pack_decoder_mma(h, A, O4, h->dec4.tab, err))
     return bad(err.rfind("missing", 0) == 0 ? TACO_ERR_MISSING_WEIGHT : TACO_ERR_INVALID);
+  CwOff O6;
+  if (mma_ok && !pack_decoder_cw(h, A, O6, h->decw, err))
+    return bad(err.rfind("missing", 0) == 0 ? TACO_ERR_MISSING_WEIGHT : TACO_ERR_INVALID);
   if (h->dW) { cudaDeviceSynchronize(); cudaFree(h->dW); h->dW = nullptr; }
   CUDA_OK(h, cudaMalloc(&h->dW, sizeof(float) * A.buf.size()));
   CUDA_OK(h, cudaMemcpy(h->dW, A.buf.data(), sizeof(float) * A.buf.size(), cudaMemcpyHostToDevice));
@@ -1254,8 +1263,12 @@ int taco_finalize_weights(taco_handle* h) {
     d.stream = B + O4.stream; d.bias = B + O4.bias; d.att_v = B + O4.att_v;
     h->max_clusters_mma = mma_ok ? decoder_mma_max_clusters() : 0;
     const char* ei = getenv("TACO_DEC_IMPL");   // "mma" (default) | "v2" | "v3": developer switch between decoder kernels
-    h->use_mma = mma_ok && h->max_clusters_mma >= 1 && !(ei && strcmp(ei, "mma") != 0);
+    h->use_mma = mma_ok && h->max_clusters_mma >= 1 && ei && strcmp(ei, "mma") == 0;
     if (ei && strcmp(ei, "v3") == 0 && h->max_clusters[1] >= 1) h->use_v3 = 1;
+    // "cw" (default): decoder_cw.cu
+    h->decw.tmem_img = B + O6.tmem; h->decw.ring = B + O6.ring; h->decw.bias = B + O6.bias; h->decw.att_v = B + O6.att_v;
+    h->use_cw = mma_ok && decoder_cw_max_clusters() >= 1 && !(ei && strcmp(ei, "cw") != 0);
+    if (h->use_cw) h->max_clusters_mma = decoder_cw_max_clusters();
   }
   for (int ci = 0; ci < 2; ++ci) {
     DecoderWeights& d = h->dec[ci];
@@ -1673,7 +1686,7 @@ int taco_decoder_geometry(const taco_handle* h, int N, int* cluster_size, int* s
   int CS = 16, S = 8;
   pick_geometry(h, N, &CS, &S);
   int ncl = (N + S - 1) / S;
-  if (h->use_mma && N > 0) {
+  if ((h->use_mma || h->use_cw) && N > 0) {
     ncl = pick_mma_clusters(h, N);
     CS = 16;
     S = (N + ncl - 1) / ncl;
