@@ -462,6 +462,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
         }
       store_tile(myslot, g, t, hh, hl, lh);
     };
+    const int al_pp = tid - 12 * 32, al_n = (p0 + al_pp) % S, al_j = (p0 + al_pp) / S;   // the pair this thread writes the alignment of
     tload(TC_P2, 4);   // step 0 has no late part in P1 (zero go frame / zero state)
     for (int step = 0; step < a.steps; ++step) {
       const uint32_t par = (uint32_t)step & 1u;
@@ -493,7 +494,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
         nb_sync(NB_CRIT, 128);
         late1 = true;
       }
-      nb_sync(NB_H1, 256);
+      TRM(50); nb_sync(NB_H1, 256); TRM(51);
       {
         float v = sum4(red_nc, SL_P1E) + BIAS(late1 ? BI_P1 : BI_P1S0);
         if (late1) v += sum4(red_nc, SL_CRIT);
@@ -518,7 +519,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       late(XADDR(XP2 + 2 * gw), 2);
       tload(TC_P4, 4);
       nb_sync(NB_CRIT, 128);
-      nb_sync(NB_H3, 256);
+      TRM(52); nb_sync(NB_H3, 256); TRM(53);
       stage_x(stg_n, rc, sigmoid_f(sum4(red_nc, SL_CRIT) + sum4(red_nc, SL_RE0) + BIAS(BI_RA)) * st_ha);
       send_rows(OFF_X + (uint32_t)(XRA + q) * csb, MB_P3, false);
       twait();
@@ -529,7 +530,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       late(XADDR(XRA + 4 * gw), 4);
       tload(TC_P5, 4);
       nb_sync(NB_CRIT, 128);
-      nb_sync(NB_H4, 384);
+      TRM(54); nb_sync(NB_H4, 384); TRM(55);
       {
         const float u = sigmoid_f(sum4(red_nc, SL_U) + BIAS(BI_UA));
         const float c = tanh_f(sum4(red_nc, SL_CRIT) + sum4(red_nc, SL_CX) + BIAS(BI_CA));
@@ -553,12 +554,15 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       TRM(10);
       // ================= P6 / P7: attention (all warps) ====
       p6_compute();
+      TRW(112);
       __syncthreads();
       TRM(11);
       p6_send();
       mbar_wait(mb0 + MB_P6 * 8, par);
       TRM(12);
+      TRW(128);
       p7_compute();
+      TRW(144);
       __syncthreads();
       TRM(13);
       {
@@ -581,7 +585,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       late(XADDR(XC + 4 * gw), 4);
       tload(TC_P10, 4);
       nb_sync(NB_CRIT, 128);
-      nb_sync(NB_H9, 256);
+      TRM(56); nb_sync(NB_H9, 256); TRM(57);
       stage_x(stg_n, rc, sigmoid_f(sum4(red_nc, SL_CRIT) + sum4(red_nc, SL_RE1) + BIAS(BI_R1)) * st_h1);
       send_rows(OFF_X + (uint32_t)(XR1 + q) * csb, MB_P9, false);
       twait();
@@ -591,7 +595,8 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
         const float* invs = reinterpret_cast<const float*>(smem_raw + OFF_INV);
         const float* mxs = reinterpret_cast<const float*>(smem_raw + OFF_MX);
         for (int pp = tid - 12 * 32; pp < npq; pp += 128) {
-          const int n = smem_raw[L.pn + pp], j = (p0 + pp - n) / S;
+          const bool first = pp < 128;
+          const int n = first ? al_n : (int)smem_raw[L.pn + pp], j = first ? al_j : (p0 + pp - n) / S;
           const float e = exact ? __expf(stage[pp] - mxs[n]) : stage[pp];
           a.align_out[((size_t)(n0 + n) * T_in + j) * a.max_steps + step] = e * invs[n];
         }
@@ -603,7 +608,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       late(XADDR(XR1 + 4 * gw), 4);
       tload(TC_P11, 4);
       nb_sync(NB_CRIT, 128);
-      nb_sync(NB_H10, 384);
+      TRM(58); nb_sync(NB_H10, 384); TRM(59);
       {
         const float u = sigmoid_f(sum4(red_nc, SL_U) + BIAS(BI_U1));
         const float c = tanh_f(sum4(red_nc, SL_CRIT) + sum4(red_nc, SL_CX) + BIAS(BI_C1));
@@ -619,7 +624,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       late(XADDR(XH1c + 4 * gw), 4);
       tload(TC_P12, 4);
       nb_sync(NB_CRIT, 128);
-      nb_sync(NB_H11, 256);
+      TRM(60); nb_sync(NB_H11, 256); TRM(61);
       stage_x(stg_n, rc, sigmoid_f(sum4(red_nc, SL_CRIT) + sum4(red_nc, SL_RE2) + BIAS(BI_R2)) * st_h2);
       send_rows(OFF_X + (uint32_t)(XR2 + q) * csb, MB_P11, false);
       twait();
@@ -630,7 +635,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       late(XADDR(XR2 + 4 * gw), 4);
       if (free_run) tload(TC_P1, 4); else tload(TC_P2, 4);
       nb_sync(NB_CRIT, 128);
-      nb_sync(NB_H12, 384);
+      TRM(62); nb_sync(NB_H12, 384); TRM(63);
       {
         const float u = sigmoid_f(sum4(red_nc, SL_U) + BIAS(BI_U2));
         const float c = tanh_f(sum4(red_nc, SL_CRIT) + sum4(red_nc, SL_CX) + BIAS(BI_C2));
@@ -681,7 +686,9 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
     const int fb_lane_n = min(g, S - 1);
     auto run_items = [&](const Item* items, int n_items, int step) {
       const uint32_t par = (uint32_t)step & 1u;
+#define ITSTAMP(k) do { if (TRACE && a.trace != nullptr && step == 8 && blockIdx.x == a.trace_cta && warp == a.trace_warp && lane == 0) a.trace[320 + (items == prog.post[warp] ? 40 : 0) + it * 4 + (k)] = clock64(); } while (0)
       for (int it = 0; it < n_items; ++it) {
+        ITSTAMP(0);
         const uint32_t w0 = items[it].w[0];
         const int n = (int)(w0 & 7u), nops = (int)((w0 >> 19) & 3u);
         if (w0 & 16u) {
@@ -708,7 +715,13 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
                 wa[2 * k + 1] = lds128(src + 512u);
                 rp = rp + 1 == D ? 0 : rp + 1;
               }
+            // the slots are free as soon as the fragments sit in registers: request the next entries NOW, before the operand
+            // waits and the MMAs of this item (the refill then lands while this item runs)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) reg_fence(wa[2 * k], wa[2 * k + 1]);
+            refill(n);
           }
+          ITSTAMP(1);
           // ---- operands ----
           for (int o = 0; o < nops; ++o) {
             const uint32_t od = items[it].w[2 + o];
@@ -743,8 +756,8 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
                 mma16816(hl, wa[2 * i], xf[i].z, xf[i].w);
               }
           }
-          if (!(w0 & 8u)) refill(n);
         }
+        ITSTAMP(2);
         if (w0 & 32u) {
           const uint32_t slot = (w0 >> 6) & 63u;
           store_tile(sbase + OFF_SLOTS + slot * (SLOT_F * 4), g, t, hh, hl, lh);
@@ -770,6 +783,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
             if (2 * q + 1 < ntiles) dst[(2 * q + 1) * 16] = ob;
           }
         }
+        ITSTAMP(3);
       }
     };
     if (warp >= 8) { __syncwarp(); nb_arrive(NB_H1, 256); }   // P1 of step 0: zero context, zero go frame -> the (zeroed) early slots are complete
@@ -778,11 +792,15 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       run_items(prog.pre[warp], prog.n_pre[warp], step);
       TRW(64);
       mbar_wait(mb0 + MB_P5 * 8, par);
+      TRW(160);
       p6_compute();
+      TRW(112);
       __syncthreads();
       p6_send();
       mbar_wait(mb0 + MB_P6 * 8, par);
+      TRW(128);
       p7_compute();
+      TRW(144);
       __syncthreads();
       TRW(80);
       run_items(prog.post[warp], prog.n_post[warp], step);

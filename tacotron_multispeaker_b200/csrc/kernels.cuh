@@ -116,6 +116,7 @@ struct DecoderArgs {
   float* align_out;      // [N,T_in,max_steps] or null
   long long* trace;      // developer aid: per-phase clock stamps of one CTA (TACO_DEC_TRACE), or null
   int trace_cta;         // which CTA writes them (TACO_DEC_TRACE_CTA, default 0)
+  int trace_warp;        // decoder_cw: background warp whose items are stamped (TACO_DEC_TRACE_WARP, default 8)
   int ring_d0, ring_d1;  // decoder_mma: depth (KB = chunk-tiles) of the weight ring of warps 0-7 / 8-15 (set by the launcher)
 };
 // v3 (decoder_v3.cu): cluster of 16, warp-owned hidden units.  `stream`: per (CTA, warp) blocks of

@@ -993,7 +993,7 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
   DecoderArgs a;
   a.memory = memory; a.keys = keys; a.targets = teacher_force ? mel_targets : nullptr;
   a.N = N; a.T_in = T_in; a.T_tgt = T_tgt; a.r = hp.outputs_per_step; a.steps = max_steps; a.max_steps = max_steps;
-  a.dec_out = dec_out; a.align_out = align_out; a.att_res = 0; a.s_max = 0; a.trace = nullptr; a.trace_cta = 0; a.ring_d0 = 0; a.ring_d1 = 0;
+  a.dec_out = dec_out; a.align_out = align_out; a.att_res = 0; a.s_max = 0; a.trace = nullptr; a.trace_cta = 0; a.trace_warp = 8; a.ring_d0 = 0; a.ring_d1 = 0;
   const char* trace_path = getenv("TACO_DEC_TRACE");   // developer aid: per-phase clock stamps of CTA 0
   long long* d_trace = nullptr;
   if (trace_path) {
@@ -1001,6 +1001,7 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
     cudaMemsetAsync(d_trace, 0, 512 * sizeof(long long), st);
     a.trace = d_trace;
     if (const char* tc = getenv("TACO_DEC_TRACE_CTA")) a.trace_cta = atoi(tc);
+    if (const char* tw = getenv("TACO_DEC_TRACE_WARP")) a.trace_warp = atoi(tw);
   }
   int CS = 16, S = 8;
   pick_geometry(h, N, &CS, &S);
