@@ -208,12 +208,6 @@ int64_t taco_launch_count(const taco_handle* h);
  * cluster used for batch N. */
 int taco_decoder_geometry(const taco_handle* h, int N, int* cluster_size, int* samples_per_cluster,
                           int* num_clusters);
-/* Host-only introspection (no GPU needed): the work table of the mma.sync
- * decoder for a given num_mels -- which 16-row chunks of which activation
- * buffer each of the 16 warps multiplies in each of the 11 MMA phases.
- * out[(phase*16 + warp)*5 + {0..4}] = {tile, buffer, first chunk, chunk count,
- * extra activation buffers multiplied by the same weights}; out_len >= 880. */
-int taco_decoder_work_table(int num_mels, int32_t* out, int out_len);
 /* Decoder geometry: 0 (default) picks the number of 16-CTA clusters for the shortest decode (batch 32: 7 clusters of
  * 5/4 utterances, 112 SMs for 2.2 ms); n > 0 uses n clusters of up to 8 utterances each -- a throughput setting for
  * callers that keep several batches in flight (batch 32, n = 4: 64 SMs for 2.9 ms; +10 % mel frames/s with four batches

@@ -33,7 +33,7 @@ SYMBOLS = [
     "taco_forward_host_end",
     "taco_embed", "taco_check_ids", "taco_encoder", "taco_decode", "taco_cbhg", "taco_postnet",
     "taco_bigru", "taco_conv1d",
-    "taco_set_gemm_mode", "taco_launch_count", "taco_decoder_geometry", "taco_decoder_work_table", "taco_set_decoder_clusters", "taco_set_profiling", "taco_last_stage_ms",
+    "taco_set_gemm_mode", "taco_launch_count", "taco_decoder_geometry", "taco_set_decoder_clusters", "taco_set_profiling", "taco_last_stage_ms",
     "taco_wav_length", "taco_griffin_lim",
 ]
 
@@ -92,7 +92,6 @@ def load() -> C.CDLL:
     lib.taco_forward_host_begin.argtypes = [H, ip, ip, ip, fp, i, i, i, i, i, fp, fp, fp, vp]
     lib.taco_forward_host_wait.argtypes = [H, i]
     lib.taco_forward_host_end.argtypes = [H, C.POINTER(C.c_int32), vp]
-    lib.taco_decoder_work_table.argtypes = [i, C.POINTER(C.c_int32), i]
     lib.taco_set_decoder_clusters.argtypes = [H, i]
     lib.taco_embed.argtypes = [H, ip, ip, i, i, fp, vp]
     lib.taco_check_ids.argtypes = [H, vp]

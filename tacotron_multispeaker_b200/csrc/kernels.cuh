@@ -111,48 +111,13 @@ struct DecoderArgs {
   const float* targets;  // [N,T_tgt,M] or null (free running)
   int N, T_in, T_tgt, r, steps, max_steps;
   int att_res;           // keys/memory slices resident in shared memory (set by launch_decoder)
-  int s_max;             // decoder_mma: largest number of samples per cluster in this launch (set by the launcher)
+  int s_max;             // decoder_cw: largest number of samples per cluster in this launch (set by the launcher)
   float* dec_out;        // [N,max_steps,Dout]
   float* align_out;      // [N,T_in,max_steps] or null
   long long* trace;      // developer aid: per-phase clock stamps of one CTA (TACO_DEC_TRACE), or null
   int trace_cta;         // which CTA writes them (TACO_DEC_TRACE_CTA, default 0)
   int trace_warp;        // decoder_cw: background warp whose items are stamped (TACO_DEC_TRACE_WARP, default 8)
-  int ring_d0, ring_d1;  // decoder_mma: depth (KB = chunk-tiles) of the weight ring of warps 0-7 / 8-15 (set by the launcher)
 };
-// v3 (decoder_v3.cu): cluster of 16, warp-owned hidden units.  `stream`: per (CTA, warp) blocks of
-// the weights that multiply freshly exchanged activations, in consumption order; `ew`: the gate
-// halves that multiply the previous state (resident in shared memory); raw (unpermuted) biases.
-struct DecoderWeightsV3 {
-  int M, Dout;
-  const float* stream;   // [16 CTAs][16 warps][36 float4][32 lanes][4]
-  const float* ew;       // [16 CTAs][16 warps][3 GRUs][4 float4][32 lanes][4]
-  const float *p1_b, *p2_b, *ga_b, *ca_b, *pc_b, *g1_b, *c1_b, *g2_b, *c2_b, *o_b, *att_v;
-};
-cudaError_t launch_decoder_v3(const DecoderWeightsV3& w, const DecoderArgs& a, int S, cudaStream_t st);
-size_t decoder_v3_smem_bytes(int S, int T_in, bool att_res);
-int decoder_v3_stream_floats_per_cta();
-int decoder_v3_resident_floats_per_cta();
-
-// v4 (decoder_mma.cu): cluster of 16, mat-vecs on mma.sync m16n8k16 (bf16 hi/lo split), runtime samples per cluster.
-// Activation buffers (MMA-fragment order), in the order of their shared-memory carve-up:
-enum { DM_BF = 0, DM_BC, DM_BP1, DM_BP2, DM_BHA, DM_BRA, DM_BY0, DM_BH1, DM_BR1, DM_BY1, DM_BH2, DM_BR2, DM_BY2, DM_NBUF };
-constexpr int DM_NCH1 = 3;        // chunk-tiles per warp in phase 1 (upper bound)
-constexpr int DM_F4_STEP = 66;    // 128-bit words per lane and step in the weight stream
-constexpr int DM_NBIAS = 224;     // floats per CTA in the bias table
-constexpr int DM_P1_SLOTS = 11;   // warps that contribute to phase 1 (8 context + 3 frame)
-constexpr int DM_NPHASE = 11;     // MMA phases (P1..P5, P8..P13)
-// tab[phase][warp] = count | chunk0 << 3 | buffer << 8 | tile << 12
-struct DecoderMmaWeights {
-  int M, Dout;
-  const void* stream;    // [16 CTAs][16 warps][DM_F4_STEP][32 lanes] uint4: A fragments (hi, lo) in consumption order
-  const float* bias;     // [16 CTAs][DM_NBIAS], tile order
-  const float* att_v;    // [256]
-  uint32_t tab[DM_NPHASE][16];
-};
-cudaError_t launch_decoder_mma(const DecoderMmaWeights& w, const DecoderArgs& a, int nclusters, cudaStream_t st);
-size_t decoder_mma_smem_bytes(int s_max, int T_in, int M, int att_res, int ring_d0, int ring_d1);
-int decoder_mma_max_clusters();
-
 // v6 (decoder_cw.cu): cluster of 16, critical warp group + background groups, 11 exchanges per step (layout: decoder_cw.h).
 cudaError_t launch_decoder_cw(const cw::Weights& w, const DecoderArgs& a, int nclusters, cudaStream_t st);
 size_t decoder_cw_smem_bytes(int s_max, int T_in, int att_res, int ring_kb);

@@ -92,11 +92,7 @@ struct taco_handle {
   DecoderWeights dec[2];               // slices cut for clusters of 8 ([0]) and 16 ([1]) CTAs
   int max_clusters[2] = {0, 0};        // co-resident clusters of each size on this device
   int force_cs = 0;
-  DecoderWeightsV3 dec3;               // warp-owned-unit kernel (cluster of 16)
-  int use_v3 = 1;
-  DecoderMmaWeights dec4;              // mma.sync kernel, all warps in lock step (decoder_mma.cu)
-  int use_mma = 0;
-  int max_clusters_mma = 0;
+  int max_clusters_mma = 0;            // co-resident clusters of 16 of the default decoder
   cw::Weights decw;                    // critical-warp kernel (decoder_cw.cu): the default decoder
   int use_cw = 0;
   // workspace
@@ -120,6 +116,7 @@ struct taco_handle {
     size_t lin_bytes = 0;
   } spec;
   int64_t launches = 0;
+  bool launch_failed = false;        // a kernel launcher returned an error (sticky until check_launch reports it)
   bool profiling = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [4],[5] bracket the decoder kernel
   cudaEvent_t ev_compute = nullptr;   // taco_forward_host_begin: last kernel enqueued, output copies not yet
@@ -435,143 +432,7 @@ bool pack_decoder(taco_handle* h, Arena& A, int CS, DecOff& O, int& McO, std::st
   return true;
 }
 
-struct Dec3Off { size_t stream, ew, p1_b, p2_b, ga_b, ca_b, pc_b, g1_b, c1_b, g2_b, c2_b, o_b, att_v; };
-
-// Weight blocks of decoder_v3.cu: for CTA q, warp w (hidden unit c = 16q + w) and phase block f,
-// float4 (f + g*NCOL + col) of lane l holds W[col][k = l + 32*(4g + j)], j = 0..3.
-bool pack_decoder_v3(taco_handle* h, Arena& A, Dec3Off& O, std::string& err) {
-  const int M = h->hp.num_mels, r = h->hp.outputs_per_step, Dout = M * r;
-  const std::string att = kATT, dpw = att + "decoder_prenet_wrapper/", mrc = kMRC;
-  GETV(w1, dpw + "decoder_prenet/dense_1/kernel", M + DH, 256);
-  GETV(b1, dpw + "decoder_prenet/dense_1/bias", 256);
-  GETV(w2, dpw + "decoder_prenet/dense_2/kernel", 256, 128);
-  GETV(b2, dpw + "decoder_prenet/dense_2/bias", 128);
-  GETV(wga, dpw + "gru_cell/gates/kernel", DP + DH, 2 * DH);
-  GETV(bga, dpw + "gru_cell/gates/bias", 2 * DH);
-  GETV(wca, dpw + "gru_cell/candidate/kernel", DP + DH, DH);
-  GETV(bca, dpw + "gru_cell/candidate/bias", DH);
-  GETV(wq, att + "bahdanau_attention/query_layer/kernel", 256, 256);
-  GETV(v, att + "bahdanau_attention/attention_v", 256);
-  GETV(wp, mrc + "cell_0/output_projection_wrapper/kernel", 512, 256);
-  GETV(bp, mrc + "cell_0/output_projection_wrapper/bias", 256);
-  GETV(wg1, mrc + "cell_1/gru_cell/gates/kernel", 2 * DH, 2 * DH);
-  GETV(bg1, mrc + "cell_1/gru_cell/gates/bias", 2 * DH);
-  GETV(wc1, mrc + "cell_1/gru_cell/candidate/kernel", 2 * DH, DH);
-  GETV(bc1, mrc + "cell_1/gru_cell/candidate/bias", DH);
-  GETV(wg2, mrc + "cell_2/gru_cell/gates/kernel", 2 * DH, 2 * DH);
-  GETV(bg2, mrc + "cell_2/gru_cell/gates/bias", 2 * DH);
-  GETV(wc2, mrc + "cell_2/gru_cell/candidate/kernel", 2 * DH, DH);
-  GETV(bc2, mrc + "cell_2/gru_cell/candidate/bias", DH);
-  GETV(wo, "decoder/output_projection_wrapper/kernel", 256, Dout);
-  GETV(bo, "decoder/output_projection_wrapper/bias", Dout);
-  const int F4_STEP = decoder_v3_stream_floats_per_cta() / (16 * 128);   // float4 per lane per step
-  O.stream = A.alloc((size_t)16 * decoder_v3_stream_floats_per_cta());
-  O.ew = A.alloc((size_t)16 * decoder_v3_resident_floats_per_cta());
-  auto M2 = [](const HostVar* m, int ld, int row, int col) { return m->data[(size_t)row * ld + col]; };
-  for (int q = 0; q < 16; ++q)
-    for (int w = 0; w < 16; ++w) {
-      const int c = q * 16 + w;
-      size_t f = 0;   // float4 index inside this warp's streamed block
-      const size_t sbase = O.stream + (size_t)(q * 16 + w) * F4_STEP * 128;
-      auto blk = [&](size_t base, size_t& fidx, int ncol, int kg, auto val) {
-        for (int g = 0; g < kg; ++g)
-          for (int col = 0; col < ncol; ++col)
-            for (int l = 0; l < 32; ++l)
-              for (int j = 0; j < 4; ++j)
-                A.buf[base + ((fidx + g * ncol + col) * 32 + l) * 4 + j] = val(col, l + 32 * (4 * g + j));
-        fidx += (size_t)kg * ncol;
-      };
-      // P1  prenet dense_1: rows [frame(M) | ctx(256)], zero padded to 384
-      blk(sbase, f, 1, 3, [&](int, int k) { return k < M + DH ? M2(w1, 256, k, c) : 0.f; });
-      // P2  prenet dense_2: 8 units per CTA (warps 0..7)
-      blk(sbase, f, 1, 2, [&](int, int k) { return w < 8 ? M2(w2, 128, k, q * 8 + w) : 0.f; });
-      // P3  attention GRU: gates x-rows (r,u) + candidate x-rows, K = 128
-      blk(sbase, f, 3, 1, [&](int col, int k) {
-        return col == 0 ? M2(wga, 512, k, c) : (col == 1 ? M2(wga, 512, k, DH + c) : M2(wca, 256, k, c)); });
-      // P4  candidate h-rows
-      blk(sbase, f, 1, 2, [&](int, int k) { return M2(wca, 256, DP + k, c); });
-      // P5  query layer | projection rows of h_att
-      blk(sbase, f, 2, 2, [&](int col, int k) { return col == 0 ? M2(wq, 256, k, c) : M2(wp, 256, k, c); });
-      // P8  projection rows of the context
-      blk(sbase, f, 1, 2, [&](int, int k) { return M2(wp, 256, DH + k, c); });
-      // P9  GRU-1 x-rows: r, u, candidate
-      blk(sbase, f, 3, 2, [&](int col, int k) {
-        return col == 0 ? M2(wg1, 512, k, c) : (col == 1 ? M2(wg1, 512, k, DH + c) : M2(wc1, 256, k, c)); });
-      blk(sbase, f, 1, 2, [&](int, int k) { return M2(wc1, 256, DH + k, c); });                 // P10
-      blk(sbase, f, 3, 2, [&](int col, int k) {                                                 // P11
-        return col == 0 ? M2(wg2, 512, k, c) : (col == 1 ? M2(wg2, 512, k, DH + c) : M2(wc2, 256, k, c)); });
-      blk(sbase, f, 1, 2, [&](int, int k) { return M2(wc2, 256, DH + k, c); });                 // P12
-      blk(sbase, f, 2, 2, [&](int col, int k) {                                                 // P13
-        const int oc = q * 32 + 2 * w + col;
-        return oc < Dout ? M2(wo, Dout, k, oc) : 0.f; });
-      if ((int)f != F4_STEP) { err = "decoder v3 packing: block table out of sync with the kernel"; return false; }
-      // resident recurrent halves of the gates: [gru][g*2 + col]
-      size_t e = 0;
-      const size_t ebase = O.ew + (size_t)(q * 16 + w) * 3 * 4 * 128;
-      blk(ebase, e, 2, 2, [&](int col, int k) { return M2(wga, 512, DP + k, col == 0 ? c : DH + c); });
-      blk(ebase, e, 2, 2, [&](int col, int k) { return M2(wg1, 512, DH + k, col == 0 ? c : DH + c); });
-      blk(ebase, e, 2, 2, [&](int col, int k) { return M2(wg2, 512, DH + k, col == 0 ? c : DH + c); });
-    }
-  O.p1_b = put_vec(A, b1->data.data(), 256);   O.p2_b = put_vec(A, b2->data.data(), 128);
-  O.ga_b = put_vec(A, bga->data.data(), 512);  O.ca_b = put_vec(A, bca->data.data(), 256);
-  O.pc_b = put_vec(A, bp->data.data(), 256);
-  O.g1_b = put_vec(A, bg1->data.data(), 512);  O.c1_b = put_vec(A, bc1->data.data(), 256);
-  O.g2_b = put_vec(A, bg2->data.data(), 512);  O.c2_b = put_vec(A, bc2->data.data(), 256);
-  O.o_b = A.alloc(512);
-  memcpy(&A.buf[O.o_b], bo->data.data(), sizeof(float) * Dout);
-  O.att_v = put_vec(A, v->data.data(), 256);
-  return true;
-}
-
-
-// ---- decoder_mma.cu packing -------------------------------------------------------------------
-// Work table of the MMA decoder: which 16-row chunks of which activation buffer every warp
-// multiplies in every phase (see decoder_mma.cu).  Entry = count | chunk0 << 3 | buffer << 8 | tile << 12.
-struct DmItem { int tile = 0, buf = 0, c0 = 0, cnt = 0, nx = 0, early = 0; };   // early: operand complete before the phase's exchange   // nx: extra activation buffers multiplied by the same weights
-void dm_table(int FC, DmItem (&tab)[DM_NPHASE][16]) {
-  for (auto& ph : tab) for (auto& e : ph) e = DmItem();
-  auto single = [&](int ph, int buf) { for (int w = 0; w < 8; ++w) tab[ph][w] = {0, buf, 2 * w, 2}; };
-  auto two = [&](int ph, int buf) {
-    for (int w = 0; w < 8; ++w) { tab[ph][w] = {0, buf, 2 * w, 2}; tab[ph][8 + w] = {1, buf, 2 * w, 2}; }
-  };
-  // P1: context chunks on warps 0..7, frame chunks on warps 8..10
-  single(0, DM_BC);
-  for (int i = 0, c = 0; i < 3; ++i) { const int n = FC / 3 + (i < FC % 3 ? 1 : 0); tab[0][8 + i] = {0, DM_BF, c, n}; c += n; }
-  single(1, DM_BP1);                                   // P2
-  for (int tile = 0; tile < 2; ++tile) {               // P3: r, u over [prenet(8 chunks) | h_att(16 chunks)]
-    tab[2][tile * 6 + 0] = {tile, DM_BP2, 0, 4};
-    tab[2][tile * 6 + 1] = {tile, DM_BP2, 4, 4};
-    for (int i = 0; i < 4; ++i) tab[2][tile * 6 + 2 + i] = {tile, DM_BHA, 4 * i, 4};
-  }
-  for (int i = 0; i < 4; ++i) tab[2][12 + i] = {2, DM_BP2, 2 * i, 2};
-  single(3, DM_BRA);                                   // P4
-  two(4, DM_BHA);                                      // P5: query | projection(h_att)
-  single(5, DM_BC);                                    // P8
-  auto gru = [&](int ph, int bx, int bh, int nx) {     // P9 / P11
-    const int c0[3] = {0, 6, 11}, n[3] = {6, 5, 5};
-    for (int tile = 0; tile < 2; ++tile)
-      for (int i = 0; i < 3; ++i) {
-        tab[ph][tile * 6 + i] = {tile, bx, c0[i], n[i], nx};
-        tab[ph][tile * 6 + 3 + i] = {tile, bh, c0[i], n[i], 0};
-      }
-    for (int i = 0; i < 4; ++i) tab[ph][12 + i] = {2, bx, 4 * i, 4, nx};
-  };
-  gru(6, DM_BY0, DM_BH1, 0);
-  single(7, DM_BR1);                                   // P10
-  // GRU 2 reads y1 = y0 + h1' by linearity: the x rows multiply the y0 buffer AND the h1' buffer (nothing extra is pushed)
-  gru(8, DM_BY0, DM_BH2, 1);
-  single(9, DM_BR2);                                   // P12
-  two(10, DM_BY0);                                     // P13: y2 = y0 + h1' + h2' the same way
-  for (int w = 0; w < 16; ++w) tab[10][w].nx = 2;
-  // operands that are complete one exchange earlier: the context of the previous step (P1) and the recurrent states
-  for (int w = 0; w < 16; ++w) {
-    if (tab[0][w].cnt && tab[0][w].buf == DM_BC) tab[0][w].early = 1;
-    if (tab[2][w].cnt && tab[2][w].buf == DM_BHA) tab[2][w].early = 1;
-    if (tab[6][w].cnt && tab[6][w].buf == DM_BH1) tab[6][w].early = 1;
-    if (tab[8][w].cnt && tab[8][w].buf == DM_BH2) tab[8][w].early = 1;
-  }
-}
-
+// bf16 split helpers of the packers
 inline uint16_t bf16_rn(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
@@ -580,122 +441,6 @@ inline uint16_t bf16_rn(float f) {
   return (uint16_t)(u >> 16);
 }
 inline float bf16_f(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
-
-struct DmOff { size_t stream, bias, att_v; };
-
-bool pack_decoder_mma(taco_handle* h, Arena& A, DmOff& O, uint32_t (&tabw)[DM_NPHASE][16], std::string& err) {
-  const int M = h->hp.num_mels, r = h->hp.outputs_per_step, Dout = M * r, FC = M / 16;
-  const std::string att = kATT, dpw = att + "decoder_prenet_wrapper/", mrc = kMRC;
-  GETV(w1, dpw + "decoder_prenet/dense_1/kernel", M + DH, 256);
-  GETV(b1, dpw + "decoder_prenet/dense_1/bias", 256);
-  GETV(w2, dpw + "decoder_prenet/dense_2/kernel", 256, 128);
-  GETV(b2, dpw + "decoder_prenet/dense_2/bias", 128);
-  GETV(wga, dpw + "gru_cell/gates/kernel", DP + DH, 2 * DH);
-  GETV(bga, dpw + "gru_cell/gates/bias", 2 * DH);
-  GETV(wca, dpw + "gru_cell/candidate/kernel", DP + DH, DH);
-  GETV(bca, dpw + "gru_cell/candidate/bias", DH);
-  GETV(wq, att + "bahdanau_attention/query_layer/kernel", 256, 256);
-  GETV(v, att + "bahdanau_attention/attention_v", 256);
-  GETV(wp, mrc + "cell_0/output_projection_wrapper/kernel", 512, 256);
-  GETV(bp, mrc + "cell_0/output_projection_wrapper/bias", 256);
-  GETV(wg1, mrc + "cell_1/gru_cell/gates/kernel", 2 * DH, 2 * DH);
-  GETV(bg1, mrc + "cell_1/gru_cell/gates/bias", 2 * DH);
-  GETV(wc1, mrc + "cell_1/gru_cell/candidate/kernel", 2 * DH, DH);
-  GETV(bc1, mrc + "cell_1/gru_cell/candidate/bias", DH);
-  GETV(wg2, mrc + "cell_2/gru_cell/gates/kernel", 2 * DH, 2 * DH);
-  GETV(bg2, mrc + "cell_2/gru_cell/gates/bias", 2 * DH);
-  GETV(wc2, mrc + "cell_2/gru_cell/candidate/kernel", 2 * DH, DH);
-  GETV(bc2, mrc + "cell_2/gru_cell/candidate/bias", DH);
-  GETV(wo, "decoder/output_projection_wrapper/kernel", 256, Dout);
-  GETV(bo, "decoder/output_projection_wrapper/bias", Dout);
-  DmItem tab[DM_NPHASE][16];
-  dm_table(FC, tab);
-  static const int nch[DM_NPHASE] = {DM_NCH1, 2, 4, 2, 2, 2, 6, 2, 6, 2, 2};
-  int off[DM_NPHASE + 1];
-  off[0] = 0;
-  for (int p = 0; p < DM_NPHASE; ++p) off[p + 1] = off[p] + 2 * nch[p];
-  if (off[DM_NPHASE] != DM_F4_STEP) { err = "decoder_mma packing: stream table out of sync"; return false; }
-  for (int p = 0; p < DM_NPHASE; ++p)
-    for (int wp = 0; wp < 16; ++wp) {
-      const DmItem& e = tab[p][wp];
-      if (e.cnt > nch[p] || e.cnt > 7 || e.c0 > 31) { err = "decoder_mma packing: work table overflow"; return false; }
-      tabw[p][wp] = (uint32_t)e.cnt | ((uint32_t)e.c0 << 3) | ((uint32_t)e.buf << 8) | ((uint32_t)e.tile << 12) | ((uint32_t)e.nx << 14) | ((uint32_t)e.early << 16);
-    }
-  auto M2 = [](const HostVar* m, int ld, int row, int col) { return m->data[(size_t)row * ld + col]; };
-  // first K row of chunk 0 of buffer `buf` inside the TF kernel of phase `p`
-  auto krow0 = [&](int p, int buf) -> int {
-    switch (p) {
-      case 0: return buf == DM_BF ? 0 : M;          // [frame | ctx]
-      case 2: return buf == DM_BP2 ? 0 : DP;        // [prenet | h_att]
-      case 3: return DP;                            // candidate rows of r*h_att
-      case 5: return DH;                            // projection rows of the context
-      case 6: case 8: return buf == DM_BY0 ? 0 : DH;
-      case 7: case 9: return DH;
-      default: return 0;
-    }
-  };
-  // weight A[c][k] of (phase, tile) for CTA q: TF kernel element (row k, column of tile row c)
-  auto wval = [&](int p, int q, int tile, int k, int c) -> float {
-    const int col = 16 * q + c;
-    switch (p) {
-      case 0: return M2(w1, 256, k, col);
-      case 1: return M2(w2, 128, k, 16 * (q >> 1) + c);
-      case 2: return tile == 0 ? M2(wga, 512, k, col) : (tile == 1 ? M2(wga, 512, k, DH + col) : M2(wca, 256, k, col));
-      case 3: return M2(wca, 256, k, col);
-      case 4: return tile == 0 ? M2(wq, 256, k, col) : M2(wp, 256, k, col);
-      case 5: return M2(wp, 256, k, col);
-      case 6: return tile == 0 ? M2(wg1, 512, k, col) : (tile == 1 ? M2(wg1, 512, k, DH + col) : M2(wc1, 256, k, col));
-      case 7: return M2(wc1, 256, k, col);
-      case 8: return tile == 0 ? M2(wg2, 512, k, col) : (tile == 1 ? M2(wg2, 512, k, DH + col) : M2(wc2, 256, k, col));
-      case 9: return M2(wc2, 256, k, col);
-      default: {
-        const int oc = (2 * q + tile) * 16 + c;
-        return oc < Dout ? M2(wo, Dout, k, oc) : 0.0f;
-      }
-    }
-  };
-  O.stream = A.alloc((size_t)16 * 16 * DM_F4_STEP * 32 * 4);
-  uint32_t* S32 = reinterpret_cast<uint32_t*>(&A.buf[O.stream]);
-  for (int q = 0; q < 16; ++q)
-    for (int wp = 0; wp < 16; ++wp)
-      for (int p = 0; p < DM_NPHASE; ++p) {
-        const DmItem& e = tab[p][wp];
-        for (int i = 0; i < e.cnt; ++i) {
-          const int kbase = krow0(p, e.buf) + (e.c0 + i) * 16;
-          for (int lane = 0; lane < 32; ++lane) {
-            const int g = lane >> 2, t = lane & 3;
-            const int rows[4] = {g, g + 8, g, g + 8}, ks[4] = {2 * t, 2 * t, 2 * t + 8, 2 * t + 8};
-            uint32_t* hi = S32 + ((((size_t)(q * 16 + wp) * DM_F4_STEP) + off[p] + 2 * i) * 32 + lane) * 4;
-            uint32_t* lo = hi + 32 * 4;
-            for (int j = 0; j < 4; ++j) {
-              const float a0 = wval(p, q, e.tile, kbase + ks[j], rows[j]), a1 = wval(p, q, e.tile, kbase + ks[j] + 1, rows[j]);
-              const uint16_t h0 = bf16_rn(a0), h1 = bf16_rn(a1);
-              const uint16_t l0 = bf16_rn(a0 - bf16_f(h0)), l1 = bf16_rn(a1 - bf16_f(h1));
-              hi[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-              lo[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-            }
-          }
-        }
-      }
-  O.bias = A.alloc((size_t)16 * DM_NBIAS);
-  for (int q = 0; q < 16; ++q) {
-    float* B = &A.buf[O.bias + (size_t)q * DM_NBIAS];
-    for (int c = 0; c < 16; ++c) {
-      const int col = 16 * q + c, ps = c;
-      B[0 + ps] = b1->data[col];
-      B[16 + ps] = b2->data[16 * (q >> 1) + c];
-      B[32 + ps] = bga->data[col];   B[48 + ps] = bga->data[DH + col];   B[64 + ps] = bca->data[col];
-      B[80 + ps] = bp->data[col];
-      B[96 + ps] = bg1->data[col];   B[112 + ps] = bg1->data[DH + col];  B[128 + ps] = bc1->data[col];
-      B[144 + ps] = bg2->data[col];  B[160 + ps] = bg2->data[DH + col];  B[176 + ps] = bc2->data[col];
-      const int oa = (2 * q) * 16 + c, ob = (2 * q + 1) * 16 + c;
-      B[192 + ps] = oa < Dout ? bo->data[oa] : 0.0f;
-      B[208 + ps] = ob < Dout ? bo->data[ob] : 0.0f;
-    }
-  }
-  O.att_v = put_vec(A, v->data.data(), 256);
-  return true;
-}
 
 #include "decoder_cw_pack.inc"
 
@@ -780,7 +525,10 @@ void gemm(Ctx& c, const GemmW& g, const BfScratch& sc, const float* x, int64_t x
   u.bias = bias; u.scale = scale; u.shift = shift; u.res = res; u.res_bs = res_bs; u.ldres = ldres;
   u.out = out; u.out_bs = out_bs; u.ldo = ldo; u.col_off = col_off; u.act = act; u.epi = epi;
   cudaError_t e = launch_conv_umma(u, c.st);
-  if (e != cudaSuccess && h->err.empty()) h->err = std::string("conv_umma launch: ") + cudaGetErrorString(e);
+  if (e != cudaSuccess) {
+    if (!h->launch_failed) h->err = std::string("conv_umma launch: ") + cudaGetErrorString(e);
+    h->launch_failed = true;
+  }
   h->launches += presplit ? 1 : 2;
 }
 
@@ -792,7 +540,10 @@ void run_bigru(Ctx& c, const CbhgDev& D, const float* xproj, const int32_t* leng
   const bool use_mma = impl && std::string(impl) == "mma";
   if (use_mma) {
     cudaError_t e = launch_bigru_mma(xproj, c.W(D.gru_frag), lengths, N, T, out, out_bs, c.st);
-    if (e != cudaSuccess && c.h->err.empty()) c.h->err = std::string("bigru_mma launch: ") + cudaGetErrorString(e);
+    if (e != cudaSuccess) {
+      if (!c.h->launch_failed) c.h->err = std::string("bigru_mma launch: ") + cudaGetErrorString(e);
+      c.h->launch_failed = true;
+    }
   } else {
     launch_bigru(xproj, c.W(D.gru_ug), c.W(D.gru_uc), lengths, N, T, out, out_bs, c.st);
   }
@@ -931,6 +682,11 @@ void pick_geometry(const taco_handle* h, int N, int* cs_out, int* s_out) {
 }
 
 int check_launch(taco_handle* h, const char* what) {
+  if (h->launch_failed) {   // a launcher already consumed the CUDA error: report it instead of returning TACO_OK with garbage outputs
+    h->launch_failed = false;
+    cudaGetLastError();
+    return TACO_ERR_CUDA;   // h->err was set where the launch failed
+  }
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -993,7 +749,7 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
   DecoderArgs a;
   a.memory = memory; a.keys = keys; a.targets = teacher_force ? mel_targets : nullptr;
   a.N = N; a.T_in = T_in; a.T_tgt = T_tgt; a.r = hp.outputs_per_step; a.steps = max_steps; a.max_steps = max_steps;
-  a.dec_out = dec_out; a.align_out = align_out; a.att_res = 0; a.s_max = 0; a.trace = nullptr; a.trace_cta = 0; a.trace_warp = 8; a.ring_d0 = 0; a.ring_d1 = 0;
+  a.dec_out = dec_out; a.align_out = align_out; a.att_res = 0; a.s_max = 0; a.trace = nullptr; a.trace_cta = 0; a.trace_warp = 8;
   const char* trace_path = getenv("TACO_DEC_TRACE");   // developer aid: per-phase clock stamps of CTA 0
   long long* d_trace = nullptr;
   if (trace_path) {
@@ -1007,14 +763,12 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
   pick_geometry(h, N, &CS, &S);
   if (getenv("TACO_DEBUG"))
     fprintf(stderr, "[taco] decode N=%d T_in=%d steps=%d CS=%d S=%d kernel=%s max_clusters(8)=%d (16)=%d\n", N, T_in,
-            max_steps, CS, S, h->use_cw ? "cw" : h->use_mma ? "mma" : ((h->use_v3 && CS == 16) ? "v3" : "v2"), h->max_clusters[0], h->max_clusters[1]);
+            max_steps, CS, S, h->use_cw ? "cw" : "v2", h->max_clusters[0], h->max_clusters[1]);
   if (h->profiling) cudaEventRecord(h->ev[4], st);
   const bool fits8 = (N + pick_mma_clusters(h, N) - 1) / pick_mma_clusters(h, N) <= 8;
-  const bool use_cw = h->use_cw && fits8, use_mma = h->use_mma && fits8;
+  const bool use_cw = h->use_cw && fits8;
   cudaError_t e = use_cw ? launch_decoder_cw(h->decw, a, pick_mma_clusters(h, N), st)
-                  : use_mma ? launch_decoder_mma(h->dec4, a, pick_mma_clusters(h, N), st)
-                  : (h->use_v3 && CS == 16) ? launch_decoder_v3(h->dec3, a, S, st)
-                                            : launch_decoder(h->dec[CS == 16 ? 1 : 0], a, S, st);
+                         : launch_decoder(h->dec[CS == 16 ? 1 : 0], a, S, st);
   if (h->profiling) cudaEventRecord(h->ev[5], st);
   if (e != cudaSuccess) return fail(h, TACO_ERR_CUDA, std::string("decoder launch: ") + cudaGetErrorString(e));
   h->launches += 1;
@@ -1205,13 +959,7 @@ int taco_finalize_weights(taco_handle* h) {
   for (int ci = 0; ci < 2; ++ci)
     if (!pack_decoder(h, A, ci ? 16 : 8, O[ci], McO[ci], err))
       return bad(err.rfind("missing", 0) == 0 ? TACO_ERR_MISSING_WEIGHT : TACO_ERR_INVALID);
-  Dec3Off O3;
-  if (!pack_decoder_v3(h, A, O3, err)) return bad(err.rfind("missing", 0) == 0 ? TACO_ERR_MISSING_WEIGHT : TACO_ERR_INVALID);
-  // mma.sync decoder (default): needs num_mels and num_mels*r to be multiples of the 16-column tile
-  DmOff O4{0, 0, 0};
-  const bool mma_ok = hp.num_mels % 16 == 0 && hp.num_mels <= 128;
-  if (mma_ok && !pack_decoder_mma(h, A, O4, h->dec4.tab, err))
-    return bad(err.rfind("missing", 0) == 0 ? TACO_ERR_MISSING_WEIGHT : TACO_ERR_INVALID);
+  const bool mma_ok = hp.num_mels % 16 == 0 && hp.num_mels <= 128;   // decoder_cw: num_mels and num_mels*r multiples of the 16-column tile
   CwOff O6;
   if (mma_ok && !pack_decoder_cw(h, A, O6, h->decw, err))
     return bad(err.rfind("missing", 0) == 0 ? TACO_ERR_MISSING_WEIGHT : TACO_ERR_INVALID);
@@ -1248,28 +996,11 @@ int taco_finalize_weights(taco_handle* h) {
   }
   const float* B = h->dW;
   {
-    DecoderWeightsV3& d = h->dec3;
-    d.M = hp.num_mels; d.Dout = hp.num_mels * hp.outputs_per_step;
-    d.stream = B + O3.stream; d.ew = B + O3.ew;
-    d.p1_b = B + O3.p1_b; d.p2_b = B + O3.p2_b; d.ga_b = B + O3.ga_b; d.ca_b = B + O3.ca_b; d.pc_b = B + O3.pc_b;
-    d.g1_b = B + O3.g1_b; d.c1_b = B + O3.c1_b; d.g2_b = B + O3.g2_b; d.c2_b = B + O3.c2_b; d.o_b = B + O3.o_b;
-    d.att_v = B + O3.att_v;
-    const char* e3 = getenv("TACO_DEC_V3");
-    h->use_v3 = e3 ? atoi(e3) : 0;
-    if (h->max_clusters[1] < 1) h->use_v3 = 0;
-  }
-  {
-    DecoderMmaWeights& d = h->dec4;
-    d.M = hp.num_mels; d.Dout = hp.num_mels * hp.outputs_per_step;
-    d.stream = B + O4.stream; d.bias = B + O4.bias; d.att_v = B + O4.att_v;
-    h->max_clusters_mma = mma_ok ? decoder_mma_max_clusters() : 0;
-    const char* ei = getenv("TACO_DEC_IMPL");   // "mma" (default) | "v2" | "v3": developer switch between decoder kernels
-    h->use_mma = mma_ok && h->max_clusters_mma >= 1 && ei && strcmp(ei, "mma") == 0;
-    if (ei && strcmp(ei, "v3") == 0 && h->max_clusters[1] >= 1) h->use_v3 = 1;
+    const char* ei = getenv("TACO_DEC_IMPL");   // "cw" (default) | "v2": developer switch to the fp32 FFMA decoder
     // "cw" (default): decoder_cw.cu
     h->decw.tmem_img = B + O6.tmem; h->decw.ring = B + O6.ring; h->decw.bias = B + O6.bias; h->decw.att_v = B + O6.att_v;
     h->use_cw = mma_ok && decoder_cw_max_clusters() >= 1 && !(ei && strcmp(ei, "cw") != 0);
-    if (h->use_cw) h->max_clusters_mma = decoder_cw_max_clusters();
+    h->max_clusters_mma = h->use_cw ? decoder_cw_max_clusters() : 0;
   }
   for (int ci = 0; ci < 2; ++ci) {
     DecoderWeights& d = h->dec[ci];
@@ -1668,26 +1399,12 @@ int taco_griffin_lim(taco_handle* h, const taco_audio_params* ap, const float* l
 
 int64_t taco_launch_count(const taco_handle* h) { return h ? h->launches : 0; }
 
-// Host-only: the decoder's work table for a given num_mels (no GPU, no handle).  out[phase][warp][5] =
-// {tile, buffer, first chunk, chunk count, extra activation buffers}.
-int taco_decoder_work_table(int num_mels, int32_t* out, int out_len) {
-  if (num_mels <= 0 || num_mels > 128 || (num_mels & 15) || !out || out_len < DM_NPHASE * 16 * 5) return TACO_ERR_INVALID;
-  DmItem tab[DM_NPHASE][16];
-  dm_table(num_mels / 16, tab);
-  for (int p = 0; p < DM_NPHASE; ++p)
-    for (int w = 0; w < 16; ++w) {
-      int32_t* e = out + (p * 16 + w) * 5;
-      e[0] = tab[p][w].tile; e[1] = tab[p][w].buf; e[2] = tab[p][w].c0; e[3] = tab[p][w].cnt; e[4] = tab[p][w].nx;
-    }
-  return TACO_OK;
-}
-
 int taco_decoder_geometry(const taco_handle* h, int N, int* cluster_size, int* samples_per_cluster, int* num_clusters) {
   if (!h || !h->finalized) return TACO_ERR_STATE;
   int CS = 16, S = 8;
   pick_geometry(h, N, &CS, &S);
   int ncl = (N + S - 1) / S;
-  if ((h->use_mma || h->use_cw) && N > 0) {
+  if (h->use_cw && N > 0) {
     ncl = pick_mma_clusters(h, N);
     CS = 16;
     S = (N + ncl - 1) / ncl;

@@ -197,6 +197,33 @@ def test_decode_free_running(eng, ow, small_hp, N, T_in, S):
     assert e_dec < 1e-3 and e_al < 1e-4
 
 
+@pytest.mark.parametrize("scale,N,T_in,tol_al", [(10.0, 3, 29, 1e-5), (25.0, 6, 50, 1e-4)])   # scores of +-350 carry ~4e-5 of fp32 rounding into exp()
+def test_decode_large_attention_v(small_hp, small_weights, scale, N, T_in, tol_al):
+    """A trained checkpoint can have ||attention_v||_1 far above the 40 for which exp(score - ||v||_1) is safe in fp32: the decoder
+    then exchanges raw scores and subtracts the row maximum (a true softmax, reference BahdanauAttention).  Random-init v has
+    ||v||_1 ~ 14, so scale it (and the keys through the memory layer) until scores spread over +-100."""
+    from tacotron_multispeaker_b200.engine import Engine
+    w = dict(small_weights)
+    vname = [k for k in w if k.endswith("bahdanau_attention/attention_v")][0]
+    mname = [k for k in w if k.endswith("memory_layer/kernel")][0]
+    w[vname] = (w[vname] * scale).astype(np.float32)
+    w[mname] = (w[mname] * 3.0).astype(np.float32)
+    assert np.abs(w[vname]).sum() > 100.0
+    e = Engine(small_hp, id_num=6)
+    try:
+        e.load_weights(w)
+        wo = O.W(w, torch.float32)
+        for teacher in (True, False):
+            e_dec, e_al, al, ral = _decode_case(e, wo, small_hp, N, T_in, teacher, int(scale) + N)
+            assert e_dec < (2e-4 if teacher else 1e-3), (teacher, e_dec)
+            assert e_al < (tol_al if teacher else 10 * tol_al), (teacher, e_al)
+            assert float(ral.max()) > 0.5          # the attention is sharply peaked: rows far below the maximum must underflow to 0, not to a floor
+            if teacher:
+                assert torch.equal(al.cpu().argmax(dim=1), ral.argmax(dim=1))
+    finally:
+        e.close()
+
+
 def test_postnet(eng, ow, small_hp):
     rng = np.random.default_rng(5)
     mel = rng.uniform(-0.5, 1.0, (2, 35, 80)).astype(np.float32)

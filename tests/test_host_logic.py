@@ -147,51 +147,3 @@ def test_output_gather_world_size_2_gloo(n_total):
     assert res == [(0, True), (1, True)]
 
 
-def test_decoder_work_table_covers_every_chunk_once():
-    """Host logic of the mma.sync decoder (csrc/taco_abi.cu dm_table, no GPU): in every phase the 16 warps together
-    multiply each 16-row chunk of each tile's inputs exactly once, no warp holds more chunk-tiles than its six weight
-    register slots, and the tensor-pipe work is balanced over the four SM sub-partitions (warps w, w+4, w+8, w+12)."""
-    import ctypes as C
-    import numpy as np
-    from tacotron_multispeaker_b200 import _abi
-    lib = _abi.load()
-    BF, BC, BP1, BP2, BHA, BRA, BY0, BH1, BR1, BY1, BH2, BR2, BY2 = range(13)
-    for num_mels in (80, 16, 128):
-        FC = num_mels // 16
-        buf = (C.c_int32 * (11 * 16 * 5))()
-        assert lib.taco_decoder_work_table(num_mels, buf, len(buf)) == 0
-        tab = np.array(buf[:]).reshape(11, 16, 5)
-        nchunks = {BF: FC, BP2: 8}
-        # phase -> {tile: [(buffer, chunks expected)]}
-        expect = [
-            {0: [(BC, 16), (BF, FC)]},
-            {0: [(BP1, 16)]},
-            {0: [(BP2, 8), (BHA, 16)], 1: [(BP2, 8), (BHA, 16)], 2: [(BP2, 8)]},
-            {0: [(BRA, 16)]},
-            {0: [(BHA, 16)], 1: [(BHA, 16)]},
-            {0: [(BC, 16)]},
-            {0: [(BY0, 16), (BH1, 16)], 1: [(BY0, 16), (BH1, 16)], 2: [(BY0, 16)]},
-            {0: [(BR1, 16)]},
-            {0: [(BY0, 16), (BH2, 16)], 1: [(BY0, 16), (BH2, 16)], 2: [(BY0, 16)]},
-            {0: [(BR2, 16)]},
-            {0: [(BY0, 16)], 1: [(BY0, 16)]},
-        ]
-        max_cnt = [3, 2, 4, 2, 2, 2, 6, 2, 6, 2, 2]
-        for p in range(11):
-            seen = {}
-            for w in range(16):
-                tile, b, c0, cnt, nx = tab[p, w]
-                assert 0 <= cnt <= max_cnt[p] <= 6
-                for c in range(c0, c0 + cnt):
-                    key = (int(tile), int(b), int(c))
-                    assert key not in seen, (p, key)
-                    seen[key] = int(nx)
-            want = {(t, b, c) for t, lst in expect[p].items() for b, n in lst for c in range(n)}
-            assert set(seen) == want, (num_mels, p)
-            # y1 = y0 + h1' (GRU 2) and y2 = y0 + h1' + h2' (output projection) by linearity on the y0 chunks
-            for (t, b, c), nx in seen.items():
-                assert nx == ((1 if p == 8 else 2 if p == 10 else 0) if b == BY0 else 0)
-            work = [int(tab[p, w, 3]) * (1 + int(tab[p, w, 4])) for w in range(16)]
-            per_smsp = [sum(work[k::4]) for k in range(4)]
-            assert max(per_smsp) - min(per_smsp) <= 6, (p, per_smsp)
-        assert lib.taco_decoder_work_table(81, buf, len(buf)) != 0
