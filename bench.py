@@ -311,12 +311,12 @@ def run_ours(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     # DRAM traffic of that kernel per launch from the committed ncu capture (dram__bytes_read.sum + dram__bytes_write.sum)
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_decoder_traffic.json")
-    if os.path.exists(tpath) and os.environ.get("TACO_DEC_IMPL", "mma") == "mma":
+    tpath = os.path.join(ROOT, "profiles", "r2_decoder_traffic.json")
+    if os.path.exists(tpath) and os.environ.get("TACO_DEC_IMPL", "cw") == "cw":
         tj = json.load(open(tpath))
         traffic, traffic_src = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"], tj["source"]
-    kname = ("decoder_mma_kernel (cluster 16, <=%d utterances per cluster, %d clusters)" % (geo["samples_per_cluster"], geo["num_clusters"])
-             if os.environ.get("TACO_DEC_IMPL", "mma") == "mma" else
+    kname = ("decoder_cw_kernel (cluster 16, <=%d utterances per cluster, %d clusters)" % (geo["samples_per_cluster"], geo["num_clusters"])
+             if os.environ.get("TACO_DEC_IMPL", "cw") == "cw" else
              "decoder_kernel<S=%d,CS=%d>" % (geo["samples_per_cluster"], geo["cluster_size"]))
     roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -491,6 +491,14 @@ def run_ours(args):
                "frames_per_s": frames_per_step / (v_ms / 1e3), "launches_per_batch": (eng.launch_count() - voc_l0) // 6, "ms_per_call": v_calls,
                "audio_seconds_per_batch": BATCH * wav.shape[-1] / hp.sample_rate, "clocks": voc_clocks}
 
+    # ---- the other configurations BASELINE.json names (extra keys; bench_configs.py) ----
+    extra = {}
+    if not args.no_configs:
+        import bench_configs
+        from tacotron_multispeaker_b200 import sharding
+        extra = bench_configs.run(torch, Engine, HParams, random_init, _abi, sharding, dev, local, rank, world, dist, barrier,
+                                  eng, hp, ID_NUM, args.steps, quick=args.quick_configs)
+
     # ---- CPU restatement on the host cores (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -511,6 +519,7 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "decoder_geometry": geo,
         }
+        line.update(extra)
         emit(line)
     for l in lanes:
         l["eng"].close()
@@ -531,6 +540,8 @@ def main():
     ap.add_argument("--no-latency", action="store_true", help="skip the batch-1 latency leg")
     ap.add_argument("--no-vocoder", action="store_true", help="skip the informational Griffin-Lim leg")
     ap.add_argument("--no-throughput-mode", action="store_true", help="skip the informational 4-cluster decoder legs")
+    ap.add_argument("--no-configs", action="store_true", help="skip the legs for BASELINE configs 1, 2, 4, 5 and the synthesize-shaped e2e")
+    ap.add_argument("--quick-configs", action="store_true", help="fewer runs in those legs")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on stdout when
     # NCCL_DEBUG is set): file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved one.

@@ -292,6 +292,13 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
+  if (tid == 12 * 32) {   // expected byte counts of step 0 (later steps: re-armed after each wait)
+    const uint32_t blk = CS * (uint32_t)S * 64u;
+    mbar_expect_tx(mb0 + MB_P1 * 8, blk);  mbar_expect_tx(mb0 + MB_P2 * 8, blk / 2); mbar_expect_tx(mb0 + MB_P3 * 8, blk);
+    mbar_expect_tx(mb0 + MB_P4 * 8, blk);  mbar_expect_tx(mb0 + MB_P5 * 8, blk);     mbar_expect_tx(mb0 + MB_P6 * 8, (uint32_t)NQ * 16u);
+    mbar_expect_tx(mb0 + MB_P7 * 8, blk);  mbar_expect_tx(mb0 + MB_P9 * 8, blk);     mbar_expect_tx(mb0 + MB_Y0 * 8, blk);
+    mbar_expect_tx(mb0 + MB_P10 * 8, blk); mbar_expect_tx(mb0 + MB_P11 * 8, blk);    mbar_expect_tx(mb0 + MB_P12 * 8, blk);
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   cluster_sync_all();   // buffers zeroed, mbarriers initialised, tensor memory filled everywhere before anyone pushes
@@ -463,28 +470,20 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       store_tile(myslot, g, t, hh, hl, lh);
     };
     const int al_pp = tid - 12 * 32, al_n = (p0 + al_pp) % S, al_j = (p0 + al_pp) / S;   // the pair this thread writes the alignment of
+    // wait for an exchange of this step, then re-arm its mbarrier for the next step (the phase that has just completed cannot be
+    // disturbed any more; one lane of one critical warp, so no burst of twelve arrivals at the top of a step)
+    auto wait_rearm = [&](int mb, uint32_t parity, uint32_t bytes) {
+      mbar_wait(mb0 + (uint32_t)mb * 8u, parity);
+      if (tid == (12 + (mb & 3)) * 32) mbar_expect_tx(mb0 + (uint32_t)mb * 8u, bytes);
+    };
     tload(TC_P2, 4);   // step 0 has no late part in P1 (zero go frame / zero state)
     for (int step = 0; step < a.steps; ++step) {
       const uint32_t par = (uint32_t)step & 1u;
       const uint32_t XHAc = XHA + 16 * par, XH1c = XH1 + 16 * par, XH2c = XH2 + 16 * par, XH2p = XH2 + 16 * (par ^ 1u);
       bool late1 = false;
       if (step > 0) {
-        mbar_wait(mb0 + MB_P12 * 8, par ^ 1u);     // h2' of the previous step has landed (and every earlier exchange with it)
-        mbar_wait(mb0 + MB_Y0 * 8, par ^ 1u);
-      }
-      if (tid == 12 * 32) {   // this step's expected byte counts (remote credits may already have arrived)
-        mbar_expect_tx(mb0 + MB_P1 * 8, BLK);
-        mbar_expect_tx(mb0 + MB_P2 * 8, BLK / 2);
-        mbar_expect_tx(mb0 + MB_P3 * 8, BLK);
-        mbar_expect_tx(mb0 + MB_P4 * 8, BLK);
-        mbar_expect_tx(mb0 + MB_P5 * 8, BLK);
-        mbar_expect_tx(mb0 + MB_P6 * 8, (uint32_t)NQ * 16u);
-        mbar_expect_tx(mb0 + MB_P7 * 8, BLK);
-        mbar_expect_tx(mb0 + MB_P9 * 8, BLK);
-        mbar_expect_tx(mb0 + MB_Y0 * 8, BLK);
-        mbar_expect_tx(mb0 + MB_P10 * 8, BLK);
-        mbar_expect_tx(mb0 + MB_P11 * 8, BLK);
-        mbar_expect_tx(mb0 + MB_P12 * 8, BLK);
+        wait_rearm(MB_P12, par ^ 1u, BLK);     // h2' of the previous step has landed (and every earlier exchange with it)
+        wait_rearm(MB_Y0, par ^ 1u, BLK);
       }
       TRM(0);
       // ================= P1: decoder prenet dense_1 + ReLU.  free run: W_f y2 (late: the h2' term) + W_1c ctx; teacher: background only ====
@@ -503,7 +502,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       }
       twait();
       TRM(1);
-      mbar_wait(mb0 + MB_P1 * 8, par);
+      wait_rearm(MB_P1, par, BLK);
       TRM(2);
       // ================= P2: prenet dense_2 + ReLU (CTA pair 2c, 2c+1 computes chunk c; each feeds the peers of its parity) ====
       late(XADDR(XP1 + 4 * gw), 4);
@@ -513,7 +512,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       send_rows(OFF_X + (uint32_t)(XP2 + (q >> 1)) * csb, MB_P2, true);
       twait();
       TRM(3);
-      mbar_wait(mb0 + MB_P2 * 8, par);
+      wait_rearm(MB_P2, par, BLK / 2);
       TRM(4);
       // ================= P3: attention GRU reset gate on [prenet | h_att]; r * h_att goes out ====
       late(XADDR(XP2 + 2 * gw), 2);
@@ -524,7 +523,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       send_rows(OFF_X + (uint32_t)(XRA + q) * csb, MB_P3, false);
       twait();
       TRM(5);
-      mbar_wait(mb0 + MB_P3 * 8, par);
+      wait_rearm(MB_P3, par, BLK);
       TRM(6);
       // ================= P4: candidate; h_att' = u h + (1-u) tanh(c_h + c_x + b) ====
       late(XADDR(XRA + 4 * gw), 4);
@@ -540,7 +539,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       }
       twait();
       TRM(7);
-      mbar_wait(mb0 + MB_P4 * 8, par);
+      wait_rearm(MB_P4, par, BLK);
       TRM(8);
       // ================= P5: query layer; pushed as e^{2 pq} (fp32) for the score phase ====
       late(XADDR(XHAc + 4 * gw), 4);
@@ -550,7 +549,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       send_rows(L.pq + (uint32_t)q * csb, MB_P5, false);
       twait();
       TRM(9);
-      mbar_wait(mb0 + MB_P5 * 8, par);
+      wait_rearm(MB_P5, par, BLK);
       TRM(10);
       // ================= P6 / P7: attention (all warps) ====
       p6_compute();
@@ -558,7 +557,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       __syncthreads();
       TRM(11);
       p6_send();
-      mbar_wait(mb0 + MB_P6 * 8, par);
+      wait_rearm(MB_P6, par, (uint32_t)NQ * 16u);
       TRM(12);
       TRW(128);
       p7_compute();
@@ -579,7 +578,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
         send_rows(OFF_X + (uint32_t)(XC + q) * csb, MB_P7, false);
       }
       TRM(14);
-      mbar_wait(mb0 + MB_P7 * 8, par);
+      wait_rearm(MB_P7, par, BLK);
       TRM(15);
       // ================= P9: GRU-1 reset gate on [h_att' | ctx'] (512->256 projection folded in) and h1 ====
       late(XADDR(XC + 4 * gw), 4);
@@ -602,7 +601,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
         }
       }
       TRM(16);
-      mbar_wait(mb0 + MB_P9 * 8, par);
+      wait_rearm(MB_P9, par, BLK);
       TRM(17);
       // ================= P10: GRU-1 candidate, h1' ====
       late(XADDR(XR1 + 4 * gw), 4);
@@ -618,7 +617,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       }
       twait();
       TRM(18);
-      mbar_wait(mb0 + MB_P10 * 8, par);
+      wait_rearm(MB_P10, par, BLK);
       TRM(19);
       // ================= P11: GRU-2 reset gate on [y1 = y0 + h1' | h2] (late: the h1' term) ====
       late(XADDR(XH1c + 4 * gw), 4);
@@ -629,7 +628,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       send_rows(OFF_X + (uint32_t)(XR2 + q) * csb, MB_P11, false);
       twait();
       TRM(20);
-      mbar_wait(mb0 + MB_P11 * 8, par);
+      wait_rearm(MB_P11, par, BLK);
       TRM(21);
       // ================= P12: GRU-2 candidate, h2' ====
       late(XADDR(XR2 + 4 * gw), 4);
@@ -773,20 +772,17 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
           stage_x(stg_n, rc, sum4(red_nc, SL_Y0) + BIAS(BI_Y0));
           send_rows(OFF_X + (uint32_t)(XY0 + q) * csb, MB_Y0, false);
         } else if (post == POST_OUT) {
-          // frames of this step: tiles 2q and 2q+1 of y2 W_o + b_o  (tacotron.py:83)
-          nb_sync(NB_BGRP, 128);
-          const int ntiles = Dout >> 4;
-          const float oa = sum4(red_nc, SL_O) + BIAS(BI_OA), ob = sum4(red_nc, SL_O + 4) + BIAS(BI_OB);
-          if (rn < S) {
-            float* dst = a.dec_out + ((size_t)(n0 + rn) * a.max_steps + step) * Dout + rc;
-            if (2 * q < ntiles) dst[(2 * q) * 16] = oa;
-            if (2 * q + 1 < ntiles) dst[(2 * q + 1) * 16] = ob;
-          }
+          // frames of this step: group B reduces tile 2q, group C tile 2q+1 of y2 W_o + b_o  (tacotron.py:83)
+          const int hb = warp >= 8 ? 1 : 0;
+          nb_sync(hb ? NB_CGRP : NB_BGRP, 128);
+          const int tile = 2 * q + hb;
+          const float o = sum4(red_nc, SL_O + 4 * hb) + BIAS(hb ? BI_OB : BI_OA);
+          if (rn < S && tile < (Dout >> 4)) a.dec_out[((size_t)(n0 + rn) * a.max_steps + step) * Dout + tile * 16 + rc] = o;
         }
         ITSTAMP(3);
       }
     };
-    if (warp >= 8) { __syncwarp(); nb_arrive(NB_H1, 256); }   // P1 of step 0: zero context, zero go frame -> the (zeroed) early slots are complete
+    if (warp < 4) { __syncwarp(); nb_arrive(NB_H1, 256); }   // P1 of step 0: zero context, zero go frame -> the (zeroed) early slots are complete
     for (int step = 0; step < a.steps; ++step) {
       const uint32_t par = (uint32_t)step & 1u;
       run_items(prog.pre[warp], prog.n_pre[warp], step);
