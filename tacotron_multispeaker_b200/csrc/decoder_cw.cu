@@ -40,7 +40,8 @@ constexpr uint32_t OFF_MX = OFF_INV + 32;                          // exact-soft
 constexpr uint32_t OFF_BIAS = 256;
 constexpr uint32_t OFF_VATT = OFF_BIAS + N_BIAS * 4;               // 1216
 constexpr uint32_t OFF_STG = OFF_VATT + DHID * 4;                  // staged rows: warps 8..15, 2 samples x 64 B each
-constexpr uint32_t OFF_REDS = OFF_STG + 8 * 128;                   // partial softmax normalisers [16 warps][8]
+constexpr uint32_t OFF_Y0S = OFF_STG + 8 * 128;                    // this CTA's y0 tile, fp32 [8 samples][16 columns]
+constexpr uint32_t OFF_REDS = OFF_Y0S + 8 * 16 * 4;                // partial softmax normalisers [16 warps][8]
 constexpr uint32_t OFF_SLOTS = (OFF_REDS + NW * 8 * 4 + 127u) & ~127u;
 constexpr uint32_t OFF_X = (OFF_SLOTS + N_SLOTS * SLOT_F * 4 + 127u) & ~127u;
 static_assert(OFF_BIAS % 16 == 0 && OFF_VATT % 16 == 0 && OFF_STG % 16 == 0 && OFF_SLOTS % 16 == 0, "alignment");
@@ -296,8 +297,9 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
     const uint32_t blk = CS * (uint32_t)S * 64u;
     mbar_expect_tx(mb0 + MB_P1 * 8, blk);  mbar_expect_tx(mb0 + MB_P2 * 8, blk / 2); mbar_expect_tx(mb0 + MB_P3 * 8, blk);
     mbar_expect_tx(mb0 + MB_P4 * 8, blk);  mbar_expect_tx(mb0 + MB_P5 * 8, blk);     mbar_expect_tx(mb0 + MB_P6 * 8, (uint32_t)NQ * 16u);
-    mbar_expect_tx(mb0 + MB_P7 * 8, blk);  mbar_expect_tx(mb0 + MB_P9 * 8, blk);     mbar_expect_tx(mb0 + MB_Y0 * 8, blk);
+    mbar_expect_tx(mb0 + MB_P7 * 8, blk);  mbar_expect_tx(mb0 + MB_P9 * 8, blk);     mbar_expect_tx(mb0 + MB_H1 * 8, blk);
     mbar_expect_tx(mb0 + MB_P10 * 8, blk); mbar_expect_tx(mb0 + MB_P11 * 8, blk);    mbar_expect_tx(mb0 + MB_P12 * 8, blk);
+    mbar_expect_tx(mb0 + MB_H2 * 8, blk);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -439,7 +441,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
     // CRITICAL GROUP
     // =====================================================================================================================
     uint4 wa[8];                                   // A fragments of the next late part: four chunk-tiles (hi, lo)
-    float st_ha = 0.f, st_h1 = 0.f, st_h2 = 0.f;   // recurrent state of element (rn, rc), fp32
+    float st_ha = 0.f, st_h1 = 0.f, st_h2 = 0.f, st_y1 = 0.f;   // recurrent state (and y1) of element (rn, rc), fp32
     const uint32_t myslot = sbase + OFF_SLOTS + (uint32_t)(SL_CRIT + gw) * (SLOT_F * 4);
     // chunk-tile index of each critical phase inside this warp's tensor-memory slice
     constexpr int TC_P1 = 0, TC_P2 = 4, TC_P3 = 8, TC_P4 = 10, TC_P5 = 14, TC_P9 = 18, TC_P10 = 22, TC_P11 = 26, TC_P12 = 30;
@@ -479,16 +481,17 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
     tload(TC_P2, 4);   // step 0 has no late part in P1 (zero go frame / zero state)
     for (int step = 0; step < a.steps; ++step) {
       const uint32_t par = (uint32_t)step & 1u;
-      const uint32_t XHAc = XHA + 16 * par, XH1c = XH1 + 16 * par, XH2c = XH2 + 16 * par, XH2p = XH2 + 16 * (par ^ 1u);
+      const uint32_t XHAc = XHA + 16 * par, XH1c = XH1 + 16 * par, XH2c = XH2 + 16 * par;
       bool late1 = false;
       if (step > 0) {
         wait_rearm(MB_P12, par ^ 1u, BLK);     // h2' of the previous step has landed (and every earlier exchange with it)
-        wait_rearm(MB_Y0, par ^ 1u, BLK);
+        wait_rearm(MB_H1, par ^ 1u, BLK);
+        wait_rearm(MB_H2, par ^ 1u, BLK);
       }
       TRM(0);
       // ================= P1: decoder prenet dense_1 + ReLU.  free run: W_f y2 (late: the h2' term) + W_1c ctx; teacher: background only ====
       if (free_run && step > 0) {
-        late(XADDR(XH2p + 4 * gw), 4);
+        late(XADDR(XY2 + 4 * gw), 4);
         tload(TC_P2, 4);
         nb_sync(NB_CRIT, 128);
         late1 = true;
@@ -607,20 +610,24 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       late(XADDR(XR1 + 4 * gw), 4);
       tload(TC_P11, 4);
       nb_sync(NB_CRIT, 128);
-      TRM(58); nb_sync(NB_H10, 384); TRM(59);
+      TRM(58); nb_sync(NB_H10, 512); TRM(59);
       {
         const float u = sigmoid_f(sum4(red_nc, SL_U) + BIAS(BI_U1));
         const float c = tanh_f(sum4(red_nc, SL_CRIT) + sum4(red_nc, SL_CX) + BIAS(BI_C1));
         st_h1 = u * st_h1 + (1.0f - u) * c;
+        st_y1 = lds_f(sbase + OFF_Y0S + (uint32_t)(rn * 16 + rc) * 4u) + st_h1;     // ResidualWrapper: y1 = y0 + h1'
+        stage_x(stg_n, rc, st_y1);
+        send_rows(OFF_X + (uint32_t)(XY1 + q) * csb, MB_P10, false);             // critical: GRU 2's gates wait for y1
+        __syncwarp();
         stage_x(stg_n, rc, st_h1);
-        send_rows(OFF_X + (uint32_t)(XH1c + q) * csb, MB_P10, false);
+        send_rows(OFF_X + (uint32_t)(XH1c + q) * csb, MB_H1, false);             // the state itself: first needed in the next step
       }
       twait();
       TRM(18);
       wait_rearm(MB_P10, par, BLK);
       TRM(19);
       // ================= P11: GRU-2 reset gate on [y1 = y0 + h1' | h2] (late: the h1' term) ====
-      late(XADDR(XH1c + 4 * gw), 4);
+      late(XADDR(XY1 + 4 * gw), 4);
       tload(TC_P12, 4);
       nb_sync(NB_CRIT, 128);
       TRM(60); nb_sync(NB_H11, 256); TRM(61);
@@ -639,8 +646,11 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
         const float u = sigmoid_f(sum4(red_nc, SL_U) + BIAS(BI_U2));
         const float c = tanh_f(sum4(red_nc, SL_CRIT) + sum4(red_nc, SL_CX) + BIAS(BI_C2));
         st_h2 = u * st_h2 + (1.0f - u) * c;
+        stage_x(stg_n, rc, st_y1 + st_h2);                                        // y2 = y1 + h2': the next prenet and the frames need it
+        send_rows(OFF_X + (uint32_t)(XY2 + q) * csb, MB_P12, false);
+        __syncwarp();
         stage_x(stg_n, rc, st_h2);
-        send_rows(OFF_X + (uint32_t)(XH2c + q) * csb, MB_P12, false);
+        send_rows(OFF_X + (uint32_t)(XH2c + q) * csb, MB_H2, false);
       }
       twait();
       TRM(22);
@@ -725,7 +735,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
           for (int o = 0; o < nops; ++o) {
             const uint32_t od = items[it].w[2 + o];
             const uint32_t mb = (od >> 10) & 31u;
-            if (mb) mbar_wait(mb0 + (mb - 1u) * 8u, par);
+            if (mb) mbar_wait(mb0 + (mb - 1u) * 8u, (od & 0x10000u) ? par ^ 1u : par);
             const uint32_t pb = (od >> 8) & 3u;
             const uint32_t chunk = (od & 255u) + (pb == 1u ? 16u * par : (pb == 2u ? 16u * (par ^ 1u) : 0u));
             uint4 xf[4];
@@ -765,19 +775,24 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
         if (post == POST_ARRIVE) {
           const int nb = (int)((w0 >> 15) & 15u);
           __syncwarp();
-          nb_arrive(nb, (nb == NB_H4 || nb == NB_H10 || nb == NB_H12) ? 384 : 256);
+          nb_arrive(nb, nb == NB_H10 ? 512 : ((nb == NB_H4 || nb == NB_H12) ? 384 : 256));
         } else if (post == POST_Y0) {
-          // y0 = [h_att' | ctx'] W_p + b_p: reduce the group's four partial tiles and push the rows (every CTA needs all of y0)
+          // y0 tile of this CTA = [h_att' | ctx'] W_p + b_p: reduce the group's four partial tiles into the local fp32 copy that the
+          // candidate phase of GRU 1 adds to h1' (nothing is exchanged: every consumer of y0 reads y1 or y2)
           nb_sync(NB_CGRP, 128);
-          stage_x(stg_n, rc, sum4(red_nc, SL_Y0) + BIAS(BI_Y0));
-          send_rows(OFF_X + (uint32_t)(XY0 + q) * csb, MB_Y0, false);
+          sts_f(sbase + OFF_Y0S + (uint32_t)(rn * 16 + rc) * 4u, sum4(red_nc, SL_Y0) + BIAS(BI_Y0));
+          __syncwarp();
+          nb_arrive(NB_H10, 512);
         } else if (post == POST_OUT) {
-          // frames of this step: group B reduces tile 2q, group C tile 2q+1 of y2 W_o + b_o  (tacotron.py:83)
-          const int hb = warp >= 8 ? 1 : 0;
-          nb_sync(hb ? NB_CGRP : NB_BGRP, 128);
-          const int tile = 2 * q + hb;
-          const float o = sum4(red_nc, SL_O + 4 * hb) + BIAS(hb ? BI_OB : BI_OA);
-          if (rn < S && tile < (Dout >> 4)) a.dec_out[((size_t)(n0 + rn) * a.max_steps + step) * Dout + tile * 16 + rc] = o;
+          // frames of this step: tiles 2q and 2q+1 of y2 W_o + b_o  (tacotron.py:83)
+          nb_sync(NB_BGRP, 128);
+          const int ntiles = Dout >> 4;
+          const float oa = sum4(red_nc, SL_O) + BIAS(BI_OA), ob = sum4(red_nc, SL_O + 4) + BIAS(BI_OB);
+          if (rn < S) {
+            float* dst = a.dec_out + ((size_t)(n0 + rn) * a.max_steps + step) * Dout + rc;
+            if (2 * q < ntiles) dst[(2 * q) * 16] = oa;
+            if (2 * q + 1 < ntiles) dst[(2 * q + 1) * 16] = ob;
+          }
         }
         ITSTAMP(3);
       }

@@ -27,14 +27,17 @@ constexpr int SLOT_F = 8 * RS;    // floats per partial-tile slot
 // ---- activation buffers in MMA B-fragment order; sizes in 16-row chunks (one chunk = S x 64 bytes) ----------------
 // XHA / XH1 / XH2 hold the recurrent states and are double buffered by step parity (background warps read the value of
 // step s while the exchange of step s+1 lands).
-enum { XC = 0, XP1 = 16, XP2 = 32, XHA = 40, XRA = 72, XY0 = 88, XH1 = 104, XR1 = 136, XH2 = 152, XR2 = 184, X_CHUNKS = 200 };
+// y1 = y0 + h1' and y2 = y1 + h2' are formed by the critical reducers from CTA-local tiles (y0 never leaves its CTA) and pushed as
+// the critical exchanges of the GRU candidate phases; h1' / h2' themselves follow on mbarriers nobody waits for before the next step.
+enum { XC = 0, XP1 = 16, XP2 = 32, XHA = 40, XRA = 72, XY1 = 88, XH1 = 104, XR1 = 136, XH2 = 152, XR2 = 184, XY2 = 200, X_CHUNKS = 216 };
 
 // ---- partial-tile slots ------------------------------------------------------------------------------------------
 enum { SL_CRIT = 0, SL_P1E = 4, SL_RE0 = 8, SL_RE1 = 12, SL_RE2 = 16, SL_U = 20, SL_CX = 24, SL_Y0 = 28, SL_CTX = 32,
        SL_O = SL_CTX /* the output projection reuses the context partials */, N_SLOTS = 48 };
 
 // ---- mbarriers (one per exchange) -----------------------------------------------------------------------------------
-enum { MB_P1 = 0, MB_P2, MB_P3, MB_P4, MB_P5, MB_P6, MB_P7, MB_P9, MB_Y0, MB_P10, MB_P11, MB_P12, N_MBAR = 16 };
+enum { MB_P1 = 0, MB_P2, MB_P3, MB_P4, MB_P5, MB_P6, MB_P7, MB_P9, MB_H1 /* h1' (not critical) */, MB_P10 /* y1 */, MB_P11,
+       MB_P12 /* y2 */, MB_H2 /* h2' (not critical) */, N_MBAR = 16 };
 
 // ---- named barriers ---------------------------------------------------------------------------------------------------
 enum { NB_SYNC = 0, NB_CRIT = 1, NB_H1 = 2, NB_H3 = 3, NB_H4 = 4, NB_H9 = 5, NB_H10 = 6, NB_H11 = 7, NB_H12 = 8, NB_CGRP = 9,
@@ -48,7 +51,8 @@ enum { NB_SYNC = 0, NB_CRIT = 1, NB_H1 = 2, NB_H3 = 3, NB_H4 = 4, NB_H9 = 5, NB_
 //   w1: tensor-memory column of the first chunk-tile (tmem items)
 //   w2..w4: operands: chunk index (8 bits) | pbuf << 8 (0 single, 1 parity of this step, 2 parity of the previous step)
 //           | (mbarrier + 1) << 10 (5 bits; 0 = no wait) | frames << 15 (operand = teacher-forcing frame chunks from global memory)
-enum { POST_NONE = 0, POST_ARRIVE = 1, POST_Y0 = 2, POST_OUT = 3 };
+//           | prev << 16 (wait for the PREVIOUS step's phase of that mbarrier: recurrent states h1, h2)
+enum { POST_NONE = 0, POST_ARRIVE = 1, POST_Y0 = 2 /* reduce the y0 tile into the CTA-local fp32 copy, then arrive */, POST_OUT = 3 };
 struct Item { uint32_t w[5]; };
 constexpr int MAX_ITEMS = 8;      // per warp and half step (before the attention phases / after them)
 struct Program {
