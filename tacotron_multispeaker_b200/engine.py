@@ -261,10 +261,52 @@ class Engine:
         return (mel[:, :T], lin[:, :T] if lin is not None else None,
                 al[:, :, :s] if al is not None else None, s)
 
+    def _check_host_buffers(self, ids, lengths, spk, mel_targets, teacher_force, mel_out, linear_out, align_out):
+        """The C ABI reads and writes raw host pointers: refuse anything that is not the dtype / layout it expects instead of
+        reinterpreting an int64 id array as int32 or overrunning a short output buffer.  Returns the (possibly converted)
+        input arrays; outputs must already be C-contiguous float32 of the full size."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        if ids.ndim != 2:
+            raise ValueError("ids must be [N, T_in]")
+        N, T_in = ids.shape
+        lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+        if lengths.shape != (N,):
+            raise ValueError("lengths must be [N]")
+        if spk is not None:
+            spk = np.ascontiguousarray(spk, dtype=np.int32)
+            if spk.shape != (N,):
+                raise ValueError("speaker ids must be [N]")
+        T_tgt = 0
+        if teacher_force:
+            if mel_targets is None:
+                raise ValueError("teacher_force needs mel_targets")
+            mel_targets = np.ascontiguousarray(mel_targets, dtype=np.float32)
+            if mel_targets.ndim != 3 or mel_targets.shape[0] != N or mel_targets.shape[2] != self.hp.num_mels:
+                raise ValueError("mel_targets must be [N, T_tgt, num_mels]")
+            T_tgt = mel_targets.shape[1]
+        ms = self.max_steps(teacher_force, T_tgt)
+        maxT = ms * self.hp.outputs_per_step
+        for name, buf, shape in (("mel_out", mel_out, (N, maxT, self.hp.num_mels)),
+                                 ("linear_out", linear_out, (N, maxT, self.hp.num_freq)),
+                                 ("align_out", align_out, (N, T_in, ms))):
+            if buf is None:
+                if name == "mel_out":
+                    raise ValueError("mel_out is required")
+                continue
+            if not isinstance(buf, np.ndarray) or buf.dtype != np.float32 or not buf.flags["C_CONTIGUOUS"] or not buf.flags["WRITEABLE"]:
+                raise TypeError("%s must be a writeable C-contiguous float32 numpy array" % name)
+            if tuple(buf.shape) != shape:
+                raise ValueError("%s must have shape %s (max_steps = %d), got %s" % (name, shape, ms, tuple(buf.shape)))
+        return ids, lengths, spk, mel_targets
+
     def forward_host_begin(self, ids: np.ndarray, lengths: np.ndarray, spk: Optional[np.ndarray],
                            mel_targets: Optional[np.ndarray], teacher_force: bool, bn_mode: int,
                            mel_out: np.ndarray, linear_out: Optional[np.ndarray], align_out: Optional[np.ndarray]) -> None:
-        """``taco_forward_host_begin``: inputs copied, forward run, output copies ENQUEUED (see ``forward_host_end``)."""
+        """``taco_forward_host_begin``: inputs copied, forward run, output copies ENQUEUED (see ``forward_host_end``).
+        The input arrays must stay alive (and unchanged) until ``forward_host_end`` returns."""
+        ids, lengths, spk, mel_targets = self._check_host_buffers(ids, lengths, spk, mel_targets, teacher_force,
+                                                                  mel_out, linear_out, align_out)
+        self._host_keepalive = (ids, lengths, spk, mel_targets)
         N, T_in = ids.shape
         T_tgt = mel_targets.shape[1] if (teacher_force and mel_targets is not None) else 0
 
@@ -292,6 +334,8 @@ class Engine:
                      mel_targets: Optional[np.ndarray], teacher_force: bool, bn_mode: int,
                      mel_out: np.ndarray, linear_out: Optional[np.ndarray], align_out: Optional[np.ndarray]) -> int:
         """``taco_forward_host``: HOST numpy buffers in and out (H2D/D2H inside)."""
+        ids, lengths, spk, mel_targets = self._check_host_buffers(ids, lengths, spk, mel_targets, teacher_force,
+                                                                  mel_out, linear_out, align_out)
         N, T_in = ids.shape
         T_tgt = mel_targets.shape[1] if (teacher_force and mel_targets is not None) else 0
 

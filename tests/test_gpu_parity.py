@@ -436,6 +436,29 @@ def test_decode_mma_cluster_cuts(eng, ow, small_hp, N, S):
     assert e_dec < 1e-3 and e_al < 1e-4
 
 
+def test_forward_host_validates_buffers(eng, small_hp):
+    """The host entry points take raw pointers: default-dtype (int64 / float64) inputs are converted, output buffers of the
+    wrong dtype, layout or size are refused instead of being reinterpreted or overrun."""
+    hp = small_hp
+    ids, lengths, spk = make_inputs(2, 9, 6, 5)
+    ms = eng.max_steps(False)
+    T = ms * hp.outputs_per_step
+    mel = np.zeros((2, T, hp.num_mels), np.float32); lin = np.zeros((2, T, hp.num_freq), np.float32)
+    al = np.zeros((2, 9, ms), np.float32)
+    s_ref = eng.forward_host(ids, lengths, spk, None, False, 0, mel, lin, al)
+    mel64 = np.zeros_like(mel)
+    s2 = eng.forward_host(ids.astype(np.int64), lengths.astype(np.int64), spk.astype(np.int64), None, False, 0, mel64, None, None)
+    assert s2 == s_ref and np.array_equal(mel64, mel)
+    with pytest.raises(TypeError):
+        eng.forward_host(ids, lengths, spk, None, False, 0, mel.astype(np.float64), lin, al)
+    with pytest.raises(TypeError):
+        eng.forward_host(ids, lengths, spk, None, False, 0, mel, lin.transpose(0, 2, 1).copy().transpose(0, 2, 1), al)
+    with pytest.raises(ValueError):
+        eng.forward_host(ids, lengths, spk, None, False, 0, mel[:, : T - 1].copy(), lin, al)
+    with pytest.raises(ValueError):
+        eng.forward_host(ids, lengths[:1], spk, None, False, 0, mel, lin, al)
+
+
 def test_forward_host_begin_end(eng, small_hp):
     """taco_forward_host == taco_forward_host_begin + taco_forward_host_end (outputs land after _end)."""
     hp = small_hp
