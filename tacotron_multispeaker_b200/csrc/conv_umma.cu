@@ -26,24 +26,28 @@
 
 #include <stdlib.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
 namespace taco {
 
 namespace {
-constexpr int BM = 128, BN = 128, BK = 64, MAX_STAGES = 3, NTHREADS = 192;
+constexpr int BM = 128, BN = 128, BK = 64, MAX_STAGES = 3, NTHREADS_MAX = 320;   // 2 role warps + 4 or 8 epilogue warps
 constexpr uint32_t TILE_BYTES = BM * BK * 2;            // 16 KB: one bf16 operand tile (A or B)
 constexpr uint32_t STAGE_BYTES = 4 * TILE_BYTES;        // A_hi | A_lo | B_hi | B_lo
 constexpr int EPI_LD = 36;                              // floats per staged row: 32 + 4 keeps 128-bit rows conflict free
-constexpr uint32_t EPI_BYTES = 4 * 32 * EPI_LD * 4;     // per-warp 32 x 36 fp32 transpose staging (both epilogue paths)
+constexpr uint32_t EPI_WARP_BYTES = 32 * EPI_LD * 4;    // per-warp 32 x 36 fp32 transpose staging (both epilogue paths)
 // dynamic smem: 1024 (alignment slack) + stages * 64 KB + [transpose staging] + barriers
-__host__ __device__ constexpr uint32_t smem_bytes(int stages, bool transpose_epi) {
-  return 1024u + (uint32_t)stages * STAGE_BYTES + (transpose_epi ? EPI_BYTES : 0u) + 256u;
+__host__ __device__ constexpr uint32_t smem_bytes(int stages, int epi_warps) {
+  return 1024u + (uint32_t)stages * STAGE_BYTES + (uint32_t)epi_warps * EPI_WARP_BYTES + 256u;
 }
 
 struct UmmaArgs {
   int N, T, Cp;            // activation rows / padded channels (Cp % 64 == 0)
+  int kvalid;              // input channels rounded up to 16: k-steps beyond them multiply zero padding and are skipped
   int taps, bank;          // bank > 1: conv index ci = bank-1-blockIdx.z has ci+1 taps
   int Cout;                // output channels per conv
   const float* bias; const float* scale; const float* shift;
@@ -54,6 +58,7 @@ struct UmmaArgs {
   int vec_epi;             // 1: rows are 16 B aligned -> direct 128-bit stores from the TMEM registers
   int nx, ny, ntiles;      // tile list: nx = N * ceil(T / 128) row tiles, ny column tiles, ntiles = nx * ny * bank
   int acc_cols;            // TMEM columns to allocate: 256 (two accumulators, persistent CTAs) or 128 (one tile per CTA)
+  int epi_warps;           // 4 or 8 (block = 64 + 32 * epi_warps threads)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------
@@ -122,14 +127,227 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int NSPLIT>
-__global__ void __launch_bounds__(NTHREADS, 3)
+
+// ---- epilogue -----------------------------------------------------------------------------------------------------
+struct EpiTile {
+  int n, tq, o0;           // utterance, first row of this warp's 32 rows, first column of the tile
+  const float* bias; const float* scale; const float* shift;
+  int col_off;
+};
+template <int ACT> __device__ __forceinline__ float act_t(float v, int act) {
+  if (ACT == 0) return v;
+  if (ACT == 1) return fmaxf(v, 0.0f);
+  return apply_act(v, act);
+}
+__device__ __forceinline__ void stage_rows_f4(float* stg, int lane, const uint32_t (&v)[32]) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * g) =
+        make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+}
+
+// Vector path (rows 16 B aligned): a thread reads ONE ROW of the accumulator from TMEM (32 columns per load).  Storing from
+// there would touch 32 different rows per instruction (32 half-used sectors); the chunk is transposed through a 32 x 36
+// shared-memory tile instead, so that a store instruction covers 4 rows x 128 contiguous bytes and the residual is read the
+// same way.  Bias / activation / BN affine / residual run after the transpose.
+template <int ACT, bool SC, bool RES>
+__device__ __forceinline__ void epi_plain_vec(const UmmaArgs& p, const EpiTile& e, float* stg, uint32_t acc, int ch_lo, int ch_hi, int lane) {
+  const int rsub = lane >> 3, c4 = lane & 7;                              // after the transpose: row 4 i + rsub, columns 4 c4 .. 4 c4 + 3
+#pragma unroll 1
+  for (int ch = ch_lo; ch < ch_hi; ++ch) {
+    const int cbase = e.o0 + ch * 32;
+    if (cbase >= p.Cout) break;                                           // warp-uniform
+    uint32_t v[32];
+    tmem_ld32(acc + (uint32_t)(ch * 32), v);
+    stage_rows_f4(stg, lane, v);
+    __syncwarp();
+    const int col = cbase + 4 * c4;
+    const bool cok = col < p.Cout;                                        // Cout % 4 == 0 on this path
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cok) {
+      if (e.bias) b4 = ldg_f4(e.bias + col);
+      if (SC && e.scale) { sc4 = ldg_f4(e.scale + col); sh4 = ldg_f4(e.shift + col); }
+    }
+    float* orow = p.out + (long long)e.n * p.out_bs + (long long)(e.tq + rsub) * p.ldo + e.col_off + col;
+    const bool has_res = RES && p.res != nullptr;
+    const float* rrow = has_res ? p.res + (long long)e.n * p.res_bs + (long long)(e.tq + rsub) * p.ldres + col : nullptr;
+    const int rows_left = p.T - e.tq - rsub;                              // row 4 i + rsub is valid iff 4 i < rows_left
+#pragma unroll
+    for (int i0 = 0; i0 < 8; i0 += 4) {                                  // four rows per thread at a time: residuals requested up front
+      float4 r4[4];
+      if (RES) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_res && cok && 4 * (i0 + i) < rows_left) r4[i] = ldg_f4(rrow + (4 * (i0 + i)) * p.ldres);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 x = *reinterpret_cast<const float4*>(stg + (4 * (i0 + i) + rsub) * EPI_LD + 4 * c4);
+        x.x = act_t<ACT>(x.x + b4.x, p.act); x.y = act_t<ACT>(x.y + b4.y, p.act);
+        x.z = act_t<ACT>(x.z + b4.z, p.act); x.w = act_t<ACT>(x.w + b4.w, p.act);
+        if (SC) { x.x = fmaf(x.x, sc4.x, sh4.x); x.y = fmaf(x.y, sc4.y, sh4.y); x.z = fmaf(x.z, sc4.z, sh4.z); x.w = fmaf(x.w, sc4.w, sh4.w); }
+        if (cok && 4 * (i0 + i) < rows_left) {
+          if (RES) { x.x += r4[i].x; x.y += r4[i].y; x.z += r4[i].z; x.w += r4[i].w; }
+          *reinterpret_cast<float4*>(orow + (4 * (i0 + i)) * p.ldo) = x;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Scalar path (rows not 16 B aligned, e.g. the 1025-wide linear output): the chunk is staged with a pitch of 33 floats (scalar
+// stores of a row-per-lane tile are then conflict free), lane = column afterwards: one store instruction writes 128 contiguous
+// bytes of one output row.
+template <int ACT, bool SC, bool RES>
+__device__ __forceinline__ void epi_plain_scalar(const UmmaArgs& p, const EpiTile& e, float* stg, uint32_t acc, int ch_lo, int ch_hi, int lane) {
+  constexpr int LD = 33;
+#pragma unroll 1
+  for (int ch = ch_lo; ch < ch_hi; ++ch) {
+    const int cbase = e.o0 + ch * 32;
+    if (cbase >= p.Cout) break;                                           // warp-uniform
+    uint32_t v[32];
+    tmem_ld32(acc + (uint32_t)(ch * 32), v);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) stg[lane * LD + c] = __uint_as_float(v[c]);
+    __syncwarp();
+    const int col = cbase + lane;
+    const bool cok = col < p.Cout;
+    float b = 0.f, sc = 1.f, sh = 0.f;
+    if (cok) {
+      if (e.bias) b = __ldg(e.bias + col);
+      if (SC && e.scale) { sc = __ldg(e.scale + col); sh = __ldg(e.shift + col); }
+    }
+    const int nrows = min(32, p.T - e.tq);                                // warp-uniform
+    float* optr = p.out + (long long)e.n * p.out_bs + (long long)e.tq * p.ldo + e.col_off + col;
+    const bool has_res = RES && p.res != nullptr;
+    const float* rptr = has_res ? p.res + (long long)e.n * p.res_bs + (long long)e.tq * p.ldres + col : nullptr;
+    const float* sp = stg + lane;
+    const int ldo = p.ldo, ldres = p.ldres;
+    if (nrows == 32) {                                                    // full tile: no row predicates, row pointers advance by ldo
+#pragma unroll
+      for (int r0 = 0; r0 < 32; r0 += 8) {
+        float x[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          x[r] = act_t<ACT>(sp[(r0 + r) * LD] + b, p.act);
+          if (SC) x[r] = fmaf(x[r], sc, sh);
+        }
+        if (cok) {
+          if (has_res) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) { x[r] += __ldg(rptr); rptr += ldres; }
+          }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) { *optr = x[r]; optr += ldo; }
+        }
+      }
+    } else if (cok) {
+      for (int r = 0; r < nrows; ++r) {
+        float x = act_t<ACT>(sp[r * LD] + b, p.act);
+        if (SC) x = fmaf(x, sc, sh);
+        if (has_res) { x += __ldg(rptr); rptr += ldres; }
+        *optr = x;
+        optr += ldo;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Highway gate (modules.py:79-89): GEMM columns (2c, 2c+1) = (H_c, T_c); out_c = relu(H_c) T + x_c (1 - T), T = sigmoid(T_c).
+__device__ __forceinline__ void epi_highway_vec(const UmmaArgs& p, const EpiTile& e, float* stg, uint32_t acc, int ch_lo, int ch_hi, int lane) {
+#pragma unroll 1
+  for (int ch = ch_lo; ch < ch_hi; ++ch) {
+    const int cbase = e.o0 + ch * 32;
+    if (cbase >= p.Cout) break;
+    uint32_t v[32];
+    tmem_ld32(acc + (uint32_t)(ch * 32), v);
+    // staged per row: a_c = relu(H_c) * sigmoid(T_c) at floats 0..15, b_c = 1 - sigmoid(T_c) at floats 16..31
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int colb = cbase + 8 * g;
+      const bool bok = colb < p.Cout;                                     // Cout % 8 == 0 on this path
+      const float4 b0 = bok ? ldg_f4(e.bias + colb) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 b1 = bok ? ldg_f4(e.bias + colb + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float a4[4], g4[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c2 = 8 * g + 2 * k;
+        const float H = fmaxf(__uint_as_float(v[c2]) + bb[2 * k], 0.f), Tg = sigmoid_f(__uint_as_float(v[c2 + 1]) + bb[2 * k + 1]);
+        a4[k] = H * Tg; g4[k] = 1.0f - Tg;
+      }
+      *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * g) = make_float4(a4[0], a4[1], a4[2], a4[3]);
+      *reinterpret_cast<float4*>(stg + lane * EPI_LD + 16 + 4 * g) = make_float4(g4[0], g4[1], g4[2], g4[3]);
+    }
+    __syncwarp();
+    const int chn0 = cbase >> 1;                                          // first of the 16 output channels of this chunk
+    const int rs2 = lane >> 2, q4 = lane & 3;                             // row 8 i + rs2, channels chn0 + 4 q4 ..
+    const bool cok = cbase + 8 * q4 < p.Cout;
+    const int rows_left = p.T - e.tq - rs2;
+    const float* rrow = p.res + (long long)e.n * p.res_bs + (long long)(e.tq + rs2) * p.ldres + chn0 + 4 * q4;
+    float* orow = p.out + (long long)e.n * p.out_bs + (long long)(e.tq + rs2) * p.ldo + e.col_off + chn0 + 4 * q4;
+    float4 xin[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (cok && 8 * i < rows_left) xin[i] = ldg_f4(rrow + (8 * i) * p.ldres);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = 8 * i + rs2;
+      const float4 av = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 4 * q4);
+      const float4 gv = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 16 + 4 * q4);
+      if (cok && 8 * i < rows_left)
+        *reinterpret_cast<float4*>(orow + (8 * i) * p.ldo) =
+            make_float4(fmaf(xin[i].x, gv.x, av.x), fmaf(xin[i].y, gv.y, av.y), fmaf(xin[i].z, gv.z, av.z), fmaf(xin[i].w, gv.w, av.w));
+    }
+    __syncwarp();
+  }
+}
+__device__ __forceinline__ void epi_highway_scalar(const UmmaArgs& p, const EpiTile& e, float* stg, uint32_t acc, int ch_lo, int ch_hi, int lane) {
+  constexpr int LD = 33;
+#pragma unroll 1
+  for (int ch = ch_lo; ch < ch_hi; ++ch) {
+    const int cbase = e.o0 + ch * 32;
+    if (cbase >= p.Cout) break;
+    uint32_t v[32];
+    tmem_ld32(acc + (uint32_t)(ch * 32), v);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) stg[lane * LD + c] = __uint_as_float(v[c]);
+    __syncwarp();
+    const int col = cbase + lane;                                         // even lane = H_c, odd lane = T_c of channel c = col / 2
+    const bool cok = col < p.Cout;
+    const float b = cok ? __ldg(e.bias + col) : 0.f;
+    const int rmax = min(32, p.T - e.tq);
+    const int chn = col >> 1;
+    float* optr = p.out + (long long)e.n * p.out_bs + (long long)e.tq * p.ldo + e.col_off + chn;
+    const float* rptr = p.res + (long long)e.n * p.res_bs + (long long)e.tq * p.ldres + chn;
+#pragma unroll 4
+    for (int r = 0; r < rmax; ++r) {
+      const float x = stg[r * LD + lane] + b;
+      const float tg = __shfl_down_sync(0xffffffffu, x, 1);
+      if (cok && !(lane & 1)) {
+        const float H = fmaxf(x, 0.f), Tg = sigmoid_f(tg);
+        const float xin = __ldg(rptr);
+        *optr = H * Tg + xin * (1.0f - Tg);
+      }
+      optr += p.ldo;
+      rptr += p.ldres;
+    }
+    __syncwarp();
+  }
+}
+
+template <int NSPLIT, int EV>
+__global__ void __launch_bounds__(NTHREADS_MAX, 2)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                  const UmmaArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const int STAGES = p.stages;
-  const uint32_t epi_bytes = EPI_BYTES;
+  const uint32_t epi_bytes = (uint32_t)p.epi_warps * EPI_WARP_BYTES;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   float* epi = reinterpret_cast<float*>(smem_al + STAGES * STAGE_BYTES);
@@ -168,7 +386,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB_lo)) : "memory");
     }
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }   // 4 epilogue warps release a buffer
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), (uint32_t)p.epi_warps); }   // every epilogue warp releases a buffer
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {   // TMEM: two 128-column fp32 accumulators, allocated (and later freed) by this warp
@@ -221,8 +439,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           const uint32_t st = smem_base + s * STAGE_BYTES;
           const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + TILE_BYTES);
           const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES), b_lo = umma_desc(st + 3 * TILE_BYTES);
+          const int nk = min(BK / 16, (p.kvalid - (kb % kcb) * BK + 15) >> 4);   // e.g. 80 channels: 4 + 1 k-steps per tap, not 8
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
+            if (kk >= nk) break;
             const uint64_t adv = (uint64_t)(kk * 32 >> 4);                // 16 bf16 = 32 B along K inside the swizzle row
             umma_bf16(acc, a_hi + adv, b_hi + adv, idesc, (kb | kk) != 0);
             if (NSPLIT > 1) {
@@ -236,160 +456,41 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2 .. 2 + EW - 1) =====================
+    // A warp may read the TMEM lane quarter (warp & 3); with eight epilogue warps two warps share a quarter and split the
+    // four 32-column chunks of a tile between them.  The per-element work is compiled for the launch's (activation, BN
+    // affine, residual) combination: a run-time switch inside the loops cost ~30 instructions per stored row.
     const int quarter = warp & 3;                                         // TMEM lanes this warp may read
+    const int half = (warp - 2) >> 2;                                     // 0 (warps 2..5) or 1 (warps 6..9)
+    const int ch_lo = p.epi_warps == 8 ? 2 * half : 0, ch_hi = p.epi_warps == 8 ? 2 * half + 2 : BN / 32;
+    float* stg = epi + (warp - 2) * 32 * EPI_LD;
     int i = 0;
     for (int L = blockIdx.x; L < p.ntiles; L += gridDim.x, ++i) {
-    const Tile q = decode(L);
-    const int n = q.n, t0 = q.t0, o0 = q.o0, ci = q.ci;
-    const int ab = i & 1;
-    const uint32_t acc = tmem_base + (uint32_t)(ab * BN);
-    mbar_wait(tfull_bar(ab), (i >> 1) & 1);
-    tc_fence_after();
-    const float* bias = p.bias ? p.bias + ci * p.Cout : nullptr;
-    const float* scale = p.scale ? p.scale + ci * p.Cout : nullptr;
-    const float* shift = p.shift ? p.shift + ci * p.Cout : nullptr;
-    const int col_off = p.col_off + ci * p.Cout;
-    if (p.vec_epi) {
-      // ---- vector path: a thread reads ONE ROW of the accumulator from TMEM (32 columns per load).  Storing from there
-      // would touch 32 different rows per instruction (32 half-used sectors); the chunk is transposed through a
-      // 32 x 36 shared-memory tile instead, so that a store instruction covers 4 rows x 128 contiguous bytes and the
-      // residual is read the same way.  Bias / activation / BN affine / residual / highway gate run after the transpose.
-      float* stg = epi + (warp - 2) * 32 * EPI_LD;
-      const int tq = t0 + quarter * 32;
-      const int rsub = lane >> 3, c4 = lane & 7;                          // after the transpose: row 4 i + rsub, columns 4 c4 .. 4 c4 + 3
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        const int cbase = o0 + ch * 32;
-        if (cbase >= p.Cout) break;                                       // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), v);
-        if (p.epi == EPI_PLAIN) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * g) =
-                make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
-          __syncwarp();
-          const int col = cbase + 4 * c4;
-          const bool cok = col < p.Cout;                                  // Cout % 4 == 0 on this path
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (cok) {
-            if (bias) b4 = ldg_f4(bias + col);
-            if (scale) { sc4 = ldg_f4(scale + col); sh4 = ldg_f4(shift + col); }
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = 4 * i + rsub, t = tq + r;
-            float4 x = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 4 * c4);
-            x.x = apply_act(x.x + b4.x, p.act); x.y = apply_act(x.y + b4.y, p.act);
-            x.z = apply_act(x.z + b4.z, p.act); x.w = apply_act(x.w + b4.w, p.act);
-            if (scale) { x.x = fmaf(x.x, sc4.x, sh4.x); x.y = fmaf(x.y, sc4.y, sh4.y); x.z = fmaf(x.z, sc4.z, sh4.z); x.w = fmaf(x.w, sc4.w, sh4.w); }
-            if (cok && t < p.T) {
-              if (p.res) {
-                const float4 r4 = ldg_f4(p.res + (long long)n * p.res_bs + (long long)t * p.ldres + col);
-                x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
-              }
-              *reinterpret_cast<float4*>(p.out + (long long)n * p.out_bs + (long long)t * p.ldo + col_off + col) = x;
-            }
-          }
-        } else {   // EPI_HIGHWAY: columns (2c, 2c+1) = (H_c, T_c); 16 channels per 32-column load
-          // staged per row: a_c = relu(H_c) * sigmoid(T_c) at floats 0..15, b_c = 1 - sigmoid(T_c) at floats 16..31
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int colb = cbase + 8 * g;
-            const bool bok = colb < p.Cout;                               // Cout % 8 == 0 on this path
-            const float4 b0 = bok ? ldg_f4(bias + colb) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 b1 = bok ? ldg_f4(bias + colb + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            float a4[4], g4[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int c2 = 8 * g + 2 * k;
-              const float H = fmaxf(__uint_as_float(v[c2]) + bb[2 * k], 0.f), Tg = sigmoid_f(__uint_as_float(v[c2 + 1]) + bb[2 * k + 1]);
-              a4[k] = H * Tg; g4[k] = 1.0f - Tg;
-            }
-            *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * g) = make_float4(a4[0], a4[1], a4[2], a4[3]);
-            *reinterpret_cast<float4*>(stg + lane * EPI_LD + 16 + 4 * g) = make_float4(g4[0], g4[1], g4[2], g4[3]);
-          }
-          __syncwarp();
-          const int chn0 = cbase >> 1;                                    // first of the 16 output channels of this chunk
-          const int rs2 = lane >> 2, q4 = lane & 3;                       // row 8 i + rs2, channels chn0 + 4 q4 ..
-          const bool cok = cbase + 8 * q4 < p.Cout;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = 8 * i + rs2, t = tq + r;
-            const float4 av = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 4 * q4);
-            const float4 gv = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 16 + 4 * q4);
-            if (cok && t < p.T) {
-              const float4 xin = ldg_f4(p.res + (long long)n * p.res_bs + (long long)t * p.ldres + chn0 + 4 * q4);
-              *reinterpret_cast<float4*>(p.out + (long long)n * p.out_bs + (long long)t * p.ldo + col_off + chn0 + 4 * q4) =
-                  make_float4(fmaf(xin.x, gv.x, av.x), fmaf(xin.y, gv.y, av.y), fmaf(xin.z, gv.z, av.z), fmaf(xin.w, gv.w, av.w));
-            }
-          }
-        }
-        __syncwarp();
+      const Tile q = decode(L);
+      const int ab = i & 1;
+      const uint32_t acc = tmem_base + (uint32_t)(ab * BN) + ((uint32_t)(quarter * 32) << 16);
+      mbar_wait(tfull_bar(ab), (i >> 1) & 1);
+      tc_fence_after();
+      EpiTile e;
+      e.n = q.n; e.tq = q.t0 + quarter * 32; e.o0 = q.o0;
+      e.bias = p.bias ? p.bias + q.ci * p.Cout : nullptr;
+      e.scale = p.scale ? p.scale + q.ci * p.Cout : nullptr;
+      e.shift = p.shift ? p.shift + q.ci * p.Cout : nullptr;
+      e.col_off = p.col_off + q.ci * p.Cout;
+      // EV: the launch's epilogue variant, compiled in (0 = any combination, decided at run time)
+      if (EV == 5) {
+        if (p.vec_epi) epi_highway_vec(p, e, stg, acc, ch_lo, ch_hi, lane);
+        else epi_highway_scalar(p, e, stg, acc, ch_lo, ch_hi, lane);
+      } else {
+        constexpr int A = EV == 0 ? 2 : ((EV == 2 || EV == 3) ? 1 : 0);
+        constexpr bool S = EV == 0 || EV == 3 || EV == 4, R = EV == 0 || EV == 4;
+        if (p.vec_epi) epi_plain_vec<A, S, R>(p, e, stg, acc, ch_lo, ch_hi, lane);
+        else epi_plain_scalar<A, S, R>(p, e, stg, acc, ch_lo, ch_hi, lane);
       }
-    } else {
-      // ---- transpose path (rows not 16 B aligned, e.g. ldo = 1025): smem transpose -> coalesced scalar stores ----
-      float* stg = epi + (warp - 2) * 32 * EPI_LD;
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        const int cbase = o0 + ch * 32;
-        if (cbase >= p.Cout) break;                                       // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), v);
-#pragma unroll
-        for (int c = 0; c < 32; ++c) stg[lane * EPI_LD + c] = __uint_as_float(v[c]);
-        __syncwarp();
-        const int col = cbase + lane;
-        const bool cok = col < p.Cout;
-        float b = 0.f, sc = 1.f, sh = 0.f;
-        if (cok) {
-          if (bias) b = __ldg(bias + col);
-          if (scale) { sc = __ldg(scale + col); sh = __ldg(shift + col); }
-        }
-        const int rmax = min(32, p.T - (t0 + quarter * 32));
-        // row pointers advance by the leading dimension: no 64-bit index arithmetic per element
-        const int tq = t0 + quarter * 32;
-        if (p.epi == EPI_PLAIN) {
-          float* optr = p.out + (long long)n * p.out_bs + (long long)tq * p.ldo + col_off + col;
-          const float* rptr = p.res ? p.res + (long long)n * p.res_bs + (long long)tq * p.ldres + col : nullptr;
-          const bool has_scale = scale != nullptr;
-#pragma unroll 8
-          for (int r = 0; r < rmax; ++r) {
-            float x = apply_act(stg[r * EPI_LD + lane] + b, p.act);
-            if (has_scale) x = fmaf(x, sc, sh);
-            if (cok) {
-              if (rptr) x += __ldg(rptr);
-              *optr = x;
-            }
-            optr += p.ldo;
-            if (rptr) rptr += p.ldres;
-          }
-        } else {   // EPI_HIGHWAY: even lane = H_c, odd lane = T_c of channel c = col/2
-          const int chn = col >> 1;
-          float* optr = p.out + (long long)n * p.out_bs + (long long)tq * p.ldo + col_off + chn;
-          const float* rptr = p.res + (long long)n * p.res_bs + (long long)tq * p.ldres + chn;
-#pragma unroll 4
-          for (int r = 0; r < rmax; ++r) {
-            const float x = stg[r * EPI_LD + lane] + b;
-            const float tg = __shfl_down_sync(0xffffffffu, x, 1);
-            if (cok && !(lane & 1)) {
-              const float H = fmaxf(x, 0.f), Tg = sigmoid_f(tg);
-              const float xin = __ldg(rptr);
-              *optr = H * Tg + xin * (1.0f - Tg);
-            }
-            optr += p.ldo;
-            rptr += p.ldres;
-          }
-        }
-        __syncwarp();
-      }
-    }
-    // this warp has read its lanes of the accumulator: hand the buffer back to the MMA issuer
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(tempty_bar(ab));
+      // this warp has read its lanes of the accumulator: hand the buffer back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(ab));
     }   // tile loop
   }
   tc_fence_before();
@@ -494,49 +595,72 @@ void launch_pack_wt(const float* w, int ldw, int taps, int Cin, int Cout, int Cp
                                          reinterpret_cast<__nv_bfloat16*>(lo));
 }
 
+// Tensor maps are pure functions of (base pointer, shape, box): encoded once and kept (the workspace and the weight arena
+// are stable between forwards, so a forward re-uses its 84 maps instead of calling cuTensorMapEncodeTiled 84 times).
+namespace {
+struct MapKey {
+  const void* base; uint64_t d0, d1, d2; uint32_t rank;
+  bool operator==(const MapKey& o) const { return base == o.base && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && rank == o.rank; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.d0 + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.d1 * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2));
+    h ^= (k.d2 * 0x165667B19E3779F9ull + k.rank + (h << 6) + (h >> 2));
+    return (size_t)h;
+  }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// A: activations [N][T][Cp] bf16, box {64 channels, 128 rows, 1 utterance};  B: W^T [rows][Kld] bf16, box {64, 128}
+bool get_map_a(CUtensorMap* m, const void* base, int Cp, int T, int N) {
+  const MapKey k{base, (uint64_t)Cp, (uint64_t)T, (uint64_t)N, 3u};
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  auto it = g_maps.find(k);
+  if (it != g_maps.end()) { *m = it->second; return true; }
+  const cuuint64_t dims[3] = {(cuuint64_t)Cp, (cuuint64_t)T, (cuuint64_t)N};
+  const cuuint64_t str[2] = {(cuuint64_t)Cp * 2, (cuuint64_t)T * Cp * 2};
+  const cuuint32_t box[3] = {BK, BM, 1};
+  if (!make_map(m, base, 3, dims, str, box)) return false;
+  if (g_maps.size() > 8192) g_maps.clear();
+  g_maps.emplace(k, *m);
+  return true;
+}
+bool get_map_b(CUtensorMap* m, const void* base, int Kld, int rows) {
+  const MapKey k{base, (uint64_t)Kld, (uint64_t)rows, 0u, 2u};
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  auto it = g_maps.find(k);
+  if (it != g_maps.end()) { *m = it->second; return true; }
+  const cuuint64_t dims[2] = {(cuuint64_t)Kld, (cuuint64_t)rows};
+  const cuuint64_t str[1] = {(cuuint64_t)Kld * 2};
+  const cuuint32_t box[2] = {BK, BN};
+  if (!make_map(m, base, 2, dims, str, box)) return false;
+  if (g_maps.size() > 8192) g_maps.clear();
+  g_maps.emplace(k, *m);
+  return true;
+}
+int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+}  // namespace
+
 cudaError_t launch_conv_umma(const ConvUmma& c, cudaStream_t st) {
   if (c.N <= 0 || c.T <= 0) return cudaSuccess;
   if (c.Cp % BK || c.Kld % BK) return cudaErrorInvalidValue;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  const cuuint64_t adims[3] = {(cuuint64_t)c.Cp, (cuuint64_t)c.T, (cuuint64_t)c.N};
-  const cuuint64_t astr[2] = {(cuuint64_t)c.Cp * 2, (cuuint64_t)c.T * c.Cp * 2};
-  const cuuint32_t abox[3] = {BK, BM, 1};
-  const cuuint64_t bdims[2] = {(cuuint64_t)c.Kld, (cuuint64_t)c.b_rows};
-  const cuuint64_t bstr[1] = {(cuuint64_t)c.Kld * 2};
-  const cuuint32_t bbox[2] = {BK, BN};
   const bool split = c.nsplit > 1;
-  if (!make_map(&ma_hi, c.a_hi, 3, adims, astr, abox) || !make_map(&mb_hi, c.b_hi, 2, bdims, bstr, bbox) ||
-      !make_map(&ma_lo, split ? c.a_lo : c.a_hi, 3, adims, astr, abox) ||
-      !make_map(&mb_lo, split ? c.b_lo : c.b_hi, 2, bdims, bstr, bbox))
+  if (!get_map_a(&ma_hi, c.a_hi, c.Cp, c.T, c.N) || !get_map_b(&mb_hi, c.b_hi, c.Kld, c.b_rows) ||
+      !get_map_a(&ma_lo, split ? c.a_lo : c.a_hi, c.Cp, c.T, c.N) || !get_map_b(&mb_lo, split ? c.b_lo : c.b_hi, c.Kld, c.b_rows))
     return cudaErrorInvalidValue;
   UmmaArgs p;
-  p.N = c.N; p.T = c.T; p.Cp = c.Cp; p.taps = c.taps; p.bank = c.bank; p.Cout = c.Cout;
+  p.N = c.N; p.T = c.T; p.Cp = c.Cp; p.kvalid = c.Cin > 0 && c.Cin < c.Cp ? (c.Cin + 15) & ~15 : c.Cp; p.taps = c.taps; p.bank = c.bank; p.Cout = c.Cout;
   p.bias = c.bias; p.scale = c.scale; p.shift = c.shift; p.res = c.res; p.res_bs = c.res_bs; p.ldres = c.ldres;
   p.out = c.out; p.out_bs = c.out_bs; p.ldo = c.ldo; p.col_off = c.col_off; p.act = c.act; p.epi = c.epi;
-  // Persistent grid: one CTA per SM (three 64 KB stages), each walking its share of the tiles.
   p.nx = c.N * ((c.T + BM - 1) / BM);
   p.ny = (c.Cout + BN - 1) / BN;
   const long long ntiles = (long long)p.nx * p.ny * (c.bank > 1 ? c.bank : 1);
   if (ntiles > 0x7fffffffLL) return cudaErrorInvalidValue;
   p.ntiles = (int)ntiles;
-  // Long-K launches (the 3 x 1024 -> 256 projection, the encoder bank) are bound by loads and MMAs: persistent CTAs,
-  // one per SM with three 64 KB stages, overlap the epilogue of tile i with the main loop of tile i+1 (171 -> 140 us).
-  // Short-K launches are bound by the epilogue (four warps per CTA drain TMEM and write 64 KB per tile): there one tile
-  // per CTA with a shallow ring lets two or three CTAs share an SM, i.e. 8-12 epilogue warps (persistent: 158 -> 221 us
-  // on the final dense, measured).
-  const int nkb_max = c.taps * (c.Cp / BK);
-  static const int force = [] { const char* e = getenv("TACO_UMMA_PERSISTENT"); return e ? atoi(e) : -1; }();
-  const bool persistent = force >= 0 ? force != 0 : nkb_max >= 24;
-  if (persistent) {
-    p.stages = MAX_STAGES;
-  } else {
-    p.stages = nkb_max >= 6 ? 3 : (nkb_max >= 3 ? 2 : 1);
-    if (ntiles >= 1024) p.stages = 1;
-  }
-  {   // developer switch: TACO_UMMA_STAGES_MAX caps the ring depth
-    static const int cap = [] { const char* e = getenv("TACO_UMMA_STAGES_MAX"); return e ? atoi(e) : 0; }();
-    if (cap >= 1 && p.stages > cap) p.stages = cap;
-  }
   static int n_sm[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -545,8 +669,26 @@ cudaError_t launch_conv_umma(const ConvUmma& c, cudaStream_t st) {
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
     n_sm[dev & 63] = v;
   }
-  static const int cta_cap = [] { const char* e = getenv("TACO_UMMA_CTAS"); return e ? atoi(e) : 0; }();
-  int nctas = persistent ? (cta_cap > 0 ? cta_cap : n_sm[dev & 63]) : p.ntiles;
+  const int sms = n_sm[dev & 63];
+  // Launch shapes (developer switches read once: TACO_UMMA_PERSISTENT = 0 / 1 forces, TACO_UMMA_EW, TACO_UMMA_STAGES_MAX, TACO_UMMA_CTAS):
+  //  * long K (>= 24 k-blocks: the 3 x 1024 -> 256 projection, the conv banks): bound by loads and MMAs.  Persistent CTAs, one per
+  //    SM, three 64 KB stages, two TMEM accumulators (the epilogue of tile i overlaps the main loop of tile i+1), 4 epilogue warps.
+  //  * short K with more than two tiles per SM (the 1025-wide linear output, highway layers at full length): bound by the
+  //    epilogue.  Persistent as well, but with EIGHT epilogue warps and two stages.
+  //  * few tiles: one tile per CTA, eight epilogue warps, a shallow ring so that two CTAs share an SM.
+  static const int force = env_int("TACO_UMMA_PERSISTENT", -1), ew_force = env_int("TACO_UMMA_EW", 0);
+  static const int stage_cap = env_int("TACO_UMMA_STAGES_MAX", 0), cta_cap = env_int("TACO_UMMA_CTAS", 0);
+  const int nkb_max = c.taps * (c.Cp / BK);
+  const bool long_k = nkb_max >= 24;
+  const bool persistent = force >= 0 ? force != 0 : (long_k || p.ntiles > 2 * sms);
+  p.epi_warps = ew_force == 4 || ew_force == 8 ? ew_force : (long_k ? 4 : 8);
+  static const int stage_force = env_int("TACO_UMMA_STAGES", 0);
+  if (persistent) p.stages = long_k ? MAX_STAGES : 2;
+  else p.stages = nkb_max >= 3 ? 2 : 1;
+  if (stage_force >= 1 && !long_k) p.stages = stage_force > MAX_STAGES ? MAX_STAGES : stage_force;
+  if (stage_cap >= 1 && p.stages > stage_cap) p.stages = stage_cap;
+  while (smem_bytes(p.stages, p.epi_warps) > 227u * 1024u && p.stages > 1) --p.stages;
+  int nctas = persistent ? (cta_cap > 0 ? cta_cap : sms) : p.ntiles;
   if (nctas > p.ntiles) nctas = p.ntiles;
   p.acc_cols = nctas < p.ntiles ? 256 : 128;
   dim3 grid(nctas, 1, 1);
@@ -559,18 +701,31 @@ cudaError_t launch_conv_umma(const ConvUmma& c, cudaStream_t st) {
                (c.scale == nullptr || ((reinterpret_cast<uintptr_t>(c.scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.shift) & 15) == 0)))
                   ? 1 : 0;
   if (c.epi == EPI_HIGHWAY && (c.bias == nullptr || c.res == nullptr)) return cudaErrorInvalidValue;
-  const uint32_t smem = smem_bytes(p.stages, true);   // both epilogue paths stage through shared memory
+  if ((c.scale == nullptr) != (c.shift == nullptr)) return cudaErrorInvalidValue;
+  const uint32_t smem = smem_bytes(p.stages, p.epi_warps);
+  // epilogue variant: the combinations the forward uses are compiled in, anything else takes the run-time variant 0
+  int ev = 0;
+  if (c.epi == EPI_HIGHWAY) ev = 5;
+  else if (c.act == 0 && !c.scale && !c.res) ev = 1;
+  else if (c.act == 1 && !c.scale && !c.res) ev = 2;
+  else if (c.act == 1 && c.scale && !c.res) ev = 3;
+  else if (c.act == 0 && c.scale && c.res) ev = 4;
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const UmmaArgs);
+  static const KernelFn kernels[2][6] = {
+      {conv_umma_kernel<3, 0>, conv_umma_kernel<3, 1>, conv_umma_kernel<3, 2>, conv_umma_kernel<3, 3>, conv_umma_kernel<3, 4>, conv_umma_kernel<3, 5>},
+      {conv_umma_kernel<1, 0>, conv_umma_kernel<1, 1>, conv_umma_kernel<1, 2>, conv_umma_kernel<1, 3>, conv_umma_kernel<1, 4>, conv_umma_kernel<1, 5>}};
   static bool attr_done[64] = {false};
   bool& attr_set = attr_done[dev & 63];
   if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(conv_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_STAGES, true));
-    cudaError_t e2 = cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_STAGES, true));
-    if (e1 != cudaSuccess) return e1;
-    if (e2 != cudaSuccess) return e2;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 6; ++b) {
+        cudaError_t e1 = cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e1 != cudaSuccess) return e1;
+      }
     attr_set = true;
   }
-  if (split) conv_umma_kernel<3><<<grid, NTHREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
-  else conv_umma_kernel<1><<<grid, NTHREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  const int nthreads = 64 + 32 * p.epi_warps;
+  kernels[split ? 0 : 1][ev]<<<grid, nthreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   return cudaGetLastError();
 }
 

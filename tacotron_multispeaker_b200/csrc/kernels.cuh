@@ -41,6 +41,7 @@ void launch_conv_gemm(const ConvGemm& p, cudaStream_t st);
 // offset col_off + ci*Cout  (the CBHG conv bank, reference modules.py:39-42).
 struct ConvUmma {
   const void* a_hi; const void* a_lo; int N, T, Cp;
+  int Cin;                                  // real input channels (<= Cp; 0 = Cp): trailing all-zero k-steps are skipped
   const void* b_hi; const void* b_lo; int b_rows, Kld;
   int taps, bank, Cout, nsplit;
   const float* bias; const float* scale; const float* shift;

@@ -519,7 +519,7 @@ void gemm(Ctx& c, const GemmW& g, const BfScratch& sc, const float* x, int64_t x
   }
   if (!presplit) launch_split_bf16(x, x_bs, ldx, N, T, g.Cin, g.Cp, sc.hi, sc.lo, c.st);
   ConvUmma u;
-  u.a_hi = sc.hi; u.a_lo = sc.lo; u.N = N; u.T = T; u.Cp = g.Cp;
+  u.a_hi = sc.hi; u.a_lo = sc.lo; u.N = N; u.T = T; u.Cp = g.Cp; u.Cin = g.Cin;
   u.b_hi = h->dB + g.bt; u.b_lo = h->dB + g.bt + (size_t)g.b_rows * g.Kld; u.b_rows = g.b_rows; u.Kld = g.Kld;
   u.taps = g.taps; u.bank = g.bank; u.Cout = g.Cout; u.nsplit = h->gemm_mode == 2 ? 1 : 3;
   u.bias = bias; u.scale = scale; u.shift = shift; u.res = res; u.res_bs = res_bs; u.ldres = ldres;
@@ -1143,7 +1143,7 @@ int taco_conv1d(taco_handle* h, const float* x, int N, int T, int Cin, const flo
     launch_pack_wt(kernel, Cout, k, Cin, Cout, g.Cp, g.Kld, 0, bhi, blo, st);
     launch_split_bf16(x, (int64_t)T * Cin, Cin, N, T, Cin, g.Cp, sc.hi, sc.lo, st);
     ConvUmma u;
-    u.a_hi = sc.hi; u.a_lo = sc.lo; u.N = N; u.T = T; u.Cp = g.Cp;
+    u.a_hi = sc.hi; u.a_lo = sc.lo; u.N = N; u.T = T; u.Cp = g.Cp; u.Cin = g.Cin;
     u.b_hi = bhi; u.b_lo = blo; u.b_rows = g.b_rows; u.Kld = g.Kld;
     u.taps = k; u.bank = 1; u.Cout = Cout; u.nsplit = h->gemm_mode == 2 ? 1 : 3;
     u.bias = bias; u.scale = nullptr; u.shift = nullptr; u.res = nullptr; u.res_bs = 0; u.ldres = 0;
