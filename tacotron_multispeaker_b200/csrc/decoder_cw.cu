@@ -236,6 +236,8 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
   const int p0 = 4 * ((q * NQ) / CS), npq = min(NP, 4 * (((q + 1) * NQ) / CS)) - p0;
   const bool free_run = a.targets == nullptr;
   if (S == 0) { cluster_sync_all(); cluster_sync_all(); return; }
+#define TRX(i) do { if (TRACE && a.trace != nullptr && blockIdx.x == a.trace_cta && tid == 12 * 32) a.trace[i] = clock64(); } while (0)
+  TRX(24);
 
   // ---- prologue ------------------------------------------------------------------------------------------------------
   for (uint32_t i = OFF_TMEM + tid * 4; i < L.ring; i += NT * 4) *reinterpret_cast<uint32_t*>(smem_raw + i) = 0u;
@@ -305,6 +307,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   cluster_sync_all();   // buffers zeroed, mbarriers initialised, tensor memory filled everywhere before anyone pushes
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  TRX(25);
 
   const uint32_t BLK = CS * csb;
   const uint32_t xl = sbase + OFF_X + (uint32_t)min(g, S - 1) * 64u + (uint32_t)t * 16u;   // lane part of a B-fragment address
@@ -336,6 +339,8 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
   // ---- attention phases (all 16 warps) --------------------------------------------------------------------------------
   // P6: Bahdanau scores of this CTA's (position, sample) pairs: exp(v . tanh(keys + pq) - B)
   // v.tanh(k + p) = sum v - 2 sum_k v_k / (1 + e^{2k} e^{2p}); four elements share one MUFU.RCP (denominators clamped to 2^30).
+  const int p6_wr = (warp + 4) & 15;                                         // pair slot of this warp: 12, 13, 14, 15, 0, 1, ...
+  const int p6_na = (p0 + min(2 * p6_wr, max(npq - 1, 0))) % S, p6_nb = (p0 + min(2 * p6_wr + 1, max(npq - 1, 0))) % S;
   auto p6_compute = [&]() {
     const uint32_t pq_l = sbase + L.pq + (uint32_t)(lane >> 2) * csb + (uint32_t)(lane & 3) * 16u;
     const float4 v0 = lds_f4(sbase + OFF_VATT + lane * 16), v1 = lds_f4(sbase + OFF_VATT + 512 + lane * 16);
@@ -347,9 +352,8 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       const float nab = fmaf(v.x, db, v.y * da), ncd = fmaf(v.z, dd, v.w * dc);
       return fmaf(nab, cd, ncd * ab) * rcp_approx(ab * cd);
     };
-    auto pair_sum = [&](int pl) -> float {
-      const int n = smem_raw[L.pn + pl];
-      const float4 e0 = lds_f4(pq_l + (uint32_t)n * 64u), e1 = lds_f4(pq_l + (uint32_t)n * 64u + 8 * csb);
+    // keys first (their address does not depend on the sample index), then the query of the pair's sample
+    auto pair_sum = [&](int pl, int n) -> float {
       float4 k0, k1;
       if (res_k) {
         k0 = lds_f4(sbase + L.ksl + (uint32_t)pl * (DHID * 4) + lane * 16);
@@ -363,12 +367,15 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
         k1.x = __expf(2.0f * fminf(fmaxf(k1.x, -30.f), 30.f)); k1.y = __expf(2.0f * fminf(fmaxf(k1.y, -30.f), 30.f));
         k1.z = __expf(2.0f * fminf(fmaxf(k1.z, -30.f), 30.f)); k1.w = __expf(2.0f * fminf(fmaxf(k1.w, -30.f), 30.f));
       }
+      const float4 e0 = lds_f4(pq_l + (uint32_t)n * 64u), e1 = lds_f4(pq_l + (uint32_t)n * 64u + 8 * csb);
       return quad(k0, e0, v0) + quad(k1, e1, v1);
     };
     const float vb = lds_f(sbase + OFF_VB);
-    for (int pp = 2 * warp; pp < npq; pp += 2 * NW) {
-      const bool two = pp + 1 < npq;
-      const float sa = pair_sum(pp), sb = pair_sum(two ? pp + 1 : pp);
+    // the critical warps (12..15) own the first pairs: with few utterances per cluster nobody waits for a background warp here
+    for (int pp = 2 * p6_wr; pp < npq; pp += 2 * NW) {
+      const bool two = pp + 1 < npq, first = pp == 2 * p6_wr;
+      const int na = first ? p6_na : (int)smem_raw[L.pn + pp], nb = first ? p6_nb : (int)smem_raw[L.pn + (two ? pp + 1 : pp)];
+      const float sa = pair_sum(pp, na), sb = pair_sum(two ? pp + 1 : pp, nb);
       const bool up = lane >= 16;
       float sv = (up ? sb : sa) + __shfl_xor_sync(0xffffffffu, up ? sa : sb, 16);
 #pragma unroll
@@ -402,22 +409,28 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       if (res_m) {
         uint32_t ma = sbase + L.msl + (uint32_t)((warp * S + g) * 16 + t * 4) * 4u;
         const uint32_t dm = (uint32_t)NW * S * 64u;
-        int j = warp;
-        for (; j + NW < T_in; j += 2 * NW) {
-          float p0v = lds_f(pa), p1v = lds_f(pa + dp);
-          if (exact) { p0v = __expf(p0v - mx); p1v = __expf(p1v - mx); }
-          const float4 m0 = lds_f4(ma), m1 = lds_f4(ma + dm);
-          acc.x = fmaf(p0v, m0.x, acc.x); acc.y = fmaf(p0v, m0.y, acc.y); acc.z = fmaf(p0v, m0.z, acc.z); acc.w = fmaf(p0v, m0.w, acc.w);
-          acc2.x = fmaf(p1v, m1.x, acc2.x); acc2.y = fmaf(p1v, m1.y, acc2.y); acc2.z = fmaf(p1v, m1.z, acc2.z); acc2.w = fmaf(p1v, m1.w, acc2.w);
-          ssum += p0v; ssum2 += p1v;
-          pa += 2 * dp; ma += 2 * dm;
-        }
-        if (j < T_in) {
-          float p0v = lds_f(pa);
-          if (exact) p0v = __expf(p0v - mx);
-          const float4 m0 = lds_f4(ma);
-          acc.x = fmaf(p0v, m0.x, acc.x); acc.y = fmaf(p0v, m0.y, acc.y); acc.z = fmaf(p0v, m0.z, acc.z); acc.w = fmaf(p0v, m0.w, acc.w);
-          ssum += p0v;
+        // four positions per trip, all eight loads issued before the first FMA; positions past T_in re-read the trip's first
+        // (valid) address and count as zero: no branches inside the loop
+        for (int j = warp; j < T_in; j += 4 * NW) {
+          float pv[4];
+          float4 mv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t o = j + i * NW < T_in ? (uint32_t)i : 0u;
+            pv[i] = lds_f(pa + o * dp);
+            mv[i] = lds_f4(ma + o * dm);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (exact) pv[i] = __expf(pv[i] - mx);
+            if (j + i * NW >= T_in) pv[i] = 0.f;
+          }
+          acc.x = fmaf(pv[0], mv[0].x, acc.x); acc.y = fmaf(pv[0], mv[0].y, acc.y); acc.z = fmaf(pv[0], mv[0].z, acc.z); acc.w = fmaf(pv[0], mv[0].w, acc.w);
+          acc2.x = fmaf(pv[1], mv[1].x, acc2.x); acc2.y = fmaf(pv[1], mv[1].y, acc2.y); acc2.z = fmaf(pv[1], mv[1].z, acc2.z); acc2.w = fmaf(pv[1], mv[1].w, acc2.w);
+          acc.x = fmaf(pv[2], mv[2].x, acc.x); acc.y = fmaf(pv[2], mv[2].y, acc.y); acc.z = fmaf(pv[2], mv[2].z, acc.z); acc.w = fmaf(pv[2], mv[2].w, acc.w);
+          acc2.x = fmaf(pv[3], mv[3].x, acc2.x); acc2.y = fmaf(pv[3], mv[3].y, acc2.y); acc2.z = fmaf(pv[3], mv[3].z, acc2.z); acc2.w = fmaf(pv[3], mv[3].w, acc2.w);
+          ssum += pv[0] + pv[2]; ssum2 += pv[1] + pv[3];
+          pa += 4 * dp; ma += 4 * dm;
         }
       } else {
         for (int j = warp; j < T_in; j += NW) {
@@ -654,7 +667,9 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       }
       twait();
       TRM(22);
+      if (step == 0) TRX(27);
     }
+    TRX(26);
   } else {
     // =====================================================================================================================
     // BACKGROUND GROUPS: A = warps 0-3 (update gates), B = 4-7 (candidate x-parts, output projection), C = 8-11 (early parts of the
@@ -804,14 +819,20 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       TRW(64);
       mbar_wait(mb0 + MB_P5 * 8, par);
       TRW(160);
-      p6_compute();
-      TRW(112);
+      {
+        const int reps = (TRACE && a.trace != nullptr && step == 8) ? 3 : 1;
+#pragma unroll 1
+        for (int rep = 0; rep < reps; ++rep) { p6_compute(); TRW(112 + 64 * rep); }
+      }
       __syncthreads();
       p6_send();
       mbar_wait(mb0 + MB_P6 * 8, par);
       TRW(128);
-      p7_compute();
-      TRW(144);
+      {   // trace build: the phase runs three times at the stamped step (same code, warm on the repeats)
+        const int reps = (TRACE && a.trace != nullptr && step == 8) ? 3 : 1;
+#pragma unroll 1
+        for (int rep = 0; rep < reps; ++rep) { p7_compute(); TRW(144 + 64 * rep); }
+      }
       __syncthreads();
       TRW(80);
       run_items(prog.post[warp], prog.n_post[warp], step);

@@ -52,6 +52,7 @@ def run(N, T_in, S, tag, iters=40, teacher=False, cta=0):
         print("   warp %s %s items: %s" % (os.environ.get("TACO_DEC_TRACE_WARP", "8"), nm, " ".join(rows)))
     print("   P7 intra (warp 0, last rep): %s" % [st[300 + i] - st[300] for i in range(4)])
     print("   crit P11 intra (from P10 arr): late %d, sync CRIT %d, H11+reduce+stage %d, send %d, twait %d" % (st[45] - st[19], st[46] - st[45], st[47] - st[46], st[48] - st[47], st[20] - st[48]))
+    print("   kernel: prologue %d clk, step 0 %d clk, steps 0..%d %d clk (%.0f per step)" % (st[25] - st[24], st[27] - st[25], iters - 1, st[26] - st[25], (st[26] - st[25]) / iters))
     hn = ["H1", "H3", "H4", "H9", "H10", "H11", "H12"]
     print("   crit handoff waits: " + " ".join("%s:%d" % (hn[i], st[51 + 2 * i] - st[50 + 2 * i]) for i in range(7)))
     print("   crit: P5 arr %d, SYNC6 %d, P6 arr %d, SYNC7 %d" % (st[10] - t0, st[11] - t0, st[12] - t0, st[13] - t0))
@@ -63,3 +64,5 @@ if __name__ == "__main__":
     for wtr in os.environ.get("TRACE_WARPS", "8,0,4").split(","):
         os.environ["TACO_DEC_TRACE_WARP"] = wtr
         run(32, 100, 5, "cw_n32_s5_w" + wtr)
+    if os.environ.get("TRACE_N1"):
+        run(1, 100, 1, "cw_n1_s1")
