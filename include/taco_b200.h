@@ -217,6 +217,11 @@ int taco_set_decoder_clusters(taco_handle* h, int n);
  * taco_forward when profiling is on: [0]=encoder [1]=decoder stage (memory
  * layer + loop + step count) [2]=postnet [3]=the decoder loop kernel alone. */
 int taco_set_profiling(taco_handle* h, int on);
+/* The forward (taco_forward, taco_forward_host*) is ~49 dependent kernel launches; the reference runs its graph with one
+ * session.run (synthesizer.py:47).  When the same call (same device pointers, shapes and modes) arrives twice in a row on a
+ * non-default stream, the launches are captured into a CUDA graph and replayed from then on.  On by default
+ * (TACO_GRAPHS=0 in the environment, or on = 0 here, keeps plain launches). */
+int taco_set_cuda_graphs(taco_handle* h, int on);
 int taco_last_stage_ms(const taco_handle* h, float* ms4_host);
 
 #ifdef __cplusplus

@@ -33,7 +33,7 @@ SYMBOLS = [
     "taco_forward_host_end",
     "taco_embed", "taco_check_ids", "taco_encoder", "taco_decode", "taco_cbhg", "taco_postnet",
     "taco_bigru", "taco_conv1d",
-    "taco_set_gemm_mode", "taco_launch_count", "taco_decoder_geometry", "taco_set_decoder_clusters", "taco_set_profiling", "taco_last_stage_ms",
+    "taco_set_gemm_mode", "taco_launch_count", "taco_decoder_geometry", "taco_set_decoder_clusters", "taco_set_profiling", "taco_last_stage_ms", "taco_set_cuda_graphs",
     "taco_wav_length", "taco_griffin_lim",
 ]
 
@@ -106,6 +106,7 @@ def load() -> C.CDLL:
     lib.taco_launch_count.restype = i64
     lib.taco_decoder_geometry.argtypes = [H, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     lib.taco_set_profiling.argtypes = [H, i]
+    lib.taco_set_cuda_graphs.argtypes = [H, i]
     lib.taco_last_stage_ms.argtypes = [H, C.POINTER(C.c_float)]
     lib.taco_wav_length.argtypes = [C.POINTER(TacoAudioParams), i]
     lib.taco_wav_length.restype = i64

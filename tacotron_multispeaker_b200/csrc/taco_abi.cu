@@ -116,6 +116,16 @@ struct taco_handle {
     size_t lin_bytes = 0;
   } spec;
   int64_t launches = 0;
+  // CUDA graph of the forward's ~49 launches: captured the second time the same call (pointers, shapes, modes) arrives on a
+  // non-default stream, replayed afterwards (one graph per handle)
+  struct FwdKey {
+    const void *ids, *len, *spk, *tgt, *mel, *lin, *al, *ws, *ints;
+    void* stream;
+    int N, T_in, T_tgt, bn, tf, gemm_mode, dec_clusters, defer;
+    bool operator==(const FwdKey& o) const { return memcmp(this, &o, sizeof(FwdKey)) == 0; }
+  };
+  struct FwdGraph { FwdKey key; bool have_key = false; cudaGraphExec_t exec = nullptr; int64_t launches = 0; } fwd_graph;
+  bool graphs_on = true;
   bool launch_failed = false;        // a kernel launcher returned an error (sticky until check_launch reports it)
   bool profiling = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [4],[5] bracket the decoder kernel
@@ -854,6 +864,8 @@ int taco_create(const taco_hparams* hp, int device, taco_handle** out) {
     // makes taco_forward_host_wait / _end sleep on blocking-sync events instead.
     const char* bs = getenv("TACO_BLOCKING_SYNC");
     h->blocking = bs && atoi(bs) != 0;
+    const char* gr = getenv("TACO_GRAPHS");
+    h->graphs_on = !(gr && atoi(gr) == 0);
     const unsigned flags = cudaEventDisableTiming | (h->blocking ? cudaEventBlockingSync : 0u);
     cudaEventCreateWithFlags(&h->ev_compute, flags);
     cudaEventCreateWithFlags(&h->ev_decoder, flags);
@@ -868,6 +880,7 @@ int taco_destroy(taco_handle* h) {
   if (!h) return TACO_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  if (h->fwd_graph.exec) cudaGraphExecDestroy(h->fwd_graph.exec);
   if (h->dW) cudaFree(h->dW);
   if (h->dB) cudaFree(h->dB);
   if (h->ws) cudaFree(h->ws);
@@ -909,6 +922,8 @@ int taco_set_weight(taco_handle* h, const char* tf_name, const float* data_host,
 }
 
 int taco_finalize_weights(taco_handle* h) {
+  if (h && h->fwd_graph.exec) { cudaGraphExecDestroy(h->fwd_graph.exec); h->fwd_graph.exec = nullptr; }
+  if (h) h->fwd_graph.have_key = false;
   if (!h) return TACO_ERR_INVALID;
   CUDA_OK(h, cudaSetDevice(h->device));
   const taco_hparams& hp = h->hp;
@@ -1201,27 +1216,82 @@ static int forward_impl(taco_handle* h, const int32_t* ids, const int32_t* lengt
   if (rc) return rc;
   rc = ensure_ints(h, 2 + N);
   if (rc) return rc;
-  Bump ws(h->ws, h->ws_bytes);
-  float* memory = ws.take<float>((size_t)N * T_in * 256);
-  const size_t mark = ws.off;
-  if (h->profiling) cudaEventRecord(h->ev[0], st);
-  rc = do_encoder(h, ws, ids, lengths, spk, N, T_in, bn_mode, memory, st);
-  if (rc) return rc;
-  if (h->profiling) cudaEventRecord(h->ev[1], st);
-  ws.off = mark;   // encoder scratch is dead; stream order keeps reuse safe
-  int steps = 0;
-  rc = do_decode(h, ws, memory, N, T_in, mel_targets, T_tgt, teacher_force, mel_out, align_out, &steps, st,
-                 /*defer_count=*/true);
-  if (rc) return rc;
-  if (h->profiling) cudaEventRecord(h->ev[2], st);
-  if (defer_final) cudaEventRecord(h->ev_decoder, st);
-  if (steps_out_host) *steps_out_host = steps;
-  if (linear_out) {
-    ws.off = mark;
-    rc = do_postnet(h, ws, mel_out, N, steps * r, bn_mode, (int64_t)maxT * M, linear_out,
-                    (int64_t)maxT * hp.num_freq, st);
+  // ---- CUDA graph: replay / capture / plain enqueue ----
+  taco_handle::FwdKey key;
+  memset(&key, 0, sizeof(key));
+  key.ids = ids; key.len = lengths; key.spk = spk; key.tgt = mel_targets; key.mel = mel_out; key.lin = linear_out; key.al = align_out;
+  key.ws = h->ws; key.ints = h->d_ints; key.stream = stream;
+  key.N = N; key.T_in = T_in; key.T_tgt = T_tgt; key.bn = bn_mode; key.tf = teacher_force; key.gemm_mode = h->gemm_mode;
+  key.dec_clusters = h->dec_clusters; key.defer = defer_final ? 1 : 0;
+  const bool graph_ok = h->graphs_on && !h->profiling && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread &&
+                        getenv("TACO_DEC_TRACE") == nullptr && getenv("TACO_DEBUG") == nullptr;
+  auto& G = h->fwd_graph;
+  bool capture = false, replayed = false;
+  if (!graph_ok || !G.have_key || !(G.key == key)) {
+    if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+    G.have_key = graph_ok;
+    G.key = key;
+  } else if (G.exec) {
+    const cudaError_t ge = cudaGraphLaunch(G.exec, st);
+    if (ge != cudaSuccess) return fail(h, TACO_ERR_CUDA, std::string("graph launch: ") + cudaGetErrorString(ge));
+    h->launches += G.launches;
+    replayed = true;
+  } else {
+    capture = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (!capture) cudaGetLastError();
+  }
+  int steps = max_steps;
+  const int64_t launches0 = h->launches;
+  auto enqueue = [&]() -> int {
+    Bump ws(h->ws, h->ws_bytes);
+    float* memory = ws.take<float>((size_t)N * T_in * 256);
+    const size_t mark = ws.off;
+    if (h->profiling) cudaEventRecord(h->ev[0], st);
+    int rc2 = do_encoder(h, ws, ids, lengths, spk, N, T_in, bn_mode, memory, st);
+    if (rc2) return rc2;
+    if (h->profiling) cudaEventRecord(h->ev[1], st);
+    ws.off = mark;   // encoder scratch is dead; stream order keeps reuse safe
+    rc2 = do_decode(h, ws, memory, N, T_in, mel_targets, T_tgt, teacher_force, mel_out, align_out, &steps, st,
+                    /*defer_count=*/true);
+    if (rc2) return rc2;
+    if (h->profiling) cudaEventRecord(h->ev[2], st);
+    if (defer_final) {
+      if (capture) cudaEventRecordWithFlags(h->ev_decoder, st, cudaEventRecordExternal);
+      else cudaEventRecord(h->ev_decoder, st);
+    }
+    if (linear_out) {
+      ws.off = mark;
+      rc2 = do_postnet(h, ws, mel_out, N, steps * r, bn_mode, (int64_t)maxT * M, linear_out,
+                       (int64_t)maxT * hp.num_freq, st);
+      if (rc2) return rc2;
+    }
+    return TACO_OK;
+  };
+  if (!replayed) {
+    rc = enqueue();
+    if (capture) {
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (rc == TACO_OK && ce == cudaSuccess && graph != nullptr) {
+        cudaError_t ie = cudaGraphInstantiate(&G.exec, graph, 0);
+        if (ie == cudaSuccess) ie = cudaGraphLaunch(G.exec, st);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {
+          if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+          G.have_key = false;
+          return fail(h, TACO_ERR_CUDA, std::string("graph instantiate / launch: ") + cudaGetErrorString(ie));
+        }
+        G.launches = h->launches - launches0;
+      } else {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        G.have_key = false;
+        if (rc == TACO_OK) return fail(h, TACO_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+      }
+    }
     if (rc) return rc;
   }
+  if (steps_out_host) *steps_out_host = steps;
   if (h->profiling) cudaEventRecord(h->ev[3], st);
   h->spec.active = false;
   if (!teacher_force) {
@@ -1424,6 +1494,14 @@ int taco_set_gemm_mode(taco_handle* h, int mode) {
 int taco_set_decoder_clusters(taco_handle* h, int n) {
   if (!h || n < 0) return TACO_ERR_INVALID;
   h->dec_clusters = n;
+  return TACO_OK;
+}
+
+int taco_set_cuda_graphs(taco_handle* h, int on) {
+  if (!h) return TACO_ERR_INVALID;
+  h->graphs_on = on != 0;
+  if (!h->graphs_on && h->fwd_graph.exec) { cudaGraphExecDestroy(h->fwd_graph.exec); h->fwd_graph.exec = nullptr; }
+  h->fwd_graph.have_key = false;
   return TACO_OK;
 }
 

@@ -127,6 +127,10 @@ class Engine:
         """0 = geometry for the shortest decode (default); n > 0 = n clusters of <= 8 utterances (throughput setting)."""
         self._ck(self.lib.taco_set_decoder_clusters(self._h, int(n)))
 
+    def set_cuda_graphs(self, on: bool):
+        """``taco_set_cuda_graphs``: capture / replay of the forward's launches (default on; needs a non-default stream)."""
+        self._ck(self.lib.taco_set_cuda_graphs(self._h, int(on)))
+
     def set_profiling(self, on: bool):
         self._ck(self.lib.taco_set_profiling(self._h, int(on)))
 

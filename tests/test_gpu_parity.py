@@ -459,6 +459,45 @@ def test_forward_host_validates_buffers(eng, small_hp):
         eng.forward_host(ids, lengths[:1], spk, None, False, 0, mel, lin, al)
 
 
+def test_forward_cuda_graph_replay(small_weights, small_hp):
+    """The same forward call (same device pointers, shapes, modes) on a non-default stream is captured into a CUDA graph on
+    its second arrival and replayed afterwards: results must be bit-identical to plain launches, the launch counter keeps
+    counting the kernels inside the graph, and a call with other pointers falls back to plain launches."""
+    hp = small_hp
+    ids, lengths, spk = make_inputs(3, 19, 6, 21)
+    from tacotron_multispeaker_b200.engine import Engine
+    dev = torch.device("cuda", 0)
+    e_plain = Engine(hp, 6); e_plain.load_weights(small_weights); e_plain.set_cuda_graphs(False)
+    e_graph = Engine(hp, 6); e_graph.load_weights(small_weights)
+    try:
+        ref = e_plain.forward(ids, lengths, spk)
+        ids_d, len_d, spk_d = (torch.from_numpy(x).to(dev) for x in (ids, lengths, spk))
+        ms = e_graph.max_steps(False)
+        T = ms * hp.outputs_per_step
+        out = (torch.zeros(3, T, hp.num_mels, device=dev), torch.zeros(3, T, hp.num_freq, device=dev), torch.zeros(3, 19, ms, device=dev))
+        st = torch.cuda.Stream(device=dev)
+        st.wait_stream(torch.cuda.current_stream())
+        counts = []
+        with torch.cuda.stream(st):
+            for rep in range(4):        # plain, capture + launch, replay, replay
+                for o in out:
+                    o.zero_()
+                c0 = e_graph.launch_count()
+                mel, lin, al, s = e_graph.forward(ids_d, len_d, spk_d, out=out)
+                st.synchronize()
+                counts.append(e_graph.launch_count() - c0)
+                assert s == ref[3]
+                for got, want in zip((mel, lin, al), ref[:3]):
+                    assert torch.equal(got, want), "rep %d differs from plain launches" % rep
+            # other pointers: plain launches again, still correct
+            mel2, lin2, al2, s2 = e_graph.forward(ids, lengths, spk)
+            st.synchronize()
+            assert torch.equal(lin2, ref[1])
+        assert len(set(counts)) == 1 and counts[0] > 40, counts
+    finally:
+        e_plain.close(); e_graph.close()
+
+
 def test_forward_host_begin_end(eng, small_hp):
     """taco_forward_host == taco_forward_host_begin + taco_forward_host_end (outputs land after _end)."""
     hp = small_hp
