@@ -72,5 +72,35 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+TORCH_OPS_SRC = os.path.join(CSRC, "torch_ops.cpp")
+TORCH_OPS_LIB = os.path.join(HERE, "libtaco_b200_torch.so")
+
+
+def build_torch_ops(force: bool = False) -> str:
+    """Compile ``csrc/torch_ops.cpp`` (TORCH_LIBRARY(taco_b200, ...): the C ABI as PyTorch custom operators) with g++ against
+    the installed torch headers and link it to ``libtaco_b200.so`` (rpath $ORIGIN).  Load with ``torch.ops.load_library``."""
+    build_library()
+    if not force and not _stale(TORCH_OPS_LIB, [TORCH_OPS_SRC, LIB, os.path.join(HERE, "..", "include", "taco_b200.h")]):
+        return TORCH_OPS_LIB
+    import torch
+    from torch.utils import cpp_extension as ce
+    inc = []
+    for d in ce.include_paths("cuda") if hasattr(ce, "include_paths") else []:
+        inc += ["-I", d]
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    inc += ["-I", os.path.join(cuda_home, "include")]
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI),
+           "-DTORCH_API_INCLUDE_EXTENSION_H", *inc, TORCH_OPS_SRC, "-o", TORCH_OPS_LIB,
+           "-L", tlib, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch",
+           "-L", HERE, "-l:libtaco_b200.so", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + tlib]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
+    return TORCH_OPS_LIB
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--torch-ops" in sys.argv:
+        print(build_torch_ops(force="--force" in sys.argv))

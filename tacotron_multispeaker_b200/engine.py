@@ -71,6 +71,11 @@ class Engine:
         except Exception:
             pass
 
+    @property
+    def handle(self) -> int:
+        """The ``taco_handle*`` as an integer (first argument of the ``torch.ops.taco_b200`` operators)."""
+        return int(self._h.value or 0)
+
     def _ck(self, rc):
         _abi.check(self.lib, self._h, rc)
 
