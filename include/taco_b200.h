@@ -196,8 +196,10 @@ int taco_griffin_lim(taco_handle* h, const taco_audio_params* ap, const float* l
 /* ---- arithmetic mode of the dense layers ----------------------------------- */
 /* The reference computes in fp32.  0 = fp32 FFMA kernels; 1 (default) = tcgen05 tensor
  * cores with every operand split into bf16 hi+lo and three products per k-step
- * (fp32-class accuracy, meets the 1e-3 parity bound); 2 = plain bf16 tensor cores
- * (looser, separately stated tolerance).  Recurrent kernels always run in fp32. */
+ * (fp32-class accuracy, meets the 1e-3 parity bound); 2 = plain bf16 operands with fp32
+ * accumulation in the dense layers AND in the decoder loop's mat-vecs (one product per
+ * k-step instead of three; separately stated tolerance 5e-2, tests/test_gpu_parity.py).
+ * The BiGRU recurrences always run in fp32. */
 enum { TACO_GEMM_FFMA = 0, TACO_GEMM_BF16X3 = 1, TACO_GEMM_BF16 = 2 };
 int taco_set_gemm_mode(taco_handle* h, int mode);
 

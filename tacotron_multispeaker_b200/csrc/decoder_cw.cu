@@ -214,7 +214,9 @@ struct Args {
 #define TRM(i) do { if (TRACE && a.trace != nullptr && step == 8 && blockIdx.x == a.trace_cta && tid == 12 * 32) a.trace[i] = clock64(); } while (0)
 #define TRW(base) do { if (TRACE && a.trace != nullptr && step == 8 && blockIdx.x == a.trace_cta && lane == 0) a.trace[(base) + warp] = clock64(); } while (0)
 
-template <bool TRACE>
+// BF16: plain bf16 mode (taco_set_gemm_mode(2)): only W_hi * x_hi is multiplied (one MMA per chunk-tile instead of three);
+// the lo halves of the packed weights and of the staged activations are carried but not used.  Stated tolerance: 5e-2.
+template <bool TRACE, bool BF16>
 __global__ void __launch_bounds__(NT, 1)
 decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Program prog, const DecoderArgs a, const int nclusters) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -479,8 +481,10 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       for (int i = 0; i < 4; ++i)
         if (i < n) {
           mma16816(hh, wa[2 * i], xf[i].x, xf[i].y);       // W_hi * x_hi
-          mma16816(lh, wa[2 * i + 1], xf[i].x, xf[i].y);   // W_lo * x_hi
-          mma16816(hl, wa[2 * i], xf[i].z, xf[i].w);       // W_hi * x_lo
+          if (!BF16) {
+            mma16816(lh, wa[2 * i + 1], xf[i].x, xf[i].y);   // W_lo * x_hi
+            mma16816(hl, wa[2 * i], xf[i].z, xf[i].w);       // W_hi * x_lo
+          }
         }
       store_tile(myslot, g, t, hh, hl, lh);
     };
@@ -776,8 +780,10 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
             for (int i = 0; i < 4; ++i)
               if (i < n) {
                 mma16816(hh, wa[2 * i], xf[i].x, xf[i].y);
-                mma16816(lh, wa[2 * i + 1], xf[i].x, xf[i].y);
-                mma16816(hl, wa[2 * i], xf[i].z, xf[i].w);
+                if (!BF16) {
+                  mma16816(lh, wa[2 * i + 1], xf[i].x, xf[i].y);
+                  mma16816(hl, wa[2 * i], xf[i].z, xf[i].w);
+                }
               }
           }
         }
@@ -851,7 +857,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
 size_t decoder_cw_smem_bytes(int s_max, int T_in, int att_res, int ring_kb) { return make_dyn(s_max, T_in, att_res, ring_kb).total; }
 
 int decoder_cw_max_clusters() {
-  auto kern = decoder_cw_kernel<false>;
+  auto kern = decoder_cw_kernel<false, false>;
   const int smem = 200 * 1024;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
@@ -875,7 +881,7 @@ int decoder_cw_max_clusters() {
   return n;
 }
 
-cudaError_t launch_decoder_cw(const cw::Weights& wt, const DecoderArgs& a_in, int nclusters, cudaStream_t st) {
+cudaError_t launch_decoder_cw(const cw::Weights& wt, const DecoderArgs& a_in, int nclusters, cudaStream_t st, bool bf16_only) {
   if (a_in.N <= 0 || a_in.steps <= 0) return cudaSuccess;
   if (nclusters < 1 || nclusters > a_in.N) return cudaErrorInvalidValue;
   DecoderArgs a = a_in;
@@ -913,7 +919,7 @@ cudaError_t launch_decoder_cw(const cw::Weights& wt, const DecoderArgs& a_in, in
   k.M = wt.M; k.Dout = wt.Dout;
   k.exact_softmax = wt.v_l1 > 40.0f ? 1 : 0;
   k.ring_kb = ring_kb;
-  auto kern = a.trace != nullptr ? decoder_cw_kernel<true> : decoder_cw_kernel<false>;
+  auto kern = a.trace != nullptr ? decoder_cw_kernel<true, false> : (bf16_only ? decoder_cw_kernel<false, true> : decoder_cw_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);

@@ -120,7 +120,8 @@ struct DecoderArgs {
   int trace_warp;        // decoder_cw: background warp whose items are stamped (TACO_DEC_TRACE_WARP, default 8)
 };
 // v6 (decoder_cw.cu): cluster of 16, critical warp group + background groups, 11 exchanges per step (layout: decoder_cw.h).
-cudaError_t launch_decoder_cw(const cw::Weights& w, const DecoderArgs& a, int nclusters, cudaStream_t st);
+// bf16_only: one product per chunk-tile (W_hi x_hi) instead of the fp32-class three (taco_set_gemm_mode(2)).
+cudaError_t launch_decoder_cw(const cw::Weights& w, const DecoderArgs& a, int nclusters, cudaStream_t st, bool bf16_only = false);
 size_t decoder_cw_smem_bytes(int s_max, int T_in, int att_res, int ring_kb);
 int decoder_cw_max_clusters();
 

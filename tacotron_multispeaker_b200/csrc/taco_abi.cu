@@ -777,7 +777,7 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
   if (h->profiling) cudaEventRecord(h->ev[4], st);
   const bool fits8 = (N + pick_mma_clusters(h, N) - 1) / pick_mma_clusters(h, N) <= 8;
   const bool use_cw = h->use_cw && fits8;
-  cudaError_t e = use_cw ? launch_decoder_cw(h->decw, a, pick_mma_clusters(h, N), st)
+  cudaError_t e = use_cw ? launch_decoder_cw(h->decw, a, pick_mma_clusters(h, N), st, /*bf16_only=*/h->gemm_mode == 2)
                          : launch_decoder(h->dec[CS == 16 ? 1 : 0], a, S, st);
   if (h->profiling) cudaEventRecord(h->ev[5], st);
   if (e != cudaSuccess) return fail(h, TACO_ERR_CUDA, std::string("decoder launch: ") + cudaGetErrorString(e));

@@ -191,6 +191,24 @@ def test_decode_teacher_forced(eng, ow, small_hp, N, T_in, S):
     assert torch.equal(al.cpu().argmax(dim=1), ral.argmax(dim=1))
 
 
+@pytest.mark.parametrize("N,T_in", [(3, 19), (17, 100)])
+def test_decode_bf16_mode(eng, ow, small_hp, N, T_in):
+    """taco_set_gemm_mode(2): the decoder multiplies W_hi x_hi only (plain bf16 operands, fp32 accumulation, one MMA per
+    chunk-tile instead of three).  Stated tolerance of the decoder in this mode: 1e-2 max-abs on its outputs, 1e-3 on the
+    alignments (measured 2.7e-3 / 1.7e-4; the fp32-class default meets 2e-4 / 1e-5 on the same cases).  At full size (32 x 1000
+    frames, free running) the mode differs from the default by 4.4e-3 on mel and 1.4e-3 on linear."""
+    eng.set_gemm_mode(2)
+    try:
+        e_dec, e_al, al, ral = _decode_case(eng, ow, small_hp, N, T_in, True, N * 7 + T_in, None)
+        e_dec_f, e_al_f, _, _ = _decode_case(eng, ow, small_hp, N, T_in, False, N * 7 + T_in, None)
+    finally:
+        eng.set_gemm_mode(1)
+    print("bf16 decoder mode: teacher-forced %.2e / %.2e, free-running %.2e / %.2e" % (e_dec, e_al, e_dec_f, e_al_f))
+    assert e_dec < 1e-2 and e_al < 1e-3
+    assert e_dec_f < 1e-2 and e_al_f < 1e-3
+    assert e_dec > 1e-5          # the mode really is coarser than the default: it ran the one-product kernel
+
+
 @pytest.mark.parametrize("N,T_in,S", [(1, 11, None), (4, 25, None), (6, 40, 4)])
 def test_decode_free_running(eng, ow, small_hp, N, T_in, S):
     e_dec, e_al, _, _ = _decode_case(eng, ow, small_hp, N, T_in, False, N * 11 + T_in, S)
