@@ -452,64 +452,78 @@ def run_ours(args):
         import statistics
         lat = {"what": "one utterance, device resident, one stream; CUDA events around taco_forward (gather -> linear "
                        "output, step count read back), p50 over 30 runs per input length", "unit": "ms", "p50": {}}
-        out1 = (torch.zeros(1, T_out, hp.num_mels, device=dev), torch.zeros(1, T_out, hp.num_freq, device=dev), None)
-        for t_in in (20, 60, 100, 200):
-            rng1 = np.random.default_rng(500 + t_in)
-            ids1 = torch.from_numpy(rng1.integers(7108, 7325, (1, t_in)).astype(np.int32)).to(dev)
-            len1 = torch.tensor([t_in], dtype=torch.int32, device=dev)
-            spk1 = torch.tensor([3], dtype=torch.int32, device=dev)
-            al1 = torch.zeros(1, t_in, MAX_ITERS, device=dev)
+        lat_stream = lanes[0]["stream"]          # a non-default stream: taco_forward replays its CUDA graph there
+        lat_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(lat_stream):
+            out1 = (torch.zeros(1, T_out, hp.num_mels, device=dev), torch.zeros(1, T_out, hp.num_freq, device=dev), None)
+            for t_in in (20, 60, 100, 200):
+                rng1 = np.random.default_rng(500 + t_in)
+                ids1 = torch.from_numpy(rng1.integers(7108, 7325, (1, t_in)).astype(np.int32)).to(dev)
+                len1 = torch.tensor([t_in], dtype=torch.int32, device=dev)
+                spk1 = torch.tensor([3], dtype=torch.int32, device=dev)
+                al1 = torch.zeros(1, t_in, MAX_ITERS, device=dev)
+                ts = []
+                for i in range(33):
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a0.record()
+                    eng.forward(ids1, len1, spk1, out=(out1[0], out1[1], al1))
+                    a1.record()
+                    a1.synchronize()
+                    if i >= 3:
+                        ts.append(a0.elapsed_time(a1))
+                lat["p50"]["T_in=%d" % t_in] = statistics.median(ts)
+            # the same utterance down to the waveform (reference Synthesizer.synthesize: + Griffin-Lim, 100 iterations)
             ts = []
-            for i in range(33):
+            wav1 = None
+            for i in range(13):
                 a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a0.record()
-                eng.forward(ids1, len1, spk1, out=(out1[0], out1[1], al1))
+                _, lin1, _, _ = eng.forward(ids1, len1, spk1, out=(out1[0], out1[1], al1))
+                if wav1 is None:
+                    wav1 = eng.griffin_lim(lin1)
+                else:
+                    eng.griffin_lim(lin1, out=wav1)
                 a1.record()
                 a1.synchronize()
                 if i >= 3:
                     ts.append(a0.elapsed_time(a1))
-            lat["p50"]["T_in=%d" % t_in] = statistics.median(ts)
-        # the same utterance down to the waveform (reference Synthesizer.synthesize: + Griffin-Lim, 100 iterations)
-        ts = []
-        for i in range(13):
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            _, lin1, _, _ = eng.forward(ids1, len1, spk1, out=(out1[0], out1[1], al1))
-            eng.griffin_lim(lin1)
-            a1.record()
-            a1.synchronize()
-            if i >= 3:
-                ts.append(a0.elapsed_time(a1))
         lat["p50_with_griffin_lim_T_in=200"] = statistics.median(ts)
+        torch.cuda.current_stream().wait_stream(lat_stream)
 
     # ---- the step after the path (informational): Griffin-Lim vocoder on the last linear output of lane 0 ----
     voc = None
     if not args.no_vocoder and world == 1:
         lin = lanes[0]["outs"][1]
-        eng.griffin_lim(lin)                                   # warm-up (workspace growth)
+        voc_stream = lanes[0]["stream"]
+        voc_stream.wait_stream(torch.cuda.current_stream())
+        torch.cuda.set_stream(voc_stream)                      # non-default stream + a fixed output buffer: graph replay
+        wav = eng.griffin_lim(lin)                             # warm-up (workspace growth)
         torch.cuda.synchronize()
         voc_l0 = eng.launch_count()
         voc_sampler = ClockSampler(local)
         t_dead = time.time() + 3.0
         while voc_sampler.proc is not None and not voc_sampler.lines and time.time() < t_dead:
             time.sleep(0.02)
-        eng.griffin_lim(lin)                                   # second warm-up
+        eng.griffin_lim(lin, out=wav)                          # second warm-up (captures the graph)
+        eng.griffin_lim(lin, out=wav)
         vt0 = time.time()
         v_calls = []
         for _ in range(5):
             v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             v0.record()
-            wav = eng.griffin_lim(lin)
+            eng.griffin_lim(lin, out=wav)
             v1.record()
             v1.synchronize()
             v_calls.append(v0.elapsed_time(v1))
         vt1 = time.time()
+        torch.cuda.synchronize()
+        torch.cuda.set_stream(torch.cuda.default_stream(dev))
         voc_clocks = voc_sampler.stop(vt0, vt1)
         v_ms = float(np.median(v_calls))                       # per-call device times; the median is reported
         voc = {"what": "taco_griffin_lim: %d iterations + inverse pre-emphasis on the batch's linear spectrograms "
                        "(reference synthesizer.py:27,50); not part of `value`" % hp.griffin_lim_iters,
                "ms_per_batch": v_ms, "us_per_iteration": 1e3 * v_ms / hp.griffin_lim_iters,
-               "frames_per_s": frames_per_step / (v_ms / 1e3), "launches_per_batch": (eng.launch_count() - voc_l0) // 6, "ms_per_call": v_calls,
+               "frames_per_s": frames_per_step / (v_ms / 1e3), "launches_per_batch": (eng.launch_count() - voc_l0) // 7, "ms_per_call": v_calls,
                "audio_seconds_per_batch": BATCH * wav.shape[-1] / hp.sample_rate, "clocks": voc_clocks}
 
     # ---- the other configurations BASELINE.json names (extra keys; bench_configs.py) ----

@@ -126,6 +126,9 @@ struct taco_handle {
   };
   struct FwdGraph { FwdKey key; bool have_key = false; cudaGraphExec_t exec = nullptr; int64_t launches = 0; } fwd_graph;
   bool graphs_on = true;
+  // the vocoder's ~105 launches per call likewise (key: arguments, workspace, stream)
+  struct GlKey { GriffinLimArgs a; const void* ws; void* stream; };
+  struct GlGraph { GlKey key; bool have_key = false; cudaGraphExec_t exec = nullptr; int launches = 0; } gl_graph;
   bool launch_failed = false;        // a kernel launcher returned an error (sticky until check_launch reports it)
   bool profiling = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [4],[5] bracket the decoder kernel
@@ -881,6 +884,7 @@ int taco_destroy(taco_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   if (h->fwd_graph.exec) cudaGraphExecDestroy(h->fwd_graph.exec);
+  if (h->gl_graph.exec) cudaGraphExecDestroy(h->gl_graph.exec);
   if (h->dW) cudaFree(h->dW);
   if (h->dB) cudaFree(h->dB);
   if (h->ws) cudaFree(h->ws);
@@ -1462,7 +1466,47 @@ int taco_griffin_lim(taco_handle* h, const taco_audio_params* ap, const float* l
   a.power = (float)ap->power; a.preemphasis = (float)ap->preemphasis;
   a.wav = wav_out;
   int launches = 0;
-  CUDA_OK(h, launch_griffin_lim(a, h->ws, (cudaStream_t)stream, &launches));
+  cudaStream_t st = (cudaStream_t)stream;
+  taco_handle::GlKey key;
+  memset(&key, 0, sizeof(key));
+  key.a.linear = a.linear; key.a.linear_bs = a.linear_bs; key.a.N = a.N; key.a.T = a.T; key.a.n_fft = a.n_fft; key.a.win = a.win;
+  key.a.hop = a.hop; key.a.iters = a.iters; key.a.min_level_db = a.min_level_db; key.a.ref_level_db = a.ref_level_db;
+  key.a.power = a.power; key.a.preemphasis = a.preemphasis; key.a.wav = a.wav;
+  key.ws = h->ws; key.stream = stream;
+  const bool graph_ok = h->graphs_on && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+  auto& G = h->gl_graph;
+  bool capture = false;
+  if (!graph_ok || !G.have_key || memcmp(&G.key, &key, sizeof(key)) != 0) {
+    if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+    G.have_key = graph_ok;
+    G.key = key;
+  } else if (G.exec) {                     // third and later identical calls: one graph launch instead of ~105 kernel launches
+    CUDA_OK(h, cudaGraphLaunch(G.exec, st));
+    h->launches += G.launches;
+    return TACO_OK;
+  } else {
+    capture = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (!capture) cudaGetLastError();
+  }
+  const cudaError_t le = launch_griffin_lim(a, h->ws, st, &launches);
+  if (capture) {
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    cudaError_t ie = (le == cudaSuccess && ce == cudaSuccess && graph) ? cudaGraphInstantiate(&G.exec, graph, 0) : cudaErrorUnknown;
+    if (graph) cudaGraphDestroy(graph);
+    if (ie == cudaSuccess) ie = cudaGraphLaunch(G.exec, st);
+    if (ie != cudaSuccess) {               // capture not possible here: plain launches from now on for this key
+      cudaGetLastError();
+      if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+      G.have_key = false;
+      launches = 0;
+      CUDA_OK(h, launch_griffin_lim(a, h->ws, st, &launches));
+    } else {
+      G.launches = launches;
+    }
+  } else {
+    CUDA_OK(h, le);
+  }
   h->launches += launches;
   return check_launch(h, "griffin_lim");
 }
@@ -1501,7 +1545,9 @@ int taco_set_cuda_graphs(taco_handle* h, int on) {
   if (!h) return TACO_ERR_INVALID;
   h->graphs_on = on != 0;
   if (!h->graphs_on && h->fwd_graph.exec) { cudaGraphExecDestroy(h->fwd_graph.exec); h->fwd_graph.exec = nullptr; }
+  if (!h->graphs_on && h->gl_graph.exec) { cudaGraphExecDestroy(h->gl_graph.exec); h->gl_graph.exec = nullptr; }
   h->fwd_graph.have_key = false;
+  h->gl_graph.have_key = false;
   return TACO_OK;
 }
 

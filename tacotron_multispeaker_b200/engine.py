@@ -222,7 +222,7 @@ class Engine:
             float(hp.frame_length_ms), float(hp.frame_shift_ms), float(hp.preemphasis),
             float(hp.min_level_db), float(hp.ref_level_db), float(hp.power))
 
-    def griffin_lim(self, linear, griffin_lim_iters: Optional[int] = None, inv_preemphasis: bool = True):
+    def griffin_lim(self, linear, griffin_lim_iters: Optional[int] = None, inv_preemphasis: bool = True, out=None):
         """``audio.inv_spectrogram_tensorflow`` + ``audio.inv_preemphasis`` (reference synthesizer.py:27,50) for a
         batch ``linear [N,T,num_freq]`` (or one ``[T,num_freq]``): returns wav ``[N,(T-1)*hop+win]`` on the device."""
         linear = self._f32(linear)
@@ -238,7 +238,12 @@ class Engine:
         L = self.lib.taco_wav_length(C.byref(ap), T)
         if L < 0:
             raise ValueError("bad audio hparams")
-        wav = torch.empty(N, L, device=self.device, dtype=torch.float32)
+        if out is None:
+            wav = torch.empty(N, L, device=self.device, dtype=torch.float32)
+        else:                                          # caller's buffer (stable pointers let the C ABI replay its CUDA graph)
+            wav = out
+            if tuple(wav.shape) != (N, L) or wav.dtype != torch.float32 or not wav.is_contiguous() or wav.device != linear.device:
+                raise ValueError("out must be a contiguous float32 [%d, %d] tensor on the engine's device" % (N, L))
         self._ck(self.lib.taco_griffin_lim(self._h, C.byref(ap), _ptr(linear), N, T, 0, _ptr(wav), self.stream))
         return wav[0] if single else wav
 

@@ -149,6 +149,29 @@ def test_full_size_utterances(eng):
         assert rel_err(got[i], A.synthesize_wav(xs[i], eng.hp, iters=2)) < 2e-4
 
 
+def test_cuda_graph_replay_is_bit_identical(eng):
+    """taco_griffin_lim on a non-default stream with the same buffers: captured into a CUDA graph on the second call and replayed
+    afterwards; every call must give the plain launches' waveform bit for bit and count the same number of kernels."""
+    dev = torch.device("cuda", 0)
+    lin = torch.from_numpy(np.stack([spectrogram(23, 5), spectrogram(23, 6)])).to(dev)
+    eng.set_cuda_graphs(False)
+    ref = eng.griffin_lim(lin, 4)
+    eng.set_cuda_graphs(True)
+    st = torch.cuda.Stream(device=dev)
+    st.wait_stream(torch.cuda.current_stream())
+    counts = []
+    with torch.cuda.stream(st):
+        out = torch.zeros_like(ref)
+        for rep in range(4):
+            out.zero_()
+            c0 = eng.launch_count()
+            eng.griffin_lim(lin, 4, out=out)
+            st.synchronize()
+            counts.append(eng.launch_count() - c0)
+            assert torch.equal(out, ref), "call %d differs" % rep
+    assert len(set(counts)) == 1 and counts[0] == 4 + 4 + 1, counts
+
+
 def test_bad_arguments(eng):
     from tacotron_multispeaker_b200 import _abi
     with pytest.raises(ValueError):
