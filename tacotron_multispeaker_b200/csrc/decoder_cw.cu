@@ -645,11 +645,15 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       TRM(19);
       // ================= P11: GRU-2 reset gate on [y1 = y0 + h1' | h2] (late: the h1' term) ====
       late(XADDR(XY1 + 4 * gw), 4);
+      TRM(45);
       tload(TC_P12, 4);
       nb_sync(NB_CRIT, 128);
+      TRM(46);
       TRM(60); nb_sync(NB_H11, 256); TRM(61);
       stage_x(stg_n, rc, sigmoid_f(sum4(red_nc, SL_CRIT) + sum4(red_nc, SL_RE2) + BIAS(BI_R2)) * st_h2);
+      TRM(47);
       send_rows(OFF_X + (uint32_t)(XR2 + q) * csb, MB_P11, false);
+      TRM(48);
       twait();
       TRM(20);
       wait_rearm(MB_P11, par, BLK);
