@@ -443,6 +443,30 @@ def test_full_size_free_running_config3():
     assert torch.equal(al.cpu().argmax(dim=1), ref["alignments"].argmax(dim=1))
 
 
+@pytest.mark.parametrize("bn_mode", ["batch", "moving"])
+def test_full_size_teacher_forced_config2(bn_mode):
+    """BASELINE config 2 at full size (batch 32, T_in 100, 1000 target frames -> 200 teacher-forced steps, r=5), in the reference's
+    own training-graph semantics (batch-statistics BN, `is_training` keyed off linear_targets: models/tacotron.py:36) and with
+    moving statistics: mel / linear within the north-star 1e-3 of the oracle, identical per-step attention argmax."""
+    from tacotron_multispeaker_b200.engine import Engine
+    from tacotron_multispeaker_b200.hparams import HParams
+    from tacotron_multispeaker_b200.weights import random_init
+    hp = HParams(outputs_per_step=5, max_iters=200)
+    w = random_init(hp, 60, seed=1234, randomize_bn=True)
+    ids, lengths, spk = make_inputs(32, 100, 60, 2, min_len=60, vocab=(7108, 7325))
+    mel_t = np.random.default_rng(22).uniform(0, 1, (32, 1000, hp.num_mels)).astype(np.float32)
+    ref = O.tacotron_forward(w, hp, ids, lengths, mel_targets=mel_t, identities=spk, id_num=60, teacher_force=True, bn_mode=bn_mode)
+    e = Engine(hp, 60)
+    e.load_weights(w)
+    mel, lin, al, steps = e.forward(ids, lengths, spk, mel_t, True, 1 if bn_mode == "batch" else 0)
+    e.close()
+    assert steps == ref["steps"] == 200
+    assert maxabs(mel, ref["mel_outputs"]) < 1e-3
+    assert maxabs(lin, ref["linear_outputs"]) < 1e-3
+    assert maxabs(al, ref["alignments"]) < 1e-5
+    assert torch.equal(al.cpu().argmax(dim=1), ref["alignments"].argmax(dim=1))
+
+
 @pytest.mark.parametrize("N,S", [(1, 1), (7, 1), (13, 2), (8, 8), (23, 3), (40, 8)])
 def test_decode_mma_cluster_cuts(eng, ow, small_hp, N, S):
     """The mma.sync decoder cuts a batch into clusters of S <= 8 utterances (uneven cuts, more clusters than fit at
