@@ -178,6 +178,7 @@ def canonicalize(weights: Dict[str, np.ndarray], hp: HParams, id_num: int) -> Di
             out[short] = arr
         else:
             leftovers[name] = arr
+    ambiguous = {}
     if leftovers:
         for short in specs:
             if short in out:
@@ -185,10 +186,15 @@ def canonicalize(weights: Dict[str, np.ndarray], hp: HParams, id_num: int) -> Di
             hits = [n for n in leftovers if n.endswith("/" + short) or n.endswith(short)]
             if len(hits) == 1:
                 out[short] = leftovers.pop(hits[0])
+            elif len(hits) > 1:
+                ambiguous[short] = sorted(hits)      # reported below instead of being skipped silently
     missing = [n for n in specs if n not in out]
     if missing:
-        raise KeyError("missing variables: " + ", ".join(PREFIX + m for m in missing[:8])
-                       + (" ..." if len(missing) > 8 else ""))
+        msg = "missing variables: " + ", ".join(PREFIX + m for m in missing[:8]) + (" ..." if len(missing) > 8 else "")
+        amb = [m for m in missing if m in ambiguous]
+        if amb:
+            msg += "; ambiguous suffix matches: " + "; ".join("%s <- %s" % (m, ambiguous[m][:3]) for m in amb[:4])
+        raise KeyError(msg)
     for short, (shape, _) in specs.items():
         a = np.ascontiguousarray(np.asarray(out[short], dtype=np.float32))
         if tuple(a.shape) != tuple(shape):

@@ -147,3 +147,18 @@ def test_output_gather_world_size_2_gloo(n_total):
     assert res == [(0, True), (1, True)]
 
 
+
+
+def test_canonicalize_reports_ambiguous_suffix_matches():
+    """Two checkpoint variables ending in the same expected name are not skipped silently: the KeyError names them."""
+    from tacotron_multispeaker_b200.hparams import HParams
+    from tacotron_multispeaker_b200 import weights as W
+    hp = HParams()
+    full = W.random_init(hp, 4, seed=0)
+    name = W.PREFIX + "embedding"
+    arr = full.pop(name)
+    full["tower_0/" + name[len(W.PREFIX):]] = arr
+    full["tower_1/" + name[len(W.PREFIX):]] = arr
+    with pytest.raises(KeyError) as ei:
+        W.canonicalize(full, hp, 4)
+    assert "ambiguous suffix matches" in str(ei.value) and "tower_0/" in str(ei.value)
