@@ -216,7 +216,8 @@ struct Args {
 
 // BF16: plain bf16 mode (taco_set_gemm_mode(2)): only W_hi * x_hi is multiplied (one MMA per chunk-tile instead of three);
 // the lo halves of the packed weights and of the staged activations are carried but not used.  Stated tolerance: 5e-2.
-template <bool TRACE, bool BF16>
+// SMALL: launches whose clusters all hold <= 2 utterances run the attention phases on the critical group alone (compiled out otherwise)
+template <bool TRACE, bool BF16, bool SMALL>
 __global__ void __launch_bounds__(NT, 1)
 decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Program prog, const DecoderArgs a, const int nclusters) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -343,7 +344,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
   // v.tanh(k + p) = sum v - 2 sum_k v_k / (1 + e^{2k} e^{2p}); four elements share one MUFU.RCP (denominators clamped to 2^30).
   const int p6_wr = (warp + 4) & 15;                                         // pair slot of this warp: 12, 13, 14, 15, 0, 1, ...
   const int p6_na = (p0 + min(2 * p6_wr, max(npq - 1, 0))) % S, p6_nb = (p0 + min(2 * p6_wr + 1, max(npq - 1, 0))) % S;
-  auto p6_compute = [&]() {
+  auto p6_compute = [&](int pair_stride) {
     const uint32_t pq_l = sbase + L.pq + (uint32_t)(lane >> 2) * csb + (uint32_t)(lane & 3) * 16u;
     const float4 v0 = lds_f4(sbase + OFF_VATT + lane * 16), v1 = lds_f4(sbase + OFF_VATT + 512 + lane * 16);
     constexpr float BIG = 1073741824.0f;   // 2^30
@@ -374,7 +375,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
     };
     const float vb = lds_f(sbase + OFF_VB);
     // the critical warps (12..15) own the first pairs: with few utterances per cluster nobody waits for a background warp here
-    for (int pp = 2 * p6_wr; pp < npq; pp += 2 * NW) {
+    for (int pp = 2 * p6_wr; pp < npq; pp += pair_stride) {
       const bool two = pp + 1 < npq, first = pp == 2 * p6_wr;
       const int na = first ? p6_na : (int)smem_raw[L.pn + pp], nb = first ? p6_nb : (int)smem_raw[L.pn + (two ? pp + 1 : pp)];
       const float sa = pair_sum(pp, na), sb = pair_sum(two ? pp + 1 : pp, nb);
@@ -449,6 +450,49 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
     }
     sts_f4(sbase + OFF_SLOTS + (uint32_t)(SL_CTX + warp) * (SLOT_F * 4) + (uint32_t)(g * RS + t * 4) * 4u, acc);
     if (t == 0) sts_f(sbase + OFF_REDS + (uint32_t)(warp * 8 + g) * 4u, ssum);
+  };
+
+  // ---- attention on the critical group alone (S <= 2, operands resident, bounded-score softmax): batch-1 latency -----------
+  // With one or two utterances per cluster the pairs of a CTA fit the four critical warps, and a 512-thread phase costs more in
+  // barriers and late background warps than it saves: the background groups skip the attention phases altogether.
+  const bool small_att = SMALL && S <= 2 && res_k && res_m && !exact;
+  auto p6_send_crit = [&]() {   // critical warp gw -> peers 4 gw .. 4 gw + 3, eight 16-byte words per peer and trip
+    const uint32_t peer = (uint32_t)(4 * gw + (lane >> 3));
+    const uint32_t rsc = mapa_u32(sbase + L.sc + (uint32_t)p0 * 4u, peer), rmb = mapa_u32(mb0 + MB_P6 * 8, peer);
+    for (int word = lane & 7; word < ((npq + 3) >> 2); word += 8)
+      st_async_v4(rsc + (uint32_t)word * 16u, lds128(sbase + L.stage + (uint32_t)word * 16u), rmb);
+  };
+  // partial context of critical warp gw: positions j = gw + 4 (sub + nsub i); lane = (sub, sample, column quad t)
+  auto p7_compute_crit = [&](uint32_t slot) {
+    const int smp = S == 2 ? (g & 1) : 0, sub = S == 2 ? (g >> 1) : g, nsub = S == 2 ? 4 : 8;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ssum = 0.f, ssum2 = 0.f;
+    const int j0 = gw + 4 * sub, dj = 4 * nsub;
+    uint32_t pa = sbase + L.sc + (uint32_t)(j0 * S + smp) * 4u;
+    uint32_t ma = sbase + L.msl + (uint32_t)((j0 * S + smp) * 16 + t * 4) * 4u;
+    const uint32_t dp = (uint32_t)(dj * S) * 4u, dm = (uint32_t)(dj * S) * 64u;
+    for (int j = j0; j < T_in; j += 2 * dj) {
+      const bool two = j + dj < T_in;
+      float pv0 = lds_f(pa), pv1 = lds_f(pa + (two ? dp : 0u));
+      const float4 m0 = lds_f4(ma), m1 = lds_f4(ma + (two ? dm : 0u));
+      if (!two) pv1 = 0.f;
+      acc.x = fmaf(pv0, m0.x, acc.x); acc.y = fmaf(pv0, m0.y, acc.y); acc.z = fmaf(pv0, m0.z, acc.z); acc.w = fmaf(pv0, m0.w, acc.w);
+      acc2.x = fmaf(pv1, m1.x, acc2.x); acc2.y = fmaf(pv1, m1.y, acc2.y); acc2.z = fmaf(pv1, m1.z, acc2.z); acc2.w = fmaf(pv1, m1.w, acc2.w);
+      ssum += pv0; ssum2 += pv1;
+      pa += 2 * dp; ma += 2 * dm;
+    }
+    acc.x += acc2.x; acc.y += acc2.y; acc.z += acc2.z; acc.w += acc2.w;
+    ssum += ssum2;
+    // sum over the position sub-slots: lane bits 2..4 (one utterance) or 3..4 (two)
+    for (int o = 16; o >= (S == 2 ? 8 : 4); o >>= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+      ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+    }
+    if (sub == 0) {
+      sts_f4(slot + (uint32_t)(smp * RS + t * 4) * 4u, acc);
+      if (t == 0) sts_f(sbase + OFF_REDS + (uint32_t)(gw * 8 + smp) * 4u, ssum);
+    }
   };
 
   if (warp >= 12) {
@@ -571,8 +615,24 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       TRM(9);
       wait_rearm(MB_P5, par, BLK);
       TRM(10);
-      // ================= P6 / P7: attention (all warps) ====
-      p6_compute();
+      // ================= P6 / P7: attention (all warps; the critical group alone when S <= 2) ====
+      if (small_att) {
+        p6_compute(8);
+        nb_sync(NB_CRIT, 128);
+        TRM(11);
+        p6_send_crit();
+        wait_rearm(MB_P6, par, (uint32_t)NQ * 16u);
+        TRM(12);
+        p7_compute_crit(myslot);
+        nb_sync(NB_CRIT, 128);
+        TRM(13);
+        const float* reds = reinterpret_cast<const float*>(smem_raw + OFF_REDS) + rn;
+        const float inv = rcp_approx((reds[0] + reds[8]) + (reds[16] + reds[24]));
+        stage_x(stg_n, rc, sum4(red_nc, SL_CRIT) * inv);
+        if (rc == 0) reinterpret_cast<float*>(smem_raw + OFF_INV)[rn] = inv;
+        send_rows(OFF_X + (uint32_t)(XC + q) * csb, MB_P7, false);
+      } else {
+      p6_compute(2 * NW);
       TRW(112);
       __syncthreads();
       TRM(11);
@@ -596,6 +656,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
         stage_x(stg_n, rc, (c0 + c1) * inv);
         if (rc == 0) reinterpret_cast<float*>(smem_raw + OFF_INV)[rn] = inv;
         send_rows(OFF_X + (uint32_t)(XC + q) * csb, MB_P7, false);
+      }
       }
       TRM(14);
       wait_rearm(MB_P7, par, BLK);
@@ -827,12 +888,15 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       const uint32_t par = (uint32_t)step & 1u;
       run_items(prog.pre[warp], prog.n_pre[warp], step);
       TRW(64);
+      if (small_att) {
+        mbar_wait(mb0 + MB_P6 * 8, par);   // pacing only: the attention phases run on the critical group
+      } else {
       mbar_wait(mb0 + MB_P5 * 8, par);
       TRW(160);
       {
         const int reps = (TRACE && a.trace != nullptr && step == 8) ? 3 : 1;
 #pragma unroll 1
-        for (int rep = 0; rep < reps; ++rep) { p6_compute(); TRW(112 + 64 * rep); }
+        for (int rep = 0; rep < reps; ++rep) { p6_compute(2 * NW); TRW(112 + 64 * rep); }
       }
       __syncthreads();
       p6_send();
@@ -844,6 +908,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
         for (int rep = 0; rep < reps; ++rep) { p7_compute(); TRW(144 + 64 * rep); }
       }
       __syncthreads();
+      }
       TRW(80);
       run_items(prog.post[warp], prog.n_post[warp], step);
       TRW(96);
@@ -861,7 +926,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
 size_t decoder_cw_smem_bytes(int s_max, int T_in, int att_res, int ring_kb) { return make_dyn(s_max, T_in, att_res, ring_kb).total; }
 
 int decoder_cw_max_clusters() {
-  auto kern = decoder_cw_kernel<false, false>;
+  auto kern = decoder_cw_kernel<false, false, false>;
   const int smem = 200 * 1024;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
@@ -923,7 +988,10 @@ cudaError_t launch_decoder_cw(const cw::Weights& wt, const DecoderArgs& a_in, in
   k.M = wt.M; k.Dout = wt.Dout;
   k.exact_softmax = wt.v_l1 > 40.0f ? 1 : 0;
   k.ring_kb = ring_kb;
-  auto kern = a.trace != nullptr ? decoder_cw_kernel<true, false> : (bf16_only ? decoder_cw_kernel<false, true> : decoder_cw_kernel<false, false>);
+  const bool small = a.s_max <= 2;
+  auto kern = a.trace != nullptr ? (small ? decoder_cw_kernel<true, false, true> : decoder_cw_kernel<true, false, false>)
+              : bf16_only ? (small ? decoder_cw_kernel<false, true, true> : decoder_cw_kernel<false, true, false>)
+                          : (small ? decoder_cw_kernel<false, false, true> : decoder_cw_kernel<false, false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
