@@ -544,12 +544,9 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       const uint32_t par = (uint32_t)step & 1u;
       const uint32_t XHAc = XHA + 16 * par, XH1c = XH1 + 16 * par, XH2c = XH2 + 16 * par;
       bool late1 = false;
-      if (step > 0) {
-        wait_rearm(MB_P12, par ^ 1u, BLK);     // h2' of the previous step has landed (and every earlier exchange with it)
-        wait_rearm(MB_H1, par ^ 1u, BLK);
-        wait_rearm(MB_H2, par ^ 1u, BLK);
-      }
+      if (step > 0) wait_rearm(MB_P12, par ^ 1u, BLK);   // y2 of the previous step has landed
       TRM(0);
+      if (TRACE && a.trace != nullptr && blockIdx.x == a.trace_cta && tid == 12 * 32 && step < 100) a.trace[400 + step] = clock64();   // step starts
       // ================= P1: decoder prenet dense_1 + ReLU.  free run: W_f y2 (late: the h2' term) + W_1c ctx; teacher: background only ====
       if (free_run && step > 0) {
         late(XADDR(XY2 + 4 * gw), 4);
@@ -614,6 +611,9 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       twait();
       TRM(9);
       wait_rearm(MB_P5, par, BLK);
+      // h1' / h2' of the previous step landed long ago (nobody pushes them again before this step's P10 / P12): their mbarriers are
+      // re-armed here instead of at the top of the step, where the critical group would wait for the trailing h2' push
+      if (step > 0) { wait_rearm(MB_H1, par ^ 1u, BLK); wait_rearm(MB_H2, par ^ 1u, BLK); }
       TRM(10);
       // ================= P6 / P7: attention (all warps; the critical group alone when S <= 2) ====
       if (small_att) {

@@ -53,6 +53,8 @@ def run(N, T_in, S, tag, iters=40, teacher=False, cta=0):
     print("   P7 intra (warp 0, last rep): %s" % [st[300 + i] - st[300] for i in range(4)])
     print("   crit P11 intra (from P10 arr): late %d, sync CRIT %d, H11+reduce+stage %d, send %d, twait %d" % (st[45] - st[19], st[46] - st[45], st[47] - st[46], st[48] - st[47], st[20] - st[48]))
     print("   kernel: prologue %d clk, step 0 %d clk, steps 0..%d %d clk (%.0f per step)" % (st[25] - st[24], st[27] - st[25], iters - 1, st[26] - st[25], (st[26] - st[25]) / iters))
+    ds = [st[401 + i] - st[400 + i] for i in range(min(iters, 100) - 1)]
+    print("   step durations (clk): first 12 %s, median %d, max %d (step %d), mean %.0f" % (ds[:12], sorted(ds)[len(ds) // 2], max(ds), ds.index(max(ds)), sum(ds) / len(ds)))
     hn = ["H1", "H3", "H4", "H9", "H10", "H11", "H12"]
     print("   crit handoff waits: " + " ".join("%s:%d" % (hn[i], st[51 + 2 * i] - st[50 + 2 * i]) for i in range(7)))
     print("   crit: P5 arr %d, SYNC6 %d, P6 arr %d, SYNC7 %d" % (st[10] - t0, st[11] - t0, st[12] - t0, st[13] - t0))
