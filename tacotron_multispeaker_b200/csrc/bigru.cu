@@ -102,27 +102,35 @@ bigru_kernel(const float* __restrict__ xproj, const float* __restrict__ ug,
     for (int i = len[s] * H + tid; i < T * H; i += 512) o[(int64_t)(i >> 7) * (2 * H) + (i & 127)] = 0.f;
   }
 
-  // cp.async producer: thread (s, q) copies float4 q of sample s' 384-float row.
+  // cp.async producer: thread (s, q) copies float4 q of sample s' 384-float row.  Only the first 3 NS warps copy; the
+  // others skip the address arithmetic altogether (warp-uniform branch), and the ring slot is a running counter.
   const int ps = tid / 96, pq = tid - ps * 96;
-  auto issue = [&](int step) {
-    const int L = ps < NS ? s_len[ps] : 0;
-    if (step < L) {
-      const int pos = dir == 0 ? step : L - 1 - step;
-      const float* src = xproj + ((int64_t)(n0 + ps) * T + pos) * XW + dir * (3 * H) + pq * 4;
-      cp_async16(ring + ((size_t)(step % RING) * NS + ps) * (3 * H) + pq * 4, src);
+  const bool copier = warp < 3 * NS;
+  const int pL = (copier && ps < NS) ? s_len[ps] : 0;
+  const float* psrc = xproj + ((int64_t)(n0 + ps) * T + (dir == 0 ? 0 : pL - 1)) * XW + dir * (3 * H) + pq * 4;
+  const int64_t pstep = dir == 0 ? XW : -XW;                     // forward walks up, backward starts at L-1 and walks down
+  float* pdst = ring + (size_t)ps * (3 * H) + pq * 4;
+  int islot = 0, istep = 0;                                       // next step to request and its ring slot
+  auto issue = [&]() {
+    if (copier) {
+      if (istep < pL) cp_async16(pdst + (size_t)islot * NS * (3 * H), psrc + (int64_t)istep * pstep);
+      cp_async_commit();
+      ++istep;
+      islot = islot + 1 == RING ? 0 : islot + 1;
     }
-    cp_async_commit();
   };
 #pragma unroll
-  for (int p = 0; p < RING - 1; ++p) issue(p);
-  cp_async_wait<RING - 2>();     // step 0's projections have landed (this thread's part) ...
+  for (int p = 0; p < RING - 1; ++p) issue();
+  if (copier) cp_async_wait<RING - 2>();     // step 0's projections have landed (this thread's part) ...
   __syncthreads();               // ... and are visible to every thread
 
+  int rslot = 0;
   for (int step = 0; step < maxlen; ++step) {
-    issue(step + RING - 1);
-    cp_async_wait<RING - 2>();   // this thread's part of step+1's projections has landed; the two
-                                 // barriers below publish it before step+1 reads it
-    const float* xr = ring + (size_t)(step % RING) * NS * (3 * H);
+    issue();
+    if (copier) cp_async_wait<RING - 2>();   // this thread's part of step+1's projections has landed; the two
+                                             // barriers below publish it before step+1 reads it
+    const float* xr = ring + (size_t)rslot * NS * (3 * H);
+    rslot = rslot + 1 == RING ? 0 : rslot + 1;
 
     // ---- gates: 8 columns x this lane's 8 k, then sum over the 16 k-slices ----
 #pragma unroll
@@ -206,7 +214,7 @@ bigru_kernel(const float* __restrict__ xproj, const float* __restrict__ ug,
     }
     __syncthreads();             // new h complete before the next step's gate phase
   }
-  cp_async_wait<0>();
+  if (copier) cp_async_wait<0>();
 }
 
 template <int NS>
