@@ -113,7 +113,7 @@ def test_conv1d_even_kernel_padding_kat(eng):
 
 
 @pytest.mark.parametrize("which,N,T,masked", [(0, 5, 23, True), (0, 3, 11, False), (1, 2, 60, False),
-                                              (0, 80, 9, True)])
+                                              (0, 80, 9, True), (1, 1, 150, False), (0, 8, 31, True), (0, 9, 31, True), (1, 33, 40, False)])
 def test_bigru(eng, ow, which, N, T, masked):
     rng = np.random.default_rng(N * 100 + T)
     x = rng.standard_normal((N, T, 128)).astype(np.float32)
