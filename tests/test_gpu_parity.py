@@ -467,6 +467,41 @@ def test_full_size_teacher_forced_config2(bn_mode):
     assert torch.equal(al.cpu().argmax(dim=1), ref["alignments"].argmax(dim=1))
 
 
+def test_forward_is_deterministic_under_repetition():
+    """compute-sanitizer is closed on this pool, so races in the cluster decoder (st.async / mbarrier exchanges, named-barrier
+    handoffs between the critical and background warps), the cp.async BiGRU and the tcgen05 pipelines are looked for the other
+    way: no kernel uses atomics on its data path, so every output must be BIT-identical from run to run.  Twelve full-size
+    forwards (config 3: 7 clusters x 16 CTAs, 200 steps) and twelve batch-1 forwards (critical-group attention), interleaved with
+    a second handle on another stream that keeps the other SMs busy."""
+    from tacotron_multispeaker_b200.engine import Engine
+    from tacotron_multispeaker_b200.hparams import HParams
+    from tacotron_multispeaker_b200.weights import random_init
+    hp = HParams(outputs_per_step=5, max_iters=200)
+    w = random_init(hp, 60, seed=1234)
+    dev = torch.device("cuda", 0)
+    e = Engine(hp, 60); e.load_weights(w)
+    noise = Engine(hp, 60); noise.load_weights(w)
+    side = torch.cuda.Stream(device=dev)
+    try:
+        for N, T_in in ((32, 100), (1, 77), (2, 60)):
+            ids, lengths, spk = make_inputs(N, T_in, 60, 7 + N, min_len=max(1, T_in // 2), vocab=(7108, 7325))
+            nids, nlen, nspk = make_inputs(8, 50, 60, 3, min_len=30, vocab=(7108, 7325))
+            first = None
+            for rep in range(12):
+                with torch.cuda.stream(side):
+                    noise.forward(nids, nlen, nspk)
+                mel, lin, al, steps = e.forward(ids, lengths, spk)
+                torch.cuda.synchronize()
+                cur = (mel.clone(), lin.clone(), al.clone())
+                if first is None:
+                    first = cur
+                else:
+                    for a_, b_ in zip(cur, first):
+                        assert torch.equal(a_, b_), "N=%d: run %d differs from run 0" % (N, rep)
+    finally:
+        e.close(); noise.close()
+
+
 @pytest.mark.parametrize("N,S", [(1, 1), (7, 1), (13, 2), (8, 8), (23, 3), (40, 8)])
 def test_decode_mma_cluster_cuts(eng, ow, small_hp, N, S):
     """The mma.sync decoder cuts a batch into clusters of S <= 8 utterances (uneven cuts, more clusters than fit at
