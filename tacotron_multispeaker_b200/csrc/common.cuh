@@ -8,10 +8,15 @@ namespace taco {
 // ---- activations ---------------------------------------------------------
 // exp-based forms on the SFU (ex2.approx): abs error ~1e-6, far inside the
 // 1e-3 parity budget, and ~5 instructions instead of ~25 for tanhf().
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// Written on the raw SFU instructions: __expf / __fdividef wrap them in range fix-ups (FSETP + two predicated FMULs around
+// EX2, a magnitude test around RCP) that these forms do not need -- 2^(+-big) saturates to inf / 0 and 1 / inf = 0, which is
+// exactly the limit wanted -- and that sat on the critical chain of every gate phase.
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_approx1(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_approx1(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_f(float x) {
   // 1 - 2/(e^{2x}+1); saturates cleanly for |x| large (inf -> 1, 0 -> -1).
-  return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f);
+  return fmaf(-2.0f, rcp_approx1(ex2_approx(2.8853900817779268f * x) + 1.0f), 1.0f);
 }
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {

@@ -501,6 +501,199 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   }
 }
 
+// ---- the four highway layers of a CBHG in ONE kernel (reference models/modules.py:63-64, 79-89) -------------------------
+// highwaynet x 4 on [rows, 128]: y = relu(x W_H + b_H) T + x (1 - T), T = sigmoid(x W_T + b_T), four times.  As four
+// conv_umma launches (+ four hi/lo split passes) the 16 MB activation made eight HBM / L2 round trips and every launch paid its
+// own pipeline fill (25.7 us each for 2.1 GF).  Here a CTA owns 128 rows for all layers: the activation lives in the epilogue
+// threads' REGISTERS (one row x 64 channels per thread, two threads per row), is re-written as bf16 hi / lo operand tiles in
+// shared memory (128-byte swizzle, K-major: what TMA would have produced) for the next layer's tcgen05.mma, and only the weights
+// (128 KB per layer, hi + lo, L2 resident) stream in by TMA -- prefetched during the previous layer's epilogue.
+struct Hw4Args {
+  const float* x; float* out;          // [rows][128] fp32, dense (out nullable: only the bf16 copy is wanted)
+  void* out_hi; void* out_lo;          // optional bf16 hi / lo copy of the result [rows][128] (operand of the next GEMM), or null
+  const float* bias[4];                // per layer [256], interleaved (b_H[c], b_T[c])
+  int rows, layers, ntiles;
+};
+constexpr uint32_t HW_A_BYTES = 4 * TILE_BYTES;                  // A_hi kb0 | A_hi kb1 | A_lo kb0 | A_lo kb1   (64 KB)
+constexpr uint32_t HW_BSTAGE = 4 * TILE_BYTES;                   // per k-block: B_hi (256 x 64, 32 KB) | B_lo (32 KB)
+constexpr uint32_t HW_SMEM = 1024u + HW_A_BYTES + 2 * HW_BSTAGE + 256u;
+constexpr int HW_THREADS = 64 + 16 * 32;                       // TMA warp, MMA warp, sixteen epilogue warps
+
+// (a, b) -> packed bf16 hi pair (return) and lo pair.  One packed conversion (F2FP, FMA pipe) per pair instead of two scalar
+// F2F on the XU pipe, which the sigmoids' EX2 / RCP already saturate (ncu: mio_throttle on the conversions).
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, uint32_t& lo_out) {
+  uint32_t hi;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));      // upper half <- first source
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo_out) : "f"(rb), "f"(ra));
+  return hi;
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(HW_THREADS, 1)
+highway4_kernel(const __grid_constant__ CUtensorMap tmB, const Hw4Args p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_base = smem_base, b_base = smem_base + HW_A_BYTES;
+  const uint32_t bar0 = b_base + 2 * HW_BSTAGE;                    // b_full[2], b_empty[2], a_ready, acc_full, tmem slot
+  auto b_full = [&](int kb) { return bar0 + 8u * kb; };
+  auto b_empty = [&](int kb) { return bar0 + 16u + 8u * kb; };
+  const uint32_t a_ready = bar0 + 32u;
+  auto acc_full = [&](int half) { return bar0 + 40u + 8u * half; };   // accumulator columns 128 half .. 128 half + 127 complete
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + HW_A_BYTES + 2 * HW_BSTAGE + 56);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int kb = 0; kb < 2; ++kb) { mbar_init(b_full(kb), 1); mbar_init(b_empty(kb), 1); }
+    mbar_init(a_ready, HW_THREADS - 64);                              // every epilogue thread arrives
+    mbar_init(acc_full(0), 1); mbar_init(acc_full(1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32((const void*)tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: the layer's W^T (hi, lo), one k-block of 64 inputs per stage =====================
+    if (lane == 0) {
+      int n = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
+        for (int l = 0; l < p.layers; ++l, ++n)
+          for (int kb = 0; kb < 2; ++kb) {
+            mbar_wait(b_empty(kb), (n & 1) ^ 1);
+            const uint32_t st = b_base + kb * HW_BSTAGE;
+            mbar_expect_tx(b_full(kb), NSPLIT > 1 ? HW_BSTAGE : HW_BSTAGE / 2);
+            tma_load_3d(st, &tmB, b_full(kb), kb * BK, 0, 2 * l);
+            if (NSPLIT > 1) tma_load_3d(st + 2 * TILE_BYTES, &tmB, b_full(kb), kb * BK, 0, 2 * l + 1);
+          }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: D[128 x 256] = A[128 x 128] W[128 x 256], three products per k-step =====================
+    if (lane == 0) {
+      // The 256 accumulator columns are produced as two halves of 128 (channels 0-63, then 64-127), each with its own commit: the
+      // epilogue warps of the first half run while the tensor core works on the second.
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int n = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
+        for (int l = 0; l < p.layers; ++l, ++n) {
+          mbar_wait(a_ready, n & 1);                                  // operand tiles written, accumulator drained
+          tc_fence_after();
+          for (int half = 0; half < 2; ++half) {
+            for (int kb = 0; kb < 2; ++kb) {
+              if (half == 0) { mbar_wait(b_full(kb), n & 1); tc_fence_after(); }
+              const uint64_t a_hi = umma_desc(a_base + kb * TILE_BYTES), a_lo = umma_desc(a_base + (2 + kb) * TILE_BYTES);
+              const uint32_t brow = (uint32_t)half * 128u * 128u;      // weight rows 128 half ..: 128 rows x 128 bytes into the tile
+              const uint64_t b_hi = umma_desc(b_base + kb * HW_BSTAGE + brow), b_lo = umma_desc(b_base + kb * HW_BSTAGE + 2 * TILE_BYTES + brow);
+#pragma unroll
+              for (int kk = 0; kk < BK / 16; ++kk) {
+                const uint64_t adv = (uint64_t)(kk * 32 >> 4);
+                umma_bf16(tmem_base + (uint32_t)half * 128u, a_hi + adv, b_hi + adv, idesc, (kb | kk) != 0);
+                if (NSPLIT > 1) {
+                  umma_bf16(tmem_base + (uint32_t)half * 128u, a_hi + adv, b_lo + adv, idesc, 1u);
+                  umma_bf16(tmem_base + (uint32_t)half * 128u, a_lo + adv, b_hi + adv, idesc, 1u);
+                }
+              }
+              if (half == 1) umma_commit(b_empty(kb));                // weights of this k-block consumed: the next layer's may land
+            }
+            umma_commit(acc_full(half));
+          }
+        }
+    }
+  } else {
+    // ===================== epilogue warps 2..17: the activation in registers, gate math, operand tiles =====================
+    // Sixteen warps (four per TMEM lane quarter, 32 channels each): the gate math is latency bound (EX2 -> RCP chains), four warps
+    // per scheduler hide it better than two (8 warps x 64 channels: 55.7 us for the post-net's 250 tiles).
+    const int quarter = warp & 3, part = (warp - 2) >> 2;             // TMEM lane quarter; channels 32 part .. 32 part + 31
+    const int hf = part >> 1, j0 = (part & 1) * 4;                    // k-block of those channels, first 16-byte chunk inside its rows
+    const int r = quarter * 32 + lane;                                // row of the tile = TMEM lane
+    const uint32_t a_row = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+    auto write_operands = [&](const float (&x)[32]) {
+      const uint32_t hi_t = a_base + hf * TILE_BYTES + a_row, lo_t = a_base + (2 + hf) * TILE_BYTES + a_row;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = j0 + jj;
+        uint4 h4, l4;
+        h4.x = pack_bf16x2(x[8 * jj + 0], x[8 * jj + 1], l4.x); h4.y = pack_bf16x2(x[8 * jj + 2], x[8 * jj + 3], l4.y);
+        h4.z = pack_bf16x2(x[8 * jj + 4], x[8 * jj + 5], l4.z); h4.w = pack_bf16x2(x[8 * jj + 6], x[8 * jj + 7], l4.w);
+        const uint32_t off = (uint32_t)((j ^ (r & 7)) << 4);          // 128-byte swizzle: 16-byte chunk j of row r sits at j ^ (r % 8)
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(hi_t + off), "r"(h4.x), "r"(h4.y), "r"(h4.z), "r"(h4.w) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(lo_t + off), "r"(l4.x), "r"(l4.y), "r"(l4.z), "r"(l4.w) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's async proxy
+      tc_fence_before();
+      mbar_arrive(a_ready);
+    };
+    int n = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const long long row = (long long)tile * BM + r;
+      const bool rok = row < p.rows;
+      float x[32];
+      {
+        const float4* src = reinterpret_cast<const float4*>(p.x + row * 128 + part * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v4 = rok ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          x[4 * i] = v4.x; x[4 * i + 1] = v4.y; x[4 * i + 2] = v4.z; x[4 * i + 3] = v4.w;
+        }
+      }
+      write_operands(x);
+      for (int l = 0; l < p.layers; ++l, ++n) {
+        mbar_wait(acc_full(hf), n & 1);
+        tc_fence_after();
+        const float* bias = p.bias[l] + part * 64;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(part * 64 + ch * 32), v);
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float4 b4 = ldg_f4(bias + ch * 32 + 2 * i);         // (b_H, b_T) of channels i, i + 1
+            const float H0 = fmaxf(__uint_as_float(v[2 * i]) + b4.x, 0.f), T0 = sigmoid_f(__uint_as_float(v[2 * i + 1]) + b4.y);
+            const float H1 = fmaxf(__uint_as_float(v[2 * i + 2]) + b4.z, 0.f), T1 = sigmoid_f(__uint_as_float(v[2 * i + 3]) + b4.w);
+            x[ch * 16 + i] = fmaf(T0, H0 - x[ch * 16 + i], x[ch * 16 + i]);              // H T + x (1 - T)
+            x[ch * 16 + i + 1] = fmaf(T1, H1 - x[ch * 16 + i + 1], x[ch * 16 + i + 1]);
+          }
+        }
+        if (l + 1 < p.layers) write_operands(x);                      // next layer's A operand (also releases the accumulator)
+      }
+      // results: fp32 rows (and, for the GEMM that follows, their bf16 hi / lo split)
+      if (rok) {
+        if (p.out != nullptr) {
+          float4* dst = reinterpret_cast<float4*>(p.out + row * 128 + part * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dst[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+        }
+        if (p.out_hi != nullptr) {
+          uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out_hi) + row * 128 + part * 32);
+          uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out_lo) + row * 128 + part * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 h4, l4;
+            h4.x = pack_bf16x2(x[8 * j + 0], x[8 * j + 1], l4.x); h4.y = pack_bf16x2(x[8 * j + 2], x[8 * j + 3], l4.y);
+            h4.z = pack_bf16x2(x[8 * j + 4], x[8 * j + 5], l4.z); h4.w = pack_bf16x2(x[8 * j + 6], x[8 * j + 7], l4.w);
+            dh[j] = h4; dl[j] = l4;
+          }
+        }
+      }
+      // the accumulator of this tile's last layer has been read: the first layer of the next tile may overwrite it (its
+      // a_ready arrival comes from write_operands at the top of the loop, after tc_fence_before)
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+  }
+}
+
 // fp32 -> bf16 hi + bf16 lo (x ~= hi + lo), channels zero-padded to Cp.
 __global__ void __launch_bounds__(256)
 split_bf16_kernel(const float* __restrict__ x, long long x_bs, int ldx, int N, int T, int C, int Cp,
@@ -726,6 +919,46 @@ cudaError_t launch_conv_umma(const ConvUmma& c, cudaStream_t st) {
   }
   const int nthreads = 64 + 32 * p.epi_warps;
   kernels[split ? 0 : 1][ev]<<<grid, nthreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  return cudaGetLastError();
+}
+
+// Four (or fewer) highway layers in one launch.  w_hi: the layers' W^T hi / lo matrices, [layer][hi|lo][256][128] bf16, contiguous.
+cudaError_t launch_highway4(const float* x, float* out, void* out_hi, void* out_lo, const void* w_hi, const float* const* bias,
+                            int layers, long long rows, int nsplit, cudaStream_t st) {
+  if (rows <= 0 || layers <= 0) return cudaSuccess;
+  if (layers > 4 || rows > 0x7fffffffLL) return cudaErrorInvalidValue;
+  CUtensorMap mb;
+  {
+    const MapKey k{w_hi, 128u, 256u, (uint64_t)(2 * layers), 33u};
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_maps.find(k);
+    if (it != g_maps.end()) mb = it->second;
+    else {
+      const cuuint64_t dims[3] = {128, 256, (cuuint64_t)(2 * layers)};
+      const cuuint64_t str[2] = {128 * 2, 256 * 128 * 2};
+      const cuuint32_t box[3] = {BK, 256, 1};
+      if (!make_map(&mb, w_hi, 3, dims, str, box)) return cudaErrorInvalidValue;
+      g_maps.emplace(k, mb);
+    }
+  }
+  Hw4Args p;
+  p.x = x; p.out = out; p.out_hi = out_hi; p.out_lo = out_lo;
+  for (int i = 0; i < 4; ++i) p.bias[i] = bias[i < layers ? i : 0];
+  p.rows = (int)rows; p.layers = layers; p.ntiles = (int)((rows + BM - 1) / BM);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  static bool attr_done[64] = {false};
+  if (!attr_done[dev & 63]) {
+    cudaError_t e1 = cudaFuncSetAttribute(highway4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HW_SMEM);
+    cudaError_t e2 = cudaFuncSetAttribute(highway4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HW_SMEM);
+    if (e1 != cudaSuccess) return e1;
+    if (e2 != cudaSuccess) return e2;
+    attr_done[dev & 63] = true;
+  }
+  const int grid = p.ntiles < sms ? p.ntiles : sms;
+  if (nsplit > 1) highway4_kernel<3><<<grid, HW_THREADS, HW_SMEM, st>>>(mb, p);
+  else highway4_kernel<1><<<grid, HW_THREADS, HW_SMEM, st>>>(mb, p);
   return cudaGetLastError();
 }
 

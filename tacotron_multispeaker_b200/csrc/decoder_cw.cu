@@ -175,9 +175,12 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
 // reducer thread (n, c) holds v = activation [n][16q + c]: split into bf16 hi/lo, pair with the neighbouring column (lane ^ 1)
 // and write the two words of the pair into the staged row `stg_n` (MMA B-fragment order).  Executed by whole warps.
 __device__ __forceinline__ void stage_x(uint32_t stg_n, int c, float v) {
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-  const uint32_t hv = __bfloat16_as_ushort(h), lv = __bfloat16_as_ushort(l);
+  // packed conversions (F2FP on the FMA pipe) instead of two scalar F2F on the XU pipe: same round-to-nearest results
+  uint32_t hp, lp;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %1;" : "=r"(hp) : "f"(v));
+  const uint32_t hv = hp & 0xffffu;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %1;" : "=r"(lp) : "f"(v - __uint_as_float(hv << 16)));
+  const uint32_t lv = lp & 0xffffu;
   const uint32_t hn = __shfl_xor_sync(0xffffffffu, hv, 1), ln = __shfl_xor_sync(0xffffffffu, lv, 1);
   if ((c & 1) == 0) {
     const uint32_t wa = stg_n + (uint32_t)((((c & 7) >> 1) * 4 + (c >> 3)) * 4);

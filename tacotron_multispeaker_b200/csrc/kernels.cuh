@@ -50,6 +50,11 @@ struct ConvUmma {
   int act, epi;
 };
 cudaError_t launch_conv_umma(const ConvUmma& c, cudaStream_t st);
+// The highway layers of a CBHG (reference modules.py:63-64, 79-89) in one launch: x, out [rows][128] fp32 dense; w_hi = the layers'
+// W^T hi / lo matrices [layer][hi|lo][256][128] bf16 (contiguous, columns interleaved (H_c, T_c)); bias[l] = [256] interleaved.
+// out_hi / out_lo (nullable): bf16 hi / lo copy of the result for the GEMM that follows.
+cudaError_t launch_highway4(const float* x, float* out, void* out_hi, void* out_lo, const void* w_hi, const float* const* bias,
+                            int layers, long long rows, int nsplit, cudaStream_t st);
 // x [N,T,C] fp32 (batch stride x_bs, row stride ldx) -> hi/lo bf16 [N][T][Cp], zero padded channels.
 void launch_split_bf16(const float* x, int64_t x_bs, int ldx, int N, int T, int C, int Cp, void* hi, void* lo,
                        cudaStream_t st);

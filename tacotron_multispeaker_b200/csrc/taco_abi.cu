@@ -629,19 +629,35 @@ void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, 
          (int64_t)T * 128, 128, 0, TACO_ACT_NONE);
     hin = hwb;
   }
-  // 4 highway layers (modules.py:63-64)
-  float* bufs[2] = {hwa, hwb};
-  int cur = 0;   // first output goes to hwa (hin is p2 or hwb)
-  for (int i = 0; i < 4; ++i) {
-    float* o = bufs[cur];
-    gemm(c, D.g_hw[i], sc, hin, (int64_t)T * 128, 128, N, T, c.W(D.hw_b[i]), nullptr, nullptr, hin, (int64_t)T * 128,
-         128, o, (int64_t)T * 128, 128, 0, TACO_ACT_NONE, EPI_HIGHWAY);
-    hin = o;
-    cur ^= 1;
+  // 4 highway layers (modules.py:63-64): one fused launch on the tensor-core path (the activation stays in registers, the result
+  // comes out as the hi / lo operand of the GRU input projection), four GEMM launches otherwise
+  static const bool hw_fuse_env = [] { const char* e = getenv("TACO_HW_FUSE"); return !(e && atoi(e) == 0); }();
+  bool hw_contig = c.h->gemm_mode != 0 && hw_fuse_env && D.g_xproj.Cp == 128;
+  for (int i = 0; i < 3 && hw_contig; ++i) hw_contig = D.g_hw[i + 1].bt == D.g_hw[i].bt + (size_t)2 * 256 * 128;
+  bool xproj_presplit = false;
+  if (hw_contig) {
+    const float* hb[4] = {c.W(D.hw_b[0]), c.W(D.hw_b[1]), c.W(D.hw_b[2]), c.W(D.hw_b[3])};
+    cudaError_t e = launch_highway4(hin, nullptr, sc.hi, sc.lo, c.h->dB + D.g_hw[0].bt, hb, 4, rows, c.h->gemm_mode == 2 ? 1 : 3, c.st);
+    if (e != cudaSuccess) {
+      if (!c.h->launch_failed) c.h->err = std::string("highway4 launch: ") + cudaGetErrorString(e);
+      c.h->launch_failed = true;
+    }
+    c.h->launches += 1;
+    xproj_presplit = true;
+  } else {
+    float* bufs[2] = {hwa, hwb};
+    int cur = 0;   // first output goes to hwa (hin is p2 or hwb)
+    for (int i = 0; i < 4; ++i) {
+      float* o = bufs[cur];
+      gemm(c, D.g_hw[i], sc, hin, (int64_t)T * 128, 128, N, T, c.W(D.hw_b[i]), nullptr, nullptr, hin, (int64_t)T * 128,
+           128, o, (int64_t)T * 128, 128, 0, TACO_ACT_NONE, EPI_HIGHWAY);
+      hin = o;
+      cur ^= 1;
+    }
   }
   // hoisted GRU input projection for both directions, then the recurrence
   gemm(c, D.g_xproj, sc, hin, (int64_t)T * 128, 128, N, T, c.W(D.gru_bx), nullptr, nullptr, nullptr, 0, 0, xproj,
-       (int64_t)T * 768, 768, 0, TACO_ACT_NONE);
+       (int64_t)T * 768, 768, 0, TACO_ACT_NONE, EPI_PLAIN, xproj_presplit);
   run_bigru(c, D, xproj, lengths, N, T, out, (int64_t)T * 256);
 }
 
