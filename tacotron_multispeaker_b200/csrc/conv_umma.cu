@@ -516,7 +516,7 @@ struct Hw4Args {
 };
 constexpr uint32_t HW_A_BYTES = 4 * TILE_BYTES;                  // A_hi kb0 | A_hi kb1 | A_lo kb0 | A_lo kb1   (64 KB)
 constexpr uint32_t HW_BSTAGE = 4 * TILE_BYTES;                   // per k-block: B_hi (256 x 64, 32 KB) | B_lo (32 KB)
-constexpr uint32_t HW_SMEM = 1024u + HW_A_BYTES + 2 * HW_BSTAGE + 256u;
+constexpr uint32_t HW_SMEM = 1024u + HW_A_BYTES + 2 * HW_BSTAGE + 256u + 4 * 256 * 4;   // + the four layers' biases
 constexpr int HW_THREADS = 64 + 16 * 32;                       // TMA warp, MMA warp, sixteen epilogue warps
 
 // (a, b) -> packed bf16 hi pair (return) and lo pair.  One packed conversion (F2FP, FMA pipe) per pair instead of two scalar
@@ -543,6 +543,8 @@ highway4_kernel(const __grid_constant__ CUtensorMap tmB, const Hw4Args p) {
   auto acc_full = [&](int half) { return bar0 + 40u + 8u * half; };   // accumulator columns 128 half .. 128 half + 127 complete
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + HW_A_BYTES + 2 * HW_BSTAGE + 56);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* bias_s = reinterpret_cast<float*>(smem_al + HW_A_BYTES + 2 * HW_BSTAGE + 256);   // [4 layers][256] (b_H, b_T) interleaved
+  for (int i = threadIdx.x; i < p.layers * 256; i += HW_THREADS) bias_s[i] = __ldg(p.bias[i >> 8] + (i & 255));
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
@@ -647,14 +649,14 @@ highway4_kernel(const __grid_constant__ CUtensorMap tmB, const Hw4Args p) {
       for (int l = 0; l < p.layers; ++l, ++n) {
         mbar_wait(acc_full(hf), n & 1);
         tc_fence_after();
-        const float* bias = p.bias[l] + part * 64;
+        const float* bias = bias_s + l * 256 + part * 64;
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(part * 64 + ch * 32), v);
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
-            const float4 b4 = ldg_f4(bias + ch * 32 + 2 * i);         // (b_H, b_T) of channels i, i + 1
+            const float4 b4 = *reinterpret_cast<const float4*>(bias + ch * 32 + 2 * i);   // (b_H, b_T) of channels i, i + 1
             const float H0 = fmaxf(__uint_as_float(v[2 * i]) + b4.x, 0.f), T0 = sigmoid_f(__uint_as_float(v[2 * i + 1]) + b4.y);
             const float H1 = fmaxf(__uint_as_float(v[2 * i + 2]) + b4.z, 0.f), T1 = sigmoid_f(__uint_as_float(v[2 * i + 3]) + b4.w);
             x[ch * 16 + i] = fmaf(T0, H0 - x[ch * 16 + i], x[ch * 16 + i]);              // H T + x (1 - T)
