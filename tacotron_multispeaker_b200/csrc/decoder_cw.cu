@@ -554,8 +554,7 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       if (free_run && step > 0) {
         late(XADDR(XY2 + 4 * gw), 4);
         tload(TC_P2, 4);
-        nb_sync(NB_CRIT, 128);
-        late1 = true;
+        late1 = true;                        // (the handoff barrier below counts the critical threads too: no NB_CRIT sync needed)
       }
       TRM(50); nb_sync(NB_H1, 256); TRM(51);
       {
@@ -581,7 +580,6 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       // ================= P3: attention GRU reset gate on [prenet | h_att]; r * h_att goes out ====
       late(XADDR(XP2 + 2 * gw), 2);
       tload(TC_P4, 4);
-      nb_sync(NB_CRIT, 128);
       TRM(52); nb_sync(NB_H3, 256); TRM(53);
       stage_x(stg_n, rc, sigmoid_f(sum4(red_nc, SL_CRIT) + sum4(red_nc, SL_RE0) + BIAS(BI_RA)) * st_ha);
       send_rows(OFF_X + (uint32_t)(XRA + q) * csb, MB_P3, false);
@@ -592,7 +590,6 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       // ================= P4: candidate; h_att' = u h + (1-u) tanh(c_h + c_x + b) ====
       late(XADDR(XRA + 4 * gw), 4);
       tload(TC_P5, 4);
-      nb_sync(NB_CRIT, 128);
       TRM(54); nb_sync(NB_H4, 384); TRM(55);
       {
         const float u = sigmoid_f(sum4(red_nc, SL_U) + BIAS(BI_UA));
@@ -667,7 +664,6 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       // ================= P9: GRU-1 reset gate on [h_att' | ctx'] (512->256 projection folded in) and h1 ====
       late(XADDR(XC + 4 * gw), 4);
       tload(TC_P10, 4);
-      nb_sync(NB_CRIT, 128);
       TRM(56); nb_sync(NB_H9, 256); TRM(57);
       stage_x(stg_n, rc, sigmoid_f(sum4(red_nc, SL_CRIT) + sum4(red_nc, SL_RE1) + BIAS(BI_R1)) * st_h1);
       send_rows(OFF_X + (uint32_t)(XR1 + q) * csb, MB_P9, false);
@@ -690,7 +686,6 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       // ================= P10: GRU-1 candidate, h1' ====
       late(XADDR(XR1 + 4 * gw), 4);
       tload(TC_P11, 4);
-      nb_sync(NB_CRIT, 128);
       TRM(58); nb_sync(NB_H10, 512); TRM(59);
       {
         const float u = sigmoid_f(sum4(red_nc, SL_U) + BIAS(BI_U1));
@@ -711,7 +706,6 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       late(XADDR(XY1 + 4 * gw), 4);
       TRM(45);
       tload(TC_P12, 4);
-      nb_sync(NB_CRIT, 128);
       TRM(46);
       TRM(60); nb_sync(NB_H11, 256); TRM(61);
       stage_x(stg_n, rc, sigmoid_f(sum4(red_nc, SL_CRIT) + sum4(red_nc, SL_RE2) + BIAS(BI_R2)) * st_h2);
@@ -725,7 +719,6 @@ decoder_cw_kernel(const __grid_constant__ Args w, const __grid_constant__ Progra
       // ================= P12: GRU-2 candidate, h2' ====
       late(XADDR(XR2 + 4 * gw), 4);
       if (free_run) tload(TC_P1, 4); else tload(TC_P2, 4);
-      nb_sync(NB_CRIT, 128);
       TRM(62); nb_sync(NB_H12, 384); TRM(63);
       {
         const float u = sigmoid_f(sum4(red_nc, SL_U) + BIAS(BI_U2));
