@@ -126,6 +126,7 @@ struct taco_handle {
   };
   struct FwdGraph { FwdKey key; bool have_key = false; cudaGraphExec_t exec = nullptr; int64_t launches = 0; } fwd_graph;
   bool graphs_on = true;
+  bool dev_env = false;   // TACO_DEV=1 at taco_create: the per-call developer switches below are read from the environment; otherwise no getenv on the forward path
   // the vocoder's ~105 launches per call likewise (key: arguments, workspace, stream)
   struct GlKey { GriffinLimArgs a; const void* ws; void* stream; };
   struct GlGraph { GlKey key; bool have_key = false; cudaGraphExec_t exec = nullptr; int launches = 0; } gl_graph;
@@ -549,7 +550,7 @@ void gemm(Ctx& c, const GemmW& g, const BfScratch& sc, const float* x, int64_t x
 // tensor-core kernel (8 utterances per CTA, weights in tensor memory: 8 CTAs instead of 64 for a batch of 32, but
 // 1.8 us instead of 0.8 us per step as it stands -- its epilogues and the tensor pipe do not overlap yet).
 void run_bigru(Ctx& c, const CbhgDev& D, const float* xproj, const int32_t* lengths, int N, int T, float* out, int64_t out_bs) {
-  const char* impl = getenv("TACO_BIGRU");   // read per call: the parity tests run both
+  const char* impl = c.h->dev_env ? getenv("TACO_BIGRU") : nullptr;   // developer switch (TACO_DEV=1): the parity tests run both
   const bool use_mma = impl && std::string(impl) == "mma";
   if (use_mma) {
     cudaError_t e = launch_bigru_mma(xproj, c.W(D.gru_frag), lengths, N, T, out, out_bs, c.st);
@@ -669,9 +670,9 @@ void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, 
 // per-wave time grows with the samples per cluster (exchange bytes), roughly 1 + 0.1 S.
 int pick_mma_clusters(const taco_handle* h, int N) {
   if (h->dec_clusters > 0) return std::min(N, std::max(h->dec_clusters, (N + 7) / 8));
-  const char* en = getenv("TACO_DEC_NCL");
+  const char* en = h->dev_env ? getenv("TACO_DEC_NCL") : nullptr;
   if (en && atoi(en) > 0) return std::min(N, std::max(atoi(en), (N + 7) / 8));
-  const char* es = getenv("TACO_DEC_S");   // samples per cluster (tests sweep it)
+  const char* es = h->dev_env ? getenv("TACO_DEC_S") : nullptr;   // samples per cluster (tests sweep it; TACO_DEV=1)
   if (es && atoi(es) > 0) return (N + std::min(atoi(es), 8) - 1) / std::min(atoi(es), 8);
   const int maxc = std::max(1, h->max_clusters_mma);
   float best = 1e30f;
@@ -689,7 +690,7 @@ int pick_mma_clusters(const taco_handle* h, int N) {
 void pick_geometry(const taco_handle* h, int N, int* cs_out, int* s_out) {
   static const float t_wave[2][4] = {{12.3f, 15.6f, 20.2f, 35.2f},    // CS = 8 : S = 1,2,4,8
                                      {11.2f, 12.7f, 15.5f, 25.6f}};   // CS = 16
-  const char* es = getenv("TACO_DEC_S");
+  const char* es = h->dev_env ? getenv("TACO_DEC_S") : nullptr;
   const int force_s = es ? atoi(es) : 0;
   float best = 1e30f;
   int bcs = 16, bs = 8;
@@ -779,7 +780,7 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
   a.memory = memory; a.keys = keys; a.targets = teacher_force ? mel_targets : nullptr;
   a.N = N; a.T_in = T_in; a.T_tgt = T_tgt; a.r = hp.outputs_per_step; a.steps = max_steps; a.max_steps = max_steps;
   a.dec_out = dec_out; a.align_out = align_out; a.att_res = 0; a.s_max = 0; a.trace = nullptr; a.trace_cta = 0; a.trace_warp = 8;
-  const char* trace_path = getenv("TACO_DEC_TRACE");   // developer aid: per-phase clock stamps of CTA 0
+  const char* trace_path = h->dev_env ? getenv("TACO_DEC_TRACE") : nullptr;   // developer aid (TACO_DEV=1): per-phase clock stamps of one CTA
   long long* d_trace = nullptr;
   if (trace_path) {
     cudaMalloc(&d_trace, 512 * sizeof(long long));
@@ -790,7 +791,7 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
   }
   int CS = 16, S = 8;
   pick_geometry(h, N, &CS, &S);
-  if (getenv("TACO_DEBUG"))
+  if (h->dev_env && getenv("TACO_DEBUG"))
     fprintf(stderr, "[taco] decode N=%d T_in=%d steps=%d CS=%d S=%d kernel=%s max_clusters(8)=%d (16)=%d\n", N, T_in,
             max_steps, CS, S, h->use_cw ? "cw" : "v2", h->max_clusters[0], h->max_clusters[1]);
   if (h->profiling) cudaEventRecord(h->ev[4], st);
@@ -885,6 +886,8 @@ int taco_create(const taco_hparams* hp, int device, taco_handle** out) {
     h->blocking = bs && atoi(bs) != 0;
     const char* gr = getenv("TACO_GRAPHS");
     h->graphs_on = !(gr && atoi(gr) == 0);
+    const char* dv = getenv("TACO_DEV");
+    h->dev_env = dv && atoi(dv) != 0;
     const unsigned flags = cudaEventDisableTiming | (h->blocking ? cudaEventBlockingSync : 0u);
     cudaEventCreateWithFlags(&h->ev_compute, flags);
     cudaEventCreateWithFlags(&h->ev_decoder, flags);
@@ -1244,7 +1247,7 @@ static int forward_impl(taco_handle* h, const int32_t* ids, const int32_t* lengt
   key.N = N; key.T_in = T_in; key.T_tgt = T_tgt; key.bn = bn_mode; key.tf = teacher_force; key.gemm_mode = h->gemm_mode;
   key.dec_clusters = h->dec_clusters; key.defer = defer_final ? 1 : 0;
   const bool graph_ok = h->graphs_on && !h->profiling && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread &&
-                        getenv("TACO_DEC_TRACE") == nullptr && getenv("TACO_DEBUG") == nullptr;
+                        !(h->dev_env && (getenv("TACO_DEC_TRACE") != nullptr || getenv("TACO_DEBUG") != nullptr));
   auto& G = h->fwd_graph;
   bool capture = false, replayed = false;
   if (!graph_ok || !G.have_key || !(G.key == key)) {

@@ -1,6 +1,8 @@
 import os
 import sys
 
+os.environ.setdefault("TACO_DEV", "1")   # the C ABI reads its per-call developer switches (TACO_DEC_S, TACO_BIGRU, ...) only then
+
 import numpy as np
 import pytest
 

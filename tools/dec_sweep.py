@@ -1,5 +1,6 @@
 """Developer aid: decoder time per step over (cluster size, samples per cluster)."""
 import os, sys, time
+os.environ.setdefault("TACO_DEV", "1")   # per-call developer switches of the C ABI
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

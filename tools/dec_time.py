@@ -1,5 +1,6 @@
 """Developer aid: decoder kernel time per step for a few geometries and implementations (TACO_DEC_IMPL)."""
 import os, sys
+os.environ.setdefault("TACO_DEV", "1")   # per-call developer switches of the C ABI
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -1,6 +1,7 @@
 """Developer aid: per-phase clock stamps of decoder_cw_kernel (TACO_DEC_TRACE): critical warp 12 stamps 0..22, background
 warps stamp 64+w (items before the attention phases done), 80+w (attention phases done), 96+w (items after them done)."""
 import os, sys
+os.environ.setdefault("TACO_DEV", "1")   # per-call developer switches of the C ABI
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -6,6 +6,7 @@ import os
 import sys
 import time
 import traceback
+os.environ.setdefault("TACO_DEV", "1")   # per-call developer switches of the C ABI
 
 import numpy as np
 import torch
