@@ -17,7 +17,7 @@ ids, lengths, spk = make_inputs(N, T_in, 60, 1, min_len=60, vocab=(7108, 7325))
 t0 = time.time()
 ref = O.tacotron_forward(w, hp, ids, lengths, identities=spk, id_num=60)
 print("oracle %.2fs steps=%d" % (time.time() - t0, ref["steps"]), flush=True)
-for impl in ("mma", "v2"):
+for impl in ("cw", "v2"):
     os.environ["TACO_DEC_IMPL"] = impl
     eng = Engine(hp, 60); eng.load_weights(w)
     mel, lin, al, s = eng.forward(ids, lengths, spk)
