@@ -39,7 +39,7 @@ def run(impl, N, T_in, S, iters=200, teacher=False):
 
 
 if __name__ == "__main__":
-    impls = os.environ.get("IMPLS", "cw,mma").split(",")
+    impls = os.environ.get("IMPLS", "cw").split(",")   # "cw,v2": also the fp32 FFMA decoder (TACO_DEC_IMPL is read at taco_finalize_weights)
     for impl in impls:
         run(impl, 32, 100, 5)
         run(impl, 32, 100, 8)
