@@ -170,6 +170,16 @@ int taco_bigru(taco_handle* h, int which, const float* x, const int32_t* lengths
 int taco_conv1d(taco_handle* h, const float* x, int N, int T, int Cin, const float* kernel,
                 const float* bias, int k, int Cout, int act, float* out, void* stream);
 
+/* The two helper operators inside cbhg() that have no stage of their own, for unit parity:
+ * tf.layers.max_pooling1d(pool_size=2, strides=1, padding='same') (modules.py:45-49) applied to scale[c] * x + shift[c]
+ * (the folded batch-norm affine of the conv bank; NULL scale / shift = identity): x, out [N,T,C], C % 4 == 0; */
+int taco_maxpool_affine(taco_handle* h, const float* x, int N, int T, int C, const float* scale,
+                        const float* shift, float* out, void* stream);
+/* and the training-mode statistics of tf.layers.batch_normalization (modules.py:101, is_training): biased moments of x [N,T,C]
+ * over (N,T), folded with gamma / beta / epsilon 1e-3 into scale_out[c], shift_out[c] so that BN(x) = scale x + shift. C <= 2048. */
+int taco_bn_batch_stats(taco_handle* h, const float* x, int N, int T, int C, const float* gamma,
+                        const float* beta, float* scale_out, float* shift_out, void* stream);
+
 /* ---- vocoder: the step right after the path ----------- */
 /* Fields of reference hparams.py:13-18,35-36 that util/audio.py reads. */
 typedef struct taco_audio_params {

@@ -32,7 +32,7 @@ SYMBOLS = [
     "taco_max_steps", "taco_forward", "taco_forward_host", "taco_forward_host_begin", "taco_forward_host_wait",
     "taco_forward_host_end",
     "taco_embed", "taco_check_ids", "taco_encoder", "taco_decode", "taco_cbhg", "taco_postnet",
-    "taco_bigru", "taco_conv1d",
+    "taco_bigru", "taco_conv1d", "taco_maxpool_affine", "taco_bn_batch_stats",
     "taco_set_gemm_mode", "taco_launch_count", "taco_decoder_geometry", "taco_set_decoder_clusters", "taco_set_profiling", "taco_last_stage_ms", "taco_set_cuda_graphs",
     "taco_wav_length", "taco_griffin_lim",
 ]
@@ -101,6 +101,8 @@ def load() -> C.CDLL:
     lib.taco_postnet.argtypes = [H, fp, i, i, i, i64, fp, i64, vp]
     lib.taco_bigru.argtypes = [H, i, fp, ip, i, i, fp, vp]
     lib.taco_conv1d.argtypes = [H, fp, i, i, i, fp, fp, i, i, i, fp, vp]
+    lib.taco_maxpool_affine.argtypes = [H, fp, i, i, i, fp, fp, fp, vp]
+    lib.taco_bn_batch_stats.argtypes = [H, fp, i, i, i, fp, fp, fp, fp, vp]
     lib.taco_set_gemm_mode.argtypes = [H, i]
     lib.taco_launch_count.argtypes = [H]
     lib.taco_launch_count.restype = i64

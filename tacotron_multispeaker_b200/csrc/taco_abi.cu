@@ -1207,6 +1207,30 @@ int taco_conv1d(taco_handle* h, const float* x, int N, int T, int Cin, const flo
 }
 
 // Post-net again on the true length after an early stop (the all-zero frame case): rare, synchronous.
+// ---- unit entry points for the two helper kernels of the CBHG that have no stage of their own --------------------------------
+int taco_maxpool_affine(taco_handle* h, const float* x, int N, int T, int C, const float* scale, const float* shift, float* out,
+                        void* stream) {
+  REQUIRE_READY(h);
+  if (!x || !out || N <= 0 || T <= 0 || C <= 0 || (C & 3) || ((scale == nullptr) != (shift == nullptr)))
+    return fail(h, TACO_ERR_INVALID, "bad argument");
+  launch_affine_maxpool(x, out, N, T, C, scale, shift, (cudaStream_t)stream);
+  h->launches += 1;
+  return check_launch(h, "maxpool_affine");
+}
+
+int taco_bn_batch_stats(taco_handle* h, const float* x, int N, int T, int C, const float* gamma, const float* beta,
+                        float* scale_out, float* shift_out, void* stream) {
+  REQUIRE_READY(h);
+  if (!x || !gamma || !beta || !scale_out || !shift_out || N <= 0 || T <= 0 || C <= 0 || C > 2048)
+    return fail(h, TACO_ERR_INVALID, "bad argument");
+  int rc = ensure_ws(h, sizeof(double) * 2 * 2048 + 256);
+  if (rc) return rc;
+  launch_bn_batch_stats(x, (int64_t)T * C, C, 0, N, T, C, gamma, beta, kBnEps, reinterpret_cast<double*>(h->ws), scale_out, shift_out,
+                        (cudaStream_t)stream);
+  h->launches += 2;
+  return check_launch(h, "bn_batch_stats");
+}
+
 static int redo_postnet(taco_handle* h, int N, int T_in, int max_steps, int steps, int bn_mode, const float* mel,
                         float* linear_out, cudaStream_t st) {
   const taco_hparams& hp = h->hp;

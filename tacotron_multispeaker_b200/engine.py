@@ -214,6 +214,25 @@ class Engine:
                                       _ptr(out), self.stream))
         return out
 
+    def maxpool_affine(self, x, scale=None, shift=None):
+        """``taco_maxpool_affine``: max_pooling1d(2, 1, 'same') of ``scale * x + shift`` (reference modules.py:45-49)."""
+        x = self._f32(x)
+        N, T, Cc = x.shape
+        sc = self._f32(scale) if scale is not None else None
+        sh = self._f32(shift) if shift is not None else None
+        out = torch.empty_like(x)
+        self._ck(self.lib.taco_maxpool_affine(self._h, _ptr(x), N, T, Cc, _ptr(sc), _ptr(sh), _ptr(out), self.stream))
+        return out
+
+    def bn_batch_stats(self, x, gamma, beta):
+        """``taco_bn_batch_stats``: (scale, shift) with BN_training(x) = scale * x + shift (reference modules.py:101)."""
+        x, gamma, beta = self._f32(x), self._f32(gamma), self._f32(beta)
+        N, T, Cc = x.shape
+        scale = torch.empty(Cc, device=self.device, dtype=torch.float32)
+        shift = torch.empty(Cc, device=self.device, dtype=torch.float32)
+        self._ck(self.lib.taco_bn_batch_stats(self._h, _ptr(x), N, T, Cc, _ptr(gamma), _ptr(beta), _ptr(scale), _ptr(shift), self.stream))
+        return scale, shift
+
     # ---- vocoder (the step after the path) ----
     def audio_params(self, griffin_lim_iters: Optional[int] = None) -> "_abi.TacoAudioParams":
         hp = self.hp

@@ -112,6 +112,41 @@ def test_conv1d_even_kernel_padding_kat(eng):
     assert np.array_equal(got, exp)
 
 
+@pytest.mark.parametrize("N,T,C,affine", [(1, 1, 4, False), (2, 7, 128, True), (3, 100, 2048, True), (5, 33, 1024, False)])
+def test_maxpool_affine_kat(eng, N, T, C, affine):
+    """a5 in isolation: max_pooling1d(2, 1, 'same') after the folded BN affine (modules.py:45-49): out[t] = max(a(x[t]), a(x[t+1])),
+    the last row passes through.  Bit exact against the oracle (max and one FMA per element)."""
+    rng = np.random.default_rng(N * 1000 + T)
+    x = rng.standard_normal((N, T, C)).astype(np.float32)
+    sc = rng.uniform(-2, 2, C).astype(np.float32) if affine else None       # negative scales: the affine must come BEFORE the max
+    sh = rng.standard_normal(C).astype(np.float32) if affine else None
+    got = eng.maxpool_affine(x, sc, sh).cpu()
+    xa = torch.from_numpy(x)
+    if affine:
+        xa = torch.addcmul(torch.from_numpy(sh), xa, torch.from_numpy(sc))   # fused multiply-add like the kernel
+    ref = O.max_pool_same2(xa)
+    assert maxabs(got, ref) < 1e-6
+    assert torch.equal(got[:, -1], xa[:, -1])
+
+
+@pytest.mark.parametrize("N,T,C", [(1, 2, 4), (3, 50, 128), (32, 100, 2048), (2, 1000, 256)])
+def test_bn_batch_stats_kat(eng, N, T, C):
+    """Training-mode batch normalisation in isolation (modules.py:101 with is_training): biased moments over (N, T) accumulated in
+    double, folded into scale / shift with epsilon 1e-3; scale * x + shift must equal the oracle's batch_norm(mode='batch')."""
+    rng = np.random.default_rng(C + T)
+    x = (rng.standard_normal((N, T, C)) * rng.uniform(0.1, 3.0, C) + rng.standard_normal(C)).astype(np.float32)
+    gamma = rng.uniform(0.5, 2.0, C).astype(np.float32)
+    beta = rng.standard_normal(C).astype(np.float32)
+    scale, shift = eng.bn_batch_stats(x, gamma, beta)
+    xt = torch.from_numpy(x)
+    got = xt * scale.cpu() + shift.cpu()
+    ref = O.batch_norm(xt.double(), torch.from_numpy(gamma).double(), torch.from_numpy(beta).double(), None, None, "batch")
+    assert maxabs(got, ref) < 2e-5
+    var = xt.double().var(dim=(0, 1), unbiased=False)
+    want = torch.from_numpy(gamma).double() / torch.sqrt(var + 1e-3)
+    assert float(((scale.cpu().double() - want).abs() / want.abs()).max()) < 1e-5
+
+
 @pytest.mark.parametrize("which,N,T,masked", [(0, 5, 23, True), (0, 3, 11, False), (1, 2, 60, False),
                                               (0, 80, 9, True), (1, 1, 150, False), (0, 8, 31, True), (0, 9, 31, True), (1, 33, 40, False)])
 def test_bigru(eng, ow, which, N, T, masked):
