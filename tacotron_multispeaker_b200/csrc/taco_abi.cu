@@ -760,9 +760,22 @@ size_t postnet_ws_bytes(const taco_handle* h, int N, int T) {
   return sizeof(float) * ((size_t)rows * 512 + cbhg_ws_floats(8, 256, h->hp.num_mels, rows)) + 65536;
 }
 
+// defer_count: do not wait for the step count (optimistic max_steps; the caller reads it after its own synchronisation).
+// count_later: do not even launch the step-count kernels here: the caller enqueues them (count_steps) after the post-net, which
+// does not depend on them, so that they leave the critical path of the forward.
+int count_steps(taco_handle* h, const float* dec_out, int N, int max_steps, cudaStream_t st) {
+  int rc = ensure_ints(h, 2 + N);
+  if (rc) return rc;
+  // The step count goes straight into mapped pinned memory: a D2H copy here would queue on the copy engine behind
+  // another handle's 144 MB output transfer and stall this forward in the middle (batches in flight on other streams).
+  launch_find_steps(dec_out, N, max_steps, h->hp.num_mels * h->hp.outputs_per_step, h->d_ints + 2, h->d_pinned + 1, st);
+  h->launches += 3;
+  return TACO_OK;
+}
+
 int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, const float* mel_targets, int T_tgt,
               int teacher_force, float* dec_out, float* align_out, int32_t* steps_out_host, cudaStream_t st,
-              bool defer_count = false) {
+              bool defer_count = false, bool count_later = false) {
   Ctx c{h, st};
   const taco_hparams& hp = h->hp;
   if (T_in > 512) return fail(h, TACO_ERR_UNSUPPORTED, "T_in > 512 not supported by the decoder kernel");
@@ -815,12 +828,10 @@ int do_decode(taco_handle* h, Bump& ws, const float* memory, int N, int T_in, co
   }
   int steps = max_steps;
   if (!teacher_force) {
-    int rc = ensure_ints(h, 2 + N);
-    if (rc) return rc;
-    // The step count goes straight into mapped pinned memory: a D2H copy here would queue on the copy engine behind
-    // another handle's 144 MB output transfer and stall this forward in the middle (batches in flight on other streams).
-    launch_find_steps(dec_out, N, max_steps, hp.num_mels * hp.outputs_per_step, h->d_ints + 2, h->d_pinned + 1, st);
-    h->launches += 3;
+    if (!count_later) {
+      int rc = count_steps(h, dec_out, N, max_steps, st);
+      if (rc) return rc;
+    }
     if (!defer_count) {
       CUDA_OK(h, cudaStreamSynchronize(st));
       steps = *(volatile int*)(h->h_pinned + 1);
@@ -1299,7 +1310,7 @@ static int forward_impl(taco_handle* h, const int32_t* ids, const int32_t* lengt
     if (h->profiling) cudaEventRecord(h->ev[1], st);
     ws.off = mark;   // encoder scratch is dead; stream order keeps reuse safe
     rc2 = do_decode(h, ws, memory, N, T_in, mel_targets, T_tgt, teacher_force, mel_out, align_out, &steps, st,
-                    /*defer_count=*/true);
+                    /*defer_count=*/true, /*count_later=*/true);
     if (rc2) return rc2;
     if (h->profiling) cudaEventRecord(h->ev[2], st);
     if (defer_final) {
@@ -1310,6 +1321,10 @@ static int forward_impl(taco_handle* h, const int32_t* ids, const int32_t* lengt
       ws.off = mark;
       rc2 = do_postnet(h, ws, mel_out, N, steps * r, bn_mode, (int64_t)maxT * M, linear_out,
                        (int64_t)maxT * hp.num_freq, st);
+      if (rc2) return rc2;
+    }
+    if (!teacher_force) {               // dynamic_decode's step count (exact-zero frames): off the critical path, after the post-net
+      rc2 = count_steps(h, mel_out, N, max_steps, st);
       if (rc2) return rc2;
     }
     return TACO_OK;
