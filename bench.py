@@ -21,6 +21,21 @@ utterance), mel + post-net linear output.  Metric: mel frames/s (whole job).
  * cpu_baseline : the CPU oracle (restatement of the reference's TF graph; TF
            itself cannot run here) on the host cores, one full batch.
 
+Extra keys of the line (informational, none of them changes `value`):
+ single_stream   one batch in flight (step latency);
+ throughput_mode the same two legs with taco_set_decoder_clusters(4);
+ bf16_mode       taco_set_gemm_mode(2) (plain bf16 operands; NOT the headline precision);
+ latency_batch1  p50 of one utterance, T_in 20..200, and down to the waveform;
+ vocoder         taco_griffin_lim on the batch's linear output (100 iterations);
+ config1 / config2 / config4 / config5 / e2e_synthesize   the other BASELINE.json configurations (bench_configs.py):
+                 single speaker, teacher forced in both BN modes, global batch 256 sharded (strong scaling) with a timed
+                 NCCL gather, the full batch-1 latency sweep (p50 + p99, r = 5 and r = 1), and the reference
+                 Synthesizer.synthesize shape (ids -> wav + alignment);
+ e2e.ms_per_step_runs   the three timed end-to-end regions (the median is `e2e.value`), e2e.d2h_floor_ms_per_step the
+                 device-to-host copy time of one batch's outputs alone (measured link rate);
+ gpu_launches    kernels of this library launched inside the timed region (CUDA-graph replays count their kernel nodes).
+The forward and the vocoder replay CUDA graphs after their second identical call (taco_set_cuda_graphs).
+
 `--impl reference` times that CPU restatement alone (rank 0 only).
 N > 1: launched under torchrun, one rank per GPU, each rank runs its own batch
 of 32 utterances (weak scaling, no collective on the data path).
