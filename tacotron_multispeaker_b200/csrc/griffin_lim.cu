@@ -27,11 +27,29 @@ namespace {
 constexpr int GL_N = 2048, GL_M = GL_N / 2, GL_BINS = GL_N / 2 + 1, GL_NT = 128;
 constexpr int GL_TW = GL_N / 4 + 1;   // twiddles W_N^k the kernel touches: k <= N/4
 
+// Complex arithmetic on the packed fp32 pair instructions of sm_100 (FADD2 / FMUL2 / FFMA2: one issue slot for both halves; the
+// kernel is issue bound, IPC 3.1 of 4).  Products and sums are rounded exactly where the scalar forms rounded them, so results
+// are bit-identical: a b = (a.x, a.x) (b.x, b.y) + (a.y, a.y) (-b.y, b.x), a conj(b) = (a.x, a.y) (b.x, b.x) + (a.y, a.x) (b.y, -b.y).
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float x, float y) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ float2 up(u64 v) { float2 o; asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(v)); return o; }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+  u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a.x, a.y)), "l"(pk(b.x, b.y))); return up(r);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+  u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a.x, a.y)), "l"(pk(b.x, b.y))); return up(r);
+}
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+  u64 t, r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(pk(a.y, a.y)), "l"(pk(-b.y, b.x)));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk(a.x, a.x)), "l"(pk(b.x, b.y)), "l"(t));
+  return up(r);
 }
 __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {   // a * conj(b)
-  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+  u64 t, r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(pk(a.y, a.x)), "l"(pk(b.y, -b.y)));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk(a.x, a.y)), "l"(pk(b.x, b.x)), "l"(t));
+  return up(r);
 }
 // element i of the transform sits at PD(i): one pad per 16 elements makes every FFT pass bank-conflict free, one more
 // per 256 spreads the bit-reversed positions of the phase step (stride 64) over the banks (3.9 -> 1.5 wavefronts)
@@ -96,8 +114,8 @@ __device__ __forceinline__ void dif_core(float2 (&v)[1 << LOGR], int lo, const f
     for (int m = 0; m < R; ++m) {
       if (m & hs) continue;
       const float2 a = v[m], b = v[m + hs];
-      v[m] = make_float2(a.x + b.x, a.y + b.y);
-      float2 t = mul_w16<false>(make_float2(a.x - b.x, a.y - b.y), (m & (hs - 1)) * (8 / hs));
+      v[m] = cadd(a, b);
+      float2 t = mul_w16<false>(csub(a, b), (m & (hs - 1)) * (8 / hs));
       if (LOGQ > 0) t = cmul(t, wb);
       v[m + hs] = t;
     }
@@ -147,8 +165,8 @@ __device__ __forceinline__ void dit_core(float2 (&v)[1 << LOGR], int lo, const f
       float2 b = mul_w16<true>(v[m + hs], (m & (hs - 1)) * (8 / hs));
       if (LOGQ > 0) b = cmul_conj(b, wbs[s]);
       const float2 a = v[m];
-      v[m] = make_float2(a.x + b.x, a.y + b.y);
-      v[m + hs] = make_float2(a.x - b.x, a.y - b.y);
+      v[m] = cadd(a, b);
+      v[m + hs] = csub(a, b);
     }
   }
 }
