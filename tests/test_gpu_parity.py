@@ -226,6 +226,39 @@ def test_decode_teacher_forced(eng, ow, small_hp, N, T_in, S):
     assert torch.equal(al.cpu().argmax(dim=1), ral.argmax(dim=1))
 
 
+@pytest.mark.parametrize("N,T_in", [(1, 1), (2, 2), (1, 512), (3, 511), (70, 9), (2, 300)])
+def test_decode_extreme_shapes(eng, ow, small_hp, N, T_in):
+    """Edges of the decoder's geometry: a single input position (softmax over one key), the largest supported T_in (512:
+    attention operands no longer resident in shared memory), more utterances than one wave of clusters holds (70 -> 9 clusters
+    of 8 in two waves), odd lengths around the 16-range pair cut.  Teacher forced and free running against the oracle."""
+    e_dec, e_al, al, ral = _decode_case(eng, ow, small_hp, N, T_in, True, 31 * N + T_in)
+    assert e_dec < 2e-4 and e_al < 1e-5
+    assert torch.equal(al.cpu().argmax(dim=1), ral.argmax(dim=1))
+    e_dec, e_al, _, _ = _decode_case(eng, ow, small_hp, N, T_in, False, 17 * N + T_in)
+    assert e_dec < 1e-3 and e_al < 1e-4
+
+
+def test_decode_rejects_longer_inputs(eng, small_hp):
+    """T_in > 512 is refused loudly (TACO_ERR_UNSUPPORTED), not truncated."""
+    mem = np.zeros((1, 513, 256), np.float32)
+    with pytest.raises(RuntimeError):
+        eng.decode(mem, None, False)
+
+
+@pytest.mark.parametrize("N,T_in", [(1, 1), (2, 3), (40, 5)])
+def test_forward_ragged_and_tiny_batches(eng, ow, small_hp, small_weights, N, T_in):
+    """Whole path on the smallest inputs the reference's feeder can produce: one symbol, lengths of 1 inside a padded batch (the
+    BiGRU masks everything but the first step), a batch larger than 32."""
+    ids, lengths, spk = make_inputs(N, T_in, 6, 3 * N + T_in, min_len=1)
+    lengths[-1] = 1
+    ids[-1, 1:] = 0
+    mel, lin, al, steps = eng.forward(ids, lengths, spk)
+    ref = O.tacotron_forward(small_weights, small_hp, ids, lengths, identities=spk, id_num=6)
+    assert steps == ref["steps"]
+    assert maxabs(mel, ref["mel_outputs"]) < 1e-3 and maxabs(lin, ref["linear_outputs"]) < 1e-3
+    assert maxabs(al, ref["alignments"]) < 1e-4
+
+
 @pytest.mark.parametrize("N,T_in", [(3, 19), (17, 100)])
 def test_decode_bf16_mode(eng, ow, small_hp, N, T_in):
     """taco_set_gemm_mode(2): the decoder multiplies W_hi x_hi only (plain bf16 operands, fp32 accumulation, one MMA per
