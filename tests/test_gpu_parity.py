@@ -259,6 +259,29 @@ def test_forward_ragged_and_tiny_batches(eng, ow, small_hp, small_weights, N, T_
     assert maxabs(al, ref["alignments"]) < 1e-4
 
 
+def test_utterances_are_independent(eng, small_hp):
+    """Moving-statistics synthesis treats the utterances of a batch independently (no op of the graph mixes batch entries): a
+    batch of six equals six batches of one.  The two runs take different decoder paths (clusters of several utterances with
+    all-warp attention vs one utterance per cluster with critical-group attention), so this also ties those together."""
+    ids, lengths, spk = make_inputs(6, 23, 6, 77)
+    mel, lin, al, steps = eng.forward(ids, lengths, spk)
+    for i in range(6):
+        m1, l1, a1, s1 = eng.forward(ids[i:i + 1], lengths[i:i + 1], spk[i:i + 1])
+        assert s1 == steps
+        assert maxabs(m1, mel[i:i + 1]) < 1e-4 and maxabs(l1, lin[i:i + 1]) < 1e-4 and maxabs(a1, al[i:i + 1]) < 1e-5
+
+
+def test_teacher_forcing_with_own_outputs_reproduces_free_run(eng, small_hp):
+    """TacoTrainingHelper fed with the model's own frames must walk the same trajectory as TacoTestHelper (helpers.py:26-38 vs
+    68-77).  On the device the two take different arithmetic: the free run never forms the fed-back frame (the output projection
+    is folded into the prenet's first layer in double precision), teacher forcing reads the frame from memory."""
+    ids, lengths, spk = make_inputs(4, 21, 6, 5)
+    mel, lin, al, steps = eng.forward(ids, lengths, spk)
+    mel2, lin2, al2, steps2 = eng.forward(ids, lengths, spk, mel_targets=mel.contiguous(), teacher_force=True, bn_mode=0)
+    assert steps2 == steps
+    assert maxabs(mel2, mel) < 1e-4 and maxabs(lin2, lin) < 1e-4 and maxabs(al2, al) < 1e-5
+
+
 @pytest.mark.parametrize("N,T_in", [(3, 19), (17, 100)])
 def test_decode_bf16_mode(eng, ow, small_hp, N, T_in):
     """taco_set_gemm_mode(2): the decoder multiplies W_hi x_hi only (plain bf16 operands, fp32 accumulation, one MMA per
