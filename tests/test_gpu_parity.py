@@ -282,6 +282,45 @@ def test_teacher_forcing_with_own_outputs_reproduces_free_run(eng, small_hp):
     assert maxabs(mel2, mel) < 1e-4 and maxabs(lin2, lin) < 1e-4 and maxabs(al2, al) < 1e-5
 
 
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_forward_random_configs(seed):
+    """Seeded sweep over hyper-parameters the fixed cases do not reach: r in 1..6 (output projection of 80 r columns cut into
+    16-column tiles over the cluster), odd max_iters, odd T_in, speaker tables of different sizes and the single-speaker branch,
+    batch sizes that cut unevenly into clusters; free running, teacher forced with moving statistics and with batch statistics."""
+    from tacotron_multispeaker_b200.engine import Engine
+    from tacotron_multispeaker_b200.hparams import HParams
+    from tacotron_multispeaker_b200.weights import random_init
+    rng = np.random.default_rng(1000 + seed)
+    r = int(rng.integers(1, 7))
+    iters = int(rng.integers(2, 8))
+    N = int(rng.integers(1, 14))
+    T_in = int(rng.integers(1, 70))
+    id_num = int(rng.choice([0, 2, 7, 400]))
+    mode = ("free", "teacher_moving", "teacher_batch")[seed % 3]
+    hp = HParams(outputs_per_step=r, max_iters=iters)
+    w = random_init(hp, id_num, seed=seed, randomize_bn=True)
+    ids, lengths, spk = make_inputs(N, T_in, max(id_num, 1), seed, min_len=1)
+    spk_arg = spk if id_num > 1 else None
+    e = Engine(hp, id_num)
+    try:
+        e.load_weights(w)
+        if mode == "free":
+            mel, lin, al, steps = e.forward(ids, lengths, spk_arg)
+            ref = O.tacotron_forward(w, hp, ids, lengths, identities=spk_arg, id_num=id_num)
+        else:
+            T_tgt = int(rng.integers(r, iters * r + 3))
+            tg = rng.uniform(0, 1, (N, T_tgt, hp.num_mels)).astype(np.float32)
+            bn = "batch" if mode == "teacher_batch" else "moving"
+            mel, lin, al, steps = e.forward(ids, lengths, spk_arg, tg, True, 1 if bn == "batch" else 0)
+            ref = O.tacotron_forward(w, hp, ids, lengths, mel_targets=tg, identities=spk_arg, id_num=id_num, teacher_force=True, bn_mode=bn)
+    finally:
+        e.close()
+    assert steps == ref["steps"], (r, iters, N, T_in, id_num, mode)
+    assert maxabs(mel, ref["mel_outputs"]) < 1e-3, (r, iters, N, T_in, id_num, mode)
+    assert maxabs(lin, ref["linear_outputs"]) < 1e-3, (r, iters, N, T_in, id_num, mode)
+    assert maxabs(al, ref["alignments"]) < 1e-4, (r, iters, N, T_in, id_num, mode)
+
+
 @pytest.mark.parametrize("N,T_in", [(3, 19), (17, 100)])
 def test_decode_bf16_mode(eng, ow, small_hp, N, T_in):
     """taco_set_gemm_mode(2): the decoder multiplies W_hi x_hi only (plain bf16 operands, fp32 accumulation, one MMA per
