@@ -62,6 +62,40 @@ UNIT = "frames/s"
 BATCH, T_IN, MAX_ITERS, R, ID_NUM = 32, 100, 200, 5, 60
 
 
+def bind_to_gpu_numa_node(torch, local: int):
+    """Pin this rank's host threads (and so, by first touch, its pinned output buffers) to the NUMA node its GPU hangs off:
+    with eight ranks copying 144 MB per batch each to buffers that all sit on one node, the device-to-host rate fell to
+    13 GB/s per GPU.  Returns {"node": n, "cpus": k} or None when the topology cannot be read."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        if bus is None:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                                 capture_output=True, text=True, timeout=20).stdout.strip()
+            bus_id = out.lower()
+            if bus_id.startswith("00000000:"):
+                bus_id = "0000:" + bus_id[len("00000000:"):]
+        else:
+            dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+            dev_id = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+            bus_id = "%04x:%02x:%02x.0" % (dom, bus, dev_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus_id) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed)}
+    except Exception:
+        return None
+
+
 def make_batch(seed: int):
     """BASELINE.md config 3 inputs: lengths ~U{60..100}, ids in the pinyin-phone block, pad id 0."""
     rng = np.random.default_rng(seed)
@@ -205,6 +239,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local) if os.environ.get("TACO_BENCH_NUMA", "1") != "0" else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -410,7 +445,7 @@ def run_ours(args):
            "api": "taco_forward_host_begin/_wait/_end (C ABI, pinned host buffers; H2D + forward + D2H per step; %d lanes, "
                   "at most %d of them between _begin and the end of their decoder loop)" % (n_lanes, n_slots),
            "host_waits": "blocking" if os.environ.get("TACO_BLOCKING_SYNC", "0") not in ("", "0") else "spinning",
-           "host_cores": os.cpu_count()}
+           "host_cores": os.cpu_count(), "numa_binding": numa}
 
     # what the link alone allows: one batch's outputs copied device -> pinned host with nothing else running
     lin_pin = torch.from_numpy(pb["lin"])
