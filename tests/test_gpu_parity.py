@@ -321,6 +321,40 @@ def test_forward_random_configs(seed):
     assert maxabs(al, ref["alignments"]) < 1e-4, (r, iters, N, T_in, id_num, mode)
 
 
+def test_ffma_decoder_fallback(monkeypatch, small_weights, small_hp):
+    """The fp32 FFMA cluster decoder (csrc/decoder.cu) ships as the fallback for shapes the tensor-core decoder does not take
+    (num_mels not a multiple of 16, or more than 128) and behind TACO_DEC_IMPL=v2: same bounds as the default decoder."""
+    from tacotron_multispeaker_b200.engine import Engine
+    from tacotron_multispeaker_b200.hparams import HParams
+    from tacotron_multispeaker_b200.weights import random_init
+    # (a) forced by the developer switch, standard hyper-parameters
+    monkeypatch.setenv("TACO_DEC_IMPL", "v2")
+    e = Engine(small_hp, 6)
+    try:
+        e.load_weights(small_weights)
+        wo = O.W(small_weights, torch.float32)
+        for N, T_in, teacher in ((3, 19, True), (9, 50, True), (4, 25, False)):
+            e_dec, e_al, al, ral = _decode_case(e, wo, small_hp, N, T_in, teacher, 5 * N + T_in)
+            assert e_dec < (2e-4 if teacher else 1e-3) and e_al < (1e-5 if teacher else 1e-4)
+    finally:
+        e.close()
+    monkeypatch.delenv("TACO_DEC_IMPL")
+    # (b) taken automatically: 72 mel channels (4.5 tiles of 16) -- whole path against the oracle
+    hp = HParams(outputs_per_step=3, max_iters=5, num_mels=72)
+    w = random_init(hp, 4, seed=9, randomize_bn=True)
+    ids, lengths, spk = make_inputs(3, 17, 4, 2)
+    e = Engine(hp, 4)
+    try:
+        e.load_weights(w)
+        mel, lin, al, steps = e.forward(ids, lengths, spk)
+        ref = O.tacotron_forward(w, hp, ids, lengths, identities=spk, id_num=4)
+        assert steps == ref["steps"]
+        assert maxabs(mel, ref["mel_outputs"]) < 1e-3 and maxabs(lin, ref["linear_outputs"]) < 1e-3
+        assert maxabs(al, ref["alignments"]) < 1e-4
+    finally:
+        e.close()
+
+
 @pytest.mark.parametrize("N,T_in", [(3, 19), (17, 100)])
 def test_decode_bf16_mode(eng, ow, small_hp, N, T_in):
     """taco_set_gemm_mode(2): the decoder multiplies W_hi x_hi only (plain bf16 operands, fp32 accumulation, one MMA per
