@@ -53,6 +53,7 @@ struct UmmaArgs {
   const float* bias; const float* scale; const float* shift;
   const float* res; long long res_bs; int ldres;
   float* out; long long out_bs; int ldo; int col_off;
+  void* out_hi; void* out_lo; int out_cp;   // bf16 hi / lo copy of the result [N][T][out_cp] (null: none)
   int act, epi;
   int stages;              // smem ring depth (1..3)
   int vec_epi;             // 1: rows are 16 B aligned -> direct 128-bit stores from the TMEM registers
@@ -128,6 +129,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 
+// (a, b) -> packed bf16 hi pair (return) and lo pair.  One packed conversion (F2FP, FMA pipe) per pair instead of two scalar
+// F2F on the XU pipe, which the sigmoids' EX2 / RCP already saturate (ncu: mio_throttle on the conversions).
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, uint32_t& lo_out) {
+  uint32_t hi;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));      // upper half <- first source
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo_out) : "f"(rb), "f"(ra));
+  return hi;
+}
+
 // ---- epilogue -----------------------------------------------------------------------------------------------------
 struct EpiTile {
   int n, tq, o0;           // utterance, first row of this warp's 32 rows, first column of the tile
@@ -156,7 +167,7 @@ __device__ __forceinline__ void epi_plain_vec(const UmmaArgs& p, const EpiTile& 
 #pragma unroll 1
   for (int ch = ch_lo; ch < ch_hi; ++ch) {
     const int cbase = e.o0 + ch * 32;
-    if (cbase >= p.Cout) break;                                           // warp-uniform
+    if (cbase >= p.Cout && !(p.out_hi != nullptr && cbase < p.out_cp)) break;   // warp-uniform (padding channels of the bf16 copy are zero-filled)
     uint32_t v[32];
     tmem_ld32(acc + (uint32_t)(ch * 32), v);
     stage_rows_f4(stg, lane, v);
@@ -168,10 +179,18 @@ __device__ __forceinline__ void epi_plain_vec(const UmmaArgs& p, const EpiTile& 
       if (e.bias) b4 = ldg_f4(e.bias + col);
       if (SC && e.scale) { sc4 = ldg_f4(e.scale + col); sh4 = ldg_f4(e.shift + col); }
     }
-    float* orow = p.out + (long long)e.n * p.out_bs + (long long)(e.tq + rsub) * p.ldo + e.col_off + col;
+    float* orow = p.out != nullptr ? p.out + (long long)e.n * p.out_bs + (long long)(e.tq + rsub) * p.ldo + e.col_off + col : nullptr;
     const bool has_res = RES && p.res != nullptr;
     const float* rrow = has_res ? p.res + (long long)e.n * p.res_bs + (long long)(e.tq + rsub) * p.ldres + col : nullptr;
     const int rows_left = p.T - e.tq - rsub;                              // row 4 i + rsub is valid iff 4 i < rows_left
+    // bf16 hi / lo copy for the consuming GEMM: row (n T + t) of [N][T][out_cp], zeros in the padding channels
+    const bool bf_out = p.out_hi != nullptr && col < p.out_cp;
+    uint16_t* hrow = nullptr; uint16_t* lrow = nullptr;
+    if (bf_out) {
+      const long long r0 = ((long long)e.n * p.T + e.tq + rsub) * p.out_cp + col;
+      hrow = reinterpret_cast<uint16_t*>(p.out_hi) + r0;
+      lrow = reinterpret_cast<uint16_t*>(p.out_lo) + r0;
+    }
 #pragma unroll
     for (int i0 = 0; i0 < 8; i0 += 4) {                                  // four rows per thread at a time: residuals requested up front
       float4 r4[4];
@@ -188,9 +207,16 @@ __device__ __forceinline__ void epi_plain_vec(const UmmaArgs& p, const EpiTile& 
         x.x = act_t<ACT>(x.x + b4.x, p.act); x.y = act_t<ACT>(x.y + b4.y, p.act);
         x.z = act_t<ACT>(x.z + b4.z, p.act); x.w = act_t<ACT>(x.w + b4.w, p.act);
         if (SC) { x.x = fmaf(x.x, sc4.x, sh4.x); x.y = fmaf(x.y, sc4.y, sh4.y); x.z = fmaf(x.z, sc4.z, sh4.z); x.w = fmaf(x.w, sc4.w, sh4.w); }
-        if (cok && 4 * (i0 + i) < rows_left) {
+        if (4 * (i0 + i) < rows_left) {
           if (RES) { x.x += r4[i].x; x.y += r4[i].y; x.z += r4[i].z; x.w += r4[i].w; }
-          *reinterpret_cast<float4*>(orow + (4 * (i0 + i)) * p.ldo) = x;
+          if (cok && orow != nullptr) *reinterpret_cast<float4*>(orow + (4 * (i0 + i)) * p.ldo) = x;
+          if (bf_out) {
+            if (!cok) x = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint2 h2, l2;
+            h2.x = pack_bf16x2(x.x, x.y, l2.x); h2.y = pack_bf16x2(x.z, x.w, l2.y);
+            *reinterpret_cast<uint2*>(hrow + (4 * (i0 + i)) * p.out_cp) = h2;
+            *reinterpret_cast<uint2*>(lrow + (4 * (i0 + i)) * p.out_cp) = l2;
+          }
         }
       }
     }
@@ -519,16 +545,6 @@ constexpr uint32_t HW_BSTAGE = 4 * TILE_BYTES;                   // per k-block:
 constexpr uint32_t HW_SMEM = 1024u + HW_A_BYTES + 2 * HW_BSTAGE + 256u + 4 * 256 * 4;   // + the four layers' biases
 constexpr int HW_THREADS = 64 + 16 * 32;                       // TMA warp, MMA warp, sixteen epilogue warps
 
-// (a, b) -> packed bf16 hi pair (return) and lo pair.  One packed conversion (F2FP, FMA pipe) per pair instead of two scalar
-// F2F on the XU pipe, which the sigmoids' EX2 / RCP already saturate (ncu: mio_throttle on the conversions).
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, uint32_t& lo_out) {
-  uint32_t hi;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));      // upper half <- first source
-  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo_out) : "f"(rb), "f"(ra));
-  return hi;
-}
-
 template <int NSPLIT>
 __global__ void __launch_bounds__(HW_THREADS, 1)
 highway4_kernel(const __grid_constant__ CUtensorMap tmB, const Hw4Args p) {
@@ -851,6 +867,7 @@ cudaError_t launch_conv_umma(const ConvUmma& c, cudaStream_t st) {
   p.N = c.N; p.T = c.T; p.Cp = c.Cp; p.kvalid = c.Cin > 0 && c.Cin < c.Cp ? (c.Cin + 15) & ~15 : c.Cp; p.taps = c.taps; p.bank = c.bank; p.Cout = c.Cout;
   p.bias = c.bias; p.scale = c.scale; p.shift = c.shift; p.res = c.res; p.res_bs = c.res_bs; p.ldres = c.ldres;
   p.out = c.out; p.out_bs = c.out_bs; p.ldo = c.ldo; p.col_off = c.col_off; p.act = c.act; p.epi = c.epi;
+  p.out_hi = c.out_hi; p.out_lo = c.out_lo; p.out_cp = c.out_cp;
   p.nx = c.N * ((c.T + BM - 1) / BM);
   p.ny = (c.Cout + BN - 1) / BN;
   const long long ntiles = (long long)p.nx * p.ny * (c.bank > 1 ? c.bank : 1);
@@ -890,12 +907,16 @@ cudaError_t launch_conv_umma(const ConvUmma& c, cudaStream_t st) {
   const int chn = c.epi == EPI_HIGHWAY ? 2 : 1;
   auto al4 = [](long long v) { return (v & 3) == 0; };
   p.vec_epi = (al4(c.ldo) && al4(c.col_off) && al4(c.out_bs) && al4(c.Cout / chn) && (c.Cout % (4 * chn) == 0) &&
-               (reinterpret_cast<uintptr_t>(c.out) & 15) == 0 &&
+               (c.out == nullptr || (reinterpret_cast<uintptr_t>(c.out) & 15) == 0) &&
                (c.res == nullptr || (al4(c.ldres) && al4(c.res_bs) && (reinterpret_cast<uintptr_t>(c.res) & 15) == 0)) &&
                (c.bias == nullptr || (reinterpret_cast<uintptr_t>(c.bias) & 15) == 0) &&
                (c.scale == nullptr || ((reinterpret_cast<uintptr_t>(c.scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.shift) & 15) == 0)))
                   ? 1 : 0;
   if (c.epi == EPI_HIGHWAY && (c.bias == nullptr || c.res == nullptr)) return cudaErrorInvalidValue;
+  if (c.out_hi != nullptr && (c.out_lo == nullptr || !p.vec_epi || c.epi != EPI_PLAIN || c.bank > 1 || c.col_off != 0 || (c.out_cp & 63) ||
+                              c.out_cp < c.Cout || c.out_cp > p.ny * BN))
+    return cudaErrorInvalidValue;
+  if (c.out == nullptr && c.out_hi == nullptr) return cudaErrorInvalidValue;
   if ((c.scale == nullptr) != (c.shift == nullptr)) return cudaErrorInvalidValue;
   const uint32_t smem = smem_bytes(p.stages, p.epi_warps);
   // epilogue variant: the combinations the forward uses are compiled in, anything else takes the run-time variant 0

@@ -46,8 +46,11 @@ struct ConvUmma {
   int taps, bank, Cout, nsplit;
   const float* bias; const float* scale; const float* shift;
   const float* res; int64_t res_bs; int ldres;
-  float* out; int64_t out_bs; int ldo; int col_off;
+  float* out; int64_t out_bs; int ldo; int col_off;   // out may be null when only the bf16 copy below is wanted
   int act, epi;
+  // optional: the result also (or only) as the bf16 hi / lo operand of the GEMM that consumes it, dense [N][T][out_cp] with the
+  // channels Cout .. out_cp-1 written as zeros (out_cp % 64 == 0); plain epilogue, 16-byte aligned rows, no bank, col_off 0
+  void* out_hi = nullptr; void* out_lo = nullptr; int out_cp = 0;
 };
 cudaError_t launch_conv_umma(const ConvUmma& c, cudaStream_t st);
 // The highway layers of a CBHG (reference modules.py:63-64, 79-89) in one launch: x, out [rows][128] fp32 dense; w_hi = the layers'

@@ -474,7 +474,7 @@ struct Bump {
 
 size_t cbhg_ws_floats(int K, int P1, int P2, int64_t rows) {
   // bank + pooled + p1 + p2 + dense + 2 highway + xproj, plus slack for alignment
-  return (size_t)rows * ((size_t)3 * K * 128 + P1 + P2 + 128 + 256 + 768) + 32768;   // + bf16 hi/lo staging
+  return (size_t)rows * ((size_t)3 * K * 128 + P1 + P2 + 128 + 256 + 768 + 256) + 32768;   // + bf16 hi/lo staging (wide + narrow)
 }
 
 int ensure_ws(taco_handle* h, size_t bytes) {
@@ -523,8 +523,11 @@ BfScratch take_bf(Bump& ws, int64_t rows, int maxCp) {
 // One conv1d/dense site: tensor cores (default) or the fp32 FFMA kernel (gemm_mode 0).
 void gemm(Ctx& c, const GemmW& g, const BfScratch& sc, const float* x, int64_t x_bs, int ldx, int N, int T,
           const float* bias, const float* scale, const float* shift, const float* res, int64_t res_bs, int ldres,
-          float* out, int64_t out_bs, int ldo, int col_off, int act, int epi = EPI_PLAIN, bool presplit = false) {
+          float* out, int64_t out_bs, int ldo, int col_off, int act, int epi = EPI_PLAIN, bool presplit = false,
+          const BfScratch* next = nullptr, int next_cp = 0, bool skip_fp32 = false) {
   // presplit: sc already holds the bf16 hi/lo operand (written by the producer), x is not read
+  // next (tensor-core path only): the epilogue also writes the result as the hi/lo operand [N][T][next_cp] of the GEMM that
+  // consumes it (no split pass in between); skip_fp32: and does not write the fp32 copy at all (nothing else reads it)
   taco_handle* h = c.h;
   if (h->gemm_mode == 0) {
     conv(c, x, x_bs, ldx, N, T, g.Cin, g.taps, c.W(g.w), g.ldw, bias, scale, shift, res, res_bs, ldres, out, out_bs, ldo,
@@ -538,6 +541,10 @@ void gemm(Ctx& c, const GemmW& g, const BfScratch& sc, const float* x, int64_t x
   u.taps = g.taps; u.bank = g.bank; u.Cout = g.Cout; u.nsplit = h->gemm_mode == 2 ? 1 : 3;
   u.bias = bias; u.scale = scale; u.shift = shift; u.res = res; u.res_bs = res_bs; u.ldres = ldres;
   u.out = out; u.out_bs = out_bs; u.ldo = ldo; u.col_off = col_off; u.act = act; u.epi = epi;
+  if (next != nullptr) {
+    u.out_hi = next->hi; u.out_lo = next->lo; u.out_cp = next_cp;
+    if (skip_fp32) u.out = nullptr;
+  }
   cudaError_t e = launch_conv_umma(u, c.st);
   if (e != cudaSuccess) {
     if (!h->launch_failed) h->err = std::string("conv_umma launch: ") + cudaGetErrorString(e);
@@ -565,8 +572,9 @@ void run_bigru(Ctx& c, const CbhgDev& D, const float* xproj, const int32_t* leng
 }
 
 // reference cbhg() (models/modules.py:35-74).  x: [N,T,Cin] with batch stride x_bs; out [N,T,256] dense.
+// x_split (tensor-core path): x already as the conv bank's hi/lo operand [N][T][g_bank.Cp] (written by the producer's epilogue)
 void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, const int32_t* lengths, int N,
-              int T, int bn_mode, float* out) {
+              int T, int bn_mode, float* out, const BfScratch* x_split = nullptr) {
   const int K = D.K, BC = K * 128, Cin = D.Cin;
   const int64_t rows = (int64_t)N * T;
   float* bank = ws.take<float>(rows * BC);
@@ -578,14 +586,19 @@ void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, 
   float* xproj = ws.take<float>(rows * 768);
   float* bnv = ws.take<float>(2 * 2048);          // batch-mode scale | shift
   double* bnacc = ws.take<double>(2 * 2048);
-  BfScratch sc;
-  if (c.h->gemm_mode != 0) sc = take_bf(ws, rows, BC);
+  BfScratch sc, sc2;                 // sc: operands as wide as the bank output; sc2: the narrow ones in between (<= 256 channels)
+  if (c.h->gemm_mode != 0) { sc = take_bf(ws, rows, BC); sc2 = take_bf(ws, rows, 256); }
   if (ws.overflow) return;
   const bool batch = bn_mode == TACO_BN_BATCH;
+  // Producer-side operand split (tensor-core path, moving statistics): a GEMM whose result is only (or also) the A operand of
+  // the next GEMM writes it as bf16 hi/lo from its own epilogue -- proj_1 -> proj_2, proj_2 -> dense -- instead of an fp32 round
+  // trip through split_bf16_kernel.  Batch statistics need the fp32 tensors (moments, in-place affine): the split passes stay.
+  const bool chain = c.h->gemm_mode != 0 && !batch;
   // conv bank: K convolutions written side by side (tf.concat, modules.py:39-42)
   if (c.h->gemm_mode != 0) {   // one launch for the whole bank
-    gemm(c, D.g_bank, sc, x, x_bs, Cin, N, T, c.W(D.bank_bias), batch ? nullptr : c.W(D.bank_scale),
-         batch ? nullptr : c.W(D.bank_shift), nullptr, 0, 0, bank, (int64_t)T * BC, BC, 0, TACO_ACT_RELU);
+    gemm(c, D.g_bank, x_split != nullptr ? *x_split : sc, x, x_bs, Cin, N, T, c.W(D.bank_bias), batch ? nullptr : c.W(D.bank_scale),
+         batch ? nullptr : c.W(D.bank_shift), nullptr, 0, 0, bank, (int64_t)T * BC, BC, 0, TACO_ACT_RELU, EPI_PLAIN,
+         /*presplit=*/x_split != nullptr);
   } else {
     for (int k = 1; k <= K; ++k) {
       const int o = (k - 1) * 128;
@@ -607,7 +620,7 @@ void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, 
   // proj_1: conv k=3 + ReLU + BN
   gemm(c, D.g_p1, sc, pooled, (int64_t)T * BC, BC, N, T, c.W(D.p1_b), batch ? nullptr : c.W(D.p1_scale),
        batch ? nullptr : c.W(D.p1_shift), nullptr, 0, 0, p1, (int64_t)T * D.P1, D.P1, 0, TACO_ACT_RELU, EPI_PLAIN,
-       fuse_split);
+       fuse_split, chain ? &sc2 : nullptr, D.g_p2.Cp, /*skip_fp32=*/chain);   // proj_1's output feeds proj_2 only
   if (batch) {
     launch_bn_batch_stats(p1, (int64_t)T * D.P1, D.P1, 0, N, T, D.P1, c.W(D.p1_gamma), c.W(D.p1_beta), kBnEps,
                           bnacc, bnv, bnv + 2048, c.st);
@@ -615,9 +628,10 @@ void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, 
     c.h->launches += 3;
   }
   // proj_2: conv k=3 + BN (no activation) + residual (modules.py:53,56)
-  gemm(c, D.g_p2, sc, p1, (int64_t)T * D.P1, D.P1, N, T, c.W(D.p2_b), batch ? nullptr : c.W(D.p2_scale),
+  const bool p2_to_dense = chain && D.P2 != 128;   // post-net: proj_2's output feeds the 80 -> 128 dense only
+  gemm(c, D.g_p2, chain ? sc2 : sc, p1, (int64_t)T * D.P1, D.P1, N, T, c.W(D.p2_b), batch ? nullptr : c.W(D.p2_scale),
        batch ? nullptr : c.W(D.p2_shift), batch ? nullptr : x, x_bs, Cin, p2, (int64_t)T * D.P2, D.P2, 0,
-       TACO_ACT_NONE);
+       TACO_ACT_NONE, EPI_PLAIN, /*presplit=*/chain, p2_to_dense ? &sc : nullptr, D.g_dense.Cp, /*skip_fp32=*/p2_to_dense);
   if (batch) {
     launch_bn_batch_stats(p2, (int64_t)T * D.P2, D.P2, 0, N, T, D.P2, c.W(D.p2_gamma), c.W(D.p2_beta), kBnEps,
                           bnacc, bnv, bnv + 2048, c.st);
@@ -627,7 +641,7 @@ void run_cbhg(Ctx& c, const CbhgDev& D, Bump& ws, const float* x, int64_t x_bs, 
   const float* hin = p2;
   if (D.P2 != 128) {   // modules.py:59-60
     gemm(c, D.g_dense, sc, p2, (int64_t)T * D.P2, D.P2, N, T, c.W(D.dense_b), nullptr, nullptr, nullptr, 0, 0, hwb,
-         (int64_t)T * 128, 128, 0, TACO_ACT_NONE);
+         (int64_t)T * 128, 128, 0, TACO_ACT_NONE, EPI_PLAIN, /*presplit=*/p2_to_dense);
     hin = hwb;
   }
   // 4 highway layers (modules.py:63-64): one fused launch on the tensor-core path (the activation stays in registers, the result
@@ -735,25 +749,27 @@ int do_encoder(taco_handle* h, Bump& ws, const int32_t* ids, const int32_t* leng
   float* emb = ws.take<float>(rows * (E + Es));
   float* a1 = ws.take<float>(rows * 256);
   float* a2 = ws.take<float>(rows * 128);
-  BfScratch sc;
-  if (h->gemm_mode != 0) sc = take_bf(ws, rows, 512);
+  BfScratch sc, sc2;
+  if (h->gemm_mode != 0) { sc = take_bf(ws, rows, 512); sc2 = take_bf(ws, rows, 512); }
   if (ws.overflow) return fail(h, TACO_ERR_INVALID, "workspace overflow (encoder)");
   launch_gather_concat(ids, multi ? spk : nullptr, c.W(h->emb), hp.num_symbols, E, multi ? c.W(h->emb_id) : nullptr,
                        hp.id_num, Es, N, T_in, emb, h->d_ints, st);
   h->launches += 1;
   // encoder prenet (modules.py:5-12; dropout is the identity)
+  // prenet: dense_1's output feeds dense_2 only, dense_2's feeds the conv bank (as its operand) and proj_2 (as the fp32 residual)
+  const bool chain = h->gemm_mode != 0;
   gemm(c, h->g_pre1, sc, emb, (int64_t)T_in * (E + Es), E + Es, N, T_in, c.W(h->pre1_b), nullptr, nullptr, nullptr, 0, 0,
-       a1, (int64_t)T_in * 256, 256, 0, TACO_ACT_RELU);
-  gemm(c, h->g_pre2, sc, a1, (int64_t)T_in * 256, 256, N, T_in, c.W(h->pre2_b), nullptr, nullptr, nullptr, 0, 0, a2,
-       (int64_t)T_in * 128, 128, 0, TACO_ACT_RELU);
-  run_cbhg(c, h->enc, ws, a2, (int64_t)T_in * 128, lengths, N, T_in, bn_mode, memory_out);
+       a1, (int64_t)T_in * 256, 256, 0, TACO_ACT_RELU, EPI_PLAIN, false, chain ? &sc2 : nullptr, h->g_pre2.Cp, /*skip_fp32=*/chain);
+  gemm(c, h->g_pre2, chain ? sc2 : sc, a1, (int64_t)T_in * 256, 256, N, T_in, c.W(h->pre2_b), nullptr, nullptr, nullptr, 0, 0, a2,
+       (int64_t)T_in * 128, 128, 0, TACO_ACT_RELU, EPI_PLAIN, /*presplit=*/chain, chain ? &sc : nullptr, h->enc.g_bank.Cp, false);
+  run_cbhg(c, h->enc, ws, a2, (int64_t)T_in * 128, lengths, N, T_in, bn_mode, memory_out, chain ? &sc : nullptr);
   if (ws.overflow) return fail(h, TACO_ERR_INVALID, "workspace overflow (encoder cbhg)");
   return check_launch(h, "encoder");
 }
 
 size_t encoder_ws_bytes(const taco_handle* h, int N, int T_in) {
   const int64_t rows = (int64_t)N * T_in;
-  return sizeof(float) * ((size_t)rows * (h->emb_dim + 256 + 128 + 512) + cbhg_ws_floats(16, 128, 128, rows)) + 65536;
+  return sizeof(float) * ((size_t)rows * (h->emb_dim + 256 + 128 + 512 + 512) + cbhg_ws_floats(16, 128, 128, rows)) + 65536;
 }
 size_t postnet_ws_bytes(const taco_handle* h, int N, int T) {
   const int64_t rows = (int64_t)N * T;
