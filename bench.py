@@ -390,7 +390,8 @@ def run_ours(args):
     # holds one of the compute slots until its decoder loop is done (its post-net then fills the SMs the next lane's
     # decoder leaves free) and gives it up before its 144 MB of D2H.  Measured on B200 (lanes, slots -> M frames/s):
     # round 1: (2,1) 6.2-7.2, (3,2) 6.4, (4,2) 8.3-8.4, (5,2) 8.3, (6,2) 8.8, (6,3) 8.7, (8,2) 8.5;
-    # round 2 (faster GEMMs, CUDA-graph forward, >= 4 batches per lane timed): (5,2) 11.0, (6,2) 10.5, (6,3) 8.9, (8,3) 11.1, (8,2) 11.5.
+    # round 2 (faster GEMMs, CUDA-graph forward, >= 4 batches per lane timed): (5,2) 11.0, (6,2) 10.5, (6,3) 8.9, (8,3) 11.1, (8,2) 11.5;
+    # at the end of round 2 (median of three regions): (6,2) 10.3, (8,2) 11.3, (10,2) 11.8, (12,2) 11.9, (10,3) 11.1 -> ten lanes.
     n_slots = int(os.environ.get("TACO_E2E_SLOTS", 2 if n_lanes >= 3 else 1))
     release_stage = int(os.environ.get("TACO_E2E_RELEASE", 0))   # 0: when the decoder loop is done, 1: all kernels
     compute_slots = threading.Semaphore(n_slots)
@@ -623,7 +624,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU restatement leg")
     ap.add_argument("--inflight", type=int, default=4, help="batches in flight per GPU (handles/streams), device-resident leg")
-    ap.add_argument("--e2e-lanes", type=int, default=8, help="batches in flight per GPU in the end-to-end leg")
+    ap.add_argument("--e2e-lanes", type=int, default=10, help="batches in flight per GPU in the end-to-end leg")
     ap.add_argument("--no-latency", action="store_true", help="skip the batch-1 latency leg")
     ap.add_argument("--no-vocoder", action="store_true", help="skip the informational Griffin-Lim leg")
     ap.add_argument("--no-throughput-mode", action="store_true", help="skip the informational 4-cluster decoder legs")
